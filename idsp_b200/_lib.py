@@ -1,0 +1,94 @@
+"""ctypes binding of the C ABI in include/idsp_b200.h (libidsp_b200.so).
+
+There is no CPU fallback: if the shared library is missing this raises.  Build
+it with ``python -m idsp_b200.build`` (nvcc, sm_100a).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libidsp_b200.so")
+
+_c_p = C.c_void_p
+_sz = C.c_size_t
+_i = C.c_int
+
+# (name, argtypes) for every symbol declared in include/idsp_b200.h
+_KINDS = ("i8", "i16", "i32", "i64", "f32", "f64")
+
+
+def _signatures():
+    sig = {
+        "idsp_b200_init": ([_i, C.POINTER(_c_p)], _i),
+        "idsp_b200_init_on_stream": ([_i, _c_p, C.POINTER(_c_p)], _i),
+        "idsp_b200_free": ([_c_p], None),
+        "idsp_b200_sync": ([_c_p], _i),
+        "idsp_b200_last_error": ([], C.c_char_p),
+        "idsp_b200_version": ([], _i),
+        "idsp_b200_launch_count": ([_c_p], C.c_uint64),
+        "idsp_b200_set_kernel_policy": ([_c_p, _i], _i),
+        "idsp_hbf_taps": ([_i, C.POINTER(_i)], C.POINTER(C.c_float)),
+        "idsp_hbf_dec_state_words": ([_i], _sz),
+        "idsp_hbf_int_state_words": ([_i], _sz),
+        "idsp_chain_state_words": ([_i], _sz),
+    }
+    lanes_tail = [_sz, _sz, _i]
+    for k in _KINDS:
+        # ctx, ba, F, clamp, state, x, y, frames, lanes, layout
+        sig[f"idsp_biquad_df1_{k}"] = ([_c_p, _c_p, _i, _c_p, _c_p, _c_p, _c_p] + lanes_tail, _i)
+        sig[f"idsp_biquad_df1_{k}_host"] = ([_c_p, _c_p, _i, _c_p, _c_p, _c_p, _c_p] + lanes_tail, _i)
+        # ctx, ba, F, nsec, state, x, y, frames, lanes, layout
+        sig[f"idsp_biquad_cascade_{k}"] = ([_c_p, _c_p, _i, _i, _c_p, _c_p, _c_p] + lanes_tail, _i)
+    for k in ("f32", "f64"):
+        sig[f"idsp_biquad_df2t_{k}"] = ([_c_p, _c_p, _c_p, _c_p, _c_p, _c_p] + lanes_tail, _i)
+    for n in ("idsp_biquad_df1wide_i32", "idsp_biquad_df1dither_i32"):
+        sig[n] = ([_c_p, _c_p, _i, _c_p, _c_p, _c_p, _c_p] + lanes_tail, _i)
+    # ctx, taps, M, state, x, y, n, lanes, layout
+    sig["idsp_hbf_dec_f32"] = ([_c_p, _c_p, _i, _c_p, _c_p, _c_p] + lanes_tail, _i)
+    sig["idsp_hbf_int_f32"] = ([_c_p, _c_p, _i, _c_p, _c_p, _c_p] + lanes_tail, _i)
+    sig["idsp_fir_f32"] = ([_c_p, _c_p, _i, _i, _i, _c_p, _c_p, _c_p] + lanes_tail, _i)
+    # ctx, log2_rate, state, x, y, n, lanes, layout
+    for n in ("idsp_hbf_dec_cascade_f32", "idsp_hbf_dec_cascade_f32_host", "idsp_hbf_int_cascade_f32"):
+        sig[n] = ([_c_p, _i, _c_p, _c_p, _c_p] + lanes_tail, _i)
+    sig["idsp_chain_f32"] = ([_c_p, _i, _c_p, _c_p, _c_p, _c_p] + lanes_tail, _i)
+    for n in ("idsp_cossin_i32", "idsp_cossin_i32_host", "idsp_atan2_i32", "idsp_atan2_i32_host"):
+        sig[n] = ([_c_p, _c_p, _c_p, _sz], _i)
+    sig["idsp_lowpass_i32"] = ([_c_p, _i, _c_p, _c_p, _c_p, _c_p] + lanes_tail, _i)
+    for n in ("idsp_lockin_i32", "idsp_lockin_i32_host"):
+        sig[n] = ([_c_p, _i, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p] + lanes_tail, _i)
+    return sig
+
+
+SIGNATURES = _signatures()
+
+_lib = None
+
+
+class IdspError(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    """Load the CUDA library; fail loudly if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise IdspError(
+                f"{LIB_PATH} not found: the CUDA extension is not built "
+                "(run `python -m idsp_b200.build`). There is no CPU fallback."
+            )
+        L = C.CDLL(LIB_PATH)
+        for name, (args, res) in SIGNATURES.items():
+            fn = getattr(L, name)  # AttributeError if a declared symbol is missing
+            fn.argtypes = args
+            fn.restype = res
+        _lib = L
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = lib().idsp_b200_last_error().decode(errors="replace")
+        raise IdspError(f"idsp_b200 error {rc}: {msg}")

@@ -1,0 +1,59 @@
+"""Build the sm_100a shared library in-tree (nvcc cross-compiles without a GPU).
+
+    python -m idsp_b200.build [--force] [--verbose]
+
+Output: idsp_b200/libidsp_b200.so  (git-ignored, travels to the GPU box with gpurun).
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "libidsp_b200.so")
+SOURCES = ["ctx.cu", "biquad.cu", "hbf.cu", "trig_lockin.cu"]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    # bit-exact float parity with the reference: no FMA contraction, no FTZ, IEEE div/sqrt
+    "-fmad=false", "-ftz=false", "-prec-div=true", "-prec-sqrt=true",
+    "-Xcompiler", "-fPIC", "-shared",
+    "-cudart", "static",
+]
+
+
+def _stale() -> bool:
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    deps.append(os.path.join(HERE, "..", "include", "idsp_b200.h"))
+    deps.append(os.path.abspath(__file__))
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not _stale():
+        return OUT
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc, *NVCC_FLAGS]
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+    cmd += ["-ccbin", "g++", "-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
+    env = dict(os.environ)
+    env.pop("CC", None)
+    env.pop("CXX", None)
+    res = subprocess.run(cmd, cwd=CSRC, env=env, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("nvcc failed building libidsp_b200.so")
+    if verbose:
+        sys.stderr.write(res.stdout + res.stderr)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

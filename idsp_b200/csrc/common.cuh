@@ -1,0 +1,86 @@
+// common.cuh -- context, error plumbing and launch helpers shared by all .cu files.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/idsp_b200.h"
+
+struct idsp_ctx {
+    int device;
+    cudaStream_t stream;
+    bool own_stream;
+    uint64_t launches;
+    int policy;  // 0 auto, 1 generic, 2 TMA
+    int sm_count;
+    // host streaming (the *_host entry points): pinned staging + device ring
+    cudaStream_t s_h2d, s_d2h;
+    void *pin_in[2], *pin_out[2];
+    void *dev_in[2], *dev_out[2];
+    size_t pin_in_bytes, pin_out_bytes, dev_in_bytes, dev_out_bytes;
+    void *dev_state;
+    size_t dev_state_bytes;
+    cudaEvent_t ev_h2d[2], ev_k[2], ev_d2h[2];
+};
+
+void idsp_set_error(const char *fmt, ...);
+
+#define IDSP_CHECK_ARG(cond, msg)                          \
+    do {                                                   \
+        if (!(cond)) {                                     \
+            idsp_set_error("%s: %s", __func__, msg);       \
+            return IDSP_EINVAL;                            \
+        }                                                  \
+    } while (0)
+
+#define IDSP_CUDA(call)                                                              \
+    do {                                                                             \
+        cudaError_t e_ = (call);                                                     \
+        if (e_ != cudaSuccess) {                                                     \
+            idsp_set_error("%s: %s failed: %s", __func__, #call, cudaGetErrorString(e_)); \
+            return IDSP_ECUDA;                                                       \
+        }                                                                            \
+    } while (0)
+
+// after a kernel launch
+#define IDSP_LAUNCHED(ctx)                                                           \
+    do {                                                                             \
+        (ctx)->launches++;                                                           \
+        cudaError_t e_ = cudaGetLastError();                                         \
+        if (e_ != cudaSuccess) {                                                     \
+            idsp_set_error("%s: kernel launch failed: %s", __func__, cudaGetErrorString(e_)); \
+            return IDSP_ECUDA;                                                       \
+        }                                                                            \
+    } while (0)
+
+static inline int idsp_use_device(idsp_ctx *ctx) {
+    if (!ctx) {
+        idsp_set_error("null ctx");
+        return IDSP_EINVAL;
+    }
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) {
+        idsp_set_error("cudaSetDevice(%d): %s", ctx->device, cudaGetErrorString(e));
+        return IDSP_ECUDA;
+    }
+    return IDSP_OK;
+}
+
+// Host streaming helper (ctx.cu): cuts the frame axis (frame-major) or the lane axis
+// (lane-major) into chunks [a0, a0+an) and runs `launch(dev_blobs, dev_x, dev_y, a0, an)`
+// per chunk with H2D / compute / D2H overlapped.  dev_x/dev_y hold only the chunk.
+#include <functional>
+struct HostStreamSpec {
+    size_t frames;            // total frames
+    size_t lanes;
+    size_t in_bytes_per_frame_lane;   // bytes per lane per frame of x
+    size_t out_bytes_per_frame_lane;  // bytes per lane per frame of y
+    int layout;
+    // state blobs (host <-> device), copied before/after
+    struct Blob { void *host; size_t bytes; bool writeback; };
+    Blob blobs[3];
+    int nblobs;
+};
+typedef std::function<int(void **dev_blobs, const void *dx, void *dy, size_t a0, size_t an)> HostStreamLaunch;
+int idsp_host_stream(idsp_ctx *ctx, const HostStreamSpec &spec, const void *x, void *y,
+                     const HostStreamLaunch &launch);

@@ -1,0 +1,245 @@
+// ctx.cu -- context lifetime, error reporting, host-buffer streaming.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void idsp_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *idsp_b200_last_error(void) { return g_err; }
+extern "C" int idsp_b200_version(void) { return IDSP_B200_VERSION; }
+
+static int ctx_create(int device, cudaStream_t stream, bool own, idsp_ctx **out) {
+    if (!out) {
+        idsp_set_error("idsp_b200_init: out is null");
+        return IDSP_EINVAL;
+    }
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        idsp_set_error("idsp_b200_init: no CUDA device (%s)", cudaGetErrorString(e));
+        return IDSP_ENODEV;
+    }
+    if (device < 0 || device >= n) {
+        idsp_set_error("idsp_b200_init: device %d out of range (0..%d)", device, n - 1);
+        return IDSP_EINVAL;
+    }
+    cudaDeviceProp prop;
+    IDSP_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        // sm_100a-only binary: there is deliberately no other code path
+        idsp_set_error("idsp_b200_init: device %d is sm_%d%d, this library is built for sm_100a only",
+                       device, prop.major, prop.minor);
+        return IDSP_ENODEV;
+    }
+    IDSP_CUDA(cudaSetDevice(device));
+    idsp_ctx *c = new idsp_ctx();
+    memset(c, 0, sizeof(*c));
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->own_stream = own;
+    if (own) {
+        e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            idsp_set_error("cudaStreamCreate: %s", cudaGetErrorString(e));
+            delete c;
+            return IDSP_ECUDA;
+        }
+    } else {
+        c->stream = stream;
+    }
+    *out = c;
+    return IDSP_OK;
+}
+
+extern "C" int idsp_b200_init(int device, idsp_ctx **out) {
+    return ctx_create(device, nullptr, true, out);
+}
+extern "C" int idsp_b200_init_on_stream(int device, void *cuda_stream, idsp_ctx **out) {
+    return ctx_create(device, (cudaStream_t)cuda_stream, false, out);
+}
+
+static void free_staging(idsp_ctx *c) {
+    for (int i = 0; i < 2; i++) {
+        if (c->pin_in[i]) cudaFreeHost(c->pin_in[i]);
+        if (c->pin_out[i]) cudaFreeHost(c->pin_out[i]);
+        if (c->dev_in[i]) cudaFree(c->dev_in[i]);
+        if (c->dev_out[i]) cudaFree(c->dev_out[i]);
+        c->pin_in[i] = c->pin_out[i] = c->dev_in[i] = c->dev_out[i] = nullptr;
+        if (c->ev_h2d[i]) cudaEventDestroy(c->ev_h2d[i]);
+        if (c->ev_k[i]) cudaEventDestroy(c->ev_k[i]);
+        if (c->ev_d2h[i]) cudaEventDestroy(c->ev_d2h[i]);
+        c->ev_h2d[i] = c->ev_k[i] = c->ev_d2h[i] = nullptr;
+    }
+    if (c->dev_state) cudaFree(c->dev_state);
+    c->dev_state = nullptr;
+    c->pin_in_bytes = c->pin_out_bytes = c->dev_in_bytes = c->dev_out_bytes = c->dev_state_bytes = 0;
+    if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
+    if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
+    c->s_h2d = c->s_d2h = nullptr;
+}
+
+extern "C" void idsp_b200_free(idsp_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    free_staging(ctx);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" int idsp_b200_sync(idsp_ctx *ctx) {
+    int r = idsp_use_device(ctx);
+    if (r) return r;
+    IDSP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return IDSP_OK;
+}
+
+extern "C" uint64_t idsp_b200_launch_count(const idsp_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int idsp_b200_set_kernel_policy(idsp_ctx *ctx, int policy) {
+    if (!ctx || policy < 0 || policy > 2) {
+        idsp_set_error("idsp_b200_set_kernel_policy: bad argument");
+        return IDSP_EINVAL;
+    }
+    ctx->policy = policy;
+    return IDSP_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Host streaming: x/y/state live in host memory.  The frame (frame-major) or
+// lane (lane-major) axis is cut into chunks that are double-buffered through the
+// device: H2D of chunk i+1 overlaps the kernel on chunk i and the D2H of chunk
+// i-1 (three streams, events).  If the caller's buffers are pinned
+// (cudaHostAlloc / cudaHostRegister / torch pin_memory) the DMA engines read and
+// write them directly; pageable buffers still work (the driver stages them).
+// ---------------------------------------------------------------------------
+static int ensure_dev(void **p, size_t *have, size_t need) {
+    if (*have >= need) return IDSP_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *have = 0;
+    cudaError_t e = cudaMalloc(p, need);
+    if (e != cudaSuccess) {
+        idsp_set_error("cudaMalloc(%zu): %s", need, cudaGetErrorString(e));
+        return IDSP_ENOMEM;
+    }
+    *have = need;
+    return IDSP_OK;
+}
+
+int idsp_host_stream(idsp_ctx *ctx, const HostStreamSpec &spec, const void *x, void *y,
+                     const HostStreamLaunch &launch) {
+    int r = idsp_use_device(ctx);
+    if (r) return r;
+    if (!ctx->s_h2d) {
+        IDSP_CUDA(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
+        IDSP_CUDA(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            IDSP_CUDA(cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming));
+            IDSP_CUDA(cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming));
+            IDSP_CUDA(cudaEventCreateWithFlags(&ctx->ev_d2h[i], cudaEventDisableTiming));
+        }
+    }
+    // state blobs -> device (one allocation, 256 B aligned sub-blobs)
+    size_t off[3] = {0, 0, 0}, tot = 0;
+    for (int i = 0; i < spec.nblobs; i++) {
+        off[i] = tot;
+        tot += (spec.blobs[i].bytes + 255) & ~(size_t)255;
+    }
+    r = ensure_dev(&ctx->dev_state, &ctx->dev_state_bytes, tot ? tot : 256);
+    if (r) return r;
+    void *dblobs[3] = {nullptr, nullptr, nullptr};
+    for (int i = 0; i < spec.nblobs; i++) {
+        dblobs[i] = (char *)ctx->dev_state + off[i];
+        IDSP_CUDA(cudaMemcpyAsync(dblobs[i], spec.blobs[i].host, spec.blobs[i].bytes,
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    }
+    const bool fm = spec.layout == IDSP_FRAME_MAJOR;
+    // chunk axis: frames (frame-major) or lanes (lane-major); unit = bytes per index
+    const size_t n_axis = fm ? spec.frames : spec.lanes;
+    const size_t other = fm ? spec.lanes : spec.frames;
+    const size_t in_unit = other * spec.in_bytes_per_frame_lane;
+    const size_t out_unit = other * spec.out_bytes_per_frame_lane;
+    const size_t target = (size_t)256 << 20;  // ~256 MiB of input per chunk
+    size_t chunk = in_unit ? target / in_unit : n_axis;
+    if (!fm) chunk &= ~(size_t)127;  // keep lane chunks warp/CTA aligned
+    if (chunk < (fm ? 1u : 128u)) chunk = fm ? 1 : 128;
+    if (chunk > n_axis) chunk = n_axis;
+    if (n_axis == 0) chunk = 0;
+    // (re)allocate the two device in/out buffers
+    const size_t need_in = chunk * in_unit, need_out = chunk * out_unit;
+    if (ctx->dev_in_bytes < need_in) {
+        for (int i = 0; i < 2; i++) {
+            if (ctx->dev_in[i]) cudaFree(ctx->dev_in[i]);
+            ctx->dev_in[i] = nullptr;
+        }
+        for (int i = 0; i < 2; i++) {
+            cudaError_t e = cudaMalloc(&ctx->dev_in[i], need_in ? need_in : 256);
+            if (e != cudaSuccess) {
+                idsp_set_error("cudaMalloc(%zu): %s", need_in, cudaGetErrorString(e));
+                ctx->dev_in_bytes = 0;
+                return IDSP_ENOMEM;
+            }
+        }
+        ctx->dev_in_bytes = need_in;
+    }
+    if (ctx->dev_out_bytes < need_out) {
+        for (int i = 0; i < 2; i++) {
+            if (ctx->dev_out[i]) cudaFree(ctx->dev_out[i]);
+            ctx->dev_out[i] = nullptr;
+        }
+        for (int i = 0; i < 2; i++) {
+            cudaError_t e = cudaMalloc(&ctx->dev_out[i], need_out ? need_out : 256);
+            if (e != cudaSuccess) {
+                idsp_set_error("cudaMalloc(%zu): %s", need_out, cudaGetErrorString(e));
+                ctx->dev_out_bytes = 0;
+                return IDSP_ENOMEM;
+            }
+        }
+        ctx->dev_out_bytes = need_out;
+    }
+    // the blobs must be on the device before the first kernel; kernels run on ctx->stream
+    size_t nchunks = chunk ? (n_axis + chunk - 1) / chunk : 0;
+    for (size_t c = 0; c < nchunks; c++) {
+        const int b = (int)(c & 1);
+        const size_t a0 = c * chunk;
+        const size_t an = (n_axis - a0) < chunk ? (n_axis - a0) : chunk;
+        // buffer b's previous kernel (chunk c-2) must be done before we overwrite its input,
+        // and its previous D2H done before the kernel overwrites its output
+        if (c >= 2) {
+            IDSP_CUDA(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_k[b], 0));
+            IDSP_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[b], 0));
+        }
+        IDSP_CUDA(cudaMemcpyAsync(ctx->dev_in[b], (const char *)x + a0 * in_unit, an * in_unit,
+                                  cudaMemcpyHostToDevice, ctx->s_h2d));
+        IDSP_CUDA(cudaEventRecord(ctx->ev_h2d[b], ctx->s_h2d));
+        IDSP_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[b], 0));
+        void *cb[3];
+        for (int i = 0; i < 3; i++) cb[i] = dblobs[i];
+        r = launch(cb, ctx->dev_in[b], ctx->dev_out[b], a0, an);
+        if (r) return r;
+        IDSP_CUDA(cudaEventRecord(ctx->ev_k[b], ctx->stream));
+        IDSP_CUDA(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_k[b], 0));
+        IDSP_CUDA(cudaMemcpyAsync((char *)y + a0 * out_unit, ctx->dev_out[b], an * out_unit,
+                                  cudaMemcpyDeviceToHost, ctx->s_d2h));
+        IDSP_CUDA(cudaEventRecord(ctx->ev_d2h[b], ctx->s_d2h));
+    }
+    for (int i = 0; i < spec.nblobs; i++) {
+        if (spec.blobs[i].writeback)
+            IDSP_CUDA(cudaMemcpyAsync(spec.blobs[i].host, dblobs[i], spec.blobs[i].bytes,
+                                      cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    IDSP_CUDA(cudaStreamSynchronize(ctx->s_d2h));
+    IDSP_CUDA(cudaStreamSynchronize(ctx->stream));
+    IDSP_CUDA(cudaStreamSynchronize(ctx->s_h2d));
+    return IDSP_OK;
+}

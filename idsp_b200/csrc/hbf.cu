@@ -1,0 +1,394 @@
+// hbf.cu -- C-ABI entry points of the half-band FIR family (include/idsp_b200.h).
+#include "common.cuh"
+#include "hbf_stages.cuh"
+#include "ops.cuh"
+#include "hbf_fast.cuh"
+
+using namespace idsp;
+
+static const float H_TAPS0[23] = IDSP_HBF_TAPS0;
+static const float H_TAPS1[10] = IDSP_HBF_TAPS1;
+static const float H_TAPS2[5] = IDSP_HBF_TAPS2;
+static const float H_TAPS3[4] = IDSP_HBF_TAPS3;
+static const float H_TAPS4[3] = IDSP_HBF_TAPS4;
+
+extern "C" const float *idsp_hbf_taps(int index, int *M) {
+    static const float *t[5] = {H_TAPS0, H_TAPS1, H_TAPS2, H_TAPS3, H_TAPS4};
+    if (index < 0 || index > 4) return nullptr;
+    if (M) *M = hbf_m(index);
+    return t[index];
+}
+extern "C" size_t idsp_hbf_dec_state_words(int k) { return (k < 0 || k > 5) ? 0 : (size_t)hbf_dec_words(k); }
+extern "C" size_t idsp_hbf_int_state_words(int k) { return (k < 0 || k > 5) ? 0 : (size_t)hbf_int_words(k); }
+extern "C" size_t idsp_chain_state_words(int k) {
+    return (k < 1 || k > 5) ? 0 : (size_t)(hbf_dec_words(k) + hbf_int_words(k) + 4);
+}
+
+// ---------------------------------------------------------------- register cascades
+template <int K> struct DecCascadeRegs {
+    DecStageRegs<K - 1> top;
+    DecCascadeRegs<K - 1> rest;
+    __device__ __forceinline__ void load(const float *st, size_t stride, size_t lane) {
+        top.load(st, stride, lane);
+        rest.load(st + (size_t)DecStageRegs<K - 1>::WORDS * stride, stride, lane);
+    }
+    __device__ __forceinline__ void store(float *st, size_t stride, size_t lane) const {
+        top.store(st, stride, lane);
+        rest.store(st + (size_t)DecStageRegs<K - 1>::WORDS * stride, stride, lane);
+    }
+    __device__ __forceinline__ float push(const float *x) {
+        float half[1 << (K - 1)];
+#pragma unroll
+        for (int j = 0; j < (1 << (K - 1)); j++) half[j] = top.push(x[2 * j], x[2 * j + 1]);
+        return rest.push(half);
+    }
+};
+template <> struct DecCascadeRegs<0> {
+    __device__ __forceinline__ void load(const float *, size_t, size_t) {}
+    __device__ __forceinline__ void store(float *, size_t, size_t) const {}
+    __device__ __forceinline__ float push(const float *x) { return x[0]; }
+};
+template <int K> struct IntCascadeRegs {
+    IntCascadeRegs<K - 1> low;
+    IntStageRegs<K - 1> top;
+    __device__ __forceinline__ void load(const float *st, size_t stride, size_t lane) {
+        low.load(st, stride, lane);
+        top.load(st + (size_t)hbf_int_words(K - 1) * stride, stride, lane);
+    }
+    __device__ __forceinline__ void store(float *st, size_t stride, size_t lane) const {
+        low.store(st, stride, lane);
+        top.store(st + (size_t)hbf_int_words(K - 1) * stride, stride, lane);
+    }
+    __device__ __forceinline__ void push(float x, float *out) {
+        float tmp[1 << (K - 1)];
+        low.push(x, tmp);
+#pragma unroll
+        for (int j = 0; j < (1 << (K - 1)); j++) {
+            float2 r = top.push(tmp[j]);
+            out[2 * j] = r.x;
+            out[2 * j + 1] = r.y;
+        }
+    }
+};
+template <> struct IntCascadeRegs<0> {
+    __device__ __forceinline__ void load(const float *, size_t, size_t) {}
+    __device__ __forceinline__ void store(float *, size_t, size_t) const {}
+    __device__ __forceinline__ void push(float x, float *out) { out[0] = x; }
+};
+
+template <int R> __device__ __forceinline__ void load_frame(const float *p, float *v) {
+    if constexpr (R >= 4) {
+#pragma unroll
+        for (int j = 0; j < R / 4; j++) {
+            float4 q = reinterpret_cast<const float4 *>(p)[j];
+            v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
+        }
+    } else if constexpr (R == 2) {
+        float2 q = *reinterpret_cast<const float2 *>(p);
+        v[0] = q.x; v[1] = q.y;
+    } else {
+        v[0] = p[0];
+    }
+}
+template <int R> __device__ __forceinline__ void store_frame(float *p, const float *v) {
+    if constexpr (R >= 4) {
+#pragma unroll
+        for (int j = 0; j < R / 4; j++)
+            reinterpret_cast<float4 *>(p)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    } else if constexpr (R == 2) {
+        *reinterpret_cast<float2 *>(p) = make_float2(v[0], v[1]);
+    } else {
+        p[0] = v[0];
+    }
+}
+
+// frame index helpers: element offset of (frame n, lane) in units of frames
+__device__ __forceinline__ size_t fidx(int layout, size_t n, size_t lane, size_t nframes, size_t lanes) {
+    return layout == IDSP_FRAME_MAJOR ? n * lanes + lane : lane * nframes + n;
+}
+
+// Generic thread-per-lane cascades (any shape / alignment). hbf_fast.cuh holds the
+// shared-memory tiled kernels used for the large aligned cases.
+template <int K>
+__global__ void __launch_bounds__(128)
+hbf_dec_cascade_generic(float *st, const float *x, float *y, size_t n_out, size_t lanes,
+                        size_t sstride, int layout) {
+    constexpr int R = 1 << K;
+    size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (lane >= lanes) return;
+    DecCascadeRegs<K> c;
+    c.load(st, sstride, lane);
+    for (size_t n = 0; n < n_out; n++) {
+        float v[R];
+        size_t f = fidx(layout, n, lane, n_out, lanes);
+        load_frame<R>(x + f * R, v);
+        y[f] = c.push(v);
+    }
+    c.store(st, sstride, lane);
+}
+template <int K>
+__global__ void __launch_bounds__(128)
+hbf_int_cascade_generic(float *st, const float *x, float *y, size_t n_in, size_t lanes,
+                        size_t sstride, int layout) {
+    constexpr int R = 1 << K;
+    size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (lane >= lanes) return;
+    IntCascadeRegs<K> c;
+    c.load(st, sstride, lane);
+    for (size_t n = 0; n < n_in; n++) {
+        float v[R];
+        size_t f = fidx(layout, n, lane, n_in, lanes);
+        c.push(x[f], v);
+        store_frame<R>(y + f * R, v);
+    }
+    c.store(st, sstride, lane);
+}
+// config-5 chain: /2^K -> x2^K -> DF1 f32 (biquad.rs:366-383)
+template <int K>
+__global__ void __launch_bounds__(128)
+chain_generic(float *st, Df1Op<float, false>::Params bp, const float *x, float *y, size_t n_low,
+              size_t lanes, size_t sstride, int layout) {
+    constexpr int R = 1 << K;
+    size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (lane >= lanes) return;
+    DecCascadeRegs<K> d;
+    IntCascadeRegs<K> u;
+    Df1Op<float, false> b;
+    d.load(st, sstride, lane);
+    u.load(st + (size_t)hbf_dec_words(K) * sstride, sstride, lane);
+    bp.st = st + (size_t)(hbf_dec_words(K) + hbf_int_words(K)) * sstride;
+    b.load(bp, lane, sstride);
+    for (size_t n = 0; n < n_low; n++) {
+        float v[R], o[R];
+        size_t f = fidx(layout, n, lane, n_low, lanes);
+        load_frame<R>(x + f * R, v);
+        u.push(d.push(v), o);
+#pragma unroll
+        for (int j = 0; j < R; j++) o[j] = b.step(bp, o[j]);
+        store_frame<R>(y + f * R, o);
+    }
+    d.store(st, sstride, lane);
+    u.store(st + (size_t)hbf_dec_words(K) * sstride, sstride, lane);
+    b.store(bp, lane, sstride);
+}
+
+// ---------------------------------------------------------------- runtime-tap single stages
+struct TapsParam {
+    float c[IDSP_HBF_MAX_M];
+    int M;
+};
+#define GEN_CH 8
+// hbf.rs:46-68 window sum for runtime M
+__device__ __forceinline__ float window_sum(const TapsParam &tp, const float *w, int odd, int sym) {
+    const int M = tp.M;
+    const float *nw = w + M + odd;
+    float a0 = sym ? (nw[M - 1] + w[0]) : (nw[M - 1] - w[0]);
+    float acc = a0 * tp.c[0];
+    for (int i = 1; i < M; i++) {
+        float a = sym ? (nw[M - 1 - i] + w[i]) : (nw[M - 1 - i] - w[i]);
+        acc = acc + a * tp.c[i];
+    }
+    if (odd && sym) acc = acc + w[M];
+    return acc;
+}
+__global__ void __launch_bounds__(128)
+hbf_dec_single(TapsParam tp, float *st, const float *x, float *y, size_t n_out, size_t lanes,
+               size_t sstride, int layout) {
+    size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (lane >= lanes) return;
+    const int M = tp.M, LEN = 2 * M - 1;
+    float ev[IDSP_HBF_MAX_M + GEN_CH], od[2 * IDSP_HBF_MAX_M + GEN_CH];
+    for (int i = 0; i < M - 1; i++) ev[i] = st[(size_t)i * sstride + lane];
+    for (int i = 0; i < LEN; i++) od[i] = st[(size_t)(M - 1 + i) * sstride + lane];
+    for (size_t o = 0; o < n_out; o += GEN_CH) {
+        int c = (int)((n_out - o) < GEN_CH ? (n_out - o) : GEN_CH);
+        for (int i = 0; i < c; i++) {
+            float2 p = *reinterpret_cast<const float2 *>(x + 2 * fidx(layout, o + i, lane, n_out, lanes));
+            ev[M - 1 + i] = p.x;
+            od[LEN + i] = p.y;
+        }
+        for (int i = 0; i < c; i++)
+            y[fidx(layout, o + i, lane, n_out, lanes)] = window_sum(tp, od + i, 0, 1) + ev[i];
+        for (int i = 0; i < M - 1; i++) ev[i] = ev[i + c];
+        for (int i = 0; i < LEN; i++) od[i] = od[i + c];
+    }
+    for (int i = 0; i < M - 1; i++) st[(size_t)i * sstride + lane] = ev[i];
+    for (int i = 0; i < LEN; i++) st[(size_t)(M - 1 + i) * sstride + lane] = od[i];
+}
+__global__ void __launch_bounds__(128)
+hbf_int_single(TapsParam tp, float *st, const float *x, float *y, size_t n_in, size_t lanes,
+               size_t sstride, int layout) {
+    size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (lane >= lanes) return;
+    const int M = tp.M, LEN = 2 * M - 1;
+    float xs[2 * IDSP_HBF_MAX_M + GEN_CH];
+    for (int i = 0; i < LEN; i++) xs[i] = st[(size_t)i * sstride + lane];
+    for (size_t o = 0; o < n_in; o += GEN_CH) {
+        int c = (int)((n_in - o) < GEN_CH ? (n_in - o) : GEN_CH);
+        for (int i = 0; i < c; i++) xs[LEN + i] = x[fidx(layout, o + i, lane, n_in, lanes)];
+        for (int i = 0; i < c; i++) {
+            float2 r = make_float2(window_sum(tp, xs + i, 0, 1), xs[M + i]);
+            *reinterpret_cast<float2 *>(y + 2 * fidx(layout, o + i, lane, n_in, lanes)) = r;
+        }
+        for (int i = 0; i < LEN; i++) xs[i] = xs[i + c];
+    }
+    for (int i = 0; i < LEN; i++) st[(size_t)i * sstride + lane] = xs[i];
+}
+__global__ void __launch_bounds__(128)
+fir_single(TapsParam tp, int odd, int sym, float *st, const float *x, float *y, size_t n,
+           size_t lanes, size_t sstride, int layout) {
+    size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (lane >= lanes) return;
+    const int M = tp.M, LEN = 2 * M - 1 + odd;
+    float xs[2 * IDSP_HBF_MAX_M + 1 + GEN_CH];
+    for (int i = 0; i < LEN; i++) xs[i] = st[(size_t)i * sstride + lane];
+    for (size_t o = 0; o < n; o += GEN_CH) {
+        int c = (int)((n - o) < GEN_CH ? (n - o) : GEN_CH);
+        for (int i = 0; i < c; i++) xs[LEN + i] = x[fidx(layout, o + i, lane, n, lanes)];
+        for (int i = 0; i < c; i++)
+            y[fidx(layout, o + i, lane, n, lanes)] = window_sum(tp, xs + i, odd, sym);
+        for (int i = 0; i < LEN; i++) xs[i] = xs[i + c];
+    }
+    for (int i = 0; i < LEN; i++) st[(size_t)i * sstride + lane] = xs[i];
+}
+
+// ---------------------------------------------------------------- ABI
+#define HBF_COMMON_CHECK(nframes)                                                    \
+    do {                                                                             \
+        int r_ = idsp_use_device(ctx);                                               \
+        if (r_) return r_;                                                           \
+        IDSP_CHECK_ARG(layout == IDSP_FRAME_MAJOR || layout == IDSP_LANE_MAJOR,      \
+                       "layout must be 0 (frame-major) or 1 (lane-major)");          \
+        if ((nframes) == 0 || lanes == 0) return IDSP_OK;                            \
+        IDSP_CHECK_ARG(state != nullptr && x != nullptr && y != nullptr,             \
+                       "state/x/y must not be null");                                \
+    } while (0)
+
+static int taps_param(const float *taps, int M, TapsParam *tp) {
+    if (!taps || M < 1 || M > IDSP_HBF_MAX_M) {
+        idsp_set_error("taps must be non-null and 1 <= M <= %d", IDSP_HBF_MAX_M);
+        return IDSP_EINVAL;
+    }
+    for (int i = 0; i < IDSP_HBF_MAX_M; i++) tp->c[i] = i < M ? taps[i] : 0.f;
+    tp->M = M;
+    return IDSP_OK;
+}
+
+extern "C" int idsp_hbf_dec_f32(idsp_ctx *ctx, const float *taps, int M, float *state,
+                                const float *x, float *y, size_t n_out, size_t lanes, int layout) {
+    HBF_COMMON_CHECK(n_out);
+    IDSP_CHECK_ARG(M >= 2, "decimator needs M >= 2");
+    TapsParam tp;
+    int r = taps_param(taps, M, &tp);
+    if (r) return r;
+    hbf_dec_single<<<(unsigned)((lanes + 127) / 128), 128, 0, ctx->stream>>>(tp, state, x, y, n_out,
+                                                                           lanes, lanes, layout);
+    IDSP_LAUNCHED(ctx);
+    return IDSP_OK;
+}
+extern "C" int idsp_hbf_int_f32(idsp_ctx *ctx, const float *taps, int M, float *state,
+                                const float *x, float *y, size_t n_in, size_t lanes, int layout) {
+    HBF_COMMON_CHECK(n_in);
+    IDSP_CHECK_ARG(M >= 2, "interpolator needs M >= 2");
+    TapsParam tp;
+    int r = taps_param(taps, M, &tp);
+    if (r) return r;
+    hbf_int_single<<<(unsigned)((lanes + 127) / 128), 128, 0, ctx->stream>>>(tp, state, x, y, n_in,
+                                                                           lanes, lanes, layout);
+    IDSP_LAUNCHED(ctx);
+    return IDSP_OK;
+}
+extern "C" int idsp_fir_f32(idsp_ctx *ctx, const float *taps, int M, int odd, int sym,
+                            float *state, const float *x, float *y, size_t frames, size_t lanes,
+                            int layout) {
+    HBF_COMMON_CHECK(frames);
+    TapsParam tp;
+    int r = taps_param(taps, M, &tp);
+    if (r) return r;
+    fir_single<<<(unsigned)((lanes + 127) / 128), 128, 0, ctx->stream>>>(
+        tp, odd ? 1 : 0, sym ? 1 : 0, state, x, y, frames, lanes, lanes, layout);
+    IDSP_LAUNCHED(ctx);
+    return IDSP_OK;
+}
+
+int hbf_dec_cascade_dev(idsp_ctx *ctx, int k, float *state, const float *x, float *y,
+                        size_t n_out, size_t lanes, size_t sstride, int layout) {
+    int fr = hbf_dec_fast_try(ctx, k, state, x, y, n_out, lanes, sstride, layout);
+    if (fr != IDSP_HBF_FAST_NOT_APPLICABLE) return fr;
+    unsigned grid = (unsigned)((lanes + 63) / 64);
+    switch (k) {
+        case 1: hbf_dec_cascade_generic<1><<<grid, 64, 0, ctx->stream>>>(state, x, y, n_out, lanes, sstride, layout); break;
+        case 2: hbf_dec_cascade_generic<2><<<grid, 64, 0, ctx->stream>>>(state, x, y, n_out, lanes, sstride, layout); break;
+        case 3: hbf_dec_cascade_generic<3><<<grid, 64, 0, ctx->stream>>>(state, x, y, n_out, lanes, sstride, layout); break;
+        case 4: hbf_dec_cascade_generic<4><<<grid, 64, 0, ctx->stream>>>(state, x, y, n_out, lanes, sstride, layout); break;
+        default: hbf_dec_cascade_generic<5><<<grid, 64, 0, ctx->stream>>>(state, x, y, n_out, lanes, sstride, layout); break;
+    }
+    IDSP_LAUNCHED(ctx);
+    return IDSP_OK;
+}
+
+extern "C" int idsp_hbf_dec_cascade_f32(idsp_ctx *ctx, int log2_rate, float *state, const float *x,
+                                        float *y, size_t n_out, size_t lanes, int layout) {
+    HBF_COMMON_CHECK(n_out);
+    IDSP_CHECK_ARG(log2_rate >= 1 && log2_rate <= 5, "log2_rate must be 1..5");
+    return hbf_dec_cascade_dev(ctx, log2_rate, state, x, y, n_out, lanes, lanes, layout);
+}
+extern "C" int idsp_hbf_dec_cascade_f32_host(idsp_ctx *ctx, int log2_rate, float *state,
+                                             const float *x, float *y, size_t n_out, size_t lanes,
+                                             int layout) {
+    HBF_COMMON_CHECK(n_out);
+    IDSP_CHECK_ARG(log2_rate >= 1 && log2_rate <= 5, "log2_rate must be 1..5");
+    HostStreamSpec s;
+    s.frames = n_out;
+    s.lanes = lanes;
+    s.in_bytes_per_frame_lane = sizeof(float) << log2_rate;
+    s.out_bytes_per_frame_lane = sizeof(float);
+    s.layout = layout;
+    s.nblobs = 1;
+    s.blobs[0] = {state, (size_t)hbf_dec_words(log2_rate) * lanes * sizeof(float), true};
+    return idsp_host_stream(ctx, s, x, y,
+                            [&](void **blobs, const void *dx, void *dy, size_t a0, size_t an) {
+                                float *st = (float *)blobs[0];
+                                if (layout == IDSP_FRAME_MAJOR)
+                                    return hbf_dec_cascade_dev(ctx, log2_rate, st, (const float *)dx,
+                                                               (float *)dy, an, lanes, lanes, layout);
+                                return hbf_dec_cascade_dev(ctx, log2_rate, st + a0, (const float *)dx,
+                                                           (float *)dy, n_out, an, lanes, layout);
+                            });
+}
+extern "C" int idsp_hbf_int_cascade_f32(idsp_ctx *ctx, int log2_rate, float *state, const float *x,
+                                        float *y, size_t n_in, size_t lanes, int layout) {
+    HBF_COMMON_CHECK(n_in);
+    IDSP_CHECK_ARG(log2_rate >= 1 && log2_rate <= 5, "log2_rate must be 1..5");
+    unsigned grid = (unsigned)((lanes + 63) / 64);
+    switch (log2_rate) {
+        case 1: hbf_int_cascade_generic<1><<<grid, 64, 0, ctx->stream>>>(state, x, y, n_in, lanes, lanes, layout); break;
+        case 2: hbf_int_cascade_generic<2><<<grid, 64, 0, ctx->stream>>>(state, x, y, n_in, lanes, lanes, layout); break;
+        case 3: hbf_int_cascade_generic<3><<<grid, 64, 0, ctx->stream>>>(state, x, y, n_in, lanes, lanes, layout); break;
+        case 4: hbf_int_cascade_generic<4><<<grid, 64, 0, ctx->stream>>>(state, x, y, n_in, lanes, lanes, layout); break;
+        default: hbf_int_cascade_generic<5><<<grid, 64, 0, ctx->stream>>>(state, x, y, n_in, lanes, lanes, layout); break;
+    }
+    IDSP_LAUNCHED(ctx);
+    return IDSP_OK;
+}
+extern "C" int idsp_chain_f32(idsp_ctx *ctx, int log2_rate, const float ba[5], float *state,
+                              const float *x, float *y, size_t n_low, size_t lanes, int layout) {
+    HBF_COMMON_CHECK(n_low);
+    IDSP_CHECK_ARG(ba != nullptr, "ba is null");
+    IDSP_CHECK_ARG(log2_rate >= 1 && log2_rate <= 5, "log2_rate must be 1..5");
+    Df1Op<float, false>::Params bp;
+    for (int i = 0; i < 5; i++) bp.ba[i] = ba[i];
+    bp.F = 0;
+    bp.u = bp.mn = bp.mx = 0.f;
+    bp.st = nullptr;
+    unsigned grid = (unsigned)((lanes + 63) / 64);
+    switch (log2_rate) {
+        case 1: chain_generic<1><<<grid, 64, 0, ctx->stream>>>(state, bp, x, y, n_low, lanes, lanes, layout); break;
+        case 2: chain_generic<2><<<grid, 64, 0, ctx->stream>>>(state, bp, x, y, n_low, lanes, lanes, layout); break;
+        case 3: chain_generic<3><<<grid, 64, 0, ctx->stream>>>(state, bp, x, y, n_low, lanes, lanes, layout); break;
+        case 4: chain_generic<4><<<grid, 64, 0, ctx->stream>>>(state, bp, x, y, n_low, lanes, lanes, layout); break;
+        default: chain_generic<5><<<grid, 64, 0, ctx->stream>>>(state, bp, x, y, n_low, lanes, lanes, layout); break;
+    }
+    IDSP_LAUNCHED(ctx);
+    return IDSP_OK;
+}

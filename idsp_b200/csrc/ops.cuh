@@ -1,0 +1,436 @@
+// ops.cuh -- per-lane sample operators ("Op"s) executed by the lane kernels.
+//
+// One Op instance lives in the registers of the thread that owns a filter lane:
+//   load()  reads the lane's state words (SoA: st[word*stride + lane]),
+//   step()  consumes one input sample and returns one output sample,
+//   store() writes the state back.
+// The arithmetic restates the reference exactly (wrapping integer accumulators,
+// arithmetic shifts, per-op rounded floats, no FMA: the library is compiled with
+// -fmad=false).  Reference file:line is cited at each Op.
+#pragma once
+#include <stdint.h>
+
+#include "tables.cuh"
+
+namespace idsp {
+
+// --------------------------------------------------------------------------
+// lookup tables (build.rs:9-69) in global memory, read through L1 (__ldg)
+// --------------------------------------------------------------------------
+__device__ const uint32_t g_cossin_lut[128] = IDSP_COSSIN_TABLE_INIT;
+__device__ const uint32_t g_divi_base[16] = IDSP_ATAN2_DIVI_BASE_INIT;
+__device__ const int32_t g_divi_slope[16] = IDSP_ATAN2_DIVI_SLOPE_INIT;
+
+template <class T> struct Wide;
+template <> struct Wide<int8_t> { using A = int16_t; using UA = uint16_t; using UT = uint8_t; };
+template <> struct Wide<int16_t> { using A = int32_t; using UA = uint32_t; using UT = uint16_t; };
+template <> struct Wide<int32_t> { using A = int64_t; using UA = uint64_t; using UT = uint32_t; };
+template <> struct Wide<int64_t> { using A = __int128; using UA = unsigned __int128; using UT = uint64_t; };
+
+template <class T> struct is_float { static constexpr bool value = false; };
+template <> struct is_float<float> { static constexpr bool value = true; };
+template <> struct is_float<double> { static constexpr bool value = true; };
+
+// num_traits::clamp (src/iir/biquad.rs:400): `<`/`>` compares so NaN passes through
+template <class T> __device__ __forceinline__ T clamp_nt(T v, T lo, T hi) {
+    return v < lo ? lo : (v > hi ? hi : v);
+}
+
+// --------------------------------------------------------------------------
+// y0 = (b0 x0 + b1 x1 + b2 x2 + a1 y1 + a2 y2) >> F      src/iir/biquad.rs:366-383
+// Q*T -> wide accu: dsp-fixedpoint/src/ops.rs:91-97, lib.rs:310-312
+// accu.as_() = (acc >> F) as T: num_traits_impl.rs:74-104, lib.rs:297-299
+// --------------------------------------------------------------------------
+template <class T, bool ISF = is_float<T>::value> struct Sos;
+
+template <class T> struct Sos<T, false> {
+    using A = typename Wide<T>::A;
+    using UA = typename Wide<T>::UA;
+    using UT = typename Wide<T>::UT;
+    __device__ __forceinline__ static T eval(const T *ba, int F, T x0, T x1, T x2, T y1, T y2) {
+        UA acc = (UA)((A)ba[0] * (A)x0) + (UA)((A)ba[1] * (A)x1) + (UA)((A)ba[2] * (A)x2) +
+                 (UA)((A)ba[3] * (A)y1) + (UA)((A)ba[4] * (A)y2);
+        A q = F >= 0 ? (A)((A)acc >> F) : (A)(UA)(acc << (-F));
+        return (T)(UT)(UA)q;
+    }
+    __device__ __forceinline__ static T add(T a, T b) { return (T)(UT)((UT)a + (UT)b); }
+};
+// i32 with 0 <= F < 32: low word of (acc >> F) is one funnel shift
+struct SosI32Fast {
+    __device__ __forceinline__ static int32_t eval(const int32_t *ba, int F, int32_t x0,
+                                                   int32_t x1, int32_t x2, int32_t y1,
+                                                   int32_t y2) {
+        uint64_t acc = (uint64_t)((int64_t)ba[0] * x0) + (uint64_t)((int64_t)ba[1] * x1) +
+                       (uint64_t)((int64_t)ba[2] * x2) + (uint64_t)((int64_t)ba[3] * y1) +
+                       (uint64_t)((int64_t)ba[4] * y2);
+        return (int32_t)__funnelshift_r((uint32_t)acc, (uint32_t)(acc >> 32), F);
+    }
+};
+template <class T> struct Sos<T, true> {
+    __device__ __forceinline__ static T eval(const T *ba, int, T x0, T x1, T x2, T y1, T y2) {
+        // left-to-right, each op rounded (no FMA contraction: -fmad=false)
+        return ba[0] * x0 + ba[1] * x1 + ba[2] * x2 + ba[3] * y1 + ba[4] * y2;
+    }
+    __device__ __forceinline__ static T add(T a, T b) { return a + b; }
+};
+
+// DF1 + optional clamp (src/iir/biquad.rs:366-404). MODE: 0 generic F, 1 i32 0<=F<32
+template <class T, bool CLAMP, int MODE = 0> struct Df1Op {
+    using In = T;
+    using Out = T;
+    struct Params {
+        T ba[5];
+        int F;
+        T u, mn, mx;
+        T *st;
+    };
+    T x1, x2, y1, y2;
+    __device__ __forceinline__ void load(const Params &p, size_t lane, size_t stride) {
+        x1 = p.st[lane];
+        x2 = p.st[stride + lane];
+        y1 = p.st[2 * stride + lane];
+        y2 = p.st[3 * stride + lane];
+    }
+    __device__ __forceinline__ void store(const Params &p, size_t lane, size_t stride) const {
+        p.st[lane] = x1;
+        p.st[stride + lane] = x2;
+        p.st[2 * stride + lane] = y1;
+        p.st[3 * stride + lane] = y2;
+    }
+    __device__ __forceinline__ T step(const Params &p, T x0) {
+        T y0;
+        if constexpr (MODE == 1)
+            y0 = SosI32Fast::eval(p.ba, p.F, x0, x1, x2, y1, y2);
+        else
+            y0 = Sos<T>::eval(p.ba, p.F, x0, x1, x2, y1, y2);
+        x2 = x1;
+        x1 = x0;
+        y2 = y1;
+        if constexpr (CLAMP) y0 = clamp_nt<T>(Sos<T>::add(y0, p.u), p.mn, p.mx);  // biquad.rs:399-402
+        y1 = y0;
+        return y0;
+    }
+};
+
+// Cascade<[Biquad;N]> on DirectForm<T,N> (src/iir/biquad.rs:339-364)
+template <class T, int NMAX> struct CascadeOp {
+    using In = T;
+    using Out = T;
+    struct Params {
+        T ba[NMAX][5];
+        int F;
+        int nsec;
+        T *st;
+    };
+    T d[2 + 2 * NMAX];  // [x0,x1,y[0][0],y[0][1],...]
+    __device__ __forceinline__ void load(const Params &p, size_t lane, size_t stride) {
+#pragma unroll
+        for (int w = 0; w < 2 + 2 * NMAX; w++)
+            if (w < 2 + 2 * p.nsec) d[w] = p.st[(size_t)w * stride + lane];
+    }
+    __device__ __forceinline__ void store(const Params &p, size_t lane, size_t stride) const {
+#pragma unroll
+        for (int w = 0; w < 2 + 2 * NMAX; w++)
+            if (w < 2 + 2 * p.nsec) p.st[(size_t)w * stride + lane] = d[w];
+    }
+    __device__ __forceinline__ T step(const Params &p, T x0) {
+#pragma unroll
+        for (int s = 0; s < NMAX; s++) {
+            if (s < p.nsec) {
+                T y0 = Sos<T>::eval(p.ba[s], p.F, x0, d[2 * s], d[2 * s + 1], d[2 * s + 2],
+                                    d[2 * s + 3]);
+                d[2 * s + 1] = d[2 * s];
+                d[2 * s] = x0;
+                x0 = y0;
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < NMAX; s++) {
+            if (s == p.nsec - 1) {
+                d[2 * s + 3] = d[2 * s + 2];
+                d[2 * s + 2] = x0;
+            }
+        }
+        return x0;
+    }
+};
+
+// DF2T (src/iir/biquad.rs:418-440)
+template <class T, bool CLAMP> struct Df2tOp {
+    using In = T;
+    using Out = T;
+    struct Params {
+        T ba[5];
+        T u, mn, mx;
+        T *st;
+    };
+    T s0, s1;
+    __device__ __forceinline__ void load(const Params &p, size_t lane, size_t stride) {
+        s0 = p.st[lane];
+        s1 = p.st[stride + lane];
+    }
+    __device__ __forceinline__ void store(const Params &p, size_t lane, size_t stride) const {
+        p.st[lane] = s0;
+        p.st[stride + lane] = s1;
+    }
+    __device__ __forceinline__ T step(const Params &p, T x0) {
+        T y0 = s0 + p.ba[0] * x0;
+        if constexpr (CLAMP) y0 = clamp_nt<T>(y0 + p.u, p.mn, p.mx);
+        s0 = s1 + p.ba[1] * x0 + p.ba[3] * y0;
+        s1 = p.ba[2] * x0 + p.ba[4] * y0;
+        return y0;
+    }
+};
+
+// DirectForm1Wide (src/iir/biquad.rs:445-480)
+template <bool CLAMP> struct Df1WideOp {
+    using In = int32_t;
+    using Out = int32_t;
+    struct Params {
+        int32_t ba[5];
+        int F;
+        int32_t u, mn, mx;
+        int32_t *st;
+    };
+    int32_t x1, x2;
+    int64_t y1, y2;
+    __device__ __forceinline__ void load(const Params &p, size_t lane, size_t stride) {
+        x1 = p.st[lane];
+        x2 = p.st[stride + lane];
+        y1 = (int64_t)(((uint64_t)(uint32_t)p.st[3 * stride + lane] << 32) |
+                       (uint32_t)p.st[2 * stride + lane]);
+        y2 = (int64_t)(((uint64_t)(uint32_t)p.st[5 * stride + lane] << 32) |
+                       (uint32_t)p.st[4 * stride + lane]);
+    }
+    __device__ __forceinline__ void store(const Params &p, size_t lane, size_t stride) const {
+        p.st[lane] = x1;
+        p.st[stride + lane] = x2;
+        p.st[2 * stride + lane] = (int32_t)(uint32_t)y1;
+        p.st[3 * stride + lane] = (int32_t)(y1 >> 32);
+        p.st[4 * stride + lane] = (int32_t)(uint32_t)y2;
+        p.st[5 * stride + lane] = (int32_t)(y2 >> 32);
+    }
+    __device__ __forceinline__ int32_t step(const Params &p, int32_t x0) {
+        uint64_t acc = (uint64_t)((int64_t)p.ba[0] * x0) + (uint64_t)((int64_t)p.ba[1] * x1) +
+                       (uint64_t)((int64_t)p.ba[2] * x2);
+        x2 = x1;
+        x1 = x0;
+        acc += (uint64_t)(((int64_t)(uint64_t)(uint32_t)y1 * (int64_t)p.ba[3]) >> 32);
+        acc += (uint64_t)((int64_t)(int32_t)(y1 >> 32) * (int64_t)p.ba[3]);
+        acc += (uint64_t)(((int64_t)(uint64_t)(uint32_t)y2 * (int64_t)p.ba[4]) >> 32);
+        acc += (uint64_t)((int64_t)(int32_t)(y2 >> 32) * (int64_t)p.ba[4]);
+        acc <<= (32 - p.F);
+        y2 = y1;
+        y1 = (int64_t)acc;
+        int32_t y0 = (int32_t)((int64_t)acc >> 32);
+        if constexpr (CLAMP) {  // biquad.rs:474-480
+            y0 = clamp_nt<int32_t>((int32_t)((uint32_t)y0 + (uint32_t)p.u), p.mn, p.mx);
+            y1 = (int64_t)(((uint64_t)(int64_t)y0 << 32) | (uint64_t)(uint32_t)y1);
+        }
+        return y0;
+    }
+};
+
+// DirectForm1Dither (src/iir/biquad.rs:484-538)
+template <bool CLAMP> struct Df1DitherOp {
+    using In = int32_t;
+    using Out = int32_t;
+    struct Params {
+        int32_t ba[5];
+        int F;
+        int32_t u, mn, mx;
+        int32_t *st;
+    };
+    int32_t x1, x2, y1, y2;
+    uint32_t e;
+    __device__ __forceinline__ void load(const Params &p, size_t lane, size_t stride) {
+        x1 = p.st[lane];
+        x2 = p.st[stride + lane];
+        y1 = p.st[2 * stride + lane];
+        y2 = p.st[3 * stride + lane];
+        e = (uint32_t)p.st[4 * stride + lane];
+    }
+    __device__ __forceinline__ void store(const Params &p, size_t lane, size_t stride) const {
+        p.st[lane] = x1;
+        p.st[stride + lane] = x2;
+        p.st[2 * stride + lane] = y1;
+        p.st[3 * stride + lane] = y2;
+        p.st[4 * stride + lane] = (int32_t)e;
+    }
+    __device__ __forceinline__ int32_t step(const Params &p, int32_t x0) {
+        uint64_t acc = (uint64_t)e + (uint64_t)((int64_t)p.ba[0] * x0) +
+                       (uint64_t)((int64_t)p.ba[1] * x1) + (uint64_t)((int64_t)p.ba[2] * x2) +
+                       (uint64_t)((int64_t)p.ba[3] * y1) + (uint64_t)((int64_t)p.ba[4] * y2);
+        acc <<= (32 - p.F);
+        e = p.F == 0 ? 0u : ((uint32_t)acc) >> (32 - p.F);
+        int32_t y0 = (int32_t)((int64_t)acc >> 32);
+        x2 = x1;
+        x1 = x0;
+        y2 = y1;
+        if constexpr (CLAMP) y0 = clamp_nt<int32_t>((int32_t)((uint32_t)y0 + (uint32_t)p.u), p.mn, p.mx);
+        y1 = y0;
+        return y0;
+    }
+};
+
+// --------------------------------------------------------------------------
+// cossin (src/cossin.rs:14-67). LUT pointer may be global (__ldg) or shared.
+// --------------------------------------------------------------------------
+template <bool SMEM_LUT>
+__device__ __forceinline__ void cossin_dev(const uint32_t *lut, int32_t phase, int32_t &co,
+                                           int32_t &so) {
+    uint32_t octant = (uint32_t)phase;
+    if (octant & (1u << 29)) phase = ~phase;
+    phase = (int32_t)((((uint32_t)phase) << 3) >> 10);
+    uint32_t lookup = SMEM_LUT ? lut[phase >> 15] : __ldg(lut + (phase >> 15));
+    phase &= (1 << 15) - 1;
+    phase -= 1 << 14;
+    int32_t dphi = (phase * 51471) >> 16;
+    int32_t c = (int32_t)(lookup & 0xffffu) + (1 << 16);
+    int32_t s = (int32_t)(lookup >> 16);
+    int32_t dcos = (s * dphi) >> 7;
+    int32_t dsin = (c * dphi) >> 8;
+    c = (c << 14) - dcos;
+    s = (s << 15) + dsin;
+    octant ^= octant >> 1;
+    if (octant & (1u << 29)) { int32_t t = c; c = s; s = t; }
+    if (octant & (1u << 30)) c = -c;
+    if (octant & (1u << 31)) s = -s;
+    co = c;
+    so = s;
+}
+
+// --------------------------------------------------------------------------
+// atan2 (src/atan2.rs:7-82)
+// --------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mul_q31(uint32_t x, uint32_t y) {
+    return (uint32_t)(((uint64_t)x * (uint64_t)y) >> 31);
+}
+__device__ __forceinline__ uint32_t divi_dev(uint32_t y, uint32_t x) {
+    if (x == 0) return 0;
+    int shift = __clz((int)x);
+    y <<= shift;
+    x <<= shift;
+    const int FRAC_BITS = 31 - IDSP_ATAN2_DIVI_DEPTH;
+    uint32_t rem = x & ((1u << FRAC_BITS) - 1);
+    uint32_t idx = (x << 1) >> (1 + FRAC_BITS);
+    uint32_t base = __ldg(g_divi_base + idx);
+    int32_t slope = __ldg(g_divi_slope + idx);
+    uint32_t step = (uint32_t)(((int64_t)slope * (int64_t)rem) >> FRAC_BITS);
+    uint32_t r0 = base + step;
+    return mul_q31(y, mul_q31(r0, 0u - mul_q31(x, r0)));
+}
+__device__ __forceinline__ uint32_t atani_dev(uint32_t x) {
+    const int32_t ATANI[6] = {0x0517c2cd, -0x06c6496b, 0x0fbdb021,
+                              -0x25b32e0a, 0x43b34c81, -0x3bc823dd};
+    int32_t x2 = (int32_t)(((int64_t)(uint64_t)x * (int64_t)(uint64_t)x) >> 32);
+    int32_t r = 0;
+#pragma unroll
+    for (int i = 5; i >= 0; i--) {
+        r = (int32_t)(((int64_t)r * (int64_t)x2) >> 32);  // Q32<32>*Q32<32>, ops.rs:145-153
+        r = (int32_t)((uint32_t)r + (uint32_t)ATANI[i]);
+    }
+    return (uint32_t)(((int64_t)r * (int64_t)(uint64_t)x) >> 28);
+}
+__device__ __forceinline__ int32_t sat_neg(int32_t a) { return a == INT32_MIN ? INT32_MAX : -a; }
+__device__ __forceinline__ int32_t atan2_dev(int32_t y, int32_t x) {
+    uint32_t k = 0;
+    if (y < 0) { y = sat_neg(y); k ^= 0xffffffffu; }
+    if (x < 0) { x = sat_neg(x); k ^= 0xffffffffu >> 1; }
+    if (y > x) { int32_t t = y; y = x; x = t; k ^= 0xffffffffu >> 2; }
+    uint32_t r = atani_dev(divi_dev((uint32_t)y, (uint32_t)x));
+    return (int32_t)(r ^ k);
+}
+
+// --------------------------------------------------------------------------
+// Lowpass<N> (src/lowpass.rs:47-78)
+// --------------------------------------------------------------------------
+__device__ __forceinline__ int32_t sat_sub(int32_t a, int32_t b) {
+    int32_t r;
+    asm("sub.sat.s32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+template <int ORDER>
+__device__ __forceinline__ int32_t lowpass_step(int32_t k0, int32_t k1, int64_t &s0, int64_t &s1,
+                                                int32_t x) {
+    uint64_t d = (uint64_t)((int64_t)sat_sub(x, (int32_t)(s0 >> 32)) * (int64_t)k0);
+    int32_t y;
+    if constexpr (ORDER == 1) {
+        s0 = (int64_t)((uint64_t)s0 + d);
+        y = (int32_t)(s0 >> 32);
+        s0 = (int64_t)((uint64_t)s0 + d);
+    } else {
+        d += (uint64_t)(s1 >> 32) * (uint64_t)(int64_t)k1;
+        s1 = (int64_t)((uint64_t)s1 + d);
+        s0 = (int64_t)((uint64_t)s0 + (uint64_t)s1);
+        y = (int32_t)(s0 >> 32);
+        s0 = (int64_t)((uint64_t)s0 + (uint64_t)s1);
+        s1 = (int64_t)((uint64_t)s1 + d);
+    }
+    return y;
+}
+template <int ORDER> struct LowpassOp {
+    using In = int32_t;
+    using Out = int32_t;
+    struct Params {
+        int32_t k[2];
+        int64_t *st;
+    };
+    int64_t s0, s1;
+    __device__ __forceinline__ void load(const Params &p, size_t lane, size_t stride) {
+        s0 = p.st[lane];
+        s1 = ORDER == 2 ? p.st[stride + lane] : 0;
+    }
+    __device__ __forceinline__ void store(const Params &p, size_t lane, size_t stride) const {
+        p.st[lane] = s0;
+        if (ORDER == 2) p.st[stride + lane] = s1;
+    }
+    __device__ __forceinline__ int32_t step(const Params &p, int32_t x) {
+        return lowpass_step<ORDER>(p.k[0], p.k[1], s0, s1, x);
+    }
+};
+
+// Accu (src/accu.rs:34-37) -> Complex::from_angle (src/complex.rs:237-240) ->
+// Lockin<Lowpass<N>> (src/lockin.rs:17-39); mix = i32 * Q32<32> -> (lo*x)>>32
+// (dsp-fixedpoint/src/lib.rs:449-456).
+template <int ORDER> struct LockinOp {
+    using In = int32_t;
+    using Out = int2;
+    struct Params {
+        int32_t k[2];
+        int32_t *accu_state;
+        const int32_t *accu_step;
+        int64_t *st;  // [2*ORDER][stride]
+        const uint32_t *lut;
+    };
+    uint32_t ph, dph;
+    int64_t i0, i1, q0, q1;
+    __device__ __forceinline__ void load(const Params &p, size_t lane, size_t stride) {
+        ph = (uint32_t)p.accu_state[lane];
+        dph = (uint32_t)p.accu_step[lane];
+        i0 = p.st[lane];
+        i1 = ORDER == 2 ? p.st[stride + lane] : 0;
+        q0 = p.st[(size_t)ORDER * stride + lane];
+        q1 = ORDER == 2 ? p.st[(size_t)(ORDER + 1) * stride + lane] : 0;
+    }
+    __device__ __forceinline__ void store(const Params &p, size_t lane, size_t stride) const {
+        p.accu_state[lane] = (int32_t)ph;
+        p.st[lane] = i0;
+        if (ORDER == 2) p.st[stride + lane] = i1;
+        p.st[(size_t)ORDER * stride + lane] = q0;
+        if (ORDER == 2) p.st[(size_t)(ORDER + 1) * stride + lane] = q1;
+    }
+    __device__ __forceinline__ int2 step(const Params &p, int32_t x) {
+        ph += dph;
+        int32_t c, s;
+        cossin_dev<false>(p.lut, (int32_t)ph, c, s);
+        int32_t mi = (int32_t)(((int64_t)c * (int64_t)x) >> 32);
+        int32_t mq = (int32_t)(((int64_t)s * (int64_t)x) >> 32);
+        int2 r;
+        r.x = lowpass_step<ORDER>(p.k[0], p.k[1], i0, i1, mi);
+        r.y = lowpass_step<ORDER>(p.k[0], p.k[1], q0, q1, mq);
+        return r;
+    }
+};
+
+}  // namespace idsp

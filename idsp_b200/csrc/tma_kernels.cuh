@@ -1,0 +1,298 @@
+// tma_kernels.cuh -- TMA-pipelined lane kernels for 4-byte samples (i32 / f32).
+//
+// Same mapping as lane_kernels.cuh (one filter lane per thread, state in
+// registers for the whole call), but the samples move through shared memory with
+// the Tensor Memory Accelerator so the threads never wait on HBM:
+//
+//   * every warp owns 32 lanes and runs its own pipeline -- no CTA-wide barrier:
+//     lane 0 issues `cp.async.bulk.tensor.2d` loads S-1 tiles ahead into a ring
+//     of S shared-memory stages guarded by mbarriers (complete_tx), all 32 lanes
+//     consume a stage, write results to one of O output stages and lane 0 hands
+//     that stage to a TMA bulk store (bulk_group / wait_group.read).
+//   * frame-major  flat[t*lanes + l]: box = [32 lanes x TF frames]; thread l reads
+//     word l of every 128-byte row -> conflict-free LDS.32.
+//   * lane-major   flat[l*frames + t]: box = [TF=16 frames x 32 lanes] written with
+//     the 64-byte TMA swizzle; thread l reads its own 64-byte row as 4 x LDS.128
+//     (chunk index XOR (l>>1)&3) -> conflict-free, 16 samples per 4 loads.
+//   * out-of-range lanes / frames are zero-filled on load and clipped on store by
+//     the TMA unit, so ragged shapes need no scalar tail code.
+// Requirements: 16-byte aligned x/y, (lanes % 4 == 0) frame-major or
+// (frames % 4 == 0) lane-major; otherwise the generic LDG kernels run.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define IDSP_TMA_NOT_APPLICABLE 12345
+
+namespace idsp {
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1,
+                                            uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(map), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::
+                     "l"(map),
+                 "r"(src), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tma_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+template <class T> struct Bits32;
+template <> struct Bits32<int32_t> {
+    __device__ __forceinline__ static int32_t from(uint32_t v) { return (int32_t)v; }
+    __device__ __forceinline__ static uint32_t to(int32_t v) { return (uint32_t)v; }
+};
+template <> struct Bits32<float> {
+    __device__ __forceinline__ static float from(uint32_t v) { return __uint_as_float(v); }
+    __device__ __forceinline__ static uint32_t to(float v) { return __float_as_uint(v); }
+};
+
+// ---------------------------------------------------------------- kernel
+// LM = false: frame-major, tile [TF rows][32 words];  LM = true: lane-major,
+// tile [32 rows (lanes)][16 words] with 64-byte swizzle (TF must be 16).
+// Op::In and Op::Out are 4-byte types.  WPC warps per CTA, each independent.
+template <class Op, bool LM, int TF, int S, int O, int WPC>
+__global__ void __launch_bounds__(WPC * 32)
+tma_lanes_kernel(typename Op::Params p, const __grid_constant__ CUtensorMap mx,
+                 const __grid_constant__ CUtensorMap my, size_t frames, size_t lanes,
+                 size_t sstride) {
+    using In = typename Op::In;
+    using Out = typename Op::Out;
+    static_assert(sizeof(In) == 4 && sizeof(Out) == 4, "4-byte samples only");
+    static_assert(!LM || TF == 16, "lane-major tiles are 16 frames (64B swizzle)");
+    constexpr int TILE_WORDS = TF * 32;
+    constexpr uint32_t TILE_BYTES = TILE_WORDS * 4;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    // per warp: S input stages, O output stages, S mbarriers
+    uint32_t *wbase = reinterpret_cast<uint32_t *>(smem_raw) + (size_t)w * (S + O) * TILE_WORDS;
+    uint32_t *sin = wbase;
+    uint32_t *sout = wbase + S * TILE_WORDS;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)WPC * (S + O) * TILE_BYTES) + w * S;
+
+    const size_t lane0 = ((size_t)blockIdx.x * WPC + w) * 32;
+    if (lane0 >= lanes) return;
+    const size_t lane = lane0 + l;
+    const bool active = lane < lanes;
+    const size_t ntiles = (frames + TF - 1) / TF;
+
+    if (l == 0) {
+#pragma unroll
+        for (int s = 0; s < S; s++) mbar_init(smem_u32(&bars[s]), 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+
+    auto issue_load = [&](size_t tile) {
+        const int s = (int)(tile % S);
+        const uint32_t bar = smem_u32(&bars[s]);
+        mbar_expect_tx(bar, TILE_BYTES);
+        if (LM)
+            tma_load_2d(smem_u32(sin + s * TILE_WORDS), &mx, (int)(tile * TF), (int)lane0, bar);
+        else
+            tma_load_2d(smem_u32(sin + s * TILE_WORDS), &mx, (int)lane0, (int)(tile * TF), bar);
+    };
+    if (l == 0) {
+#pragma unroll
+        for (int s = 0; s < S - 1; s++)
+            if ((size_t)s < ntiles) issue_load(s);
+    }
+    Op op;
+    if (active) op.load(p, lane, sstride);
+
+    for (size_t i = 0; i < ntiles; i++) {
+        const int s = (int)(i % S);
+        const int ob = (int)(i % O);
+        if (l == 0) {
+            // the output stage we are about to overwrite must have been read by its store
+            tma_wait_read<O - 1>();
+            if (i + S - 1 < ntiles) issue_load(i + S - 1);
+        }
+        __syncwarp();
+        mbar_wait(smem_u32(&bars[s]), (uint32_t)((i / S) & 1));
+        const uint32_t *tin = sin + s * TILE_WORDS;
+        uint32_t *tout = sout + ob * TILE_WORDS;
+        // frames beyond `frames` in the last tile are zero-filled by the TMA load and
+        // clipped by the TMA store; they must not advance the filter state.
+        const int nvalid = (int)((frames - i * TF) < (size_t)TF ? (frames - i * TF) : (size_t)TF);
+        if (LM) {
+            // row l = my lane, 4 chunks of 16 B, physical chunk = c ^ ((l>>1)&3)
+            const int sw = (l >> 1) & 3;
+            const uint4 *rin = reinterpret_cast<const uint4 *>(tin + l * 16);
+            uint4 *rout = reinterpret_cast<uint4 *>(tout + l * 16);
+            if (nvalid == TF) {
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    uint4 v = rin[c ^ sw];
+                    uint4 r;
+                    r.x = Bits32<Out>::to(op.step(p, Bits32<In>::from(v.x)));
+                    r.y = Bits32<Out>::to(op.step(p, Bits32<In>::from(v.y)));
+                    r.z = Bits32<Out>::to(op.step(p, Bits32<In>::from(v.z)));
+                    r.w = Bits32<Out>::to(op.step(p, Bits32<In>::from(v.w)));
+                    rout[c ^ sw] = r;
+                }
+            } else {  // frames % 4 == 0, so whole chunks are valid or not
+                for (int c = 0; c * 4 < nvalid; c++) {
+                    uint4 v = rin[c ^ sw];
+                    uint4 r;
+                    r.x = Bits32<Out>::to(op.step(p, Bits32<In>::from(v.x)));
+                    r.y = Bits32<Out>::to(op.step(p, Bits32<In>::from(v.y)));
+                    r.z = Bits32<Out>::to(op.step(p, Bits32<In>::from(v.z)));
+                    r.w = Bits32<Out>::to(op.step(p, Bits32<In>::from(v.w)));
+                    rout[c ^ sw] = r;
+                }
+            }
+        } else {
+            if (nvalid == TF) {
+#pragma unroll
+                for (int f = 0; f < TF; f++)
+                    tout[f * 32 + l] = Bits32<Out>::to(op.step(p, Bits32<In>::from(tin[f * 32 + l])));
+            } else {
+                for (int f = 0; f < nvalid; f++)
+                    tout[f * 32 + l] = Bits32<Out>::to(op.step(p, Bits32<In>::from(tin[f * 32 + l])));
+            }
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (l == 0) {
+            if (LM)
+                tma_store_2d(&my, smem_u32(tout), (int)(i * TF), (int)lane0);
+            else
+                tma_store_2d(&my, smem_u32(tout), (int)lane0, (int)(i * TF));
+            tma_commit();
+        }
+    }
+    if (l == 0) tma_wait_read<0>();
+    if (active) op.store(p, lane, sstride);
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                    const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                    const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_tiled() {
+    static PFN_encodeTiled fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) ==
+                cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)f;
+    }
+    return fn;
+}
+
+// 2-D map over a row-major [rows][cols] array of 4-byte words
+static bool make_map_2d(CUtensorMap *m, const void *base, uint64_t cols, uint64_t rows,
+                        uint32_t box_cols, uint32_t box_rows, CUtensorMapSwizzle swz) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * 4};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_INT32, 2, const_cast<void *>(base), dims, strides,
+                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+template <class Op, bool LM, int TF, int S, int O, int WPC>
+static int tma_launch_cfg(idsp_ctx *ctx, const typename Op::Params &p, const void *x, void *y,
+                          size_t frames, size_t lanes, size_t sstride) {
+    CUtensorMap mx, my;
+    bool ok;
+    if (LM) {
+        ok = make_map_2d(&mx, x, frames, lanes, TF, 32, CU_TENSOR_MAP_SWIZZLE_64B) &&
+             make_map_2d(&my, y, frames, lanes, TF, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+    } else {
+        ok = make_map_2d(&mx, x, lanes, frames, 32, TF, CU_TENSOR_MAP_SWIZZLE_NONE) &&
+             make_map_2d(&my, y, lanes, frames, 32, TF, CU_TENSOR_MAP_SWIZZLE_NONE);
+    }
+    if (!ok) return IDSP_TMA_NOT_APPLICABLE;
+    constexpr size_t smem = (size_t)WPC * (S + O) * TF * 128 + (size_t)WPC * S * 8;
+    auto kern = tma_lanes_kernel<Op, LM, TF, S, O, WPC>;
+    IDSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t warps = (lanes + 31) / 32;
+    unsigned grid = (unsigned)((warps + WPC - 1) / WPC);
+    kern<<<grid, WPC * 32, smem, ctx->stream>>>(p, mx, my, frames, lanes, sstride);
+    IDSP_LAUNCHED(ctx);
+    return IDSP_OK;
+}
+
+// Returns IDSP_TMA_NOT_APPLICABLE when the generic kernels must be used.
+template <class Op>
+static int tma_try_launch(idsp_ctx *ctx, const typename Op::Params &p, const typename Op::In *x,
+                          typename Op::Out *y, size_t frames, size_t lanes, size_t sstride,
+                          int layout) {
+    static_assert(sizeof(typename Op::In) == 4 && sizeof(typename Op::Out) == 4, "");
+    if (ctx->policy == 1) return IDSP_TMA_NOT_APPLICABLE;
+    const bool lm = layout == IDSP_LANE_MAJOR;
+    constexpr int TF_FM = 16;
+    const int tf = lm ? 16 : TF_FM;
+    bool ok = (((uintptr_t)x | (uintptr_t)y) & 15) == 0 && frames >= (size_t)tf &&
+              frames < (1ull << 31) && lanes < (1ull << 31) &&
+              (lm ? (frames % 4 == 0) : (lanes % 4 == 0));
+    if (!ok) {
+        if (ctx->policy == 2) {
+            idsp_set_error("TMA kernels forced but shape/alignment does not qualify");
+            return IDSP_EINVAL;
+        }
+        return IDSP_TMA_NOT_APPLICABLE;
+    }
+    int r;
+    if (lm)
+        r = tma_launch_cfg<Op, true, 16, 4, 2, 1>(ctx, p, x, y, frames, lanes, sstride);
+    else
+        r = tma_launch_cfg<Op, false, TF_FM, 4, 2, 1>(ctx, p, x, y, frames, lanes, sstride);
+    if (r == IDSP_TMA_NOT_APPLICABLE && ctx->policy == 2) {
+        idsp_set_error("TMA kernels forced but cuTensorMapEncodeTiled is unavailable");
+        return IDSP_EINVAL;
+    }
+    return r;
+}
+
+}  // namespace idsp

@@ -1,0 +1,209 @@
+// trig_lockin.cu -- cossin / atan2 / Lowpass / Lockin entry points (include/idsp_b200.h).
+#include "common.cuh"
+#include "ops.cuh"
+#include "lane_kernels.cuh"
+
+using namespace idsp;
+
+// ---------------------------------------------------------------- memoryless maps
+// 4 phases per thread: one 16-byte load, two 16-byte stores.
+__global__ void __launch_bounds__(256) cossin_kernel(const int32_t *phase, int32_t *cs, size_t n) {
+    __shared__ uint32_t lut[128];
+    if (threadIdx.x < 128) lut[threadIdx.x] = g_cossin_lut[threadIdx.x];
+    __syncthreads();
+    const size_t n4 = n / 4;
+    const bool vec = ((((uintptr_t)phase) | ((uintptr_t)cs)) & 15) == 0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (vec) {
+        for (; i < n4; i += stride) {
+            int4 p = reinterpret_cast<const int4 *>(phase)[i];
+            int4 a, b;
+            cossin_dev<true>(lut, p.x, a.x, a.y);
+            cossin_dev<true>(lut, p.y, a.z, a.w);
+            cossin_dev<true>(lut, p.z, b.x, b.y);
+            cossin_dev<true>(lut, p.w, b.z, b.w);
+            reinterpret_cast<int4 *>(cs)[2 * i] = a;
+            reinterpret_cast<int4 *>(cs)[2 * i + 1] = b;
+        }
+        i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    }
+    for (; i < n; i += stride) {
+        int32_t c, s;
+        cossin_dev<true>(lut, phase[i], c, s);
+        cs[2 * i] = c;
+        cs[2 * i + 1] = s;
+    }
+}
+__global__ void __launch_bounds__(256) atan2_kernel(const int32_t *xy, int32_t *p, size_t n) {
+    const size_t n2 = n / 2;
+    const bool vec = ((((uintptr_t)xy) & 15) | (((uintptr_t)p) & 7)) == 0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (vec) {
+        for (; i < n2; i += stride) {
+            int4 v = reinterpret_cast<const int4 *>(xy)[i];
+            int2 r;
+            r.x = atan2_dev(v.y, v.x);
+            r.y = atan2_dev(v.w, v.z);
+            reinterpret_cast<int2 *>(p)[i] = r;
+        }
+        i = n2 * 2 + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    }
+    for (; i < n; i += stride) p[i] = atan2_dev(xy[2 * i + 1], xy[2 * i]);
+}
+
+static unsigned map_grid(idsp_ctx *ctx, size_t work_items) {
+    size_t blocks = (work_items + 255) / 256;
+    size_t cap = (size_t)ctx->sm_count * 8;  // 8 resident CTAs of 256 threads per SM
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (unsigned)blocks;
+}
+
+extern "C" int idsp_cossin_i32(idsp_ctx *ctx, const int32_t *phase, int32_t *cs, size_t n) {
+    int r = idsp_use_device(ctx);
+    if (r) return r;
+    if (n == 0) return IDSP_OK;
+    IDSP_CHECK_ARG(phase && cs, "phase/cs must not be null");
+    cossin_kernel<<<map_grid(ctx, (n + 3) / 4), 256, 0, ctx->stream>>>(phase, cs, n);
+    IDSP_LAUNCHED(ctx);
+    return IDSP_OK;
+}
+extern "C" int idsp_atan2_i32(idsp_ctx *ctx, const int32_t *xy, int32_t *p, size_t n) {
+    int r = idsp_use_device(ctx);
+    if (r) return r;
+    if (n == 0) return IDSP_OK;
+    IDSP_CHECK_ARG(xy && p, "xy/p must not be null");
+    atan2_kernel<<<map_grid(ctx, (n + 1) / 2), 256, 0, ctx->stream>>>(xy, p, n);
+    IDSP_LAUNCHED(ctx);
+    return IDSP_OK;
+}
+extern "C" int idsp_cossin_i32_host(idsp_ctx *ctx, const int32_t *phase, int32_t *cs, size_t n) {
+    int r = idsp_use_device(ctx);
+    if (r) return r;
+    if (n == 0) return IDSP_OK;
+    IDSP_CHECK_ARG(phase && cs, "phase/cs must not be null");
+    HostStreamSpec s;
+    s.frames = n;
+    s.lanes = 1;
+    s.in_bytes_per_frame_lane = 4;
+    s.out_bytes_per_frame_lane = 8;
+    s.layout = IDSP_FRAME_MAJOR;
+    s.nblobs = 0;
+    return idsp_host_stream(ctx, s, phase, cs,
+                            [&](void **, const void *dx, void *dy, size_t, size_t an) {
+                                return idsp_cossin_i32(ctx, (const int32_t *)dx, (int32_t *)dy, an);
+                            });
+}
+extern "C" int idsp_atan2_i32_host(idsp_ctx *ctx, const int32_t *xy, int32_t *p, size_t n) {
+    int r = idsp_use_device(ctx);
+    if (r) return r;
+    if (n == 0) return IDSP_OK;
+    IDSP_CHECK_ARG(xy && p, "xy/p must not be null");
+    HostStreamSpec s;
+    s.frames = n;
+    s.lanes = 1;
+    s.in_bytes_per_frame_lane = 8;
+    s.out_bytes_per_frame_lane = 4;
+    s.layout = IDSP_FRAME_MAJOR;
+    s.nblobs = 0;
+    return idsp_host_stream(ctx, s, xy, p,
+                            [&](void **, const void *dx, void *dy, size_t, size_t an) {
+                                return idsp_atan2_i32(ctx, (const int32_t *)dx, (int32_t *)dy, an);
+                            });
+}
+
+// ---------------------------------------------------------------- Lowpass / Lockin
+#define LL_CHECK()                                                                   \
+    do {                                                                             \
+        int r_ = idsp_use_device(ctx);                                               \
+        if (r_) return r_;                                                           \
+        IDSP_CHECK_ARG(order == 1 || order == 2, "order must be 1 or 2 (lowpass.rs:74-76)"); \
+        IDSP_CHECK_ARG(k != nullptr, "k is null");                                   \
+        IDSP_CHECK_ARG(layout == IDSP_FRAME_MAJOR || layout == IDSP_LANE_MAJOR,      \
+                       "layout must be 0 (frame-major) or 1 (lane-major)");          \
+        if (frames == 0 || lanes == 0) return IDSP_OK;                               \
+    } while (0)
+
+extern "C" int idsp_lowpass_i32(idsp_ctx *ctx, int order, const int32_t *k, int64_t *state,
+                                const int32_t *x, int32_t *y, size_t frames, size_t lanes,
+                                int layout) {
+    LL_CHECK();
+    IDSP_CHECK_ARG(state && x && y, "state/x/y must not be null");
+    if (order == 1) {
+        LowpassOp<1>::Params p;
+        p.k[0] = k[0];
+        p.k[1] = 0;
+        p.st = state;
+        return launch_lanes<LowpassOp<1>>(ctx, p, x, y, frames, lanes, lanes, layout);
+    }
+    LowpassOp<2>::Params p;
+    p.k[0] = k[0];
+    p.k[1] = k[1];
+    p.st = state;
+    return launch_lanes<LowpassOp<2>>(ctx, p, x, y, frames, lanes, lanes, layout);
+}
+
+int lockin_dev(idsp_ctx *ctx, int order, const int32_t *k, int32_t *accu_state,
+               const int32_t *accu_step, int64_t *lp_state, const int32_t *x, int32_t *iq,
+               size_t frames, size_t lanes, size_t sstride, int layout) {
+    const uint32_t *lut;
+    IDSP_CUDA(cudaGetSymbolAddress((void **)&lut, g_cossin_lut));
+    if (order == 1) {
+        LockinOp<1>::Params p;
+        p.k[0] = k[0];
+        p.k[1] = 0;
+        p.accu_state = accu_state;
+        p.accu_step = accu_step;
+        p.st = lp_state;
+        p.lut = lut;
+        return launch_lanes<LockinOp<1>>(ctx, p, x, (int2 *)iq, frames, lanes, sstride, layout);
+    }
+    LockinOp<2>::Params p;
+    p.k[0] = k[0];
+    p.k[1] = k[1];
+    p.accu_state = accu_state;
+    p.accu_step = accu_step;
+    p.st = lp_state;
+    p.lut = lut;
+    return launch_lanes<LockinOp<2>>(ctx, p, x, (int2 *)iq, frames, lanes, sstride, layout);
+}
+
+extern "C" int idsp_lockin_i32(idsp_ctx *ctx, int order, const int32_t *k, int32_t *accu_state,
+                               const int32_t *accu_step, int64_t *lp_state, const int32_t *x,
+                               int32_t *iq, size_t frames, size_t lanes, int layout) {
+    LL_CHECK();
+    IDSP_CHECK_ARG(accu_state && accu_step && lp_state && x && iq, "null pointer argument");
+    IDSP_CHECK_ARG((((uintptr_t)iq) & 7) == 0, "iq must be 8-byte aligned");
+    return lockin_dev(ctx, order, k, accu_state, accu_step, lp_state, x, iq, frames, lanes, lanes,
+                      layout);
+}
+
+extern "C" int idsp_lockin_i32_host(idsp_ctx *ctx, int order, const int32_t *k,
+                                    int32_t *accu_state, const int32_t *accu_step,
+                                    int64_t *lp_state, const int32_t *x, int32_t *iq, size_t frames,
+                                    size_t lanes, int layout) {
+    LL_CHECK();
+    IDSP_CHECK_ARG(accu_state && accu_step && lp_state && x && iq, "null pointer argument");
+    HostStreamSpec s;
+    s.frames = frames;
+    s.lanes = lanes;
+    s.in_bytes_per_frame_lane = 4;
+    s.out_bytes_per_frame_lane = 8;
+    s.layout = layout;
+    s.nblobs = 3;
+    s.blobs[0] = {accu_state, lanes * 4, true};
+    s.blobs[1] = {const_cast<int32_t *>(accu_step), lanes * 4, false};
+    s.blobs[2] = {lp_state, (size_t)2 * order * lanes * 8, true};
+    return idsp_host_stream(
+        ctx, s, x, iq, [&](void **b, const void *dx, void *dy, size_t a0, size_t an) {
+            if (layout == IDSP_FRAME_MAJOR)
+                return lockin_dev(ctx, order, k, (int32_t *)b[0], (const int32_t *)b[1],
+                                  (int64_t *)b[2], (const int32_t *)dx, (int32_t *)dy, an, lanes,
+                                  lanes, layout);
+            return lockin_dev(ctx, order, k, (int32_t *)b[0] + a0, (const int32_t *)b[1] + a0,
+                              (int64_t *)b[2] + a0, (const int32_t *)dx, (int32_t *)dy, frames, an,
+                              lanes, layout);
+        });
+}

@@ -1,0 +1,278 @@
+"""Thin functional layer over the C ABI: argument marshalling only.
+
+Device path: ``torch`` CUDA tensors (PyTorch is used for device memory and
+streams only).  Host path: numpy arrays / CPU tensors go through the ``*_host``
+entry points of the C ABI (chunked H2D / compute / D2H inside the library) where
+one exists, otherwise they are staged through a device tensor.  Either way the
+arithmetic runs in the CUDA kernels; there is no CPU implementation here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+
+FRAME_MAJOR = 0
+LANE_MAJOR = 1
+
+KINDS = {
+    "i8": (np.int8, torch.int8, C.c_int8),
+    "i16": (np.int16, torch.int16, C.c_int16),
+    "i32": (np.int32, torch.int32, C.c_int32),
+    "i64": (np.int64, torch.int64, C.c_int64),
+    "f32": (np.float32, torch.float32, C.c_float),
+    "f64": (np.float64, torch.float64, C.c_double),
+}
+_TORCH2KIND = {v[1]: k for k, v in KINDS.items()}
+_NP2KIND = {np.dtype(v[0]): k for k, v in KINDS.items()}
+
+
+def kind_of(a) -> str:
+    if isinstance(a, torch.Tensor):
+        return _TORCH2KIND[a.dtype]
+    return _NP2KIND[np.asarray(a).dtype]
+
+
+def _small(values, kind):
+    """Small host coefficient array -> ctypes array (kept alive by the caller)."""
+    ct = KINDS[kind][2]
+    vals = list(np.asarray(values).ravel().tolist())
+    return (ct * len(vals))(*vals)
+
+
+def _is_dev(a) -> bool:
+    return isinstance(a, torch.Tensor) and a.is_cuda
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, torch.Tensor):
+        if not a.is_contiguous():
+            raise ValueError("tensor must be contiguous")
+        return C.c_void_p(a.data_ptr())
+    if not a.flags["C_CONTIGUOUS"]:
+        raise ValueError("array must be C-contiguous")
+    return C.c_void_p(a.ctypes.data)
+
+
+class Context:
+    """One device + one stream (``idsp_ctx``).  Not thread-safe, like ``&mut`` state."""
+
+    def __init__(self, device: int = 0, use_torch_stream: bool = True):
+        self._L = _lib.lib()
+        self.device = int(device)
+        h = C.c_void_p()
+        if use_torch_stream:
+            torch.cuda.init()
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            _lib.check(self._L.idsp_b200_init_on_stream(self.device, C.c_void_p(stream), C.byref(h)))
+        else:
+            _lib.check(self._L.idsp_b200_init(self.device, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.idsp_b200_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        _lib.check(self._L.idsp_b200_sync(self._h))
+
+    @property
+    def launches(self) -> int:
+        return int(self._L.idsp_b200_launch_count(self._h))
+
+    def set_kernel_policy(self, policy: int):
+        _lib.check(self._L.idsp_b200_set_kernel_policy(self._h, int(policy)))
+
+    # ------------------------------------------------------------------ helpers
+    def _stage(self, a):
+        """host array -> device tensor (for ops without a *_host entry point)."""
+        if _is_dev(a):
+            return a
+        t = torch.from_numpy(np.ascontiguousarray(a)) if not isinstance(a, torch.Tensor) else a
+        return t.to(f"cuda:{self.device}")
+
+    @staticmethod
+    def _unstage(dev, host):
+        if host is None or _is_dev(host):
+            return
+        if isinstance(host, torch.Tensor):
+            host.copy_(dev.cpu())
+        else:
+            host[...] = dev.cpu().numpy().reshape(host.shape)
+
+    def _out_like(self, x, out, n=None, dtype=None):
+        if out is not None:
+            return out
+        n = x.numel() if (n is None and isinstance(x, torch.Tensor)) else (x.size if n is None else n)
+        if isinstance(x, torch.Tensor):
+            return torch.empty(n, dtype=dtype or x.dtype, device=x.device)
+        return np.empty(n, dtype=dtype or x.dtype)
+
+    def _run(self, name, host_name, host_capable, arrays, call):
+        """arrays: dict of name -> array (samples/state). call(ptrs) -> rc."""
+        any_dev = any(_is_dev(a) for a in arrays.values() if a is not None)
+        all_dev = all(_is_dev(a) for a in arrays.values() if a is not None)
+        if any_dev and not all_dev:
+            raise ValueError(f"{name}: mix of device tensors and host arrays")
+        if all_dev:
+            for a in arrays.values():
+                if a is not None and a.device.index != self.device:
+                    raise ValueError(f"{name}: tensor on {a.device}, ctx on cuda:{self.device}")
+            _lib.check(call(getattr(self._L, name), {k: _ptr(v) for k, v in arrays.items()}))
+            return
+        if host_capable:
+            _lib.check(call(getattr(self._L, host_name), {k: _ptr(v) for k, v in arrays.items()}))
+            return
+        dev = {k: (None if v is None else self._stage(v)) for k, v in arrays.items()}
+        _lib.check(call(getattr(self._L, name), {k: _ptr(v) for k, v in dev.items()}))
+        self.sync()
+        for k, v in arrays.items():
+            if v is not None and k not in ("x", "accu_step"):
+                self._unstage(dev[k], v)
+
+    # ------------------------------------------------------------------ biquads
+    def biquad(self, form: str, ba, F: int, clamp, state, x, out=None, *, lanes: int,
+               layout: int = FRAME_MAJOR, nsec: int = 1):
+        """form: df1 | df2t | df1wide | df1dither | cascade.  state is [words, lanes] SoA."""
+        kind = kind_of(x)
+        y = self._out_like(x, out)
+        frames = (x.numel() if isinstance(x, torch.Tensor) else x.size) // max(lanes, 1)
+        cba = _small(ba, kind)
+        ccl = None if clamp is None else _small(clamp, kind)
+        tail = (C.c_size_t(frames), C.c_size_t(lanes), C.c_int(layout))
+        h = self._h
+        arrays = {"state": state, "x": x, "y": y}
+        if form == "df1":
+            self._run(f"idsp_biquad_df1_{kind}", f"idsp_biquad_df1_{kind}_host", True, arrays,
+                      lambda fn, p: fn(h, cba, F, ccl, p["state"], p["x"], p["y"], *tail))
+        elif form == "cascade":
+            self._run(f"idsp_biquad_cascade_{kind}", None, False, arrays,
+                      lambda fn, p: fn(h, cba, F, nsec, p["state"], p["x"], p["y"], *tail))
+        elif form == "df2t":
+            self._run(f"idsp_biquad_df2t_{kind}", None, False, arrays,
+                      lambda fn, p: fn(h, cba, ccl, p["state"], p["x"], p["y"], *tail))
+        elif form in ("df1wide", "df1dither"):
+            if kind != "i32":
+                raise ValueError(f"{form} is i32 only")
+            self._run(f"idsp_biquad_{form}_i32", None, False, arrays,
+                      lambda fn, p: fn(h, cba, F, ccl, p["state"], p["x"], p["y"], *tail))
+        else:
+            raise ValueError(form)
+        return y
+
+    # ------------------------------------------------------------------ hbf
+    def hbf_dec(self, taps, state, x, out=None, *, lanes: int, layout: int = FRAME_MAJOR):
+        taps = np.asarray(taps, np.float32)
+        n = (x.numel() if isinstance(x, torch.Tensor) else x.size) // (2 * lanes)
+        y = self._out_like(x, out, n * lanes)
+        ct = _small(taps, "f32")
+        self._run("idsp_hbf_dec_f32", None, False, {"state": state, "x": x, "y": y},
+                  lambda fn, p: fn(self._h, ct, int(taps.size), p["state"], p["x"], p["y"], n, lanes, layout))
+        return y
+
+    def hbf_int(self, taps, state, x, out=None, *, lanes: int, layout: int = FRAME_MAJOR):
+        taps = np.asarray(taps, np.float32)
+        n = (x.numel() if isinstance(x, torch.Tensor) else x.size) // lanes
+        y = self._out_like(x, out, 2 * n * lanes)
+        ct = _small(taps, "f32")
+        self._run("idsp_hbf_int_f32", None, False, {"state": state, "x": x, "y": y},
+                  lambda fn, p: fn(self._h, ct, int(taps.size), p["state"], p["x"], p["y"], n, lanes, layout))
+        return y
+
+    def fir(self, taps, odd: bool, sym: bool, state, x, out=None, *, lanes: int, layout: int = FRAME_MAJOR):
+        taps = np.asarray(taps, np.float32)
+        n = (x.numel() if isinstance(x, torch.Tensor) else x.size) // lanes
+        y = self._out_like(x, out)
+        ct = _small(taps, "f32")
+        self._run("idsp_fir_f32", None, False, {"state": state, "x": x, "y": y},
+                  lambda fn, p: fn(self._h, ct, int(taps.size), int(odd), int(sym), p["state"], p["x"], p["y"], n, lanes, layout))
+        return y
+
+    def hbf_dec_cascade(self, log2_rate: int, state, x, out=None, *, lanes: int, layout: int = FRAME_MAJOR):
+        R = 1 << log2_rate
+        n = (x.numel() if isinstance(x, torch.Tensor) else x.size) // (R * lanes)
+        y = self._out_like(x, out, n * lanes)
+        self._run("idsp_hbf_dec_cascade_f32", "idsp_hbf_dec_cascade_f32_host", True,
+                  {"state": state, "x": x, "y": y},
+                  lambda fn, p: fn(self._h, log2_rate, p["state"], p["x"], p["y"], n, lanes, layout))
+        return y
+
+    def hbf_int_cascade(self, log2_rate: int, state, x, out=None, *, lanes: int, layout: int = FRAME_MAJOR):
+        R = 1 << log2_rate
+        n = (x.numel() if isinstance(x, torch.Tensor) else x.size) // lanes
+        y = self._out_like(x, out, n * lanes * R)
+        self._run("idsp_hbf_int_cascade_f32", None, False, {"state": state, "x": x, "y": y},
+                  lambda fn, p: fn(self._h, log2_rate, p["state"], p["x"], p["y"], n, lanes, layout))
+        return y
+
+    def chain(self, log2_rate: int, ba, state, x, out=None, *, lanes: int, layout: int = FRAME_MAJOR):
+        R = 1 << log2_rate
+        n = (x.numel() if isinstance(x, torch.Tensor) else x.size) // (R * lanes)
+        y = self._out_like(x, out)
+        cba = _small(ba, "f32")
+        self._run("idsp_chain_f32", None, False, {"state": state, "x": x, "y": y},
+                  lambda fn, p: fn(self._h, log2_rate, cba, p["state"], p["x"], p["y"], n, lanes, layout))
+        return y
+
+    # ------------------------------------------------------------------ trig
+    def cossin(self, phase, out=None):
+        n = phase.numel() if isinstance(phase, torch.Tensor) else phase.size
+        cs = self._out_like(phase, out, 2 * n)
+        self._run("idsp_cossin_i32", "idsp_cossin_i32_host", True, {"x": phase, "y": cs},
+                  lambda fn, p: fn(self._h, p["x"], p["y"], n))
+        return cs.reshape(n, 2) if out is None else cs
+
+    def atan2(self, xy, out=None):
+        n = (xy.numel() if isinstance(xy, torch.Tensor) else xy.size) // 2
+        pp = self._out_like(xy, out, n)
+        self._run("idsp_atan2_i32", "idsp_atan2_i32_host", True, {"x": xy, "y": pp},
+                  lambda fn, p: fn(self._h, p["x"], p["y"], n))
+        return pp
+
+    # ------------------------------------------------------------------ lowpass / lockin
+    def lowpass(self, k: Sequence[int], state, x, out=None, *, lanes: int, layout: int = FRAME_MAJOR):
+        order = len(k)
+        ck = _small(k, "i32")
+        frames = (x.numel() if isinstance(x, torch.Tensor) else x.size) // lanes
+        y = self._out_like(x, out)
+        self._run("idsp_lowpass_i32", None, False, {"state": state, "x": x, "y": y},
+                  lambda fn, p: fn(self._h, order, ck, p["state"], p["x"], p["y"], frames, lanes, layout))
+        return y
+
+    def lockin(self, k: Sequence[int], accu_state, accu_step, lp_state, x, out=None, *, lanes: int,
+               layout: int = FRAME_MAJOR):
+        order = len(k)
+        ck = _small(k, "i32")
+        n = x.numel() if isinstance(x, torch.Tensor) else x.size
+        frames = n // lanes
+        iq = self._out_like(x, out, 2 * n)
+        self._run("idsp_lockin_i32", "idsp_lockin_i32_host", True,
+                  {"accu_state": accu_state, "accu_step": accu_step, "lp_state": lp_state, "x": x, "y": iq},
+                  lambda fn, p: fn(self._h, order, ck, p["accu_state"], p["accu_step"], p["lp_state"],
+                                   p["x"], p["y"], frames, lanes, layout))
+        return iq
+
+
+_default_ctx: dict = {}
+
+
+def default_context(device: Optional[int] = None) -> Context:
+    if device is None:
+        device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+    c = _default_ctx.get(device)
+    if c is None:
+        c = _default_ctx[device] = Context(device)
+    return c

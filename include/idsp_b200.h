@@ -1,0 +1,200 @@
+/*
+ * idsp_b200.h -- C ABI of the B200 multi-lane sample-processing engine.
+ *
+ * Drop-in boundary for the filter hot path of quartiq/idsp: every entry point
+ * replaces the inner loop of one reference `SplitProcess::block()` /
+ * `Lanes::process_view()` / PyO3 function and cites it (paths relative to the
+ * reference tree).  Plain pointers and sizes only; no torch / C++ types.
+ *
+ * Conventions
+ *  - return value: 0 = ok, <0 = idsp_status_t error; idsp_b200_last_error()
+ *    returns a thread-local message.  Nothing aborts or throws across the ABI.
+ *    (The reference hot path is infallible; length mismatches are caller
+ *    preconditions there -- dsp-process/src/process.rs:42-45,121-123 -- here they
+ *    are IDSP_EINVAL.)
+ *  - one idsp_ctx = one device + one CUDA stream; calls are asynchronous on that
+ *    stream; idsp_b200_sync() waits.  A ctx is not thread-safe (mirrors `&mut`
+ *    state exclusivity); different ctxs are independent.
+ *  - unless a function name ends in `_host`, sample and state pointers are
+ *    DEVICE pointers owned by the caller; coefficient pointers (`ba`, `clamp`,
+ *    `k`, `taps`) are always small HOST arrays copied at launch.
+ *    `_host` variants take host pointers for samples and state, stream them
+ *    through the device in chunks (H2D / compute / D2H overlapped) and return
+ *    after the results are in host memory.
+ *  - layout: IDSP_FRAME_MAJOR  flat[t*lanes + l]  = `[[T; N]]` frames
+ *            (dsp-process/src/view.rs:106-131, compose.rs:468-476)
+ *            IDSP_LANE_MAJOR   flat[l*frames + t] = View<LaneMajor>
+ *            (dsp-process/src/view.rs:176-225, compose.rs:478-494)
+ *    Multi-sample frames (HBF: X = [f32; R]) keep R innermost:
+ *    frame-major flat[(t*lanes + l)*R + r], lane-major flat[(l*frames + t)*R + r].
+ *  - state is caller-owned, persists across calls (= streaming; the reference
+ *    `block()` may be called repeatedly on the same state) and is SoA over
+ *    lanes: state[word*lanes + lane].  Word order is the reference struct's
+ *    field order and is given per function.  Zero-initialised state = the
+ *    reference's `Default`.  x and y may alias exactly (in-place) wherever the
+ *    reference implements SplitInplace.
+ *  - integer arithmetic wraps like Rust release builds; f32/f64 arithmetic is
+ *    IEEE round-to-nearest per operation, never fused, denormals preserved:
+ *    results are bit-identical to the reference.
+ */
+#ifndef IDSP_B200_H
+#define IDSP_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IDSP_B200_VERSION 100
+
+typedef struct idsp_ctx idsp_ctx;
+
+typedef enum {
+    IDSP_OK = 0,
+    IDSP_EINVAL = -1,   /* bad argument (null pointer, F out of range, size mismatch) */
+    IDSP_ECUDA = -2,    /* CUDA runtime/driver error, see idsp_b200_last_error() */
+    IDSP_ENOMEM = -3,   /* allocation failed */
+    IDSP_ENODEV = -4    /* no usable sm_100 device */
+} idsp_status_t;
+
+typedef enum { IDSP_FRAME_MAJOR = 0, IDSP_LANE_MAJOR = 1 } idsp_layout_t;
+
+/* ------------------------------------------------------------------ context */
+/* Create a context on `device` with its own non-blocking stream. */
+int idsp_b200_init(int device, idsp_ctx **out);
+/* Create a context that launches on a caller-owned cudaStream_t (e.g. the
+ * current torch stream); the stream must outlive the ctx. */
+int idsp_b200_init_on_stream(int device, void *cuda_stream, idsp_ctx **out);
+void idsp_b200_free(idsp_ctx *ctx);
+int idsp_b200_sync(idsp_ctx *ctx);
+const char *idsp_b200_last_error(void);
+int idsp_b200_version(void);
+/* Number of kernels this ctx has launched so far (bench `gpu_launches`). */
+uint64_t idsp_b200_launch_count(const idsp_ctx *ctx);
+/* Kernel selection: 0 = automatic (default), 1 = force the generic LDG kernels,
+ * 2 = force the TMA kernels (IDSP_EINVAL if the shape does not qualify). */
+int idsp_b200_set_kernel_policy(idsp_ctx *ctx, int policy);
+
+/* ------------------------------------------------------------------ iir::Biquad
+ * ba = [b0,b1,b2,a1,a2] raw coefficients exactly as in `Biquad::ba`
+ * (src/iir/biquad.rs:96-116).  F = fractional bits of Q<T,A,F> (ignored for
+ * floats).  clamp = NULL for `Biquad`, or {u,min,max} for `BiquadClamp`
+ * (src/iir/biquad.rs:121-157).
+ *
+ * DF1: `SplitProcess<T,T,DirectForm1<T>> for Biquad<C>` src/iir/biquad.rs:366-383,
+ * clamp :394-404, applied to N lanes by `Lanes<C>` dsp-process/src/compose.rs:468-513.
+ * state words: [x[0], x[1], y[0][0], y[0][1]] (DirectForm<T,1,2>, biquad.rs:260-269). */
+#define IDSP_DECL_DF1(S, T)                                                          \
+    int idsp_biquad_df1_##S(idsp_ctx *ctx, const T ba[5], int F, const T *clamp,     \
+                            T *state, const T *x, T *y, size_t frames, size_t lanes, \
+                            int layout);                                             \
+    int idsp_biquad_df1_##S##_host(idsp_ctx *ctx, const T ba[5], int F,              \
+                                   const T *clamp, T *state, const T *x, T *y,       \
+                                   size_t frames, size_t lanes, int layout);         \
+    /* Cascade<[Biquad<C>;N]> on DirectForm<T,N>: src/iir/biquad.rs:339-364.         \
+     * ba = [nsec][5]; state words [x[0],x[1],y[0][0],y[0][1],...,y[N-1][1]];        \
+     * 1 <= nsec <= IDSP_MAX_SECTIONS. */                                            \
+    int idsp_biquad_cascade_##S(idsp_ctx *ctx, const T *ba, int F, int nsec,         \
+                                T *state, const T *x, T *y, size_t frames,           \
+                                size_t lanes, int layout);
+#define IDSP_MAX_SECTIONS 8
+IDSP_DECL_DF1(i8, int8_t)
+IDSP_DECL_DF1(i16, int16_t)
+IDSP_DECL_DF1(i32, int32_t)
+IDSP_DECL_DF1(i64, int64_t)
+IDSP_DECL_DF1(f32, float)
+IDSP_DECL_DF1(f64, double)
+
+/* DF2T: `SplitProcess<T,T,DirectForm2Transposed<T>> for Biquad<T>` src/iir/biquad.rs:418-440.
+ * state words: [x[0], x[1]] (= s0, s1). */
+int idsp_biquad_df2t_f32(idsp_ctx *ctx, const float ba[5], const float *clamp, float *state,
+                         const float *x, float *y, size_t frames, size_t lanes, int layout);
+int idsp_biquad_df2t_f64(idsp_ctx *ctx, const double ba[5], const double *clamp, double *state,
+                         const double *x, double *y, size_t frames, size_t lanes, int layout);
+
+/* DirectForm1Wide: src/iir/biquad.rs:445-480; 0 <= F < 32.
+ * state words (int32): [x[0], x[1], y[0] lo, y[0] hi, y[1] lo, y[1] hi]. */
+int idsp_biquad_df1wide_i32(idsp_ctx *ctx, const int32_t ba[5], int F, const int32_t *clamp,
+                            int32_t *state, const int32_t *x, int32_t *y, size_t frames,
+                            size_t lanes, int layout);
+/* DirectForm1Dither: src/iir/biquad.rs:484-538; 0 <= F < 32.
+ * state words (int32): [x[0], x[1], y[0][0], y[0][1], e]. */
+int idsp_biquad_df1dither_i32(idsp_ctx *ctx, const int32_t ba[5], int F, const int32_t *clamp,
+                              int32_t *state, const int32_t *x, int32_t *y, size_t frames,
+                              size_t lanes, int layout);
+
+/* ------------------------------------------------------------------ hbf
+ * Built-in taps: HBF_TAPS (src/hbf.rs:308-349), index 0 = lowest rate. */
+const float *idsp_hbf_taps(int index, int *M);
+size_t idsp_hbf_dec_state_words(int log2_rate);
+size_t idsp_hbf_int_state_words(int log2_rate);
+#define IDSP_HBF_MAX_M 32
+
+/* /2 decimator `SplitProcess<[T;2],T,HbfDec<[T;N]>> for EvenSymmetric<[C;M]>`
+ * src/hbf.rs:155-192.  x: n_out pairs per lane (R = 2), y: n_out per lane.
+ * state words: [even history (M-1, oldest first) | odd history (2M-1)]. */
+int idsp_hbf_dec_f32(idsp_ctx *ctx, const float *taps, int M, float *state, const float *x,
+                     float *y, size_t n_out, size_t lanes, int layout);
+/* x2 interpolator `SplitProcess<T,[T;2],HbfInt<[T;N]>>` src/hbf.rs:207-236.
+ * state words: [x history (2M-1, oldest first)]. */
+int idsp_hbf_int_f32(idsp_ctx *ctx, const float *taps, int M, float *state, const float *x,
+                     float *y, size_t n_in, size_t lanes, int layout);
+/* HBF_DEC_CASCADE /2^k (src/hbf.rs:385-421; `.inner().1` etc. select the depth):
+ * stages TAPS[k-1] -> ... -> TAPS[0].  1 <= log2_rate <= 5.  x: n_out frames of
+ * R = 2^k samples per lane, y: n_out per lane.  state = stage states
+ * concatenated, highest-rate stage first. */
+int idsp_hbf_dec_cascade_f32(idsp_ctx *ctx, int log2_rate, float *state, const float *x,
+                             float *y, size_t n_out, size_t lanes, int layout);
+int idsp_hbf_dec_cascade_f32_host(idsp_ctx *ctx, int log2_rate, float *state, const float *x,
+                                  float *y, size_t n_out, size_t lanes, int layout);
+/* HBF_INT_CASCADE x2^k (src/hbf.rs:476-512): stages TAPS[0] -> ... -> TAPS[k-1];
+ * state = stage states concatenated, lowest-rate stage first. */
+int idsp_hbf_int_cascade_f32(idsp_ctx *ctx, int log2_rate, float *state, const float *x,
+                             float *y, size_t n_in, size_t lanes, int layout);
+/* Single-rate linear-phase FIRs `type_fir!` src/hbf.rs:70-138:
+ * odd/sym = (1,1) OddSymmetric, (0,1) EvenSymmetric, (1,0) OddAntiSymmetric,
+ * (0,0) EvenAntiSymmetric.  state words: [history (2M-1+odd)]. */
+int idsp_fir_f32(idsp_ctx *ctx, const float *taps, int M, int odd, int sym, float *state,
+                 const float *x, float *y, size_t frames, size_t lanes, int layout);
+
+/* ------------------------------------------------------------------ cossin / atan2
+ * `cossin()` src/cossin.rs:14-67 over an array like idsp.cossin (src/py.rs:11-28):
+ * cs[i] = (cos, sin). */
+int idsp_cossin_i32(idsp_ctx *ctx, const int32_t *phase, int32_t *cs, size_t n);
+int idsp_cossin_i32_host(idsp_ctx *ctx, const int32_t *phase, int32_t *cs, size_t n);
+/* `atan2()` src/atan2.rs:66-82 over rows xy[i] = (x, y) like idsp.atan2
+ * (src/py.rs:31-46: p[i] = atan2(xy[i][1], xy[i][0])). */
+int idsp_atan2_i32(idsp_ctx *ctx, const int32_t *xy, int32_t *p, size_t n);
+int idsp_atan2_i32_host(idsp_ctx *ctx, const int32_t *xy, int32_t *p, size_t n);
+
+/* ------------------------------------------------------------------ Lowpass / Lockin
+ * `Lowpass<N>` src/lowpass.rs:47-78, order N = 1|2, k = [i32; N] gains.
+ * state words (int64): LowpassState<N>.0[0..N]. */
+int idsp_lowpass_i32(idsp_ctx *ctx, int order, const int32_t *k, int64_t *state,
+                     const int32_t *x, int32_t *y, size_t frames, size_t lanes, int layout);
+/* `Lockin<Lowpass<N>>` fed by (sample, phase) src/lockin.rs:30-39 with the phase
+ * produced per lane by `Accu` (src/accu.rs:29-38): phase += step before use.
+ * accu_state[lanes] (in/out), accu_step[lanes] (device);
+ * lp_state words (int64): [I state (N) | Q state (N)];
+ * iq = Complex<i32> per sample: flat index of x, times 2, + {0: re, 1: im}. */
+int idsp_lockin_i32(idsp_ctx *ctx, int order, const int32_t *k, int32_t *accu_state,
+                    const int32_t *accu_step, int64_t *lp_state, const int32_t *x, int32_t *iq,
+                    size_t frames, size_t lanes, int layout);
+int idsp_lockin_i32_host(idsp_ctx *ctx, int order, const int32_t *k, int32_t *accu_state,
+                         const int32_t *accu_step, int64_t *lp_state, const int32_t *x,
+                         int32_t *iq, size_t frames, size_t lanes, int layout);
+
+/* ------------------------------------------------------------------ fused chain
+ * HbfDec(/2^k) -> HbfInt(x2^k) -> Biquad<f32> DF1 in one pass (BASELINE config 5;
+ * composition of hbf.rs:385-421, :476-512 and biquad.rs:366-383).
+ * state = [dec cascade state | int cascade state | DF1 state (4)].
+ * x, y: n_low frames of 2^k samples per lane. */
+size_t idsp_chain_state_words(int log2_rate);
+int idsp_chain_f32(idsp_ctx *ctx, int log2_rate, const float ba[5], float *state,
+                   const float *x, float *y, size_t n_low, size_t lanes, int layout);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IDSP_B200_H */

@@ -1,0 +1,353 @@
+"""Pins the CPU oracle against every known-answer test the reference carries for
+the hot path.  Each test cites the reference test it
+reproduces.  CPU only."""
+import math
+
+import numpy as np
+import pytest
+
+import pymodel
+from idsp_b200.coefficients import Filter
+from idsp_b200.iir import Q8, Q32, Biquad
+
+
+def _q30(ba6):
+    return Biquad.from_ba6(ba6, Q32(30)).ba
+
+
+# ---------------------------------------------------------------- biquad KATs
+def test_coefficients_lowpass_golden(oracle):
+    """src/iir/coefficients.rs:289-301"""
+    ba = _q30(Filter().critical_frequency(0.1).set_gain(1000.0).lowpass())
+    assert list(ba) == [2147483647, 2147483647, 2147483647, 1227265970, -443242341]
+    st = np.zeros(4, np.int32)
+    y = oracle.biquad_df1("i32", ba, 30, None, st, np.array([3, -4, 5, 7, -3, 2], np.int32))
+    assert list(y) == [5, 3, 9, 25, 42, 49]
+
+
+def test_coefficients_highpass_golden(oracle):
+    """src/iir/coefficients.rs:316-327"""
+    ba = _q30(Filter().critical_frequency(0.1).set_gain(1000.0).highpass())
+    assert ba[1] == -(1 << 31)
+    st = np.zeros(4, np.int32)
+    y = oracle.biquad_df1("i32", ba, 30, None, st, np.array([3, -4, 5, 7, -3, 2], np.int32))
+    assert list(y) == [5, -9, 11, 12, -1, 17]
+
+
+def test_oracle_quantize_matches_host_q(oracle):
+    """float -> Q (num_traits_impl.rs:32-45): oracle C vs host-side Python"""
+    rng = np.random.default_rng(0)
+    vals = np.concatenate([rng.normal(size=200) * 3, [0.5 / (1 << 30), -0.5 / (1 << 30), 1e30, -1e30, float("nan"), 2.0, -2.0]])
+    for v in vals:
+        assert int(oracle.quantize(v, 30, "i32")[0]) == Q32(30).from_float(v)
+        assert int(oracle.quantize(v, 4, "i8")[0]) == Q8(4).from_float(v)
+
+
+def test_df1_state_shift_identity(oracle):
+    """src/iir/biquad.rs:326-338"""
+    st = np.array([0.0, 1.0, 2.0, 3.0], np.float32)
+    y = oracle.biquad_df1("f32", [1, 0, 0, 0, 0], 0, None, st, np.array([4.0], np.float32))
+    assert y[0] == 4.0
+    assert list(st) == [4.0, 0.0, 4.0, 2.0]
+
+
+def test_dither_identity_state(oracle):
+    """src/iir/biquad.rs:493-510"""
+    st = np.array([1, 2, 3, 4, 5], np.int32)
+    y = oracle.biquad_df1dither([1 << 30, 0, 0, 0, 0], 30, None, st, np.array([6], np.int32))
+    assert y[0] == 6
+    assert list(st) == [6, 1, 6, 3, 5]
+
+
+def test_clamp_offset_min_max(oracle):
+    """src/iir/biquad.rs:130-155: default coefficients are all zero"""
+    fmax = np.finfo(np.float32).max
+    z = [0, 0, 0, 0, 0]
+    x = np.array([0.0], np.float32)
+    for clamp, want in (([5.0, -fmax, fmax], 5.0), ([0.0, 5.0, fmax], 5.0), ([0.0, -fmax, -5.0], -5.0)):
+        st = np.zeros(4, np.float32)
+        assert oracle.biquad_df1("f32", z, 0, clamp, st, x)[0] == want
+
+
+def test_identity_proportional_hold(oracle):
+    """src/iir/biquad.rs:176-212"""
+    x = np.array([3.0], np.float32)
+    assert oracle.biquad_df1("f32", [1, 0, 0, 0, 0], 0, None, np.zeros(4, np.float32), x)[0] == 3.0
+    assert oracle.biquad_df1("f32", [2, 0, 0, 0, 0], 0, None, np.zeros(4, np.float32), x)[0] == 6.0
+    st = np.array([0, 0, 2.0, 2.0], np.float32)  # set_y(2.0)
+    assert oracle.biquad_df1("f32", [0, 0, 0, 1, 0], 0, None, st, np.array([7.0], np.float32))[0] == 2.0
+
+
+def test_df2t_identity_and_clamp(oracle):
+    """doctests at src/iir/biquad.rs:385-393, 409-417"""
+    x = np.array([3.0], np.float32)
+    assert oracle.biquad_df2t("f32", [1, 0, 0, 0, 0], None, np.zeros(2, np.float32), x)[0] == 3.0
+    fmax = np.finfo(np.float32).max
+    assert oracle.biquad_df2t("f32", [1, 0, 0, 0, 0], [0, -fmax, fmax], np.zeros(2, np.float32), x)[0] == 3.0
+
+
+def test_df1_matches_df2t(oracle):
+    """src/iir/biquad.rs:671-682"""
+    ba = Biquad.from_ba6([[0.7, -0.4, 0.1], [1.0, -0.2, 0.05]], "f32").ba
+    x = np.array([-1.0, 0.25, 0.75, -0.5, 0.125, 0.0, 0.5, -0.25], np.float32)
+    y1 = oracle.biquad_df1("f32", ba, 0, None, np.zeros(4, np.float32), x)
+    y2 = oracle.biquad_df2t("f32", ba, None, np.zeros(2, np.float32), x)
+    assert np.all(np.abs(y1 - y2) < 1e-6)
+
+
+def test_cascade_matches_repeated(oracle):
+    """src/iir/biquad.rs:684-699"""
+    ba = Biquad.from_ba6([[0.5, 0.25, 0.125], [1.0, -0.1, 0.02]], "f32").ba
+    x = np.array([-0.75, 0.5, 0.0, 0.25, -0.125, 1.0, -0.5, 0.375], np.float32)
+    yc = oracle.biquad_cascade("f32", np.tile(ba, 3), 0, np.zeros(8, np.float32), x)
+    yr = x
+    for _ in range(3):
+        yr = oracle.biquad_df1("f32", ba, 0, None, np.zeros(4, np.float32), yr)
+    assert np.all(np.abs(yc - yr) < 1e-6)
+    # in fact the shared-delay-line cascade is bit-identical to repeated stages
+    assert np.array_equal(yc, yr)
+
+
+def test_fixed_point_mul_kats(oracle):
+    """dsp-fixedpoint/src/lib.rs:138-144, 501-517 and dsp-process/src/lib.rs:106-117:
+    T*Q -> T is the b0 path of the DF1 update."""
+    def gain(kind, raw, F, x):
+        dt = {"i8": np.int8, "i32": np.int32}[kind]
+        return int(oracle.biquad_df1(kind, [raw, 0, 0, 0, 0], F, None, np.zeros(4, dt), np.array([x], dt))[0])
+
+    assert gain("i8", 24, 4, 7) == 10  # 7 * Q8<4>(1.5)
+    assert gain("i32", 0x33, 4, 7) == 7 * 3 + ((3 * 7) >> 4)
+    assert gain("i32", 4, 1, 5) == (5 * 4) >> 1  # Gain(Q32<1>::from_bits(4)) * 5
+    assert gain("i8", 4, 4, 7) == math.floor(7 * 0.25)  # Q8<4>(0.25).apply(7) == 1
+
+
+# ---------------------------------------------------------------- unpinned paths vs big-int model
+@pytest.mark.parametrize("kind,bits,F", [("i8", 8, 5), ("i16", 16, 13), ("i32", 32, 30), ("i64", 64, 60), ("i32", 32, 40), ("i16", 16, -2)])
+def test_df1_fixed_vs_bigint_model(oracle, kind, bits, F):
+    rng = np.random.default_rng(bits + F)
+    dt = np.dtype(kind.replace("i", "int"))
+    lim = 1 << (bits - 2)
+    ba = [int(v) for v in rng.integers(-lim, lim, 5)]
+    x = rng.integers(-(1 << (bits - 1)), (1 << (bits - 1)) - 1, 500, dtype=np.int64).astype(dt)
+    for clamp in (None, [int(3), int(-lim // 2), int(lim // 2)]):
+        st = np.zeros(4, dt)
+        y = oracle.biquad_df1(kind, ba, F, clamp, st, x)
+        ms = [0, 0, 0, 0]
+        ym = pymodel.df1_fixed(ba, F, bits, ms, [int(v) for v in x], clamp)
+        assert [int(v) for v in y] == ym
+        assert [int(v) for v in st] == ms
+
+
+def test_wide_and_dither_vs_bigint_model(oracle):
+    rng = np.random.default_rng(7)
+    ba = Biquad.from_ba6(Filter().critical_frequency(0.02).lowpass(), Q32(29)).ba
+    ba = [int(v) for v in ba]
+    x = rng.integers(-(1 << 30), 1 << 30, 2000).astype(np.int32)
+    xs = [int(v) for v in x]
+    for clamp in (None, [17, -(1 << 28), 1 << 28]):
+        st = np.zeros(6, np.int32)
+        y = oracle.biquad_df1wide(ba, 29, clamp, st, x)
+        sx, sy = [0, 0], [0, 0]
+        assert [int(v) for v in y] == pymodel.df1_wide(ba, 29, sx, sy, xs, clamp)
+        assert int(st[0]) == sx[0] and int(st[1]) == sx[1]
+        y0 = (int(st[3]) << 32) | (int(st[2]) & 0xFFFFFFFF)
+        assert y0 == sy[0]
+        st = np.zeros(5, np.int32)
+        y = oracle.biquad_df1dither(ba, 29, clamp, st, x)
+        ms = [0, 0, 0, 0, 0]
+        assert [int(v) for v in y] == pymodel.df1_dither(ba, 29, ms, xs, clamp)
+        assert int(np.uint32(st[4])) == ms[4]
+
+
+def test_sos_entry_points(oracle):
+    """src/py.rs:50-108 restated: sos() == per-stage Q29 DF1; sos_clamp_wide on Wide state"""
+    rng = np.random.default_rng(3)
+    rows = np.array([Filter().critical_frequency(f).lowpass()[0] + Filter().critical_frequency(f).lowpass()[1] for f in (0.05, 0.1)])
+    x = rng.integers(-(1 << 24), 1 << 24, 300).astype(np.int32)
+    xy = x.copy()
+    oracle.sos(rows, xy)
+    ref = x
+    for r in rows:
+        ba = Biquad.from_ba6([r[:3], r[3:]], Q32(29)).ba
+        ref = oracle.biquad_df1("i32", ba, 29, None, np.zeros(4, np.int32), ref)
+    assert np.array_equal(xy, ref)
+    rows9 = np.concatenate([rows, np.array([[3.4, -1e6, 1e6], [-2.5, -5e5, 5e5]])], axis=1)
+    xy = x.copy()
+    oracle.sos_clamp_wide(rows9, xy)
+    ref = [int(v) for v in x]
+    for r in rows9:
+        ba = [int(v) for v in Biquad.from_ba6([r[:3], r[3:6]], Q32(29)).ba]
+        cl = [Q32(0).from_float(r[6]), Q32(0).from_float(r[7]), Q32(0).from_float(r[8])]
+        ref = pymodel.df1_wide(ba, 29, [0, 0], [0, 0], ref, cl)
+    assert [int(v) for v in xy] == ref
+
+
+# ---------------------------------------------------------------- HBF KATs
+def test_hbf_dec_simple(oracle):
+    """src/hbf.rs:548-556"""
+    st = np.zeros(3 * 1 - 2, np.float32)
+    y = oracle.hbf_dec([0.5], st, np.ones(8, np.float32))
+    assert list(y) == [1.5, 2.0, 2.0, 2.0]
+
+
+def test_hbf_dec_response_length(oracle):
+    """src/hbf.rs:576-595"""
+    assert oracle.hbf_dec_response_length(4) == 57
+    rng = np.random.default_rng(1)
+    st = np.zeros(oracle.hbf_dec_state_words(4), np.float32)
+    oracle.hbf_dec_cascade(4, st, rng.random(100 << 4, dtype=np.float32))
+    y = oracle.hbf_dec_cascade(4, st, np.zeros(1 << 10, np.float32))
+    n = 57
+    assert y[n - 1] != 0.0
+    assert y[n] == 0.0
+
+
+def test_hbf_int_impulse_and_response(oracle):
+    """src/hbf.rs:597-634"""
+    R = 4
+    r = oracle.hbf_int_response_length(R)
+    assert r == 922
+    x = np.zeros((r >> R) + 1, np.float32)
+    x[0] = 1.0
+    st = np.zeros(oracle.hbf_int_state_words(R), np.float32)
+    y = oracle.hbf_int_cascade(R, st, x)
+    assert y[r] != 0.0
+    assert np.all(y[r + 1:] == 0.0)
+    z = np.zeros(5 << 10, np.float64)
+    z[: y.size] = y.astype(np.float64) / (1 << R)
+    p = 10.0 * np.log10(np.abs(np.fft.fft(z)) ** 2 + 1e-300)
+    f = p.size / (1 << R)
+    p_pass = np.max(np.abs(p[: int(math.floor(f * 0.4))]))
+    assert p_pass < 1e-6, p_pass
+    p_stop = np.max(p[int(math.ceil(f * 0.6)): p.size // 2])
+    assert p_stop < -141.5, p_stop
+
+
+def test_hbf_block_independence(oracle):
+    """output does not depend on how the stream is cut into block() calls"""
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal(64 * 16).astype(np.float32)
+    st = np.zeros(oracle.hbf_dec_state_words(4), np.float32)
+    y_all = oracle.hbf_dec_cascade(4, st, x)
+    st2 = np.zeros_like(st)
+    parts = [oracle.hbf_dec_cascade(4, st2, x[a * 16:b * 16]) for a, b in ((0, 1), (1, 8), (8, 41), (41, 64))]
+    assert np.array_equal(np.concatenate(parts), y_all)
+    assert np.array_equal(st, st2)
+
+
+# ---------------------------------------------------------------- cossin / atan2
+def test_cossin_tables(oracle):
+    """build.rs:9-69 regenerated by the oracle == the committed tables of the product"""
+    import re
+    t = oracle.cossin_table()
+    assert [hex(v) for v in t[:4]] == ["0xc9fffd", "0x25bfff8", "0x3edffef", "0x57fffe0"]
+    assert hex(t[-1]) == "0xb4766b24"
+    src = open("idsp_b200/csrc/tables.cuh").read()
+    body = src.split("IDSP_COSSIN_TABLE_INIT {")[1].split("}")[0]
+    committed = [int(v, 16) for v in re.findall(r"0x([0-9a-f]{8})u", body)]
+    assert committed == [int(v) for v in t]
+    assert committed == pymodel.cossin_table()
+    base, slope = oracle.atan2_divi_table()
+    b = [int(v) for v in re.findall(r"(\d+)u", src.split("IDSP_ATAN2_DIVI_BASE_INIT {")[1].split("}")[0])]
+    s = [int(v) for v in re.findall(r"(-?\d+)", src.split("IDSP_ATAN2_DIVI_SLOPE_INIT {")[1].split("}")[0])]
+    assert b == [int(v) for v in base] and s == [int(v) for v in slope]
+
+
+def test_cossin_error_bounds(oracle):
+    """src/cossin.rs:130-196: all 2^20 phases, max < 1e-5, rms < 4e-6 and sum checks"""
+    n = 1 << 20
+    AMPLITUDE = float(1 << 31) - 0.85 * float(1 << 15)  # cossin.rs:77
+    ph = (np.arange(n, dtype=np.int64) << 12).astype(np.uint32).view(np.int32)
+    have = oracle.cossin(ph).astype(np.float64) / AMPLITUDE
+    a = 2.0 * math.pi * ph.astype(np.float64) / float(1 << 32)
+    wc, ws = np.cos(a), np.sin(a)
+    ec, es = have[:, 0] - wc, have[:, 1] - ws
+    assert abs(math.fsum(have[:, 0])) < 4e-10 and abs(math.fsum(have[:, 1])) < 3e-8
+    assert abs(math.fsum(have[:, 0] * wc - have[:, 1] * ws)) < 4e-10
+    assert abs(math.fsum(have[:, 1] * wc + have[:, 0] * ws)) < 1e-8
+    assert abs(math.fsum(ec)) < 4e-10 and abs(math.fsum(es)) < 4e-10
+    assert max(np.max(np.abs(ec)), np.max(np.abs(es))) < 1e-5
+    assert math.sqrt(np.mean(ec ** 2)) < 4e-6 and math.sqrt(np.mean(es ** 2)) < 4e-6
+    assert tuple(oracle.cossin(np.array([0], np.int32))[0]) == (2147454703, -1898)
+    rng = np.random.default_rng(2)
+    for p in rng.integers(-(1 << 31), 1 << 31, 2000):
+        assert tuple(int(v) for v in oracle.cossin(np.array([p], np.int32))[0]) == pymodel.cossin(int(p))
+
+
+def test_atan2_exact_and_bounds(oracle):
+    """src/atan2.rs:116-185, src/complex.rs:245-253"""
+    MAX = (1 << 31) - 1
+    at = lambda y, x: int(oracle.atan2(np.array([[x, y]], np.int32))[0])
+    assert at(0, 1) == 0 and at(0, MAX) == 0
+    assert at(1, 0) == 0x3FFFFFFF and at(MAX, 0) == 0x3FFFFFFF
+    assert at(0, 0) == 0
+    rng = np.random.default_rng(4)
+    xy = rng.integers(-(1 << 31), 1 << 31, (200000, 2)).astype(np.int32)
+    p = oracle.atan2(xy).astype(np.float64) * (math.pi / (1 << 31))
+    ref = np.arctan2(xy[:, 1].astype(np.float64), xy[:, 0].astype(np.float64))
+    err = np.angle(np.exp(1j * (p - ref)))
+    assert np.max(np.abs(err)) < 2.4e-6 and math.sqrt(np.mean(err ** 2)) < 1.4e-6
+    for x, y in xy[:3000]:
+        assert at(int(y), int(x)) == pymodel.atan2(int(y), int(x))
+    for y, x in ((-(1 << 31), -(1 << 31)), (-(1 << 31), 5), (7, -(1 << 31)), (MAX, MAX), (-1, -1)):
+        assert at(y, x) == pymodel.atan2(y, x)
+
+
+# ---------------------------------------------------------------- Lowpass / Lockin (unpinned)
+def test_lowpass_model_vectors(oracle):
+    """model-derived consistency vectors (NOT reference-pinned)"""
+    x = np.full(6000, 1 << 28, np.int32)
+    y = oracle.lowpass([67465188], np.zeros(1, np.int64), x)
+    assert list(y[:5]) == [4216574, 12517255, 20557162, 28344488, 35887168]
+    assert y[-1] == 268435456
+    y = oracle.lowpass([1048576, -94906265], np.zeros(2, np.int64), x)
+    assert list(y[:5]) == [65536, 324751, 834464, 1583229, 2559867]
+    assert int(np.max(y)) == 280035663
+
+
+def test_lowpass_and_lockin_vs_bigint_model(oracle):
+    rng = np.random.default_rng(11)
+    x = rng.integers(-(1 << 31), 1 << 31, 3000).astype(np.int32)  # exercises saturating_sub
+    for k in ([67465188], [1048576, -94906265], [(1 << 31) - 1], [1 << 16, -(1 << 30)]):
+        st = np.zeros(len(k), np.int64)
+        y = oracle.lowpass(k, st, x)
+        ms = [0] * len(k)
+        assert [int(v) for v in y] == pymodel.lowpass(k, ms, [int(v) for v in x])
+        assert [int(v) for v in st] == ms
+    lanes, frames = 3, 400
+    k = [1048576, -94906265]
+    xs = rng.integers(-(1 << 30), 1 << 30, (frames, lanes)).astype(np.int32)
+    a_state = np.array([5, -7, 1 << 30], np.int32)
+    a_step = np.array([123456789, -987654321, (1 << 31) - 1], np.int32)
+    lp = np.zeros((4, lanes), np.int64)
+    a0 = a_state.copy()
+    iq = oracle.lockin_lanes(k, a_state, a_step, lp, xs.ravel(), lanes).reshape(frames, lanes, 2)
+    for l in range(lanes):
+        si, sq = [0, 0], [0, 0]
+        out, ph = pymodel.lockin(k, int(a0[l]), int(a_step[l]), si, sq, [int(v) for v in xs[:, l]])
+        assert [tuple(int(v) for v in r) for r in iq[:, l]] == out
+        assert ph == int(a_state[l])
+        assert [int(lp[0, l]), int(lp[1, l])] == si and [int(lp[2, l]), int(lp[3, l])] == sq
+
+
+def test_accu_kat():
+    """src/accu.rs:7-13: Wrapping(0i8) step 127 -> 127, -2 (same wrapping rule the i32 NCO uses)"""
+    assert pymodel.wrap(0 + 127, 8) == 127 and pymodel.wrap(127 + 127, 8) == -2
+
+
+# ---------------------------------------------------------------- lanes drivers
+@pytest.mark.parametrize("layout", [0, 1])
+def test_lanes_equals_per_lane(oracle, layout):
+    """dsp-process/src/compose.rs:468-513: Lanes == independent per-lane streams, both layouts"""
+    rng = np.random.default_rng(9)
+    lanes, frames = 7, 33
+    ba = Biquad.from_ba6(Filter().critical_frequency(0.01).lowpass(), Q32(30)).ba
+    x = rng.integers(-(1 << 28), 1 << 28, (frames, lanes)).astype(np.int32)
+    flat = x.ravel() if layout == 0 else x.T.copy().ravel()
+    st = np.zeros((4, lanes), np.int32)
+    y = oracle.biquad_lanes("df1", "i32", ba, 30, None, st, flat, lanes, layout, nthreads=3)
+    y = y.reshape(frames, lanes) if layout == 0 else y.reshape(lanes, frames).T
+    for l in range(lanes):
+        s = np.zeros(4, np.int32)
+        assert np.array_equal(y[:, l], oracle.biquad_df1("i32", ba, 30, None, s, x[:, l].copy()))
+        assert np.array_equal(st[:, l], s)
