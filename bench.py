@@ -1,0 +1,486 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the lane engine (BASELINE.json metric: GSa/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload biquad|hbf] [--impl reference]
+
+Workloads (BASELINE.json `configs`):
+  biquad (default, configs[1]): 65 536-lane i32 iir::Biquad DF1, Q30 Butterworth lowpass
+      f0 = 0.01, shared coefficients (dsp_process::Lanes), frame-major.  The full job is
+      1e7 frames per lane (2.6 TB in + 2.6 TB out), far beyond HBM, so it is streamed: one
+      STEP = one resident block of `--frames` frames (default 16 384 = 4 GiB in + 4 GiB out),
+      filter state carried from step to step, inputs cycled through a ring of distinct
+      blocks (each >> the 126 MB L2).  `--full` runs all ceil(1e7/frames) steps.
+  hbf (configs[2]): HbfDec /16 cascade, f32, 262 144 lanes x 65 536 inputs per lane,
+      lane-major, processed as `--hbf-slices` lane slices per step.
+
+`value`  : GSa/s with inputs resident in HBM (CUDA events on the launching stream, max over ranks).
+`e2e`    : same metric through the C ABI `*_host` entry point with pinned HOST buffers
+           (H2D + kernel + D2H inside the timed region).
+`roofline`: algorithmic bytes per launch / average launch duration vs MEASURED_PEAKS.json.
+`cpu_baseline`: the CPU oracle (a C port of the reference; the Rust crate cannot be built in
+           this image) timed on the host cores on a bounded sample of the same workload.
+`--impl reference`: times that CPU path alone and prints the same JSON line with impl=reference.
+N > 1: one process per GPU (torchrun), lanes sharded, no data-path collective ("weak" scaling:
+every rank runs the full 65 536-lane workload on its own lane block).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TOTAL_FRAMES = 10_000_000
+BIQUAD_LANES = 65_536
+HBF_LANES = 262_144
+HBF_INPUTS = 65_536
+F_BITS = 30
+
+
+def biquad_coeffs():
+    from idsp_b200.coefficients import Filter
+    from idsp_b200.iir import Biquad, Q32
+
+    return Biquad.from_ba6(Filter().critical_frequency(0.01).lowpass(), Q32(F_BITS))
+
+
+def peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def traffic_from_profiles(key):
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(key)
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        for line in out.splitlines():
+            f = [s.strip() for s in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_setup(n_gpus):
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    else:
+        torch.cuda.set_device(local)
+    return rank, world, local
+
+
+def max_over_ranks(ms, world, dev):
+    import torch
+
+    if world == 1:
+        return ms
+    import torch.distributed as dist
+
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier(world):
+    import torch
+
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_biquad(frames, threads, reps=1):
+    """oracle DF1 i32 frame-major on `threads` host threads; returns GSa/s"""
+    import oracle as O
+
+    bq = biquad_coeffs()
+    rng = np.random.default_rng(2)
+    x = rng.integers(-(1 << 28), 1 << 28, frames * BIQUAD_LANES, dtype=np.int64).astype(np.int32)
+    st = np.zeros((4, BIQUAD_LANES), np.int32)
+    O.biquad_lanes("df1", "i32", bq.ba, F_BITS, None, st, x[: 8 * BIQUAD_LANES], BIQUAD_LANES, 0, nthreads=threads)
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        O.biquad_lanes("df1", "i32", bq.ba, F_BITS, None, st, x, BIQUAD_LANES, 0, nthreads=threads)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return frames * BIQUAD_LANES / best / 1e9, best
+
+
+def cpu_hbf(lanes, n_out, threads):
+    import oracle as O
+
+    rng = np.random.default_rng(3)
+    x = rng.uniform(-1, 1, lanes * n_out * 16).astype(np.float32)
+    st = np.zeros((O.hbf_dec_state_words(4), lanes), np.float32)
+    t0 = time.perf_counter()
+    O.hbf_dec_cascade_lanes(4, st, x, lanes, 1, nthreads=threads)
+    dt = time.perf_counter() - t0
+    return lanes * n_out * 16 / dt / 1e9, dt
+
+
+def cpu_calibrated(workload, threads, target_s):
+    """bounded sample sized from a short calibration run"""
+    if workload == "biquad":
+        g, _ = cpu_biquad(32, threads)
+        frames = int(max(64, min(8192, target_s * g * 1e9 / BIQUAD_LANES)))
+        g, dt = cpu_biquad(frames, threads)
+        return g, dt, f"{BIQUAD_LANES} lanes x {frames} frames (i32 DF1, frame-major)"
+    g, _ = cpu_hbf(2048, 64, threads)
+    lanes = int(max(4096, min(HBF_LANES, target_s * g * 1e9 / (1024 * 16)))) & ~127
+    g, dt = cpu_hbf(lanes, 1024, threads)
+    return g, dt, f"{lanes} lanes x {1024 * 16} inputs (f32 HbfDec/16, lane-major)"
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port; Rust crate unbuildable here)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle as O
+
+    O.build()
+    threads = O.max_threads()
+    wl = args.workload
+    g, _ = (cpu_biquad(32, threads) if wl == "biquad" else cpu_hbf(2048, 64, threads))
+    # per-step sample ~2 s of CPU work so K steps + W warm-up stay within minutes
+    if wl == "biquad":
+        frames = int(max(64, min(4096, 2.0 * g * 1e9 / BIQUAD_LANES)))
+        step = lambda: cpu_biquad(frames, threads)[1]
+        samples = frames * BIQUAD_LANES
+        sample = f"{BIQUAD_LANES} lanes x {frames} frames per step"
+        cfg = biquad_config(args, frames)
+    else:
+        lanes = int(max(4096, min(HBF_LANES, 2.0 * g * 1e9 / (1024 * 16)))) & ~127
+        step = lambda: cpu_hbf(lanes, 1024, threads)[1]
+        samples = lanes * 1024 * 16
+        sample = f"{lanes} lanes x 16384 inputs per step"
+        cfg = hbf_config(args)
+    for _ in range(args.warmup):
+        step()
+    t = 0.0
+    for _ in range(args.steps):
+        t += step()
+    val = samples * args.steps / t / 1e9
+    line = {
+        "impl": "reference", "metric": metric_name(wl), "value": val, "unit": "GSa/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "i32" if wl == "biquad" else "f32", "data": "synthetic",
+        "config": cfg,
+        "cpu_baseline": {"value": val, "unit": "GSa/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "GSa/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference = C port of the Rust crate's scalar loops (oracle/), all host threads; "
+                "rustc/cargo are not in this image so the crate itself cannot be built",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def metric_name(wl):
+    return ("GSa/s, 65536-lane i32 iir::Biquad DF1 (dsp_process::Lanes), per-step resident block"
+            if wl == "biquad" else "GSa/s, f32 hbf::HbfDec /16 cascade, 262144 lanes x 65536 inputs")
+
+
+def biquad_config(args, frames):
+    return {"workload": "configs[1]: 65536-lane i32 iir::Biquad DF1, shared Q30 lowpass f0=0.01, frame-major",
+            "lanes_per_gpu": BIQUAD_LANES, "frames_per_step": frames, "total_frames_of_full_job": TOTAL_FRAMES,
+            "streaming": "state carried across steps; ring of distinct input blocks, each >> L2",
+            "parallelism": f"lanes sharded over {args.gpus} GPU(s), no collective"}
+
+
+def hbf_config(args):
+    return {"workload": "configs[2]: hbf::HbfDec /16 (TAPS.3->2->1->0), f32, 262144 lanes x 65536 inputs, lane-major",
+            "lanes_per_gpu": HBF_LANES, "inputs_per_lane": HBF_INPUTS, "slices_per_job": args.hbf_slices,
+            "l2": "inputs (64 GiB) >> L2", "parallelism": f"lanes sharded over {args.gpus} GPU(s), no collective"}
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_biquad(args, rank, world, local):
+    import torch
+
+    import oracle as O
+    from idsp_b200 import DirectForm1, Lanes
+    from idsp_b200.engine import Context
+
+    dev = f"cuda:{local}"
+    ctx = Context(local)
+    bq = biquad_coeffs()
+    cfg = Lanes(bq)
+    lanes, frames = BIQUAD_LANES, args.frames
+    n = lanes * frames
+    nring = args.ring
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(2 + rank)
+    xin = [torch.randint(-(1 << 28), 1 << 28, (n,), dtype=torch.int32, device=dev, generator=gen) for _ in range(nring)]
+    yout = [torch.empty(n, dtype=torch.int32, device=dev) for _ in range(2)]
+    st = DirectForm1.default("i32", lanes, dev)
+    steps = args.steps
+
+    def step(i):
+        cfg.block(st, xin[i % nring], yout[i % 2])
+
+    # parity gate: first step against the oracle on a lane subset (all frames of 64 lanes)
+    step(0)
+    torch.cuda.synchronize()
+    sub = 64
+    xs = xin[0].view(frames, lanes)[:, :sub].contiguous().cpu().numpy()
+    so = np.zeros((4, sub), np.int32)
+    want = O.biquad_lanes("df1", "i32", bq.ba, F_BITS, None, so, xs.reshape(-1), sub, 0, nthreads=O.max_threads())
+    got = yout[0].view(frames, lanes)[:, :sub].contiguous().cpu().numpy().reshape(-1)
+    if not np.array_equal(got, want) or not np.array_equal(st.numpy()[:, :sub], so):
+        raise SystemExit("bench: GPU output differs from the oracle -- refusing to report a number")
+
+    for i in range(args.warmup):
+        step(i + 1)
+    sampler = ClockSampler(local)
+    barrier(world)
+    l0 = ctx.launches
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    barrier(world)
+    ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
+    launches = ctx.launches - l0
+    value = world * n * steps / (ms * 1e-3) / 1e9
+
+    # e2e: C ABI host entry point, pinned host buffers, H2D + D2H inside the timed region
+    ef = args.e2e_frames
+    xh = torch.randint(-(1 << 28), 1 << 28, (ef * lanes,), dtype=torch.int32).pin_memory()
+    yh = torch.empty(ef * lanes, dtype=torch.int32).pin_memory()
+    sth = DirectForm1.default("i32", lanes, None)
+    xa, ya = xh.numpy(), yh.numpy()
+    cfg.block(sth, xa, ya)  # warm-up (allocates the staging ring)
+    barrier(world)
+    esteps = max(1, min(steps, args.e2e_steps))
+    t0 = time.perf_counter()
+    for _ in range(esteps):
+        cfg.block(sth, xa, ya)
+        _ = int(ya[-1])  # device -> host result is read
+    torch.cuda.synchronize()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, world, dev)
+    e2e = world * ef * lanes * esteps / (e2e_ms * 1e-3) / 1e9
+
+    if rank != 0:
+        return
+    peak, peak_src = peak_hbm()
+    per_launch_bytes = 8.0 * n  # 4 B read + 4 B written per sample; state/coeff traffic ~0
+    achieved = per_launch_bytes * launches / (ms * 1e-3) / 1e9 if launches else 0.0
+    cpu_v, cpu_dt, cpu_sample = cpu_calibrated("biquad", O.max_threads(), args.cpu_seconds)
+    line = {
+        "metric": metric_name("biquad"), "value": value, "unit": "GSa/s", "n_gpus": world, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "i32", "data": "synthetic", "config": biquad_config(args, frames),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic_from_profiles("biquad_df1_i32_fm_bytes_per_launch"),
+                     "peak_source": peak_src, "kernel": "tma_lanes_kernel<Df1Op<int,false,1>,frame-major>",
+                     "algorithmic_bytes_per_launch": per_launch_bytes},
+        "cpu_baseline": {"value": cpu_v, "unit": "GSa/s", "cores": O.max_threads(), "kind": "port",
+                         "sample": cpu_sample, "seconds": cpu_dt},
+        "e2e": {"value": e2e, "unit": "GSa/s", "h2d_bytes_per_step": 4 * ef * lanes, "d2h_bytes_per_step": 4 * ef * lanes,
+                "frames_per_step": ef, "steps": esteps, "api": "idsp_biquad_df1_i32_host (pinned host buffers)"},
+        "gpu_launches": int(launches), "clocks": clocks, "parity_check": "first step == oracle on 64 lanes x all frames",
+    }
+    if args.full:
+        line["full_job"] = {"frames": steps * frames, "seconds": ms * 1e-3}
+    print(json.dumps(line), flush=True)
+
+
+def run_hbf(args, rank, world, local):
+    import torch
+
+    import oracle as O
+    from idsp_b200 import HbfDecCascade, Lanes
+    from idsp_b200.engine import Context
+    from idsp_b200.hbf import HbfDec16
+
+    dev = f"cuda:{local}"
+    ctx = Context(local)
+    cfg = Lanes(HbfDecCascade(4))
+    slices = args.hbf_slices
+    lanes_s = HBF_LANES // slices
+    n_out = HBF_INPUTS // 16
+    n_in = lanes_s * HBF_INPUTS
+    nring = min(slices, args.ring)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(3 + rank)
+    xin = []
+    for _ in range(nring):
+        t = torch.empty(n_in, dtype=torch.float32, device=dev)
+        t.uniform_(-1, 1, generator=gen)
+        xin.append(t)
+    yout = [torch.empty(lanes_s * n_out, dtype=torch.float32, device=dev) for _ in range(2)]
+    states = [HbfDec16(lanes_s, dev) for _ in range(2)]
+
+    def step(i):
+        states[i % 2].words.zero_()
+        cfg.block(states[i % 2], xin[i % nring], yout[i % 2], 1)
+
+    step(0)
+    torch.cuda.synchronize()
+    sub = 32
+    xs = xin[0].view(lanes_s, HBF_INPUTS)[:sub].contiguous().cpu().numpy().reshape(-1)
+    so = np.zeros((O.hbf_dec_state_words(4), sub), np.float32)
+    want = O.hbf_dec_cascade_lanes(4, so, xs, sub, 1, nthreads=O.max_threads())
+    got = yout[0].view(lanes_s, n_out)[:sub].contiguous().cpu().numpy().reshape(-1)
+    if not np.array_equal(got.view(np.uint32), want.view(np.uint32)):
+        raise SystemExit("bench: GPU HBF output differs from the oracle -- refusing to report a number")
+    for i in range(args.warmup):
+        step(i + 1)
+    sampler = ClockSampler(local)
+    barrier(world)
+    l0 = ctx.launches
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    barrier(world)
+    ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
+    launches = ctx.launches - l0
+    value = world * n_in * args.steps / (ms * 1e-3) / 1e9
+
+    el = 8192
+    xh = torch.empty(el * HBF_INPUTS, dtype=torch.float32).uniform_(-1, 1).pin_memory()
+    yh = torch.empty(el * n_out, dtype=torch.float32).pin_memory()
+    sth = HbfDec16(el, None)
+    cfg.block(sth, xh.numpy(), yh.numpy(), 1)
+    barrier(world)
+    esteps = max(1, min(args.steps, args.e2e_steps))
+    t0 = time.perf_counter()
+    for _ in range(esteps):
+        cfg.block(sth, xh.numpy(), yh.numpy(), 1)
+        _ = float(yh[-1])
+    torch.cuda.synchronize()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, world, dev)
+    e2e = world * el * HBF_INPUTS * esteps / (e2e_ms * 1e-3) / 1e9
+    if rank != 0:
+        return
+    peak, peak_src = peak_hbm()
+    per_launch_bytes = 4.25 * n_in
+    achieved = per_launch_bytes * launches / (ms * 1e-3) / 1e9 if launches else 0.0
+    cpu_v, cpu_dt, cpu_sample = cpu_calibrated("hbf", O.max_threads(), args.cpu_seconds)
+    line = {
+        "metric": metric_name("hbf"), "value": value, "unit": "GSa/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": hbf_config(args),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic_from_profiles("hbf_dec16_f32_lm_bytes_per_launch"), "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": per_launch_bytes},
+        "cpu_baseline": {"value": cpu_v, "unit": "GSa/s", "cores": O.max_threads(), "kind": "port",
+                         "sample": cpu_sample, "seconds": cpu_dt},
+        "e2e": {"value": e2e, "unit": "GSa/s", "h2d_bytes_per_step": 4 * el * HBF_INPUTS, "d2h_bytes_per_step": 4 * el * n_out,
+                "steps": esteps, "api": "idsp_hbf_dec_cascade_f32_host (pinned host buffers)"},
+        "gpu_launches": int(launches), "clocks": clocks, "parity_check": "first step == oracle on 32 lanes",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="biquad", choices=["biquad", "hbf"])
+    ap.add_argument("--frames", type=int, default=16384, help="frames per step (biquad)")
+    ap.add_argument("--ring", type=int, default=3, help="distinct resident input blocks")
+    ap.add_argument("--full", action="store_true", help="run the whole 1e7-frame job (biquad)")
+    ap.add_argument("--hbf-slices", type=int, default=8)
+    ap.add_argument("--e2e-frames", type=int, default=2048)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.full:
+        args.steps = (TOTAL_FRAMES + args.frames - 1) // args.frames
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    rank, world, local = dist_setup(args.gpus)
+    if args.workload == "biquad":
+        run_biquad(args, rank, world, local)
+    else:
+        run_hbf(args, rank, world, local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

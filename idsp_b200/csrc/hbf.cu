@@ -277,7 +277,6 @@ static int taps_param(const float *taps, int M, TapsParam *tp) {
 extern "C" int idsp_hbf_dec_f32(idsp_ctx *ctx, const float *taps, int M, float *state,
                                 const float *x, float *y, size_t n_out, size_t lanes, int layout) {
     HBF_COMMON_CHECK(n_out);
-    IDSP_CHECK_ARG(M >= 2, "decimator needs M >= 2");
     TapsParam tp;
     int r = taps_param(taps, M, &tp);
     if (r) return r;
@@ -289,7 +288,6 @@ extern "C" int idsp_hbf_dec_f32(idsp_ctx *ctx, const float *taps, int M, float *
 extern "C" int idsp_hbf_int_f32(idsp_ctx *ctx, const float *taps, int M, float *state,
                                 const float *x, float *y, size_t n_in, size_t lanes, int layout) {
     HBF_COMMON_CHECK(n_in);
-    IDSP_CHECK_ARG(M >= 2, "interpolator needs M >= 2");
     TapsParam tp;
     int r = taps_param(taps, M, &tp);
     if (r) return r;

@@ -552,18 +552,30 @@ size_t orc_hbf_int_response_length(int depth) { /* hbf.rs:515-539 */
     return n;
 }
 
-/* hbf.rs:46-68 for one window w[0..2M+odd): sum small taps first, sequential fold.
- * Iterator::sum::<f32>() folds from -0.0 (Rust >= 1.83; the crate needs >= 1.85),
- * i.e. the result is exactly t0 + t1 + ... */
-static inline float fir_window(const float *c, int M, int odd, int sym, const float *w) {
-    const float *newp = w + M + odd; /* last_chunk::<M>() */
-    float acc = -0.0f;
-    for (int i = 0; i < M; i++) {
-        float a = sym ? (newp[M - 1 - i] + w[i]) : (newp[M - 1 - i] - w[i]);
-        acc = acc + a * c[i];
+/* hbf.rs:46-68 for n consecutive windows starting at w[0], w[1], ...: per output the
+ * sum runs over taps j = 0..M-1 in order (small taps first, sequential fold, each op
+ * rounded).  Iterator::sum::<f32>() folds from -0.0 (Rust >= 1.83; the crate needs
+ * >= 1.85), so the result is exactly t0 + t1 + ...  The loops are tap-outer /
+ * output-inner so the compiler can vectorise across outputs like LLVM does for the
+ * reference; the per-output operation order is unchanged. */
+static inline void fir_block(const float *restrict c, int M, int odd, int sym,
+                             const float *restrict w, float *restrict out, size_t n) {
+    const int top = 2 * M - 1 + odd; /* index of the newest sample of window 0 */
+    if (sym) {
+        for (size_t i = 0; i < n; i++) out[i] = (w[i + top] + w[i]) * c[0];
+        for (int j = 1; j < M; j++) {
+            const float cj = c[j];
+            for (size_t i = 0; i < n; i++) out[i] = out[i] + (w[i + top - j] + w[i + j]) * cj;
+        }
+        if (odd)
+            for (size_t i = 0; i < n; i++) out[i] = out[i] + w[i + M];
+    } else {
+        for (size_t i = 0; i < n; i++) out[i] = (w[i + top] - w[i]) * c[0];
+        for (int j = 1; j < M; j++) {
+            const float cj = c[j];
+            for (size_t i = 0; i < n; i++) out[i] = out[i] + (w[i + top - j] - w[i + j]) * cj;
+        }
     }
-    if (odd && sym) acc = acc + w[M];
-    return acc;
 }
 
 #define HBF_CHUNK 64
@@ -579,8 +591,9 @@ void orc_hbf_dec_f32(const float *taps, int M, float *st, const float *x, float 
             even[M - 1 + i] = x[2 * (o + i)];
             odd[LEN + i] = x[2 * (o + i) + 1];
         }
-        for (size_t i = 0; i < c; i++) /* hbf.rs:178-181 */
-            y[o + i] = fir_window(taps, M, 0, 1, odd + i) + even[i];
+        float acc[HBF_CHUNK];
+        fir_block(taps, M, 0, 1, odd, acc, c);
+        for (size_t i = 0; i < c; i++) y[o + i] = acc[i] + even[i]; /* hbf.rs:178-181 */
         memmove(even, even + c, sizeof(float) * (size_t)(M - 1)); /* hbf.rs:183-184 */
         memmove(odd, odd + c, sizeof(float) * (size_t)LEN);
     }
@@ -595,8 +608,10 @@ void orc_hbf_int_f32(const float *taps, int M, float *st, const float *x, float 
     for (size_t o = 0; o < n; o += HBF_CHUNK) {
         size_t c = n - o < HBF_CHUNK ? n - o : HBF_CHUNK;
         memcpy(xs + LEN, x + o, sizeof(float) * c);
+        float acc[HBF_CHUNK];
+        fir_block(taps, M, 0, 1, xs, acc, c);
         for (size_t i = 0; i < c; i++) {
-            y[2 * (o + i)] = fir_window(taps, M, 0, 1, xs + i);
+            y[2 * (o + i)] = acc[i];
             y[2 * (o + i) + 1] = xs[M + i]; /* center tap: identity */
         }
         memmove(xs, xs + c, sizeof(float) * (size_t)LEN);
@@ -612,7 +627,9 @@ void orc_fir_f32(const float *taps, int M, int odd, int sym, float *st, const fl
     for (size_t o = 0; o < n; o += HBF_CHUNK) {
         size_t c = n - o < HBF_CHUNK ? n - o : HBF_CHUNK;
         memcpy(xs + LEN, x + o, sizeof(float) * c);
-        for (size_t i = 0; i < c; i++) y[o + i] = fir_window(taps, M, odd, sym, xs + i);
+        float acc[HBF_CHUNK];
+        fir_block(taps, M, odd, sym, xs, acc, c);
+        memcpy(y + o, acc, sizeof(float) * c);
         memmove(xs, xs + c, sizeof(float) * (size_t)LEN);
     }
     memcpy(st, xs, sizeof(float) * (size_t)LEN);

@@ -1,0 +1,190 @@
+"""GPU parity of the half-band FIR family against the CPU oracle (bit-exact f32, no FMA)."""
+import numpy as np
+import pytest
+import torch
+
+from gpu_common import DEV, assert_bits_equal, layout_flat, to_dev, to_np
+
+pytestmark = pytest.mark.gpu
+
+import idsp_b200 as ib
+from idsp_b200 import (EvenAntiSymmetric, EvenSymmetric, HbfDec, HbfDecCascade, HbfInt, HbfIntCascade,
+                       Lanes, OddAntiSymmetric, OddSymmetric, Split, hbf_taps)
+from idsp_b200.hbf import (FirState, HbfDec16, HbfInt16, hbf_dec_response_length,
+                           hbf_int_response_length, _dec_state, _int_state)
+
+
+def test_kat_hbf_dec_simple():
+    """src/hbf.rs:548-556"""
+    h = Split.new(EvenSymmetric([0.5]), HbfDec.default(1, 1, DEV))
+    h.block(torch.empty(0, dtype=torch.float32, device=DEV), torch.empty(0, dtype=torch.float32, device=DEV))
+    y = torch.zeros(4, dtype=torch.float32, device=DEV)
+    h.block(to_dev(np.ones(8, np.float32)), y)
+    assert to_np(y).tolist() == [1.5, 2.0, 2.0, 2.0]
+
+
+@pytest.mark.parametrize("idx", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("layout", [0, 1])
+def test_single_stage_dec_int(oracle, idx, layout):
+    rng = np.random.default_rng(idx)
+    taps = hbf_taps()[idx]
+    M = len(taps)
+    for n, lanes in [(1, 1), (37, 5), (64, 33), (100, 128)]:
+        x = rng.standard_normal((n, lanes, 2)).astype(np.float32)
+        st0 = rng.standard_normal((3 * M - 2, lanes)).astype(np.float32)
+        so = st0.copy()
+        want = np.empty((n, lanes), np.float32)
+        for l in range(lanes):
+            s = so[:, l].copy()
+            want[:, l] = oracle.hbf_dec(taps, s, x[:, l].reshape(-1))
+            so[:, l] = s
+        st = HbfDec(to_dev(st0), M)
+        y = torch.empty(n * lanes, dtype=torch.float32, device=DEV)
+        Lanes(EvenSymmetric(taps)).inner.block(st, to_dev(layout_flat(x, layout)), y, layout)
+        assert_bits_equal(to_np(y), layout_flat(want, layout), f"dec idx={idx}")
+        assert_bits_equal(st.numpy(), so)
+        # interpolator
+        xi = rng.standard_normal((n, lanes)).astype(np.float32)
+        si0 = rng.standard_normal((2 * M - 1, lanes)).astype(np.float32)
+        sio = si0.copy()
+        wanti = np.empty((n, lanes, 2), np.float32)
+        for l in range(lanes):
+            s = sio[:, l].copy()
+            wanti[:, l] = oracle.hbf_int(taps, s, xi[:, l].copy()).reshape(n, 2)
+            sio[:, l] = s
+        sti = HbfInt(to_dev(si0), M)
+        yi = torch.empty(2 * n * lanes, dtype=torch.float32, device=DEV)
+        EvenSymmetric(taps).block(sti, to_dev(layout_flat(xi, layout)), yi, layout)
+        assert_bits_equal(to_np(yi), layout_flat(wanti, layout), f"int idx={idx}")
+        assert_bits_equal(sti.numpy(), sio)
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("layout", [0, 1])
+def test_dec_cascade_vs_oracle(oracle, k, layout):
+    rng = np.random.default_rng(20 + k)
+    R = 1 << k
+    W = oracle.hbf_dec_state_words(k)
+    for n_out, lanes in [(1, 1), (9, 3), (40, 70), (64, 128), (130, 257), (256, 64), (512, 32)]:
+        x = rng.uniform(-1, 1, (n_out, lanes, R)).astype(np.float32)
+        st0 = rng.uniform(-1, 1, (W, lanes)).astype(np.float32)
+        so = st0.copy()
+        want = oracle.hbf_dec_cascade_lanes(k, so, layout_flat(x, layout), lanes, layout)
+        st = _dec_state(k)(lanes, DEV)
+        st.words.copy_(to_dev(st0))
+        y = torch.empty(n_out * lanes, dtype=torch.float32, device=DEV)
+        Lanes(HbfDecCascade(k)).block(st, to_dev(layout_flat(x, layout)), y, layout)
+        assert_bits_equal(to_np(y), want, f"dec cascade k={k} layout={layout} {n_out}x{lanes}")
+        assert_bits_equal(st.numpy(), so, "state")
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("layout", [0, 1])
+def test_int_cascade_vs_oracle(oracle, k, layout):
+    rng = np.random.default_rng(30 + k)
+    W = oracle.hbf_int_state_words(k)
+    for n_in, lanes in [(1, 1), (9, 3), (40, 70), (64, 128)]:
+        x = rng.uniform(-1, 1, (n_in, lanes)).astype(np.float32)
+        st0 = rng.uniform(-1, 1, (W, lanes)).astype(np.float32)
+        so = st0.copy()
+        want = oracle.hbf_int_cascade_lanes(k, so, layout_flat(x, layout), lanes, layout)
+        st = _int_state(k)(lanes, DEV)
+        st.words.copy_(to_dev(st0))
+        y = torch.empty(n_in * lanes << k, dtype=torch.float32, device=DEV)
+        Lanes(HbfIntCascade(k)).block(st, to_dev(layout_flat(x, layout)), y, layout)
+        assert_bits_equal(to_np(y), want, f"int cascade k={k}")
+        assert_bits_equal(st.numpy(), so, "state")
+
+
+def test_kat_response_lengths():
+    """src/hbf.rs:576-609 on the GPU"""
+    rng = np.random.default_rng(1)
+    h = HbfDec16(1, DEV)
+    c = HbfDecCascade(4)
+    y = torch.empty(100, dtype=torch.float32, device=DEV)
+    c.block(h, to_dev(rng.random(100 << 4, dtype=np.float32)), y)
+    y = torch.empty(64, dtype=torch.float32, device=DEV)
+    c.block(h, torch.zeros(1 << 10, dtype=torch.float32, device=DEV), y)
+    n = hbf_dec_response_length(4)
+    yy = to_np(y)
+    assert yy[n - 1] != 0.0 and yy[n] == 0.0
+    r = hbf_int_response_length(4)
+    x = np.zeros((r >> 4) + 1, np.float32); x[0] = 1.0
+    yi = torch.empty(x.size << 4, dtype=torch.float32, device=DEV)
+    HbfIntCascade(4).block(HbfInt16(1, DEV), to_dev(x), yi)
+    yi = to_np(yi)
+    assert yi[r] != 0.0 and np.all(yi[r + 1:] == 0.0)
+
+
+def test_dec_cascade_streaming_blocks(oracle):
+    """output independent of how the stream is chunked into block() calls"""
+    rng = np.random.default_rng(3)
+    lanes, n_out, k = 96, 192, 4
+    x = rng.uniform(-1, 1, (n_out, lanes, 16)).astype(np.float32)
+    so = np.zeros((oracle.hbf_dec_state_words(k), lanes), np.float32)
+    want = oracle.hbf_dec_cascade_lanes(k, so, x.reshape(-1), lanes, 0).reshape(n_out, lanes)
+    st = HbfDec16(lanes, DEV)
+    outs = []
+    for a, b in ((0, 64), (64, 65), (65, 192)):
+        y = torch.empty((b - a) * lanes, dtype=torch.float32, device=DEV)
+        Lanes(HbfDecCascade(k)).block(st, to_dev(x[a:b].reshape(-1)), y)
+        outs.append(to_np(y).reshape(b - a, lanes))
+    assert_bits_equal(np.concatenate(outs), want)
+    assert_bits_equal(st.numpy(), so)
+
+
+def test_dec_cascade_host_buffers(oracle):
+    rng = np.random.default_rng(4)
+    for layout in (0, 1):
+        lanes, n_out, k = 160, 64, 4
+        x = rng.uniform(-1, 1, n_out * lanes * 16).astype(np.float32)
+        so = np.zeros((oracle.hbf_dec_state_words(k), lanes), np.float32)
+        want = oracle.hbf_dec_cascade_lanes(k, so, x, lanes, layout)
+        st = HbfDec16(lanes, None)
+        y = np.empty(n_out * lanes, np.float32)
+        Lanes(HbfDecCascade(k)).block(st, x, y, layout)
+        assert_bits_equal(y, want)
+        assert_bits_equal(st.words, so)
+
+
+@pytest.mark.parametrize("cls,odd,sym", [(OddSymmetric, 1, 1), (EvenSymmetric, 0, 1), (OddAntiSymmetric, 1, 0), (EvenAntiSymmetric, 0, 0)])
+def test_single_rate_fir_types(oracle, cls, odd, sym):
+    """type_fir! (src/hbf.rs:70-138)"""
+    rng = np.random.default_rng(40 + odd * 2 + sym)
+    taps = rng.standard_normal(6).astype(np.float32)
+    M = 6
+    lanes, n = 19, 70
+    x = rng.standard_normal((n, lanes)).astype(np.float32)
+    W = 2 * M - 1 + odd
+    so = np.zeros((W, lanes), np.float32)
+    want = np.empty((n, lanes), np.float32)
+    for l in range(lanes):
+        s = so[:, l].copy()
+        want[:, l] = oracle.fir(taps, odd, sym, s, x[:, l].copy())
+        so[:, l] = s
+    for layout in (0, 1):
+        st = FirState.default(W, lanes, DEV)
+        y = torch.empty(n * lanes, dtype=torch.float32, device=DEV)
+        cls(taps).block(st, to_dev(layout_flat(x, layout)), y, layout)
+        assert_bits_equal(to_np(y), layout_flat(want, layout))
+        assert_bits_equal(st.numpy(), so)
+
+
+@pytest.mark.parametrize("k", [1, 4])
+def test_chain_vs_oracle(oracle, k):
+    """config 5: HbfDec -> HbfInt -> Biquad DF1 f32 fused"""
+    from idsp_b200 import Biquad, Filter
+    rng = np.random.default_rng(50 + k)
+    ba = Biquad.from_ba6(Filter().critical_frequency(0.05).lowpass(), "f32").ba
+    R = 1 << k
+    W = oracle.hbf_dec_state_words(k) + oracle.hbf_int_state_words(k) + 4
+    ctx = ib.default_context(0)
+    for layout in (0, 1):
+        lanes, n_low = 50, 40
+        x = rng.uniform(-1, 1, n_low * lanes * R).astype(np.float32)
+        so = np.zeros((W, lanes), np.float32)
+        want = oracle.chain_lanes(k, ba, so, x, lanes, layout)
+        st = torch.zeros((W, lanes), dtype=torch.float32, device=DEV)
+        y = ctx.chain(k, ba, st, to_dev(x), lanes=lanes, layout=layout)
+        assert_bits_equal(to_np(y), want)
+        assert_bits_equal(to_np(st), so)

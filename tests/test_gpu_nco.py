@@ -1,0 +1,101 @@
+"""GPU parity of cossin / atan2 / Lowpass / Lockin against the CPU oracle (bit-exact)."""
+import numpy as np
+import pytest
+import torch
+
+from gpu_common import DEV, assert_bits_equal, layout_flat, to_dev, to_np
+
+pytestmark = pytest.mark.gpu
+
+import idsp_b200 as ib
+from idsp_b200 import Accu, Lanes, Lockin, LockinState, Lowpass, LowpassState
+
+
+def test_cossin_all_2p20_phases(oracle):
+    """same sweep as src/cossin.rs:130-196, compared bit-for-bit with the oracle"""
+    ph = (np.arange(1 << 20, dtype=np.int64) << 12).astype(np.uint32).view(np.int32)
+    got = to_np(ib.cossin(to_dev(ph)))
+    assert_bits_equal(got, oracle.cossin(ph))
+    assert tuple(got[0]) == (2147454703, -1898)
+
+
+def test_cossin_random_and_ragged(oracle):
+    rng = np.random.default_rng(1)
+    for n in (1, 3, 4, 5, 1023, 100001):
+        ph = rng.integers(-(1 << 31), 1 << 31, n).astype(np.int32)
+        assert_bits_equal(to_np(ib.cossin(to_dev(ph))), oracle.cossin(ph))
+    ph = rng.integers(-(1 << 31), 1 << 31, 5000).astype(np.int32)
+    assert_bits_equal(ib.cossin(ph), oracle.cossin(ph))  # host path
+    # misaligned device pointer -> scalar path
+    t = to_dev(rng.integers(-(1 << 31), 1 << 31, 1001).astype(np.int32))
+    assert_bits_equal(to_np(ib.cossin(t[1:])), oracle.cossin(to_np(t[1:])))
+
+
+def test_atan2_exact_values_and_random(oracle):
+    """src/atan2.rs:179-185 + random bit parity"""
+    MAX = (1 << 31) - 1
+    MIN = -(1 << 31)
+    pts = np.array([[1, 0], [MAX, 0], [0, 1], [0, MAX], [0, 0], [MIN, MIN], [5, MIN], [MIN, 7], [MAX, MAX], [-1, -1]], np.int32)
+    got = to_np(ib.atan2(to_dev(pts)))
+    assert got[0] == 0 and got[1] == 0 and got[2] == 0x3FFFFFFF and got[3] == 0x3FFFFFFF and got[4] == 0
+    assert_bits_equal(got, oracle.atan2(pts))
+    rng = np.random.default_rng(2)
+    for n in (1, 2, 3, 100003):
+        xy = rng.integers(MIN, MAX + 1, (n, 2)).astype(np.int32)
+        assert_bits_equal(to_np(ib.atan2(to_dev(xy))), oracle.atan2(xy))
+    small = rng.integers(-100, 100, (5000, 2)).astype(np.int32)
+    assert_bits_equal(ib.atan2(small), oracle.atan2(small))  # host path
+
+
+@pytest.mark.parametrize("k", [[67465188], [1048576, -94906265], [(1 << 31) - 1], [1 << 16, -(1 << 30)]])
+@pytest.mark.parametrize("layout", [0, 1])
+def test_lowpass_vs_oracle(oracle, k, layout):
+    rng = np.random.default_rng(3)
+    for frames, lanes in [(100, 33), (64, 128), (1, 1)]:
+        x = rng.integers(-(1 << 31), 1 << 31, frames * lanes).astype(np.int32)
+        st0 = rng.integers(-(1 << 62), 1 << 62, (len(k), lanes)).astype(np.int64)
+        so = st0.copy()
+        want = oracle.lowpass_lanes(k, so, x, lanes, layout)
+        st = LowpassState(to_dev(st0))
+        y = torch.empty_like(to_dev(x))
+        Lanes(Lowpass(k)).block(st, to_dev(x), y, layout)
+        assert_bits_equal(to_np(y), want)
+        assert_bits_equal(st.numpy(), so)
+
+
+def test_lowpass_model_vectors():
+    """SURVEY.md 8c consistency vectors (model-derived, not reference-pinned)"""
+    x = torch.full((6000,), 1 << 28, dtype=torch.int32, device=DEV)
+    y = torch.empty_like(x)
+    Lowpass([67465188]).block(LowpassState.default(1, 1, DEV), x, y)
+    yy = to_np(y)
+    assert yy[:5].tolist() == [4216574, 12517255, 20557162, 28344488, 35887168] and yy[-1] == 268435456
+
+
+@pytest.mark.parametrize("order", [1, 2])
+@pytest.mark.parametrize("layout", [0, 1])
+def test_lockin_vs_oracle(oracle, order, layout):
+    rng = np.random.default_rng(4 + order)
+    k = [67465188] if order == 1 else [1048576, -94906265]
+    for frames, lanes in [(50, 70), (128, 128), (3, 1)]:
+        x = rng.integers(-(1 << 30), 1 << 30, frames * lanes).astype(np.int32)
+        a0 = rng.integers(-(1 << 31), 1 << 31, lanes).astype(np.int32)
+        step = rng.integers(-(1 << 31), 1 << 31, lanes).astype(np.int32)
+        ao = a0.copy()
+        so = np.zeros((2 * order, lanes), np.int64)
+        want = oracle.lockin_lanes(k, ao, step, so, x, lanes, layout)
+        st = LockinState.default(order, lanes, DEV)
+        acc = Accu(to_dev(a0), to_dev(step))
+        iq = torch.empty(2 * x.size, dtype=torch.int32, device=DEV)
+        Lockin(Lowpass(k)).block(st, acc, to_dev(x), iq, layout)
+        assert_bits_equal(to_np(iq), want)
+        assert_bits_equal(to_np(acc.state), ao)
+        assert_bits_equal(st.numpy(), so)
+        # host path (idsp_lockin_i32_host)
+        ah = a0.copy()
+        sh = LockinState.default(order, lanes, None)
+        iqh = np.empty(2 * x.size, np.int32)
+        Lockin(Lowpass(k)).block(sh, Accu(ah, step), x, iqh, layout)
+        assert_bits_equal(iqh, want)
+        assert_bits_equal(ah, ao)
+        assert_bits_equal(sh.words, so)
