@@ -156,8 +156,10 @@ def barrier(world):
 
 
 # ----------------------------------------------------------------------------- CPU arm
-def cpu_biquad(frames, threads, reps=1):
-    """oracle DF1 i32 frame-major on `threads` host threads; returns GSa/s"""
+def cpu_biquad(frames, threads, seconds=0.0):
+    """oracle DF1 i32 frame-major on `threads` host threads over a resident block of
+    `frames` frames, repeated (state carried, like the GPU steps) for >= `seconds`;
+    returns (GSa/s, elapsed s, frames processed)"""
     import oracle as O
 
     bq = biquad_coeffs()
@@ -165,38 +167,41 @@ def cpu_biquad(frames, threads, reps=1):
     x = rng.integers(-(1 << 28), 1 << 28, frames * BIQUAD_LANES, dtype=np.int64).astype(np.int32)
     st = np.zeros((4, BIQUAD_LANES), np.int32)
     O.biquad_lanes("df1", "i32", bq.ba, F_BITS, None, st, x[: 8 * BIQUAD_LANES], BIQUAD_LANES, 0, nthreads=threads)
-    best = None
-    for _ in range(reps):
-        t0 = time.perf_counter()
+    t0 = time.perf_counter()
+    done = 0
+    while True:
         O.biquad_lanes("df1", "i32", bq.ba, F_BITS, None, st, x, BIQUAD_LANES, 0, nthreads=threads)
+        done += frames
         dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    return frames * BIQUAD_LANES / best / 1e9, best
+        if dt >= seconds:
+            break
+    return done * BIQUAD_LANES / dt / 1e9, dt, done
 
 
-def cpu_hbf(lanes, n_out, threads):
+def cpu_hbf(lanes, n_out, threads, seconds=0.0):
     import oracle as O
 
     rng = np.random.default_rng(3)
     x = rng.uniform(-1, 1, lanes * n_out * 16).astype(np.float32)
     st = np.zeros((O.hbf_dec_state_words(4), lanes), np.float32)
     t0 = time.perf_counter()
-    O.hbf_dec_cascade_lanes(4, st, x, lanes, 1, nthreads=threads)
-    dt = time.perf_counter() - t0
-    return lanes * n_out * 16 / dt / 1e9, dt
+    done = 0
+    while True:
+        O.hbf_dec_cascade_lanes(4, st, x, lanes, 1, nthreads=threads)
+        done += 1
+        dt = time.perf_counter() - t0
+        if dt >= seconds:
+            break
+    return done * lanes * n_out * 16 / dt / 1e9, dt, done
 
 
 def cpu_calibrated(workload, threads, target_s):
-    """bounded sample sized from a short calibration run"""
+    """bounded sample: a resident block processed repeatedly for ~target_s seconds"""
     if workload == "biquad":
-        g, _ = cpu_biquad(32, threads)
-        frames = int(max(64, min(8192, target_s * g * 1e9 / BIQUAD_LANES)))
-        g, dt = cpu_biquad(frames, threads)
-        return g, dt, f"{BIQUAD_LANES} lanes x {frames} frames (i32 DF1, frame-major)"
-    g, _ = cpu_hbf(2048, 64, threads)
-    lanes = int(max(4096, min(HBF_LANES, target_s * g * 1e9 / (1024 * 16)))) & ~127
-    g, dt = cpu_hbf(lanes, 1024, threads)
-    return g, dt, f"{lanes} lanes x {1024 * 16} inputs (f32 HbfDec/16, lane-major)"
+        g, dt, frames = cpu_biquad(2048, threads, target_s)
+        return g, dt, f"{BIQUAD_LANES} lanes x {frames} frames (i32 DF1, frame-major, 2048-frame resident block repeated)"
+    g, dt, reps = cpu_hbf(16384, 1024, threads, target_s)
+    return g, dt, f"16384 lanes x {1024 * 16} inputs x {reps} passes (f32 HbfDec/16, lane-major)"
 
 
 def run_reference(args):
@@ -209,15 +214,16 @@ def run_reference(args):
     O.build()
     threads = O.max_threads()
     wl = args.workload
-    g, _ = (cpu_biquad(32, threads) if wl == "biquad" else cpu_hbf(2048, 64, threads))
     # per-step sample ~2 s of CPU work so K steps + W warm-up stay within minutes
     if wl == "biquad":
+        g = cpu_biquad(64, threads)[0]
         frames = int(max(64, min(4096, 2.0 * g * 1e9 / BIQUAD_LANES)))
         step = lambda: cpu_biquad(frames, threads)[1]
         samples = frames * BIQUAD_LANES
         sample = f"{BIQUAD_LANES} lanes x {frames} frames per step"
         cfg = biquad_config(args, frames)
     else:
+        g = cpu_hbf(2048, 64, threads)[0]
         lanes = int(max(4096, min(HBF_LANES, 2.0 * g * 1e9 / (1024 * 16)))) & ~127
         step = lambda: cpu_hbf(lanes, 1024, threads)[1]
         samples = lanes * 1024 * 16
@@ -267,10 +273,10 @@ def run_biquad(args, rank, world, local):
 
     import oracle as O
     from idsp_b200 import DirectForm1, Lanes
-    from idsp_b200.engine import Context
+    from idsp_b200.engine import default_context
 
     dev = f"cuda:{local}"
-    ctx = Context(local)
+    ctx = default_context(local)
     bq = biquad_coeffs()
     cfg = Lanes(bq)
     lanes, frames = BIQUAD_LANES, args.frames
@@ -283,17 +289,23 @@ def run_biquad(args, rank, world, local):
     st = DirectForm1.default("i32", lanes, dev)
     steps = args.steps
 
+    layout = args.layout
+
     def step(i):
-        cfg.block(st, xin[i % nring], yout[i % 2])
+        cfg.block(st, xin[i % nring], yout[i % 2], layout)
 
     # parity gate: first step against the oracle on a lane subset (all frames of 64 lanes)
     step(0)
     torch.cuda.synchronize()
     sub = 64
-    xs = xin[0].view(frames, lanes)[:, :sub].contiguous().cpu().numpy()
+    if layout == 0:
+        xs = xin[0].view(frames, lanes)[:, :sub].contiguous().cpu().numpy()
+        got = yout[0].view(frames, lanes)[:, :sub].contiguous().cpu().numpy().reshape(-1)
+    else:
+        xs = xin[0].view(lanes, frames)[:sub].contiguous().cpu().numpy()
+        got = yout[0].view(lanes, frames)[:sub].contiguous().cpu().numpy().reshape(-1)
     so = np.zeros((4, sub), np.int32)
-    want = O.biquad_lanes("df1", "i32", bq.ba, F_BITS, None, so, xs.reshape(-1), sub, 0, nthreads=O.max_threads())
-    got = yout[0].view(frames, lanes)[:, :sub].contiguous().cpu().numpy().reshape(-1)
+    want = O.biquad_lanes("df1", "i32", bq.ba, F_BITS, None, so, xs.reshape(-1), sub, layout, nthreads=O.max_threads())
     if not np.array_equal(got, want) or not np.array_equal(st.numpy()[:, :sub], so):
         raise SystemExit("bench: GPU output differs from the oracle -- refusing to report a number")
 
@@ -315,25 +327,31 @@ def run_biquad(args, rank, world, local):
     launches = ctx.launches - l0
     value = world * n * steps / (ms * 1e-3) / 1e9
 
+    if args.profile:
+        if rank == 0:
+            return {"profile_run": True, "value": value, "ms_per_step": ms / steps, "gpu_launches": int(launches)}
+        return None
     # e2e: C ABI host entry point, pinned host buffers, H2D + D2H inside the timed region
     ef = args.e2e_frames
     xh = torch.randint(-(1 << 28), 1 << 28, (ef * lanes,), dtype=torch.int32).pin_memory()
     yh = torch.empty(ef * lanes, dtype=torch.int32).pin_memory()
     sth = DirectForm1.default("i32", lanes, None)
     xa, ya = xh.numpy(), yh.numpy()
-    cfg.block(sth, xa, ya)  # warm-up (allocates the staging ring)
+    cfg.block(sth, xa, ya, layout)  # warm-up (allocates the staging ring)
     barrier(world)
     esteps = max(1, min(steps, args.e2e_steps))
     t0 = time.perf_counter()
     for _ in range(esteps):
-        cfg.block(sth, xa, ya)
+        cfg.block(sth, xa, ya, layout)
         _ = int(ya[-1])  # device -> host result is read
     torch.cuda.synchronize()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, world, dev)
     e2e = world * ef * lanes * esteps / (e2e_ms * 1e-3) / 1e9
 
+    del xin, yout, xh, yh
+    torch.cuda.empty_cache()
     if rank != 0:
-        return
+        return None
     peak, peak_src = peak_hbm()
     per_launch_bytes = 8.0 * n  # 4 B read + 4 B written per sample; state/coeff traffic ~0
     achieved = per_launch_bytes * launches / (ms * 1e-3) / 1e9 if launches else 0.0
@@ -344,7 +362,7 @@ def run_biquad(args, rank, world, local):
         "vs_baseline": None, "dtype": "i32", "data": "synthetic", "config": biquad_config(args, frames),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic_from_profiles("biquad_df1_i32_fm_bytes_per_launch"),
-                     "peak_source": peak_src, "kernel": "tma_lanes_kernel<Df1Op<int,false,1>,frame-major>",
+                     "peak_source": peak_src, "kernel": "tma_lanes_kernel<Df1Op<int,false,1>> (frame-major: 256-lane x 8-frame TMA boxes)" if layout == 0 else "tma_lanes_kernel<Df1Op<int,false,1>> (lane-major: swizzled 16-frame x 32-lane TMA boxes)",
                      "algorithmic_bytes_per_launch": per_launch_bytes},
         "cpu_baseline": {"value": cpu_v, "unit": "GSa/s", "cores": O.max_threads(), "kind": "port",
                          "sample": cpu_sample, "seconds": cpu_dt},
@@ -352,9 +370,11 @@ def run_biquad(args, rank, world, local):
                 "frames_per_step": ef, "steps": esteps, "api": "idsp_biquad_df1_i32_host (pinned host buffers)"},
         "gpu_launches": int(launches), "clocks": clocks, "parity_check": "first step == oracle on 64 lanes x all frames",
     }
+    if layout == 1:
+        line["config"]["workload"] = line["config"]["workload"].replace("frame-major", "lane-major")
     if args.full:
         line["full_job"] = {"frames": steps * frames, "seconds": ms * 1e-3}
-    print(json.dumps(line), flush=True)
+    return line
 
 
 def run_hbf(args, rank, world, local):
@@ -362,11 +382,11 @@ def run_hbf(args, rank, world, local):
 
     import oracle as O
     from idsp_b200 import HbfDecCascade, Lanes
-    from idsp_b200.engine import Context
+    from idsp_b200.engine import default_context
     from idsp_b200.hbf import HbfDec16
 
     dev = f"cuda:{local}"
-    ctx = Context(local)
+    ctx = default_context(local)
     cfg = Lanes(HbfDecCascade(4))
     slices = args.hbf_slices
     lanes_s = HBF_LANES // slices
@@ -414,6 +434,10 @@ def run_hbf(args, rank, world, local):
     launches = ctx.launches - l0
     value = world * n_in * args.steps / (ms * 1e-3) / 1e9
 
+    if args.profile:
+        if rank == 0:
+            return {"profile_run": True, "value": value, "ms_per_step": ms / args.steps, "gpu_launches": int(launches)}
+        return None
     el = 8192
     xh = torch.empty(el * HBF_INPUTS, dtype=torch.float32).uniform_(-1, 1).pin_memory()
     yh = torch.empty(el * n_out, dtype=torch.float32).pin_memory()
@@ -428,8 +452,10 @@ def run_hbf(args, rank, world, local):
     torch.cuda.synchronize()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, world, dev)
     e2e = world * el * HBF_INPUTS * esteps / (e2e_ms * 1e-3) / 1e9
+    del xin, yout, xh, yh
+    torch.cuda.empty_cache()
     if rank != 0:
-        return
+        return None
     peak, peak_src = peak_hbm()
     per_launch_bytes = 4.25 * n_in
     achieved = per_launch_bytes * launches / (ms * 1e-3) / 1e9 if launches else 0.0
@@ -447,13 +473,13 @@ def run_hbf(args, rank, world, local):
                 "steps": esteps, "api": "idsp_hbf_dec_cascade_f32_host (pinned host buffers)"},
         "gpu_launches": int(launches), "clocks": clocks, "parity_check": "first step == oracle on 32 lanes",
     }
-    print(json.dumps(line), flush=True)
+    return line
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="biquad", choices=["biquad", "hbf"])
@@ -464,6 +490,9 @@ def main():
     ap.add_argument("--e2e-frames", type=int, default=2048)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--layout", type=int, default=0, choices=[0, 1], help="biquad: 0 frame-major (default), 1 lane-major")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary (hbf) measurement of the default run")
+    ap.add_argument("--profile", action="store_true", help="profiling run: skip the CPU baseline and e2e legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.full:
@@ -473,9 +502,20 @@ def main():
         return
     rank, world, local = dist_setup(args.gpus)
     if args.workload == "biquad":
-        run_biquad(args, rank, world, local)
+        line = run_biquad(args, rank, world, local)
+        if not (args.no_extra or args.profile or args.full):
+            # secondary headline (BASELINE configs[2]) measured in the same run, same contract
+            import copy
+
+            a2 = copy.copy(args)
+            a2.steps = min(args.steps, 24)
+            extra = run_hbf(a2, rank, world, local)
+            if line is not None and extra is not None:
+                line["extra"] = {"hbf_dec16_f32": {k: extra[k] for k in ("metric", "value", "unit", "steps", "ms_per_step", "dtype", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "parity_check")}}
     else:
-        run_hbf(args, rank, world, local)
+        line = run_hbf(args, rank, world, local)
+    if line is not None:
+        print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist
 

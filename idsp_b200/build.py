@@ -42,6 +42,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
     cmd = [nvcc, *NVCC_FLAGS]
     if verbose:
         cmd += ["-Xptxas", "-v"]
+    if os.environ.get("IDSP_HF_NT"):  # experiment: threads per CTA of the tiled HBF kernel
+        cmd += [f"-DHF_NT={int(os.environ['IDSP_HF_NT'])}"]
+    if os.environ.get("IDSP_TUNE"):  # tile-shape sweep builds (tools/sweep_biquad.py)
+        cmd += ["-DIDSP_TUNE"]
     cmd += ["-ccbin", "g++", "-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
     env = dict(os.environ)
     env.pop("CC", None)

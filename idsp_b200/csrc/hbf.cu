@@ -111,14 +111,14 @@ __device__ __forceinline__ size_t fidx(int layout, size_t n, size_t lane, size_t
 // shared-memory tiled kernels used for the large aligned cases.
 template <int K>
 __global__ void __launch_bounds__(128)
-hbf_dec_cascade_generic(float *st, const float *x, float *y, size_t n_out, size_t lanes,
-                        size_t sstride, int layout) {
+hbf_dec_cascade_generic(float *st, const float *x, float *y, size_t n_begin, size_t n_out,
+                        size_t lanes, size_t sstride, int layout) {
     constexpr int R = 1 << K;
     size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (lane >= lanes) return;
     DecCascadeRegs<K> c;
     c.load(st, sstride, lane);
-    for (size_t n = 0; n < n_out; n++) {
+    for (size_t n = n_begin; n < n_out; n++) {
         float v[R];
         size_t f = fidx(layout, n, lane, n_out, lanes);
         load_frame<R>(x + f * R, v);
@@ -311,15 +311,23 @@ extern "C" int idsp_fir_f32(idsp_ctx *ctx, const float *taps, int M, int odd, in
 
 int hbf_dec_cascade_dev(idsp_ctx *ctx, int k, float *state, const float *x, float *y,
                         size_t n_out, size_t lanes, size_t sstride, int layout) {
-    int fr = hbf_dec_fast_try(ctx, k, state, x, y, n_out, lanes, sstride, layout);
-    if (fr != IDSP_HBF_FAST_NOT_APPLICABLE) return fr;
+    // large aligned lane-major streams: tiled TMA kernel over whole tiles, generic kernel
+    // (state carried through `state`) for the remaining frames of every lane
+    size_t done = 0;
+    int fr = hbf_dec_fast_try(ctx, k, state, x, y, n_out, lanes, sstride, layout, &done);
+    if (fr != IDSP_HBF_FAST_NOT_APPLICABLE && fr != IDSP_OK) return fr;
+    if (fr == IDSP_HBF_FAST_NOT_APPLICABLE && ctx->policy == 2 && layout == IDSP_LANE_MAJOR) {
+        idsp_set_error("tiled HBF kernel forced but shape/alignment does not qualify");
+        return IDSP_EINVAL;
+    }
+    if (done == n_out) return IDSP_OK;
     unsigned grid = (unsigned)((lanes + 63) / 64);
     switch (k) {
-        case 1: hbf_dec_cascade_generic<1><<<grid, 64, 0, ctx->stream>>>(state, x, y, n_out, lanes, sstride, layout); break;
-        case 2: hbf_dec_cascade_generic<2><<<grid, 64, 0, ctx->stream>>>(state, x, y, n_out, lanes, sstride, layout); break;
-        case 3: hbf_dec_cascade_generic<3><<<grid, 64, 0, ctx->stream>>>(state, x, y, n_out, lanes, sstride, layout); break;
-        case 4: hbf_dec_cascade_generic<4><<<grid, 64, 0, ctx->stream>>>(state, x, y, n_out, lanes, sstride, layout); break;
-        default: hbf_dec_cascade_generic<5><<<grid, 64, 0, ctx->stream>>>(state, x, y, n_out, lanes, sstride, layout); break;
+        case 1: hbf_dec_cascade_generic<1><<<grid, 64, 0, ctx->stream>>>(state, x, y, done, n_out, lanes, sstride, layout); break;
+        case 2: hbf_dec_cascade_generic<2><<<grid, 64, 0, ctx->stream>>>(state, x, y, done, n_out, lanes, sstride, layout); break;
+        case 3: hbf_dec_cascade_generic<3><<<grid, 64, 0, ctx->stream>>>(state, x, y, done, n_out, lanes, sstride, layout); break;
+        case 4: hbf_dec_cascade_generic<4><<<grid, 64, 0, ctx->stream>>>(state, x, y, done, n_out, lanes, sstride, layout); break;
+        default: hbf_dec_cascade_generic<5><<<grid, 64, 0, ctx->stream>>>(state, x, y, done, n_out, lanes, sstride, layout); break;
     }
     IDSP_LAUNCHED(ctx);
     return IDSP_OK;

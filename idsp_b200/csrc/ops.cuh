@@ -78,6 +78,7 @@ template <class T> struct Sos<T, true> {
 template <class T, bool CLAMP, int MODE = 0> struct Df1Op {
     using In = T;
     using Out = T;
+    static constexpr bool TUNABLE = true;  // tuning builds sweep tile shapes for this Op
     struct Params {
         T ba[5];
         int F;

@@ -22,6 +22,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #define IDSP_TMA_NOT_APPLICABLE 12345
 
@@ -89,7 +90,10 @@ template <> struct Bits32<float> {
 // LM = false: frame-major, tile [TF rows][32 words];  LM = true: lane-major,
 // tile [32 rows (lanes)][16 words] with 64-byte swizzle (TF must be 16).
 // Op::In and Op::Out are 4-byte types.  WPC warps per CTA, each independent.
-template <class Op, bool LM, int TF, int S, int O, int WPC>
+// WIDE (frame-major only): the WPC warps of a CTA share one [32*WPC lanes x TF] box per
+// tile (one TMA load / store per CTA tile, one __syncthreads per tile) so that a row
+// of the box is 128*WPC contiguous bytes in HBM instead of 128.
+template <class Op, bool LM, int TF, int S, int O, int WPC, bool WIDE = false>
 __global__ void __launch_bounds__(WPC * 32)
 tma_lanes_kernel(typename Op::Params p, const __grid_constant__ CUtensorMap mx,
                  const __grid_constant__ CUtensorMap my, size_t frames, size_t lanes,
@@ -98,39 +102,49 @@ tma_lanes_kernel(typename Op::Params p, const __grid_constant__ CUtensorMap mx,
     using Out = typename Op::Out;
     static_assert(sizeof(In) == 4 && sizeof(Out) == 4, "4-byte samples only");
     static_assert(!LM || TF == 16, "lane-major tiles are 16 frames (64B swizzle)");
-    constexpr int TILE_WORDS = TF * 32;
+    static_assert(!(WIDE && LM), "wide boxes are frame-major only");
+    constexpr int BW = WIDE ? 32 * WPC : 32;        // box width in lanes
+    constexpr int TILE_WORDS = TF * BW;
     constexpr uint32_t TILE_BYTES = TILE_WORDS * 4;
+    constexpr int NPIPE = WIDE ? 1 : WPC;            // independent pipelines per CTA
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    // per warp: S input stages, O output stages, S mbarriers
-    uint32_t *wbase = reinterpret_cast<uint32_t *>(smem_raw) + (size_t)w * (S + O) * TILE_WORDS;
+    const int pipe = WIDE ? 0 : w;
+    const int col = WIDE ? w * 32 + l : l;          // my column inside the box
+    // per pipeline: S input stages, O output stages, S mbarriers
+    uint32_t *wbase = reinterpret_cast<uint32_t *>(smem_raw) + (size_t)pipe * (S + O) * TILE_WORDS;
     uint32_t *sin = wbase;
     uint32_t *sout = wbase + S * TILE_WORDS;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)WPC * (S + O) * TILE_BYTES) + w * S;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)NPIPE * (S + O) * TILE_BYTES) + pipe * S;
 
-    const size_t lane0 = ((size_t)blockIdx.x * WPC + w) * 32;
-    if (lane0 >= lanes) return;
-    const size_t lane = lane0 + l;
+    const size_t box0 = WIDE ? (size_t)blockIdx.x * BW : ((size_t)blockIdx.x * WPC + w) * 32;
+    if (!WIDE && box0 >= lanes) return;
+    const size_t lane = box0 + col;
     const bool active = lane < lanes;
     const size_t ntiles = (frames + TF - 1) / TF;
+    const bool leader = WIDE ? threadIdx.x == 0 : l == 0;
+    auto sync_pipe = [&]() {
+        if (WIDE) __syncthreads();
+        else __syncwarp();
+    };
 
-    if (l == 0) {
+    if (leader) {
 #pragma unroll
         for (int s = 0; s < S; s++) mbar_init(smem_u32(&bars[s]), 1);
         mbar_fence_init();
     }
-    __syncwarp();
+    sync_pipe();
 
     auto issue_load = [&](size_t tile) {
         const int s = (int)(tile % S);
         const uint32_t bar = smem_u32(&bars[s]);
         mbar_expect_tx(bar, TILE_BYTES);
         if (LM)
-            tma_load_2d(smem_u32(sin + s * TILE_WORDS), &mx, (int)(tile * TF), (int)lane0, bar);
+            tma_load_2d(smem_u32(sin + s * TILE_WORDS), &mx, (int)(tile * TF), (int)box0, bar);
         else
-            tma_load_2d(smem_u32(sin + s * TILE_WORDS), &mx, (int)lane0, (int)(tile * TF), bar);
+            tma_load_2d(smem_u32(sin + s * TILE_WORDS), &mx, (int)box0, (int)(tile * TF), bar);
     };
-    if (l == 0) {
+    if (leader) {
 #pragma unroll
         for (int s = 0; s < S - 1; s++)
             if ((size_t)s < ntiles) issue_load(s);
@@ -141,12 +155,12 @@ tma_lanes_kernel(typename Op::Params p, const __grid_constant__ CUtensorMap mx,
     for (size_t i = 0; i < ntiles; i++) {
         const int s = (int)(i % S);
         const int ob = (int)(i % O);
-        if (l == 0) {
+        if (leader) {
             // the output stage we are about to overwrite must have been read by its store
             tma_wait_read<O - 1>();
             if (i + S - 1 < ntiles) issue_load(i + S - 1);
         }
-        __syncwarp();
+        sync_pipe();
         mbar_wait(smem_u32(&bars[s]), (uint32_t)((i / S) & 1));
         const uint32_t *tin = sin + s * TILE_WORDS;
         uint32_t *tout = sout + ob * TILE_WORDS;
@@ -184,23 +198,23 @@ tma_lanes_kernel(typename Op::Params p, const __grid_constant__ CUtensorMap mx,
             if (nvalid == TF) {
 #pragma unroll
                 for (int f = 0; f < TF; f++)
-                    tout[f * 32 + l] = Bits32<Out>::to(op.step(p, Bits32<In>::from(tin[f * 32 + l])));
+                    tout[f * BW + col] = Bits32<Out>::to(op.step(p, Bits32<In>::from(tin[f * BW + col])));
             } else {
                 for (int f = 0; f < nvalid; f++)
-                    tout[f * 32 + l] = Bits32<Out>::to(op.step(p, Bits32<In>::from(tin[f * 32 + l])));
+                    tout[f * BW + col] = Bits32<Out>::to(op.step(p, Bits32<In>::from(tin[f * BW + col])));
             }
         }
         fence_async_smem();
-        __syncwarp();
-        if (l == 0) {
+        sync_pipe();
+        if (leader) {
             if (LM)
-                tma_store_2d(&my, smem_u32(tout), (int)(i * TF), (int)lane0);
+                tma_store_2d(&my, smem_u32(tout), (int)(i * TF), (int)box0);
             else
-                tma_store_2d(&my, smem_u32(tout), (int)lane0, (int)(i * TF));
+                tma_store_2d(&my, smem_u32(tout), (int)box0, (int)(i * TF));
             tma_commit();
         }
     }
-    if (l == 0) tma_wait_read<0>();
+    if (leader) tma_wait_read<0>();
     if (active) op.store(p, lane, sstride);
 }
 
@@ -240,27 +254,44 @@ static bool make_map_2d(CUtensorMap *m, const void *base, uint64_t cols, uint64_
     return r == CUDA_SUCCESS;
 }
 
-template <class Op, bool LM, int TF, int S, int O, int WPC>
+template <class Op, bool LM, int TF, int S, int O, int WPC, bool WIDE = false>
 static int tma_launch_cfg(idsp_ctx *ctx, const typename Op::Params &p, const void *x, void *y,
                           size_t frames, size_t lanes, size_t sstride) {
     CUtensorMap mx, my;
     bool ok;
+    constexpr int BW = WIDE ? 32 * WPC : 32;
     if (LM) {
         ok = make_map_2d(&mx, x, frames, lanes, TF, 32, CU_TENSOR_MAP_SWIZZLE_64B) &&
              make_map_2d(&my, y, frames, lanes, TF, 32, CU_TENSOR_MAP_SWIZZLE_64B);
     } else {
-        ok = make_map_2d(&mx, x, lanes, frames, 32, TF, CU_TENSOR_MAP_SWIZZLE_NONE) &&
-             make_map_2d(&my, y, lanes, frames, 32, TF, CU_TENSOR_MAP_SWIZZLE_NONE);
+        ok = make_map_2d(&mx, x, lanes, frames, BW, TF, CU_TENSOR_MAP_SWIZZLE_NONE) &&
+             make_map_2d(&my, y, lanes, frames, BW, TF, CU_TENSOR_MAP_SWIZZLE_NONE);
     }
     if (!ok) return IDSP_TMA_NOT_APPLICABLE;
-    constexpr size_t smem = (size_t)WPC * (S + O) * TF * 128 + (size_t)WPC * S * 8;
-    auto kern = tma_lanes_kernel<Op, LM, TF, S, O, WPC>;
+    constexpr int NPIPE = WIDE ? 1 : WPC;
+    constexpr size_t smem = (size_t)NPIPE * (S + O) * TF * BW * 4 + (size_t)NPIPE * S * 8;
+    auto kern = tma_lanes_kernel<Op, LM, TF, S, O, WPC, WIDE>;
     IDSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const size_t warps = (lanes + 31) / 32;
     unsigned grid = (unsigned)((warps + WPC - 1) / WPC);
     kern<<<grid, WPC * 32, smem, ctx->stream>>>(p, mx, my, frames, lanes, sstride);
     IDSP_LAUNCHED(ctx);
     return IDSP_OK;
+}
+
+// Frame-major default: tiles of 8 frames, 4 load stages, 2 store stages, and the widest
+// box (32*WPC lanes, WPC <= 8) that still leaves one CTA per SM.  Measured on the
+// 65 536-lane i32 DF1 stream (tools/sweep_biquad.py, profiles/sweep_biquad_r1.md):
+// 128-byte rows (WPC 1) 4.6 TB/s, 1 KB rows (WPC 8) 6.5 TB/s = the copy peak.
+template <class Op>
+static int tma_launch_fm_auto(idsp_ctx *ctx, const typename Op::Params &p, const void *x, void *y,
+                              size_t frames, size_t lanes, size_t sstride) {
+    const size_t sms = (size_t)(ctx->sm_count > 0 ? ctx->sm_count : 148);
+    auto ctas = [&](size_t wpc) { return (lanes + 32 * wpc - 1) / (32 * wpc); };
+    if (ctas(8) >= sms) return tma_launch_cfg<Op, false, 8, 4, 2, 8, true>(ctx, p, x, y, frames, lanes, sstride);
+    if (ctas(4) >= sms) return tma_launch_cfg<Op, false, 8, 4, 2, 4, true>(ctx, p, x, y, frames, lanes, sstride);
+    if (ctas(2) >= sms) return tma_launch_cfg<Op, false, 8, 4, 2, 2, true>(ctx, p, x, y, frames, lanes, sstride);
+    return tma_launch_cfg<Op, false, 16, 4, 2, 1>(ctx, p, x, y, frames, lanes, sstride);
 }
 
 // Returns IDSP_TMA_NOT_APPLICABLE when the generic kernels must be used.
@@ -271,9 +302,7 @@ static int tma_try_launch(idsp_ctx *ctx, const typename Op::Params &p, const typ
     static_assert(sizeof(typename Op::In) == 4 && sizeof(typename Op::Out) == 4, "");
     if (ctx->policy == 1) return IDSP_TMA_NOT_APPLICABLE;
     const bool lm = layout == IDSP_LANE_MAJOR;
-    constexpr int TF_FM = 16;
-    const int tf = lm ? 16 : TF_FM;
-    bool ok = (((uintptr_t)x | (uintptr_t)y) & 15) == 0 && frames >= (size_t)tf &&
+    bool ok = (((uintptr_t)x | (uintptr_t)y) & 15) == 0 && frames >= 16 &&
               frames < (1ull << 31) && lanes < (1ull << 31) &&
               (lm ? (frames % 4 == 0) : (lanes % 4 == 0));
     if (!ok) {
@@ -284,10 +313,43 @@ static int tma_try_launch(idsp_ctx *ctx, const typename Op::Params &p, const typ
         return IDSP_TMA_NOT_APPLICABLE;
     }
     int r;
-    if (lm)
+    if (lm) {
         r = tma_launch_cfg<Op, true, 16, 4, 2, 1>(ctx, p, x, y, frames, lanes, sstride);
-    else
-        r = tma_launch_cfg<Op, false, TF_FM, 4, 2, 1>(ctx, p, x, y, frames, lanes, sstride);
+    } else {
+#ifdef IDSP_TUNE
+        // tuning builds only (tools/sweep_biquad.py): pick a tile configuration at run time
+        const char *e = getenv("IDSP_TMA_CFG");
+        int cfg = (e && Op::TUNABLE) ? atoi(e) : -1;
+        switch (cfg) {
+            case 1: r = tma_launch_cfg<Op, false, 16, 6, 2, 1>(ctx, p, x, y, frames, lanes, sstride); break;
+            case 2: r = tma_launch_cfg<Op, false, 32, 3, 2, 1>(ctx, p, x, y, frames, lanes, sstride); break;
+            case 3: r = tma_launch_cfg<Op, false, 32, 4, 2, 1>(ctx, p, x, y, frames, lanes, sstride); break;
+            case 4: r = tma_launch_cfg<Op, false, 8, 8, 3, 1>(ctx, p, x, y, frames, lanes, sstride); break;
+            case 5: r = tma_launch_cfg<Op, false, 16, 4, 2, 2>(ctx, p, x, y, frames, lanes, sstride); break;
+            case 6: r = tma_launch_cfg<Op, false, 16, 4, 2, 4>(ctx, p, x, y, frames, lanes, sstride); break;
+            case 7: r = tma_launch_cfg<Op, false, 16, 4, 2, 2, true>(ctx, p, x, y, frames, lanes, sstride); break;
+            case 8: r = tma_launch_cfg<Op, false, 16, 4, 2, 4, true>(ctx, p, x, y, frames, lanes, sstride); break;
+            case 9: r = tma_launch_cfg<Op, false, 16, 4, 2, 8, true>(ctx, p, x, y, frames, lanes, sstride); break;
+            case 10: r = tma_launch_cfg<Op, false, 8, 6, 2, 4, true>(ctx, p, x, y, frames, lanes, sstride); break;
+            case 11: r = tma_launch_cfg<Op, false, 32, 3, 2, 2, true>(ctx, p, x, y, frames, lanes, sstride); break;
+            case 12: r = tma_launch_cfg<Op, false, 16, 3, 1, 1>(ctx, p, x, y, frames, lanes, sstride); break;
+            case 13: r = tma_launch_cfg<Op, false, 16, 6, 3, 4, true>(ctx, p, x, y, frames, lanes, sstride); break;
+            case 14: r = tma_launch_cfg<Op, false, 8, 8, 4, 8, true>(ctx, p, x, y, frames, lanes, sstride); break;
+            case 15: r = tma_launch_cfg<Op, false, 16, 3, 2, 8, true>(ctx, p, x, y, frames, lanes, sstride); break;
+            case 16: r = tma_launch_cfg<Op, false, 16, 5, 2, 8, true>(ctx, p, x, y, frames, lanes, sstride); break;
+            case 17: r = tma_launch_cfg<Op, false, 32, 3, 2, 8, true>(ctx, p, x, y, frames, lanes, sstride); break;
+            case 18: r = tma_launch_cfg<Op, false, 8, 6, 2, 8, true>(ctx, p, x, y, frames, lanes, sstride); break;
+            case 19: r = tma_launch_cfg<Op, false, 16, 4, 3, 8, true>(ctx, p, x, y, frames, lanes, sstride); break;
+            case 20: r = tma_launch_cfg<Op, false, 8, 4, 2, 8, true>(ctx, p, x, y, frames, lanes, sstride); break;
+            case 21: r = tma_launch_cfg<Op, false, 4, 8, 4, 8, true>(ctx, p, x, y, frames, lanes, sstride); break;
+            case 22: r = tma_launch_cfg<Op, false, 16, 2, 2, 8, true>(ctx, p, x, y, frames, lanes, sstride); break;
+            case 0: r = tma_launch_cfg<Op, false, 16, 4, 2, 1>(ctx, p, x, y, frames, lanes, sstride); break;
+            default: r = tma_launch_fm_auto<Op>(ctx, p, x, y, frames, lanes, sstride); break;
+        }
+#else
+        r = tma_launch_fm_auto<Op>(ctx, p, x, y, frames, lanes, sstride);
+#endif
+    }
     if (r == IDSP_TMA_NOT_APPLICABLE && ctx->policy == 2) {
         idsp_set_error("TMA kernels forced but cuTensorMapEncodeTiled is unavailable");
         return IDSP_EINVAL;

@@ -1,0 +1,105 @@
+"""Lane sharding across the GPUs of one node (one process per GPU, torch.distributed).
+
+Lanes never interact (dsp-process/src/compose.rs:472-475), so the path shards by
+independent units: rank r owns the contiguous lane block [lo, hi) and the matching
+slice of the SoA state; coefficients are tiny and replicated.  There is no collective
+inside the computation.  NCCL (or gloo in the CPU tests) is used only at the edges:
+`scatter_lanes` hands lane blocks of a root-resident buffer to the ranks,
+`gather_lanes` collects outputs, both for either layout of dsp-process/src/view.rs.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from .engine import FRAME_MAJOR, LANE_MAJOR
+
+
+def lane_block(rank: int, world: int, lanes: int, align: int = 32) -> Tuple[int, int]:
+    """Contiguous lane block of `rank`: blocks are multiples of `align` lanes (a warp) except
+    the last, cover [0, lanes) exactly and differ by at most one unit."""
+    units = (lanes + align - 1) // align
+    lo_u = units * rank // world
+    hi_u = units * (rank + 1) // world
+    return min(lo_u * align, lanes), min(hi_u * align, lanes)
+
+
+def all_blocks(world: int, lanes: int, align: int = 32) -> List[Tuple[int, int]]:
+    return [lane_block(r, world, lanes, align) for r in range(world)]
+
+
+def _as_tlw(flat: torch.Tensor, frames: int, lanes: int, width: int, layout: int) -> torch.Tensor:
+    """view a flat buffer as [frames, lanes, width] (a permuted view for lane-major)"""
+    if layout == FRAME_MAJOR:
+        return flat.view(frames, lanes, width)
+    return flat.view(lanes, frames, width).permute(1, 0, 2)
+
+
+def shard_flat(flat: torch.Tensor, frames: int, lanes: int, lo: int, hi: int, layout: int,
+               width: int = 1) -> torch.Tensor:
+    """flat buffer of all lanes -> contiguous flat buffer of lanes [lo, hi) in the same layout"""
+    v = _as_tlw(flat, frames, lanes, width, layout)[:, lo:hi]
+    if layout == FRAME_MAJOR:
+        return v.contiguous().view(-1)
+    return v.permute(1, 0, 2).contiguous().view(-1)
+
+
+def unshard_into(dst_flat: torch.Tensor, part: torch.Tensor, frames: int, lanes: int, lo: int, hi: int,
+                 layout: int, width: int = 1) -> None:
+    n = hi - lo
+    if layout == FRAME_MAJOR:
+        dst_flat.view(frames, lanes, width)[:, lo:hi] = part.view(frames, n, width)
+    else:
+        dst_flat.view(lanes, frames, width)[lo:hi] = part.view(n, frames, width)
+
+
+def shard_state(words: torch.Tensor, lo: int, hi: int) -> torch.Tensor:
+    """SoA state [W, lanes] -> [W, hi-lo] (contiguous copy)"""
+    return words[:, lo:hi].contiguous()
+
+
+def scatter_lanes(flat: Optional[torch.Tensor], frames: int, lanes: int, layout: int, width: int = 1,
+                  src: int = 0, dtype=None, device=None, group=None) -> torch.Tensor:
+    """Root holds `flat` for all lanes; every rank receives its lane block (same layout)."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    blocks = all_blocks(world, lanes)
+    lo, hi = blocks[rank]
+    if rank == src:
+        dtype, device = flat.dtype, flat.device
+        parts = [shard_flat(flat, frames, lanes, a, b, layout, width) for a, b in blocks]
+    else:
+        parts = None
+    out = torch.empty(frames * (hi - lo) * width, dtype=dtype, device=device)
+    if world == 1:
+        out.copy_(parts[0])
+        return out
+    # blocks may differ in size: point-to-point sends (NCCL groups them over NVLink)
+    if rank == src:
+        reqs = [dist.isend(parts[r], r, group=group) for r in range(world) if r != src]
+        out.copy_(parts[src])
+        for q in reqs:
+            q.wait()
+    else:
+        dist.recv(out, src, group=group)
+    return out
+
+
+def gather_lanes(part: torch.Tensor, frames: int, lanes: int, layout: int, width: int = 1, dst: int = 0,
+                 group=None) -> Optional[torch.Tensor]:
+    """Inverse of scatter_lanes: root receives the full flat buffer, others None."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    blocks = all_blocks(world, lanes)
+    if rank != dst:
+        dist.send(part, dst, group=group)
+        return None
+    full = torch.empty(frames * lanes * width, dtype=part.dtype, device=part.device)
+    for r, (a, b) in enumerate(blocks):
+        if r == dst:
+            buf = part
+        else:
+            buf = torch.empty(frames * (b - a) * width, dtype=part.dtype, device=part.device)
+            dist.recv(buf, r, group=group)
+        unshard_into(full, buf, frames, lanes, a, b, layout, width)
+    return full

@@ -188,3 +188,34 @@ def test_chain_vs_oracle(oracle, k):
         y = ctx.chain(k, ba, st, to_dev(x), lanes=lanes, layout=layout)
         assert_bits_equal(to_np(y), want)
         assert_bits_equal(to_np(st), so)
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5])
+def test_dec_cascade_tiled_kernel_streaming(oracle, k):
+    """lane-major: the tiled TMA kernel + generic tail, state carried across ragged calls,
+    == one oracle pass; also the generic-only path (policy 1) gives the same bits"""
+    rng = np.random.default_rng(60 + k)
+    R = 1 << k
+    TO = 512 >> k
+    lanes = 37
+    chunks = [2 * TO + 3, TO, 1, 3 * TO - 1]
+    n_out = sum(chunks)
+    x = rng.uniform(-1, 1, (lanes, n_out, R)).astype(np.float32)
+    so = np.zeros((oracle.hbf_dec_state_words(k), lanes), np.float32)
+    want = oracle.hbf_dec_cascade_lanes(k, so, x.reshape(-1), lanes, 1).reshape(lanes, n_out)
+    ctx = ib.default_context(0)
+    for policy in (0, 1):
+        ctx.set_kernel_policy(policy)
+        try:
+            st = _dec_state(k)(lanes, DEV)
+            outs, a = [], 0
+            for c in chunks:
+                xc = np.ascontiguousarray(x[:, a:a + c]).reshape(-1)
+                y = torch.empty(lanes * c, dtype=torch.float32, device=DEV)
+                Lanes(HbfDecCascade(k)).block(st, to_dev(xc), y, 1)
+                outs.append(to_np(y).reshape(lanes, c))
+                a += c
+            assert_bits_equal(np.concatenate(outs, axis=1), want, f"k={k} policy={policy}")
+            assert_bits_equal(st.numpy(), so, "state")
+        finally:
+            ctx.set_kernel_policy(0)
