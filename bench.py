@@ -268,6 +268,146 @@ def hbf_config(args):
 
 
 # ----------------------------------------------------------------------------- GPU arm
+def time_steps(step, steps, warmup, world, local, ctx, dev):
+    """W warm-up steps, then exactly K timed steps between barrier+sync, CUDA events on the
+    launching stream, max over ranks; returns (ms, launches, clocks)."""
+    import torch
+
+    for i in range(warmup):
+        step(i)
+    sampler = ClockSampler(local)
+    barrier(world)
+    l0 = ctx.launches
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    barrier(world)
+    return max_over_ranks(e0.elapsed_time(e1), world, dev), ctx.launches - l0, clocks
+
+
+LOCKIN_LANES_TOTAL = 1_048_576
+LOCKIN_FRAMES = 16_384
+LOCKIN_K = [1048576, -94906265]  # Lowpass<2>: [k^2/2^32, -k/q], k = 2^26, q = 1/sqrt(2)
+
+
+def run_lockin(args, rank, world, local):
+    """configs[3]: DDC lock-in (Accu + cossin NCO -> mix -> Lockin<Lowpass<2>>), i32, 1 048 576 lanes
+    sharded over 8 GPUs = 131 072 lanes per GPU (kept per GPU for any N: weak scaling)."""
+    import torch
+
+    import oracle as O
+    from idsp_b200 import Accu, Lockin, LockinState, Lowpass
+    from idsp_b200.engine import default_context
+
+    dev = f"cuda:{local}"
+    ctx = default_context(local)
+    lanes, frames = LOCKIN_LANES_TOTAL // 8, LOCKIN_FRAMES
+    n = lanes * frames
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(4 + rank)
+    xin = [torch.randint(-(1 << 30), 1 << 30, (n,), dtype=torch.int32, device=dev, generator=gen) for _ in range(2)]
+    iq = [torch.empty(2 * n, dtype=torch.int32, device=dev) for _ in range(2)]
+    step_t = torch.randint(-(1 << 31), (1 << 31) - 1, (lanes,), dtype=torch.int64, device=dev, generator=gen).to(torch.int32)
+    acc = Accu(torch.zeros(lanes, dtype=torch.int32, device=dev), step_t)
+    st = LockinState.default(2, lanes, dev)
+    cfg = Lockin(Lowpass(LOCKIN_K))
+
+    def step(i):
+        cfg.block(st, acc, xin[i % 2], iq[i % 2], 0)
+
+    step(0)
+    torch.cuda.synchronize()
+    sub = 32
+    xs = xin[0].view(frames, lanes)[:, :sub].contiguous().cpu().numpy().reshape(-1)
+    a0 = np.zeros(sub, np.int32)
+    so = np.zeros((4, sub), np.int64)
+    want = O.lockin_lanes(LOCKIN_K, a0, step_t[:sub].cpu().numpy(), so, xs, sub, 0, nthreads=O.max_threads())
+    got = iq[0].view(frames, lanes, 2)[:, :sub].contiguous().cpu().numpy().reshape(-1)
+    if not np.array_equal(got, want):
+        raise SystemExit("bench: GPU lock-in output differs from the oracle -- refusing to report a number")
+    ms, launches, clocks = time_steps(step, args.steps, args.warmup, world, local, ctx, dev)
+    value = world * n * args.steps / (ms * 1e-3) / 1e9
+    if rank != 0:
+        return None
+    peak, peak_src = peak_hbm()
+    per_launch_bytes = 12.0 * n
+    achieved = per_launch_bytes * launches / (ms * 1e-3) / 1e9 if launches else 0.0
+    return {
+        "metric": "GSa/s, i32 DDC lock-in (Accu+cossin -> mix -> Lockin<Lowpass<2>>), 131072 lanes per GPU", "value": value,
+        "unit": "GSa/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i32", "data": "synthetic",
+        "config": {"workload": "configs[3]: DDC lock-in i32, 1048576 lanes over 8 GPUs (131072 per GPU), 16384 frames, frame-major",
+                   "lanes_per_gpu": lanes, "frames_per_step": frames, "parallelism": f"lanes sharded over {world} GPU(s), no collective"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": per_launch_bytes,
+                     "note": "~70 integer instructions per sample: issue-bound and HBM-bound ceilings nearly coincide"},
+        "gpu_launches": int(launches), "clocks": clocks, "parity_check": "first step == oracle on 32 lanes x all frames",
+    }
+
+
+def run_chain(args, rank, world, local):
+    """configs[4]: HbfDec(/16) -> HbfInt(x16) -> Biquad DF1 f32 chain, lane sweep 2^10..2^24 at
+    ~2^30 samples per point; reports GSa/s per lane count."""
+    import torch
+
+    import oracle as O
+    from idsp_b200.engine import default_context
+
+    dev = f"cuda:{local}"
+    ctx = default_context(local)
+    k = 4
+    ba = np.asarray(__import__("idsp_b200").Biquad.from_ba6(__import__("idsp_b200").Filter().critical_frequency(0.05).lowpass(), "f32").ba)
+    W = O.hbf_dec_state_words(k) + O.hbf_int_state_words(k) + 4
+    total = 1 << 30
+    points = []
+    for lg in range(10, 25, 2):
+        lanes = 1 << lg
+        n_low = max(total // lanes // 16, 32)
+        n = lanes * n_low * 16
+        x = torch.empty(n, dtype=torch.float32, device=dev).uniform_(-1, 1)
+        y = torch.empty_like(x)
+        st = torch.zeros((W, lanes), dtype=torch.float32, device=dev)
+
+        def step(i):
+            ctx.chain(k, ba, st, x, y, lanes=lanes, layout=1)
+
+        if lg == 10:
+            step(0)
+            torch.cuda.synchronize()
+            sub = 8
+            xs = x.view(lanes, n_low * 16)[:sub, :512 * 16].contiguous().cpu().numpy()
+            so = np.zeros((W, sub), np.float32)
+            want = O.chain_lanes(k, ba, so, xs.reshape(-1), sub, 1)
+            got = y.view(lanes, n_low * 16)[:sub, :512 * 16].contiguous().cpu().numpy().reshape(-1)
+            if not np.array_equal(got.view(np.uint32), want.view(np.uint32)):
+                raise SystemExit("bench: GPU chain output differs from the oracle")
+            st.zero_()
+        ms, launches, clocks = time_steps(step, 3, 2, world, local, ctx, dev)
+        points.append({"lanes_per_gpu": lanes, "samples_per_lane": n_low * 16, "GSa/s": world * n * 3 / (ms * 1e-3) / 1e9,
+                       "GB/s": 8.0 * n * 3 / (ms * 1e-3) / 1e9})
+        del x, y, st
+        torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    peak, peak_src = peak_hbm()
+    best = max(points, key=lambda p: p["GSa/s"])
+    return {
+        "metric": "GSa/s, f32 HbfDec(/16)->HbfInt(x16)->Biquad DF1 chain, lane sweep", "value": best["GSa/s"], "unit": "GSa/s",
+        "n_gpus": world, "steps": 3, "warmup": 2, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[4]: HbfDec->HbfInt->Biquad chain f32, lanes 2^10..2^24, ~2^30 samples per point, lane-major"},
+        "sweep": points,
+        "roofline": {"bound": "hbm", "achieved": best["GB/s"], "peak": peak, "unit": "GB/s", "frac": best["GB/s"] / peak,
+                     "traffic": None, "peak_source": peak_src},
+        "parity_check": "2^10-lane point == oracle on 8 lanes x 8192 samples",
+    }
+
+
 def run_biquad(args, rank, world, local):
     import torch
 
@@ -482,7 +622,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="biquad", choices=["biquad", "hbf"])
+    ap.add_argument("--workload", default="biquad", choices=["biquad", "hbf", "lockin", "chain"])
     ap.add_argument("--frames", type=int, default=16384, help="frames per step (biquad)")
     ap.add_argument("--ring", type=int, default=3, help="distinct resident input blocks")
     ap.add_argument("--full", action="store_true", help="run the whole 1e7-frame job (biquad)")
@@ -512,8 +652,12 @@ def main():
             extra = run_hbf(a2, rank, world, local)
             if line is not None and extra is not None:
                 line["extra"] = {"hbf_dec16_f32": {k: extra[k] for k in ("metric", "value", "unit", "steps", "ms_per_step", "dtype", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "parity_check")}}
-    else:
+    elif args.workload == "hbf":
         line = run_hbf(args, rank, world, local)
+    elif args.workload == "lockin":
+        line = run_lockin(args, rank, world, local)
+    else:
+        line = run_chain(args, rank, world, local)
     if line is not None:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -6,6 +6,8 @@
 
 #include "../../include/idsp_b200.h"
 
+#define IDSP_HOST_RING 4
+
 struct idsp_ctx {
     int device;
     cudaStream_t stream;
@@ -13,14 +15,13 @@ struct idsp_ctx {
     uint64_t launches;
     int policy;  // 0 auto, 1 generic, 2 TMA
     int sm_count;
-    // host streaming (the *_host entry points): pinned staging + device ring
+    // host streaming (the *_host entry points): ring of device chunk buffers
     cudaStream_t s_h2d, s_d2h;
-    void *pin_in[2], *pin_out[2];
-    void *dev_in[2], *dev_out[2];
-    size_t pin_in_bytes, pin_out_bytes, dev_in_bytes, dev_out_bytes;
+    void *dev_in[IDSP_HOST_RING], *dev_out[IDSP_HOST_RING];
+    size_t dev_in_bytes, dev_out_bytes;
     void *dev_state;
     size_t dev_state_bytes;
-    cudaEvent_t ev_h2d[2], ev_k[2], ev_d2h[2];
+    cudaEvent_t ev_h2d[IDSP_HOST_RING], ev_k[IDSP_HOST_RING], ev_d2h[IDSP_HOST_RING];
 };
 
 void idsp_set_error(const char *fmt, ...);

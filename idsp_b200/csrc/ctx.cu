@@ -68,12 +68,10 @@ extern "C" int idsp_b200_init_on_stream(int device, void *cuda_stream, idsp_ctx 
 }
 
 static void free_staging(idsp_ctx *c) {
-    for (int i = 0; i < 2; i++) {
-        if (c->pin_in[i]) cudaFreeHost(c->pin_in[i]);
-        if (c->pin_out[i]) cudaFreeHost(c->pin_out[i]);
+    for (int i = 0; i < IDSP_HOST_RING; i++) {
         if (c->dev_in[i]) cudaFree(c->dev_in[i]);
         if (c->dev_out[i]) cudaFree(c->dev_out[i]);
-        c->pin_in[i] = c->pin_out[i] = c->dev_in[i] = c->dev_out[i] = nullptr;
+        c->dev_in[i] = c->dev_out[i] = nullptr;
         if (c->ev_h2d[i]) cudaEventDestroy(c->ev_h2d[i]);
         if (c->ev_k[i]) cudaEventDestroy(c->ev_k[i]);
         if (c->ev_d2h[i]) cudaEventDestroy(c->ev_d2h[i]);
@@ -81,7 +79,7 @@ static void free_staging(idsp_ctx *c) {
     }
     if (c->dev_state) cudaFree(c->dev_state);
     c->dev_state = nullptr;
-    c->pin_in_bytes = c->pin_out_bytes = c->dev_in_bytes = c->dev_out_bytes = c->dev_state_bytes = 0;
+    c->dev_in_bytes = c->dev_out_bytes = c->dev_state_bytes = 0;
     if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
     if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
     c->s_h2d = c->s_d2h = nullptr;
@@ -116,11 +114,12 @@ extern "C" int idsp_b200_set_kernel_policy(idsp_ctx *ctx, int policy) {
 
 // ---------------------------------------------------------------------------
 // Host streaming: x/y/state live in host memory.  The frame (frame-major) or
-// lane (lane-major) axis is cut into chunks that are double-buffered through the
-// device: H2D of chunk i+1 overlaps the kernel on chunk i and the D2H of chunk
-// i-1 (three streams, events).  If the caller's buffers are pinned
-// (cudaHostAlloc / cudaHostRegister / torch pin_memory) the DMA engines read and
-// write them directly; pageable buffers still work (the driver stages them).
+// lane (lane-major) axis is cut into chunks of ~64 MiB that rotate through a ring of
+// IDSP_HOST_RING device buffers: the H2D copy of chunk i+1.. overlaps the kernel on
+// chunk i and the D2H copy of chunk i-1 (three streams, events), so both PCIe
+// directions stay busy.  If the caller's buffers are pinned (cudaHostAlloc /
+// cudaHostRegister / torch pin_memory) the copy engines DMA them directly; pageable
+// buffers still work (the driver stages them).
 // ---------------------------------------------------------------------------
 static int ensure_dev(void **p, size_t *have, size_t need) {
     if (*have >= need) return IDSP_OK;
@@ -136,14 +135,33 @@ static int ensure_dev(void **p, size_t *have, size_t need) {
     return IDSP_OK;
 }
 
+static int ensure_ring(void **bufs, size_t *have, size_t need) {
+    if (*have >= need) return IDSP_OK;
+    for (int i = 0; i < IDSP_HOST_RING; i++) {
+        if (bufs[i]) cudaFree(bufs[i]);
+        bufs[i] = nullptr;
+    }
+    *have = 0;
+    for (int i = 0; i < IDSP_HOST_RING; i++) {
+        cudaError_t e = cudaMalloc(&bufs[i], need ? need : 256);
+        if (e != cudaSuccess) {
+            idsp_set_error("cudaMalloc(%zu): %s", need, cudaGetErrorString(e));
+            return IDSP_ENOMEM;
+        }
+    }
+    *have = need;
+    return IDSP_OK;
+}
+
 int idsp_host_stream(idsp_ctx *ctx, const HostStreamSpec &spec, const void *x, void *y,
                      const HostStreamLaunch &launch) {
     int r = idsp_use_device(ctx);
     if (r) return r;
+    constexpr int NB = IDSP_HOST_RING;
     if (!ctx->s_h2d) {
         IDSP_CUDA(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
         IDSP_CUDA(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < NB; i++) {
             IDSP_CUDA(cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming));
             IDSP_CUDA(cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming));
             IDSP_CUDA(cudaEventCreateWithFlags(&ctx->ev_d2h[i], cudaEventDisableTiming));
@@ -169,53 +187,30 @@ int idsp_host_stream(idsp_ctx *ctx, const HostStreamSpec &spec, const void *x, v
     const size_t other = fm ? spec.lanes : spec.frames;
     const size_t in_unit = other * spec.in_bytes_per_frame_lane;
     const size_t out_unit = other * spec.out_bytes_per_frame_lane;
-    const size_t target = (size_t)256 << 20;  // ~256 MiB of input per chunk
-    size_t chunk = in_unit ? target / in_unit : n_axis;
-    if (!fm) chunk &= ~(size_t)127;  // keep lane chunks warp/CTA aligned
-    if (chunk < (fm ? 1u : 128u)) chunk = fm ? 1 : 128;
+    const size_t bigger = in_unit > out_unit ? in_unit : out_unit;
+    const size_t target = (size_t)64 << 20;  // ~64 MiB per chunk and direction
+    size_t chunk = bigger ? target / bigger : n_axis;
+    if (fm) {
+        if (chunk > 512) chunk &= ~(size_t)511;  // whole tiles of the tiled kernels
+    } else {
+        chunk &= ~(size_t)127;  // keep lane chunks warp/CTA aligned
+        if (chunk < 128) chunk = 128;
+    }
+    if (chunk < 1) chunk = 1;
     if (chunk > n_axis) chunk = n_axis;
     if (n_axis == 0) chunk = 0;
-    // (re)allocate the two device in/out buffers
-    const size_t need_in = chunk * in_unit, need_out = chunk * out_unit;
-    if (ctx->dev_in_bytes < need_in) {
-        for (int i = 0; i < 2; i++) {
-            if (ctx->dev_in[i]) cudaFree(ctx->dev_in[i]);
-            ctx->dev_in[i] = nullptr;
-        }
-        for (int i = 0; i < 2; i++) {
-            cudaError_t e = cudaMalloc(&ctx->dev_in[i], need_in ? need_in : 256);
-            if (e != cudaSuccess) {
-                idsp_set_error("cudaMalloc(%zu): %s", need_in, cudaGetErrorString(e));
-                ctx->dev_in_bytes = 0;
-                return IDSP_ENOMEM;
-            }
-        }
-        ctx->dev_in_bytes = need_in;
-    }
-    if (ctx->dev_out_bytes < need_out) {
-        for (int i = 0; i < 2; i++) {
-            if (ctx->dev_out[i]) cudaFree(ctx->dev_out[i]);
-            ctx->dev_out[i] = nullptr;
-        }
-        for (int i = 0; i < 2; i++) {
-            cudaError_t e = cudaMalloc(&ctx->dev_out[i], need_out ? need_out : 256);
-            if (e != cudaSuccess) {
-                idsp_set_error("cudaMalloc(%zu): %s", need_out, cudaGetErrorString(e));
-                ctx->dev_out_bytes = 0;
-                return IDSP_ENOMEM;
-            }
-        }
-        ctx->dev_out_bytes = need_out;
-    }
-    // the blobs must be on the device before the first kernel; kernels run on ctx->stream
-    size_t nchunks = chunk ? (n_axis + chunk - 1) / chunk : 0;
+    r = ensure_ring(ctx->dev_in, &ctx->dev_in_bytes, chunk * in_unit);
+    if (r) return r;
+    r = ensure_ring(ctx->dev_out, &ctx->dev_out_bytes, chunk * out_unit);
+    if (r) return r;
+    const size_t nchunks = chunk ? (n_axis + chunk - 1) / chunk : 0;
     for (size_t c = 0; c < nchunks; c++) {
-        const int b = (int)(c & 1);
+        const int b = (int)(c % NB);
         const size_t a0 = c * chunk;
         const size_t an = (n_axis - a0) < chunk ? (n_axis - a0) : chunk;
-        // buffer b's previous kernel (chunk c-2) must be done before we overwrite its input,
-        // and its previous D2H done before the kernel overwrites its output
-        if (c >= 2) {
+        // buffer b's previous kernel (chunk c-NB) must be done before its input is overwritten,
+        // and its previous D2H must be done before the kernel overwrites its output
+        if (c >= (size_t)NB) {
             IDSP_CUDA(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_k[b], 0));
             IDSP_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[b], 0));
         }
@@ -223,9 +218,7 @@ int idsp_host_stream(idsp_ctx *ctx, const HostStreamSpec &spec, const void *x, v
                                   cudaMemcpyHostToDevice, ctx->s_h2d));
         IDSP_CUDA(cudaEventRecord(ctx->ev_h2d[b], ctx->s_h2d));
         IDSP_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[b], 0));
-        void *cb[3];
-        for (int i = 0; i < 3; i++) cb[i] = dblobs[i];
-        r = launch(cb, ctx->dev_in[b], ctx->dev_out[b], a0, an);
+        r = launch(dblobs, ctx->dev_in[b], ctx->dev_out[b], a0, an);
         if (r) return r;
         IDSP_CUDA(cudaEventRecord(ctx->ev_k[b], ctx->stream));
         IDSP_CUDA(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_k[b], 0));

@@ -79,12 +79,15 @@ template <class T, bool CLAMP, int MODE = 0> struct Df1Op {
     using In = T;
     using Out = T;
     static constexpr bool TUNABLE = true;  // tuning builds sweep tile shapes for this Op
+    static constexpr int SMEM_EXTRA_WORDS = 0;
     struct Params {
         T ba[5];
         int F;
         T u, mn, mx;
         T *st;
     };
+    __device__ __forceinline__ static void init_smem(const Params &, uint32_t *, int, int) {}
+    __device__ __forceinline__ void bind(const Params &, const uint32_t *) {}
     T x1, x2, y1, y2;
     __device__ __forceinline__ void load(const Params &p, size_t lane, size_t stride) {
         x1 = p.st[lane];
@@ -361,7 +364,8 @@ __device__ __forceinline__ int32_t lowpass_step(int32_t k0, int32_t k1, int64_t 
         y = (int32_t)(s0 >> 32);
         s0 = (int64_t)((uint64_t)s0 + d);
     } else {
-        d += (uint64_t)(s1 >> 32) * (uint64_t)(int64_t)k1;
+        // (s1 >> 32) fits in i32: one IMAD.WIDE, same value mod 2^64 as the i64*i64 product
+        d += (uint64_t)((int64_t)(int32_t)(s1 >> 32) * (int64_t)k1);
         s1 = (int64_t)((uint64_t)s1 + d);
         s0 = (int64_t)((uint64_t)s0 + (uint64_t)s1);
         y = (int32_t)(s0 >> 32);
@@ -394,9 +398,11 @@ template <int ORDER> struct LowpassOp {
 // Accu (src/accu.rs:34-37) -> Complex::from_angle (src/complex.rs:237-240) ->
 // Lockin<Lowpass<N>> (src/lockin.rs:17-39); mix = i32 * Q32<32> -> (lo*x)>>32
 // (dsp-fixedpoint/src/lib.rs:449-456).
-template <int ORDER> struct LockinOp {
+template <int ORDER, bool SMEM_LUT = false> struct LockinOp {
     using In = int32_t;
     using Out = int2;
+    static constexpr bool TUNABLE = false;
+    static constexpr int SMEM_EXTRA_WORDS = SMEM_LUT ? 128 : 0;  // cossin LUT staged per CTA
     struct Params {
         int32_t k[2];
         int32_t *accu_state;
@@ -406,7 +412,14 @@ template <int ORDER> struct LockinOp {
     };
     uint32_t ph, dph;
     int64_t i0, i1, q0, q1;
+    const uint32_t *lutp;
+    __device__ __forceinline__ static void init_smem(const Params &p, uint32_t *extra, int tid, int nthreads) {
+        if constexpr (SMEM_LUT)
+            for (int i = tid; i < 128; i += nthreads) extra[i] = p.lut[i];
+    }
+    __device__ __forceinline__ void bind(const Params &p, const uint32_t *extra) { lutp = SMEM_LUT ? extra : p.lut; }
     __device__ __forceinline__ void load(const Params &p, size_t lane, size_t stride) {
+        if constexpr (!SMEM_LUT) lutp = p.lut;
         ph = (uint32_t)p.accu_state[lane];
         dph = (uint32_t)p.accu_step[lane];
         i0 = p.st[lane];
@@ -424,7 +437,7 @@ template <int ORDER> struct LockinOp {
     __device__ __forceinline__ int2 step(const Params &p, int32_t x) {
         ph += dph;
         int32_t c, s;
-        cossin_dev<false>(p.lut, (int32_t)ph, c, s);
+        cossin_dev<SMEM_LUT>(lutp, (int32_t)ph, c, s);
         int32_t mi = (int32_t)(((int64_t)c * (int64_t)x) >> 32);
         int32_t mq = (int32_t)(((int64_t)s * (int64_t)x) >> 32);
         int2 r;

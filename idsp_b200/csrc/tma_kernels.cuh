@@ -100,9 +100,11 @@ tma_lanes_kernel(typename Op::Params p, const __grid_constant__ CUtensorMap mx,
                  size_t sstride) {
     using In = typename Op::In;
     using Out = typename Op::Out;
-    static_assert(sizeof(In) == 4 && sizeof(Out) == 4, "4-byte samples only");
+    static_assert(sizeof(In) == 4 && (sizeof(Out) == 4 || sizeof(Out) == 8), "4-byte in, 4/8-byte out");
     static_assert(!LM || TF == 16, "lane-major tiles are 16 frames (64B swizzle)");
     static_assert(!(WIDE && LM), "wide boxes are frame-major only");
+    constexpr int OW = sizeof(Out) / 4;             // output words per sample (Complex<i32> = 2)
+    static_assert(!LM || OW == 1, "8-byte outputs are frame-major only");
     constexpr int BW = WIDE ? 32 * WPC : 32;        // box width in lanes
     constexpr int TILE_WORDS = TF * BW;
     constexpr uint32_t TILE_BYTES = TILE_WORDS * 4;
@@ -112,10 +114,15 @@ tma_lanes_kernel(typename Op::Params p, const __grid_constant__ CUtensorMap mx,
     const int pipe = WIDE ? 0 : w;
     const int col = WIDE ? w * 32 + l : l;          // my column inside the box
     // per pipeline: S input stages, O output stages, S mbarriers
-    uint32_t *wbase = reinterpret_cast<uint32_t *>(smem_raw) + (size_t)pipe * (S + O) * TILE_WORDS;
+    uint32_t *wbase = reinterpret_cast<uint32_t *>(smem_raw) + (size_t)pipe * (S + O * OW) * TILE_WORDS;
     uint32_t *sin = wbase;
     uint32_t *sout = wbase + S * TILE_WORDS;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)NPIPE * (S + O) * TILE_BYTES) + pipe * S;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)NPIPE * (S + O * OW) * TILE_BYTES) + pipe * S;
+    uint32_t *extra = reinterpret_cast<uint32_t *>(smem_raw + (size_t)NPIPE * (S + O * OW) * TILE_BYTES + (size_t)NPIPE * S * 8);
+    if constexpr (Op::SMEM_EXTRA_WORDS > 0) {
+        Op::init_smem(p, extra, threadIdx.x, WPC * 32);
+        __syncthreads();
+    }
 
     const size_t box0 = WIDE ? (size_t)blockIdx.x * BW : ((size_t)blockIdx.x * WPC + w) * 32;
     if (!WIDE && box0 >= lanes) return;
@@ -150,6 +157,7 @@ tma_lanes_kernel(typename Op::Params p, const __grid_constant__ CUtensorMap mx,
             if ((size_t)s < ntiles) issue_load(s);
     }
     Op op;
+    op.bind(p, extra);
     if (active) op.load(p, lane, sstride);
 
     for (size_t i = 0; i < ntiles; i++) {
@@ -163,11 +171,11 @@ tma_lanes_kernel(typename Op::Params p, const __grid_constant__ CUtensorMap mx,
         sync_pipe();
         mbar_wait(smem_u32(&bars[s]), (uint32_t)((i / S) & 1));
         const uint32_t *tin = sin + s * TILE_WORDS;
-        uint32_t *tout = sout + ob * TILE_WORDS;
+        uint32_t *tout = sout + ob * TILE_WORDS * OW;
         // frames beyond `frames` in the last tile are zero-filled by the TMA load and
         // clipped by the TMA store; they must not advance the filter state.
         const int nvalid = (int)((frames - i * TF) < (size_t)TF ? (frames - i * TF) : (size_t)TF);
-        if (LM) {
+        if constexpr (LM) {
             // row l = my lane, 4 chunks of 16 B, physical chunk = c ^ ((l>>1)&3)
             const int sw = (l >> 1) & 3;
             const uint4 *rin = reinterpret_cast<const uint4 *>(tin + l * 16);
@@ -195,13 +203,28 @@ tma_lanes_kernel(typename Op::Params p, const __grid_constant__ CUtensorMap mx,
                 }
             }
         } else {
-            if (nvalid == TF) {
+            if constexpr (OW == 1) {
+                if (nvalid == TF) {
 #pragma unroll
-                for (int f = 0; f < TF; f++)
-                    tout[f * BW + col] = Bits32<Out>::to(op.step(p, Bits32<In>::from(tin[f * BW + col])));
-            } else {
-                for (int f = 0; f < nvalid; f++)
-                    tout[f * BW + col] = Bits32<Out>::to(op.step(p, Bits32<In>::from(tin[f * BW + col])));
+                    for (int f = 0; f < TF; f++)
+                        tout[f * BW + col] = Bits32<Out>::to(op.step(p, Bits32<In>::from(tin[f * BW + col])));
+                } else {
+                    for (int f = 0; f < nvalid; f++)
+                        tout[f * BW + col] = Bits32<Out>::to(op.step(p, Bits32<In>::from(tin[f * BW + col])));
+                }
+            } else {  // Out = int2 (Complex<i32>): 8-byte store per sample, box row = 2*BW words
+                if (nvalid == TF) {
+#pragma unroll
+                    for (int f = 0; f < TF; f++) {
+                        Out r = op.step(p, Bits32<In>::from(tin[f * BW + col]));
+                        reinterpret_cast<uint2 *>(tout)[f * BW + col] = make_uint2((uint32_t)r.x, (uint32_t)r.y);
+                    }
+                } else {
+                    for (int f = 0; f < nvalid; f++) {
+                        Out r = op.step(p, Bits32<In>::from(tin[f * BW + col]));
+                        reinterpret_cast<uint2 *>(tout)[f * BW + col] = make_uint2((uint32_t)r.x, (uint32_t)r.y);
+                    }
+                }
             }
         }
         fence_async_smem();
@@ -210,7 +233,7 @@ tma_lanes_kernel(typename Op::Params p, const __grid_constant__ CUtensorMap mx,
             if (LM)
                 tma_store_2d(&my, smem_u32(tout), (int)(i * TF), (int)box0);
             else
-                tma_store_2d(&my, smem_u32(tout), (int)box0, (int)(i * TF));
+                tma_store_2d(&my, smem_u32(tout), (int)(box0 * OW), (int)(i * TF));
             tma_commit();
         }
     }
@@ -260,16 +283,19 @@ static int tma_launch_cfg(idsp_ctx *ctx, const typename Op::Params &p, const voi
     CUtensorMap mx, my;
     bool ok;
     constexpr int BW = WIDE ? 32 * WPC : 32;
+    constexpr int OW = sizeof(typename Op::Out) / 4;
+    static_assert(BW * OW <= 256, "TMA box dimension limit");
     if (LM) {
         ok = make_map_2d(&mx, x, frames, lanes, TF, 32, CU_TENSOR_MAP_SWIZZLE_64B) &&
              make_map_2d(&my, y, frames, lanes, TF, 32, CU_TENSOR_MAP_SWIZZLE_64B);
     } else {
         ok = make_map_2d(&mx, x, lanes, frames, BW, TF, CU_TENSOR_MAP_SWIZZLE_NONE) &&
-             make_map_2d(&my, y, lanes, frames, BW, TF, CU_TENSOR_MAP_SWIZZLE_NONE);
+             make_map_2d(&my, y, lanes * OW, frames, BW * OW, TF, CU_TENSOR_MAP_SWIZZLE_NONE);
     }
     if (!ok) return IDSP_TMA_NOT_APPLICABLE;
     constexpr int NPIPE = WIDE ? 1 : WPC;
-    constexpr size_t smem = (size_t)NPIPE * (S + O) * TF * BW * 4 + (size_t)NPIPE * S * 8;
+    constexpr size_t smem = (size_t)NPIPE * (S + O * OW) * TF * BW * 4 + (size_t)NPIPE * S * 8 +
+                            (size_t)Op::SMEM_EXTRA_WORDS * 4;
     auto kern = tma_lanes_kernel<Op, LM, TF, S, O, WPC, WIDE>;
     IDSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const size_t warps = (lanes + 31) / 32;
@@ -299,9 +325,11 @@ template <class Op>
 static int tma_try_launch(idsp_ctx *ctx, const typename Op::Params &p, const typename Op::In *x,
                           typename Op::Out *y, size_t frames, size_t lanes, size_t sstride,
                           int layout) {
-    static_assert(sizeof(typename Op::In) == 4 && sizeof(typename Op::Out) == 4, "");
+    static_assert(sizeof(typename Op::In) == 4 && (sizeof(typename Op::Out) == 4 || sizeof(typename Op::Out) == 8), "");
+    constexpr bool OUT8 = sizeof(typename Op::Out) == 8;
     if (ctx->policy == 1) return IDSP_TMA_NOT_APPLICABLE;
     const bool lm = layout == IDSP_LANE_MAJOR;
+    if (OUT8 && lm) return IDSP_TMA_NOT_APPLICABLE;
     bool ok = (((uintptr_t)x | (uintptr_t)y) & 15) == 0 && frames >= 16 &&
               frames < (1ull << 31) && lanes < (1ull << 31) &&
               (lm ? (frames % 4 == 0) : (lanes % 4 == 0));
@@ -313,7 +341,14 @@ static int tma_try_launch(idsp_ctx *ctx, const typename Op::Params &p, const typ
         return IDSP_TMA_NOT_APPLICABLE;
     }
     int r;
-    if (lm) {
+    if constexpr (OUT8) {
+        // 4-byte in / 8-byte out (lock-in): 128-lane boxes (the 8-byte box row is 256 words)
+        const size_t sms = (size_t)(ctx->sm_count > 0 ? ctx->sm_count : 148);
+        if ((lanes + 127) / 128 >= sms)
+            r = tma_launch_cfg<Op, false, 8, 4, 2, 4, true>(ctx, p, x, y, frames, lanes, sstride);
+        else
+            r = tma_launch_cfg<Op, false, 8, 4, 2, 1>(ctx, p, x, y, frames, lanes, sstride);
+    } else if (lm) {
         r = tma_launch_cfg<Op, true, 16, 4, 2, 1>(ctx, p, x, y, frames, lanes, sstride);
     } else {
 #ifdef IDSP_TUNE

@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include "ops.cuh"
 #include "lane_kernels.cuh"
+#include "tma_kernels.cuh"
 
 using namespace idsp;
 
@@ -150,24 +151,29 @@ int lockin_dev(idsp_ctx *ctx, int order, const int32_t *k, int32_t *accu_state,
                size_t frames, size_t lanes, size_t sstride, int layout) {
     const uint32_t *lut;
     IDSP_CUDA(cudaGetSymbolAddress((void **)&lut, g_cossin_lut));
-    if (order == 1) {
-        LockinOp<1>::Params p;
-        p.k[0] = k[0];
-        p.k[1] = 0;
-        p.accu_state = accu_state;
-        p.accu_step = accu_step;
-        p.st = lp_state;
-        p.lut = lut;
-        return launch_lanes<LockinOp<1>>(ctx, p, x, (int2 *)iq, frames, lanes, sstride, layout);
-    }
-    LockinOp<2>::Params p;
-    p.k[0] = k[0];
-    p.k[1] = k[1];
-    p.accu_state = accu_state;
-    p.accu_step = accu_step;
-    p.st = lp_state;
-    p.lut = lut;
-    return launch_lanes<LockinOp<2>>(ctx, p, x, (int2 *)iq, frames, lanes, sstride, layout);
+#define GO(ORDER)                                                                    \
+    do {                                                                             \
+        LockinOp<ORDER, true>::Params pt;                                            \
+        pt.k[0] = k[0];                                                              \
+        pt.k[1] = ORDER == 2 ? k[1] : 0;                                             \
+        pt.accu_state = accu_state;                                                  \
+        pt.accu_step = accu_step;                                                    \
+        pt.st = lp_state;                                                            \
+        pt.lut = lut;                                                                \
+        int tr = tma_try_launch<LockinOp<ORDER, true>>(ctx, pt, x, (int2 *)iq, frames, lanes, sstride, layout); \
+        if (tr != IDSP_TMA_NOT_APPLICABLE) return tr;                                \
+        LockinOp<ORDER, false>::Params pg;                                           \
+        pg.k[0] = pt.k[0];                                                           \
+        pg.k[1] = pt.k[1];                                                           \
+        pg.accu_state = accu_state;                                                  \
+        pg.accu_step = accu_step;                                                    \
+        pg.st = lp_state;                                                            \
+        pg.lut = lut;                                                                \
+        return launch_lanes<LockinOp<ORDER, false>>(ctx, pg, x, (int2 *)iq, frames, lanes, sstride, layout); \
+    } while (0)
+    if (order == 1) GO(1);
+    GO(2);
+#undef GO
 }
 
 extern "C" int idsp_lockin_i32(idsp_ctx *ctx, int order, const int32_t *k, int32_t *accu_state,

@@ -257,3 +257,22 @@ def test_bad_arguments_are_errors():
         Biquad([1, 0, 0, 0, 0], Q32(64)).block(st, x, x)  # F out of range
     with pytest.raises(IdspError):
         Biquad([1, 0, 0, 0, 0], Q32(32)).block(DirectForm1Wide.default(4, DEV), x, x)
+
+
+@pytest.mark.parametrize("kind", ["i32", "f32"])
+@pytest.mark.parametrize("lanes", [9476, 18948, 37892 + 8])
+def test_df1_wide_tma_boxes(oracle, kind, lanes):
+    """large lane counts select the wide-box TMA configurations (64 / 128 / 256 lanes per CTA);
+    ragged lane and frame tails are zero-filled / clipped by the TMA unit"""
+    rng = np.random.default_rng(lanes)
+    bq = _coeffs(kind, rng)
+    frames = 27
+    x = rand_samples(rng, kind, frames * lanes)
+    st0 = rand_samples(rng, kind, 4 * lanes, 20 if kind in BITS else None).reshape(4, lanes)
+    so = st0.copy()
+    want = oracle.biquad_lanes("df1", kind, bq.ba, bq.F, None, so, x, lanes, 0, nthreads=4)
+    st = DirectForm1(to_dev(st0), kind)
+    y = torch.empty_like(to_dev(x))
+    Lanes(bq).block(st, to_dev(x), y, 0)
+    assert_bits_equal(to_np(y), want)
+    assert_bits_equal(st.numpy(), so)

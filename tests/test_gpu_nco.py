@@ -99,3 +99,30 @@ def test_lockin_vs_oracle(oracle, order, layout):
         assert_bits_equal(iqh, want)
         assert_bits_equal(ah, ao)
         assert_bits_equal(sh.words, so)
+
+
+@pytest.mark.parametrize("lanes", [128, 19200 + 36])
+def test_lockin_tma_kernels(oracle, lanes):
+    """frame-major lock-in through the TMA kernel (4-byte in, 8-byte out boxes), narrow and wide"""
+    rng = np.random.default_rng(lanes)
+    k = [1048576, -94906265]
+    frames = 43
+    x = rng.integers(-(1 << 30), 1 << 30, frames * lanes).astype(np.int32)
+    a0 = rng.integers(-(1 << 31), 1 << 31, lanes).astype(np.int32)
+    step = rng.integers(-(1 << 31), 1 << 31, lanes).astype(np.int32)
+    ao = a0.copy()
+    so = np.zeros((4, lanes), np.int64)
+    want = oracle.lockin_lanes(k, ao, step, so, x, lanes, 0, nthreads=4)
+    ctx = ib.default_context(0)
+    for policy in (0, 1):
+        ctx.set_kernel_policy(policy)
+        try:
+            st = LockinState.default(2, lanes, DEV)
+            acc = Accu(to_dev(a0), to_dev(step))
+            iq = torch.empty(2 * x.size, dtype=torch.int32, device=DEV)
+            Lockin(Lowpass(k)).block(st, acc, to_dev(x), iq, 0)
+            assert_bits_equal(to_np(iq), want, f"policy={policy}")
+            assert_bits_equal(to_np(acc.state), ao)
+            assert_bits_equal(st.numpy(), so)
+        finally:
+            ctx.set_kernel_policy(0)
