@@ -42,8 +42,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
     cmd = [nvcc, *NVCC_FLAGS]
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    if os.environ.get("IDSP_HF_NT"):  # experiment: threads per CTA of the tiled HBF kernel
-        cmd += [f"-DHF_NT={int(os.environ['IDSP_HF_NT'])}"]
+    for var, macro in (("IDSP_HF_NT", "HF_NT"), ("IDSP_HFS_NT", "HFS_NT"), ("IDSP_HFS_R0", "HFS_R0"),
+                       ("IDSP_HFS_NL", "HFS_NL"), ("IDSP_HFS_MINB", "HFS_MINB")):
+        if os.environ.get(var):  # experiments on the tiled HBF kernels
+            cmd += [f"-D{macro}={int(os.environ[var])}"]
     if os.environ.get("IDSP_TUNE"):  # tile-shape sweep builds (tools/sweep_biquad.py)
         cmd += ["-DIDSP_TUNE"]
     cmd += ["-ccbin", "g++", "-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]

@@ -1,8 +1,11 @@
 // hbf.cu -- C-ABI entry points of the half-band FIR family (include/idsp_b200.h).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "hbf_stages.cuh"
 #include "ops.cuh"
 #include "hbf_fast.cuh"
+#include "hbf_fast_scalar.cuh"
 
 using namespace idsp;
 
@@ -314,7 +317,15 @@ int hbf_dec_cascade_dev(idsp_ctx *ctx, int k, float *state, const float *x, floa
     // large aligned lane-major streams: tiled TMA kernel over whole tiles, generic kernel
     // (state carried through `state`) for the remaining frames of every lane
     size_t done = 0;
-    int fr = hbf_dec_fast_try(ctx, k, state, x, y, n_out, lanes, sstride, layout, &done);
+    // two bit-identical tiled variants: scalar FP32 (more resident warps) and packed f32x2
+    // (fewer FP issue slots); IDSP_HBF_VARIANT=packed|scalar overrides the default
+    static int variant = -1;
+    if (variant < 0) {
+        const char *e = getenv("IDSP_HBF_VARIANT");
+        variant = (e && e[0] == 'p') ? 1 : 0;
+    }
+    int fr = variant == 1 ? hbf_dec_fast_try(ctx, k, state, x, y, n_out, lanes, sstride, layout, &done)
+                          : hbf_dec_fast_try_scalar(ctx, k, state, x, y, n_out, lanes, sstride, layout, &done);
     if (fr != IDSP_HBF_FAST_NOT_APPLICABLE && fr != IDSP_OK) return fr;
     if (fr == IDSP_HBF_FAST_NOT_APPLICABLE && ctx->policy == 2 && layout == IDSP_LANE_MAJOR) {
         idsp_set_error("tiled HBF kernel forced but shape/alignment does not qualify");

@@ -241,6 +241,94 @@ tma_lanes_kernel(typename Op::Params p, const __grid_constant__ CUtensorMap mx,
     if (active) op.store(p, lane, sstride);
 }
 
+// ---------------------------------------------------------------- lane-major, long rows
+// Lane-major variant with longer contiguous runs per lane: a tile is NBOX boxes of
+// [32 frames x 32 lanes] (128-byte rows, 128-byte TMA swizzle), i.e. 128*NBOX contiguous
+// bytes per lane per tile instead of 64.  Thread l reads its own row of every box as
+// 8 x LDS.128 with the chunk index XOR (l & 7) -> conflict free.  One warp per CTA.
+template <class Op, int NBOX, int S, int O>
+__global__ void __launch_bounds__(32)
+tma_lanes_lm_kernel(typename Op::Params p, const __grid_constant__ CUtensorMap mx,
+                    const __grid_constant__ CUtensorMap my, size_t frames, size_t lanes, size_t sstride) {
+    using In = typename Op::In;
+    using Out = typename Op::Out;
+    static_assert(sizeof(In) == 4 && sizeof(Out) == 4, "4-byte samples only");
+    constexpr int BOX_WORDS = 32 * 32;
+    constexpr int TILE_WORDS = NBOX * BOX_WORDS;
+    constexpr int TFT = 32 * NBOX;  // frames per tile
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const int l = threadIdx.x;
+    uint32_t *sin = reinterpret_cast<uint32_t *>(smem_raw);
+    uint32_t *sout = sin + S * TILE_WORDS;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)(S + O) * TILE_WORDS * 4);
+    const size_t lane0 = (size_t)blockIdx.x * 32;
+    const size_t lane = lane0 + l;
+    const bool active = lane < lanes;
+    const size_t ntiles = (frames + TFT - 1) / TFT;
+    if (l == 0) {
+#pragma unroll
+        for (int s = 0; s < S; s++) mbar_init(smem_u32(&bars[s]), 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+    auto issue_load = [&](size_t tile) {
+        const int s = (int)(tile % S);
+        const uint32_t bar = smem_u32(&bars[s]);
+        mbar_expect_tx(bar, TILE_WORDS * 4);
+#pragma unroll
+        for (int b = 0; b < NBOX; b++)
+            tma_load_2d(smem_u32(sin + s * TILE_WORDS + b * BOX_WORDS), &mx, (int)(tile * TFT + b * 32), (int)lane0, bar);
+    };
+    if (l == 0) {
+#pragma unroll
+        for (int s = 0; s < S - 1; s++)
+            if ((size_t)s < ntiles) issue_load(s);
+    }
+    Op op;
+    op.bind(p, nullptr);
+    if (active) op.load(p, lane, sstride);
+    const int sw = l & 7;
+    for (size_t i = 0; i < ntiles; i++) {
+        const int s = (int)(i % S);
+        const int ob = (int)(i % O);
+        if (l == 0) {
+            tma_wait_read<O - 1>();
+            if (i + S - 1 < ntiles) issue_load(i + S - 1);
+        }
+        __syncwarp();
+        mbar_wait(smem_u32(&bars[s]), (uint32_t)((i / S) & 1));
+        const size_t t0 = i * TFT;
+        const int nvalid = (int)((frames - t0) < (size_t)TFT ? (frames - t0) : (size_t)TFT);
+#pragma unroll
+        for (int b = 0; b < NBOX; b++) {
+            const uint4 *rin = reinterpret_cast<const uint4 *>(sin + s * TILE_WORDS + b * BOX_WORDS + l * 32);
+            uint4 *rout = reinterpret_cast<uint4 *>(sout + ob * TILE_WORDS + b * BOX_WORDS + l * 32);
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                if (b * 32 + c * 4 < nvalid) {  // frames % 4 == 0: whole chunks are valid or not
+                    uint4 v = rin[c ^ sw];
+                    uint4 r;
+                    r.x = Bits32<Out>::to(op.step(p, Bits32<In>::from(v.x)));
+                    r.y = Bits32<Out>::to(op.step(p, Bits32<In>::from(v.y)));
+                    r.z = Bits32<Out>::to(op.step(p, Bits32<In>::from(v.z)));
+                    r.w = Bits32<Out>::to(op.step(p, Bits32<In>::from(v.w)));
+                    rout[c ^ sw] = r;
+                }
+            }
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (l == 0) {
+#pragma unroll
+            for (int b = 0; b < NBOX; b++)
+                tma_store_2d(&my, smem_u32(sout + ob * TILE_WORDS + b * BOX_WORDS), (int)(t0 + b * 32), (int)lane0);
+            tma_commit();
+        }
+    }
+    if (l == 0) tma_wait_read<0>();
+    if (active) op.store(p, lane, sstride);
+}
+
 // ---------------------------------------------------------------- host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
                                     const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
@@ -305,6 +393,32 @@ static int tma_launch_cfg(idsp_ctx *ctx, const typename Op::Params &p, const voi
     return IDSP_OK;
 }
 
+template <class Op, int NBOX, int S, int O>
+static int tma_launch_lm(idsp_ctx *ctx, const typename Op::Params &p, const void *x, void *y,
+                         size_t frames, size_t lanes, size_t sstride) {
+    CUtensorMap mx, my;
+    if (!(make_map_2d(&mx, x, frames, lanes, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B) &&
+          make_map_2d(&my, y, frames, lanes, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B)))
+        return IDSP_TMA_NOT_APPLICABLE;
+    constexpr size_t smem = (size_t)(S + O) * NBOX * 4096 + S * 8;
+    auto kern = tma_lanes_lm_kernel<Op, NBOX, S, O>;
+    IDSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    unsigned grid = (unsigned)((lanes + 31) / 32);
+    kern<<<grid, 32, smem, ctx->stream>>>(p, mx, my, frames, lanes, sstride);
+    IDSP_LAUNCHED(ctx);
+    return IDSP_OK;
+}
+
+// Lane-major default: 2 boxes of 32 frames per tile (256 contiguous bytes per lane), 3 load
+// and 2 store stages (tools/sweep_biquad.py SWEEP_LM=1: 708 GSa/s vs 554 for 64-byte rows);
+// short streams use the 16-frame kernel.
+template <class Op>
+static int tma_launch_lm_auto(idsp_ctx *ctx, const typename Op::Params &p, const void *x, void *y,
+                              size_t frames, size_t lanes, size_t sstride) {
+    if (frames >= 128) return tma_launch_lm<Op, 2, 3, 2>(ctx, p, x, y, frames, lanes, sstride);
+    return tma_launch_cfg<Op, true, 16, 4, 2, 1>(ctx, p, x, y, frames, lanes, sstride);
+}
+
 // Frame-major default: tiles of 8 frames, 4 load stages, 2 store stages, and the widest
 // box (32*WPC lanes, WPC <= 8) that still leaves one CTA per SM.  Measured on the
 // 65 536-lane i32 DF1 stream (tools/sweep_biquad.py, profiles/sweep_biquad_r1.md):
@@ -349,7 +463,28 @@ static int tma_try_launch(idsp_ctx *ctx, const typename Op::Params &p, const typ
         else
             r = tma_launch_cfg<Op, false, 8, 4, 2, 1>(ctx, p, x, y, frames, lanes, sstride);
     } else if (lm) {
-        r = tma_launch_cfg<Op, true, 16, 4, 2, 1>(ctx, p, x, y, frames, lanes, sstride);
+#ifdef IDSP_TUNE
+        const char *e = getenv("IDSP_TMA_LMCFG");
+        int cfg = (e && Op::TUNABLE) ? atoi(e) : -1;
+        switch (cfg) {
+            case 0: r = tma_launch_cfg<Op, true, 16, 4, 2, 1>(ctx, p, x, y, frames, lanes, sstride); break;
+            case 1: r = tma_launch_lm<Op, 1, 3, 2>(ctx, p, x, y, frames, lanes, sstride); break;
+            case 2: r = tma_launch_lm<Op, 2, 3, 2>(ctx, p, x, y, frames, lanes, sstride); break;
+            case 3: r = tma_launch_lm<Op, 4, 2, 1>(ctx, p, x, y, frames, lanes, sstride); break;
+            case 4: r = tma_launch_lm<Op, 4, 2, 2>(ctx, p, x, y, frames, lanes, sstride); break;
+            case 5: r = tma_launch_lm<Op, 2, 2, 2>(ctx, p, x, y, frames, lanes, sstride); break;
+            case 6: r = tma_launch_lm<Op, 1, 4, 2>(ctx, p, x, y, frames, lanes, sstride); break;
+            case 7: r = tma_launch_lm<Op, 8, 2, 1>(ctx, p, x, y, frames, lanes, sstride); break;
+            case 8: r = tma_launch_lm<Op, 2, 4, 2>(ctx, p, x, y, frames, lanes, sstride); break;
+            case 9: r = tma_launch_lm<Op, 2, 3, 1>(ctx, p, x, y, frames, lanes, sstride); break;
+            case 10: r = tma_launch_lm<Op, 3, 3, 2>(ctx, p, x, y, frames, lanes, sstride); break;
+            case 11: r = tma_launch_lm<Op, 3, 2, 1>(ctx, p, x, y, frames, lanes, sstride); break;
+            case 12: r = tma_launch_lm<Op, 3, 3, 1>(ctx, p, x, y, frames, lanes, sstride); break;
+            default: r = tma_launch_lm_auto<Op>(ctx, p, x, y, frames, lanes, sstride); break;
+        }
+#else
+        r = tma_launch_lm_auto<Op>(ctx, p, x, y, frames, lanes, sstride);
+#endif
     } else {
 #ifdef IDSP_TUNE
         // tuning builds only (tools/sweep_biquad.py): pick a tile configuration at run time

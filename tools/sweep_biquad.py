@@ -23,7 +23,16 @@ if os.environ.get("SWEEP_ONLY"):
     CFGS = {int(k): CFGS[int(k)] for k in os.environ["SWEEP_ONLY"].split(",")}
 
 
+LM_CFGS = {0: "LM 64B-swizzle 16fr S4 O2", 1: "LM NBOX1 S3 O2", 2: "LM NBOX2 S3 O2", 3: "LM NBOX4 S2 O1", 4: "LM NBOX4 S2 O2",
+           5: "LM NBOX2 S2 O2", 6: "LM NBOX1 S4 O2", 7: "LM NBOX8 S2 O1", 8: "LM NBOX2 S4 O2", 9: "LM NBOX2 S3 O1", 10: "LM NBOX3 S3 O2",
+           11: "LM NBOX3 S2 O1", 12: "LM NBOX3 S3 O1"}
+
+
 def main():
+    layout = 1 if os.environ.get("SWEEP_LM") else 0
+    global CFGS
+    if layout == 1:
+        CFGS = LM_CFGS
     dev = "cuda:0"
     ctx = default_context(0)
     lanes, frames = BIQUAD_LANES, 16384
@@ -36,29 +45,29 @@ def main():
     ref = None
     for c, name in list(CFGS.items()) + [(-1, "generic LDG (policy 1)")]:
         if c >= 0:
-            os.environ["IDSP_TMA_CFG"] = str(c)
+            os.environ["IDSP_TMA_LMCFG" if layout else "IDSP_TMA_CFG"] = str(c)
             ctx.set_kernel_policy(0)
         else:
             ctx.set_kernel_policy(1)
         st.words.zero_()
-        cfg.block(st, x[0], y)
+        cfg.block(st, x[0], y, layout)
         torch.cuda.synchronize()
         chk = int(y.sum(dtype=torch.int64).item())
         if ref is None:
             ref = chk
         for i in range(3):
-            cfg.block(st, x[i % 2], y)
+            cfg.block(st, x[i % 2], y, layout)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         K = 20
         for i in range(K):
-            cfg.block(st, x[i % 2], y)
+            cfg.block(st, x[i % 2], y, layout)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / K
         res[name] = {"ms": ms, "GSa/s": n / ms / 1e6, "GB/s": 8 * n / ms / 1e6, "checksum_ok": chk == ref}
         print(f"{name:28s} {ms:8.3f} ms  {n / ms / 1e6:8.1f} GSa/s  {8 * n / ms / 1e6:8.1f} GB/s  checksum_ok={chk == ref}", flush=True)
-    json.dump(res, open(os.path.join("gpurun_out", "sweep_biquad.json"), "w"), indent=1)
+    json.dump(res, open(os.path.join("gpurun_out", "sweep_biquad_lm.json" if layout else "sweep_biquad.json"), "w"), indent=1)
 
 
 if __name__ == "__main__":
