@@ -29,6 +29,8 @@ def _signatures():
         "idsp_b200_version": ([], _i),
         "idsp_b200_launch_count": ([_c_p], C.c_uint64),
         "idsp_b200_set_kernel_policy": ([_c_p, _i], _i),
+        "idsp_b200_host_alloc": ([C.POINTER(_c_p), _sz], _i),
+        "idsp_b200_host_free": ([_c_p], None),
         "idsp_hbf_taps": ([_i, C.POINTER(_i)], C.POINTER(C.c_float)),
         "idsp_hbf_dec_state_words": ([_i], _sz),
         "idsp_hbf_int_state_words": ([_i], _sz),

@@ -130,7 +130,7 @@ static int cascade_impl(idsp_ctx *ctx, const T *ba, int F, int nsec, T *state, c
         p.F = F;                                                                     \
         p.nsec = nsec;                                                               \
         p.st = state;                                                                \
-        return launch_lanes<CascadeOp<T, N>>(ctx, p, x, y, frames, lanes, sstride, layout); \
+        return launch_lanes_best<CascadeOp<T, N>>(ctx, p, x, y, frames, lanes, sstride, layout); \
     } while (0)
     if (nsec <= 2) GO(2);
     if (nsec <= 4) GO(4);
@@ -181,13 +181,13 @@ static int df2t_impl(idsp_ctx *ctx, const T *ba, const T *clamp, T *state, const
         p.mn = clamp[1];
         p.mx = clamp[2];
         p.st = state;
-        return launch_lanes<Df2tOp<T, true>>(ctx, p, x, y, frames, lanes, lanes, layout);
+        return launch_lanes_best<Df2tOp<T, true>>(ctx, p, x, y, frames, lanes, lanes, layout);
     }
     typename Df2tOp<T, false>::Params p;
     for (int i = 0; i < 5; i++) p.ba[i] = ba[i];
     p.u = p.mn = p.mx = T(0);
     p.st = state;
-    return launch_lanes<Df2tOp<T, false>>(ctx, p, x, y, frames, lanes, lanes, layout);
+    return launch_lanes_best<Df2tOp<T, false>>(ctx, p, x, y, frames, lanes, lanes, layout);
 }
 extern "C" int idsp_biquad_df2t_f32(idsp_ctx *ctx, const float ba[5], const float *clamp,
                                     float *state, const float *x, float *y, size_t frames,
@@ -215,14 +215,14 @@ static int i32_variant(idsp_ctx *ctx, const int32_t *ba, int F, const int32_t *c
         p.mn = clamp[1];
         p.mx = clamp[2];
         p.st = state;
-        return launch_lanes<OP<true>>(ctx, p, x, y, frames, lanes, lanes, layout);
+        return launch_lanes_best<OP<true>>(ctx, p, x, y, frames, lanes, lanes, layout);
     }
     typename OP<false>::Params p;
     for (int i = 0; i < 5; i++) p.ba[i] = ba[i];
     p.F = F;
     p.u = p.mn = p.mx = 0;
     p.st = state;
-    return launch_lanes<OP<false>>(ctx, p, x, y, frames, lanes, lanes, layout);
+    return launch_lanes_best<OP<false>>(ctx, p, x, y, frames, lanes, lanes, layout);
 }
 extern "C" int idsp_biquad_df1wide_i32(idsp_ctx *ctx, const int32_t ba[5], int F,
                                        const int32_t *clamp, int32_t *state, const int32_t *x,

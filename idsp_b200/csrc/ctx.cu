@@ -101,6 +101,23 @@ extern "C" int idsp_b200_sync(idsp_ctx *ctx) {
     return IDSP_OK;
 }
 
+extern "C" int idsp_b200_host_alloc(void **ptr, size_t bytes) {
+    if (!ptr) {
+        idsp_set_error("idsp_b200_host_alloc: ptr is null");
+        return IDSP_EINVAL;
+    }
+    *ptr = nullptr;
+    cudaError_t e = cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        idsp_set_error("cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e));
+        return IDSP_ENOMEM;
+    }
+    return IDSP_OK;
+}
+extern "C" void idsp_b200_host_free(void *ptr) {
+    if (ptr) cudaFreeHost(ptr);
+}
+
 extern "C" uint64_t idsp_b200_launch_count(const idsp_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 extern "C" int idsp_b200_set_kernel_policy(idsp_ctx *ctx, int policy) {

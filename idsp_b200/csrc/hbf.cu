@@ -6,6 +6,7 @@
 #include "ops.cuh"
 #include "hbf_fast.cuh"
 #include "hbf_fast_scalar.cuh"
+#include "hbf_int_fast.cuh"
 
 using namespace idsp;
 
@@ -131,14 +132,14 @@ hbf_dec_cascade_generic(float *st, const float *x, float *y, size_t n_begin, siz
 }
 template <int K>
 __global__ void __launch_bounds__(128)
-hbf_int_cascade_generic(float *st, const float *x, float *y, size_t n_in, size_t lanes,
-                        size_t sstride, int layout) {
+hbf_int_cascade_generic(float *st, const float *x, float *y, size_t n_begin, size_t n_in,
+                        size_t lanes, size_t sstride, int layout) {
     constexpr int R = 1 << K;
     size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (lane >= lanes) return;
     IntCascadeRegs<K> c;
     c.load(st, sstride, lane);
-    for (size_t n = 0; n < n_in; n++) {
+    for (size_t n = n_begin; n < n_in; n++) {
         float v[R];
         size_t f = fidx(layout, n, lane, n_in, lanes);
         c.push(x[f], v);
@@ -377,13 +378,21 @@ extern "C" int idsp_hbf_int_cascade_f32(idsp_ctx *ctx, int log2_rate, float *sta
                                         float *y, size_t n_in, size_t lanes, int layout) {
     HBF_COMMON_CHECK(n_in);
     IDSP_CHECK_ARG(log2_rate >= 1 && log2_rate <= 5, "log2_rate must be 1..5");
+    size_t done = 0;
+    int fr = hbf_int_fast_try(ctx, log2_rate, state, x, y, n_in, lanes, lanes, layout, &done);
+    if (fr != IDSP_HBF_FAST_NOT_APPLICABLE && fr != IDSP_OK) return fr;
+    if (fr == IDSP_HBF_FAST_NOT_APPLICABLE && ctx->policy == 2 && layout == IDSP_LANE_MAJOR) {
+        idsp_set_error("tiled HBF kernel forced but shape/alignment does not qualify");
+        return IDSP_EINVAL;
+    }
+    if (done == n_in) return IDSP_OK;
     unsigned grid = (unsigned)((lanes + 63) / 64);
     switch (log2_rate) {
-        case 1: hbf_int_cascade_generic<1><<<grid, 64, 0, ctx->stream>>>(state, x, y, n_in, lanes, lanes, layout); break;
-        case 2: hbf_int_cascade_generic<2><<<grid, 64, 0, ctx->stream>>>(state, x, y, n_in, lanes, lanes, layout); break;
-        case 3: hbf_int_cascade_generic<3><<<grid, 64, 0, ctx->stream>>>(state, x, y, n_in, lanes, lanes, layout); break;
-        case 4: hbf_int_cascade_generic<4><<<grid, 64, 0, ctx->stream>>>(state, x, y, n_in, lanes, lanes, layout); break;
-        default: hbf_int_cascade_generic<5><<<grid, 64, 0, ctx->stream>>>(state, x, y, n_in, lanes, lanes, layout); break;
+        case 1: hbf_int_cascade_generic<1><<<grid, 64, 0, ctx->stream>>>(state, x, y, done, n_in, lanes, lanes, layout); break;
+        case 2: hbf_int_cascade_generic<2><<<grid, 64, 0, ctx->stream>>>(state, x, y, done, n_in, lanes, lanes, layout); break;
+        case 3: hbf_int_cascade_generic<3><<<grid, 64, 0, ctx->stream>>>(state, x, y, done, n_in, lanes, lanes, layout); break;
+        case 4: hbf_int_cascade_generic<4><<<grid, 64, 0, ctx->stream>>>(state, x, y, done, n_in, lanes, lanes, layout); break;
+        default: hbf_int_cascade_generic<5><<<grid, 64, 0, ctx->stream>>>(state, x, y, done, n_in, lanes, lanes, layout); break;
     }
     IDSP_LAUNCHED(ctx);
     return IDSP_OK;

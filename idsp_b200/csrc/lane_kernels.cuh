@@ -14,6 +14,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "common.cuh"
+
 namespace idsp {
 
 // streaming loads/stores: coherent (x and y may alias), no L1 allocation
@@ -140,3 +142,4 @@ static int launch_lanes(idsp_ctx *ctx, const typename Op::Params &p, const typen
 }
 
 }  // namespace idsp
+

@@ -31,6 +31,14 @@ template <class T> struct is_float { static constexpr bool value = false; };
 template <> struct is_float<float> { static constexpr bool value = true; };
 template <> struct is_float<double> { static constexpr bool value = true; };
 
+// Defaults of the optional Op hooks used by the TMA kernels (tma_kernels.cuh)
+struct OpHooks {
+    static constexpr bool TUNABLE = false;
+    static constexpr int SMEM_EXTRA_WORDS = 0;
+    template <class P> __device__ __forceinline__ static void init_smem(const P &, uint32_t *, int, int) {}
+    template <class P> __device__ __forceinline__ void bind(const P &, const uint32_t *) {}
+};
+
 // num_traits::clamp (src/iir/biquad.rs:400): `<`/`>` compares so NaN passes through
 template <class T> __device__ __forceinline__ T clamp_nt(T v, T lo, T hi) {
     return v < lo ? lo : (v > hi ? hi : v);
@@ -117,7 +125,7 @@ template <class T, bool CLAMP, int MODE = 0> struct Df1Op {
 };
 
 // Cascade<[Biquad;N]> on DirectForm<T,N> (src/iir/biquad.rs:339-364)
-template <class T, int NMAX> struct CascadeOp {
+template <class T, int NMAX> struct CascadeOp : OpHooks {
     using In = T;
     using Out = T;
     struct Params {
@@ -160,7 +168,7 @@ template <class T, int NMAX> struct CascadeOp {
 };
 
 // DF2T (src/iir/biquad.rs:418-440)
-template <class T, bool CLAMP> struct Df2tOp {
+template <class T, bool CLAMP> struct Df2tOp : OpHooks {
     using In = T;
     using Out = T;
     struct Params {
@@ -187,7 +195,7 @@ template <class T, bool CLAMP> struct Df2tOp {
 };
 
 // DirectForm1Wide (src/iir/biquad.rs:445-480)
-template <bool CLAMP> struct Df1WideOp {
+template <bool CLAMP> struct Df1WideOp : OpHooks {
     using In = int32_t;
     using Out = int32_t;
     struct Params {
@@ -236,7 +244,7 @@ template <bool CLAMP> struct Df1WideOp {
 };
 
 // DirectForm1Dither (src/iir/biquad.rs:484-538)
-template <bool CLAMP> struct Df1DitherOp {
+template <bool CLAMP> struct Df1DitherOp : OpHooks {
     using In = int32_t;
     using Out = int32_t;
     struct Params {
@@ -374,7 +382,7 @@ __device__ __forceinline__ int32_t lowpass_step(int32_t k0, int32_t k1, int64_t 
     }
     return y;
 }
-template <int ORDER> struct LowpassOp {
+template <int ORDER> struct LowpassOp : OpHooks {
     using In = int32_t;
     using Out = int32_t;
     struct Params {

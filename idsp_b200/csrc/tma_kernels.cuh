@@ -24,6 +24,9 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include "common.cuh"
+#include "lane_kernels.cuh"
+
 #define IDSP_TMA_NOT_APPLICABLE 12345
 
 namespace idsp {
@@ -525,6 +528,17 @@ static int tma_try_launch(idsp_ctx *ctx, const typename Op::Params &p, const typ
         return IDSP_EINVAL;
     }
     return r;
+}
+
+// TMA kernel when the Op has 4-byte samples and the shape qualifies, generic kernel otherwise
+template <class Op>
+static int launch_lanes_best(idsp_ctx *ctx, const typename Op::Params &p, const typename Op::In *x,
+                             typename Op::Out *y, size_t frames, size_t lanes, size_t sstride, int layout) {
+    if constexpr (sizeof(typename Op::In) == 4 && (sizeof(typename Op::Out) == 4 || sizeof(typename Op::Out) == 8)) {
+        int tr = tma_try_launch<Op>(ctx, p, x, y, frames, lanes, sstride, layout);
+        if (tr != IDSP_TMA_NOT_APPLICABLE) return tr;
+    }
+    return launch_lanes<Op>(ctx, p, x, y, frames, lanes, sstride, layout);
 }
 
 }  // namespace idsp

@@ -137,13 +137,13 @@ extern "C" int idsp_lowpass_i32(idsp_ctx *ctx, int order, const int32_t *k, int6
         p.k[0] = k[0];
         p.k[1] = 0;
         p.st = state;
-        return launch_lanes<LowpassOp<1>>(ctx, p, x, y, frames, lanes, lanes, layout);
+        return launch_lanes_best<LowpassOp<1>>(ctx, p, x, y, frames, lanes, lanes, layout);
     }
     LowpassOp<2>::Params p;
     p.k[0] = k[0];
     p.k[1] = k[1];
     p.st = state;
-    return launch_lanes<LowpassOp<2>>(ctx, p, x, y, frames, lanes, lanes, layout);
+    return launch_lanes_best<LowpassOp<2>>(ctx, p, x, y, frames, lanes, lanes, layout);
 }
 
 int lockin_dev(idsp_ctx *ctx, int order, const int32_t *k, int32_t *accu_state,

@@ -72,6 +72,11 @@ const char *idsp_b200_last_error(void);
 int idsp_b200_version(void);
 /* Number of kernels this ctx has launched so far (bench `gpu_launches`). */
 uint64_t idsp_b200_launch_count(const idsp_ctx *ctx);
+/* Page-locked host memory for the `_host` entry points: buffers obtained here (or pinned by
+ * the caller with cudaHostRegister / torch pin_memory) are DMA'd directly; pageable memory
+ * works too but is staged by the driver. */
+int idsp_b200_host_alloc(void **ptr, size_t bytes);
+void idsp_b200_host_free(void *ptr);
 /* Kernel selection: 0 = automatic (default), 1 = force the generic LDG kernels,
  * 2 = force the TMA kernels (IDSP_EINVAL if the shape does not qualify). */
 int idsp_b200_set_kernel_policy(idsp_ctx *ctx, int policy);
