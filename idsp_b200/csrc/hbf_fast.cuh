@@ -126,7 +126,7 @@ __device__ __forceinline__ f2 add2(f2 a, f2 b) {
 // rounding.  So the product is written as fma(a, b, nz) with nz = (-0.0, -0.0) supplied
 // as an opaque kernel parameter: x*y + (-0.0) rounds exactly like x*y (sign of zero
 // included), costs the same single instruction, and cannot be merged with the add that
-// follows.  tests/test_gpu_hbf.py compares bit patterns against the scalar oracle.
+// follows.  tests/test_gpu_hbf.py compares bit patterns against the scalar CPU restatement.
 __device__ __forceinline__ f2 mul2(f2 a, f2 b, f2 nz) {
     f2 r;
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(nz));
