@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libidsp_b200.so")
+# IDSP_B200_LIB selects an experimental build of the same library (tile-shape sweeps)
+LIB_PATH = os.environ.get("IDSP_B200_LIB") or os.path.join(_HERE, "libidsp_b200.so")
 
 _c_p = C.c_void_p
 _sz = C.c_size_t

@@ -35,8 +35,8 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
+def build(force: bool = False, verbose: bool = False, out: str = OUT) -> str:
+    if out == OUT and not force and not _stale():
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc, *NVCC_FLAGS]
@@ -46,9 +46,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
                        ("IDSP_HFS_NL", "HFS_NL"), ("IDSP_HFS_MINB", "HFS_MINB")):
         if os.environ.get(var):  # experiments on the tiled HBF kernels
             cmd += [f"-D{macro}={int(os.environ[var])}"]
+    for d in filter(None, os.environ.get("IDSP_DEFS", "").split(",")):  # e.g. IDSP_DEFS=HFS_BAL=1,HFS_NT=64
+        cmd += [f"-D{d}"]
     if os.environ.get("IDSP_TUNE"):  # tile-shape sweep builds (tools/sweep_biquad.py)
         cmd += ["-DIDSP_TUNE"]
-    cmd += ["-ccbin", "g++", "-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd += ["-ccbin", "g++", "-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
     env = dict(os.environ)
     env.pop("CC", None)
     env.pop("CXX", None)
@@ -58,8 +60,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed building libidsp_b200.so")
     if verbose:
         sys.stderr.write(res.stdout + res.stderr)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    o = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, out=o[0] if o else OUT))

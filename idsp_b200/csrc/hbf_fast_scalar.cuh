@@ -60,7 +60,18 @@ __host__ __device__ constexpr int st_n(int s) { return TT >> (s + 1); }  // outp
 #ifndef HFS_R0
 #define HFS_R0 16
 #endif
-__host__ __device__ constexpr int st_r(int s) { return s == 0 ? HFS_R0 : (st_n(s) / 8 >= 8 ? 8 : (st_n(s) / 8 >= 4 ? st_n(s) / 8 : 4)); }
+#ifndef HFS_BAL
+#define HFS_BAL 0
+#endif
+// outputs per work item.  HFS_BAL: every stage has exactly NT items (no idle threads in the
+// low-rate stages) at the price of more window loads per output there.
+__host__ __device__ constexpr int st_r_bal(int s) {
+    int r = NL * st_n(s) / NT;
+    return r > 8 ? 8 : (r < 1 ? 1 : r);
+}
+__host__ __device__ constexpr int st_r(int s) {
+    return s == 0 ? HFS_R0 : HFS_BAL ? st_r_bal(s) : (st_n(s) / 8 >= 8 ? 8 : (st_n(s) / 8 >= 4 ? st_n(s) / 8 : 4));
+}
 __host__ __device__ constexpr int raw_h(int K) { return up4(4 * st_m(K, 0) - 2); }
 __host__ __device__ constexpr int raw_pitch(int K) { return oddpitch(raw_h(K) + TT); }
 __host__ __device__ constexpr int he(int K, int s) { return up4(st_m(K, s) - 1); }
@@ -128,31 +139,34 @@ template <int TI, int R> struct RawItem {
 };
 
 // One item of a de-interleaved stage: erow = [HE hist | n new], orow = [HO hist | n new].
-template <int TI, int R> struct SplitItem {
+// The item spans R outputs starting at p0 (p0 % 4 == 0 keeps the LDS.128 aligned); this call
+// evaluates outputs Q0 .. Q0+QN-1 of it and only loads the part of the window they need.
+template <int TI, int R, int Q0 = 0, int QN = R> struct SplitItem {
     static constexpr int M = HbfTaps<TI>::M;
     static constexpr int LEN = 2 * M - 1;
     static constexpr int HE = up4(M - 1), HO = up4(LEN);
     static constexpr int RE = HE - (M - 1), RO = HO - LEN;
-    static constexpr int WO = up4(RO + R + 2 * M - 1), WE = up4(RE + R);
-    __device__ __forceinline__ static void run(const float *erow, const float *orow, int p0, float (&y)[R]) {
-        float wo[WO], we[WE];
+    static constexpr int JO0 = (RO + Q0) / 4, JO1 = (RO + Q0 + QN + 2 * M - 2) / 4 + 1;
+    static constexpr int JE0 = (RE + Q0) / 4, JE1 = (RE + Q0 + QN - 1) / 4 + 1;
+    __device__ __forceinline__ static void run(const float *erow, const float *orow, int p0, float (&y)[QN]) {
+        float wo[4 * JO1], we[4 * JE1];
 #pragma unroll
-        for (int j = 0; j < WO / 4; j++) {
+        for (int j = JO0; j < JO1; j++) {
             float4 v = lds128(orow + p0 + 4 * j);
             wo[4 * j] = v.x; wo[4 * j + 1] = v.y; wo[4 * j + 2] = v.z; wo[4 * j + 3] = v.w;
         }
 #pragma unroll
-        for (int j = 0; j < WE / 4; j++) {
+        for (int j = JE0; j < JE1; j++) {
             float4 v = lds128(erow + p0 + 4 * j);
             we[4 * j] = v.x; we[4 * j + 1] = v.y; we[4 * j + 2] = v.z; we[4 * j + 3] = v.w;
         }
 #pragma unroll
-        for (int q = 0; q < R; q++) {
+        for (int q = Q0; q < Q0 + QN; q++) {
             float acc = (wo[RO + q + 2 * M - 1] + wo[RO + q]) * HbfTaps<TI>::c(0);
 #pragma unroll
             for (int i = 1; i < M; i++)
                 acc = acc + (wo[RO + q + 2 * M - 1 - i] + wo[RO + q + i]) * HbfTaps<TI>::c(i);
-            y[q] = acc + we[RE + q];
+            y[q - Q0] = acc + we[RE + q];
         }
     }
 };
@@ -167,74 +181,124 @@ __device__ __forceinline__ void put_split(float *erow_new, float *orow_new, int 
             reinterpret_cast<float4 *>(erow_new + p0 / 2)[j] = make_float4(y[8 * j], y[8 * j + 2], y[8 * j + 4], y[8 * j + 6]);
             reinterpret_cast<float4 *>(orow_new + p0 / 2)[j] = make_float4(y[8 * j + 1], y[8 * j + 3], y[8 * j + 5], y[8 * j + 7]);
         }
-    } else {
+    } else if constexpr (R == 4) {
         *reinterpret_cast<float2 *>(erow_new + p0 / 2) = make_float2(y[0], y[2]);
         *reinterpret_cast<float2 *>(orow_new + p0 / 2) = make_float2(y[1], y[3]);
+    } else if constexpr (R == 2) {
+        erow_new[p0 / 2] = y[0];
+        orow_new[p0 / 2] = y[1];
+    } else {
+        ((p0 & 1) ? orow_new : erow_new)[p0 / 2] = y[0];
+    }
+}
+
+// Move the tails of the [hist | n new] rows E_s / O_s of all NL lanes to their heads (the
+// reference's copy_within, src/hbf.rs:183-184).  Executed by `nw` warps (`wsel` = index of
+// this warp among them); one 16-byte piece per thread, a whole row inside one warp so that
+// reading everything before writing anything (head and tail overlap when hist > n) only
+// needs a __syncwarp.
+template <int K, int s>
+__device__ __forceinline__ void carry_rows(float *sm, int wsel, int nw, int lid) {
+    constexpr int CE = he(K, s) / 4, CO = ho(K, s) / 4, C = CE + CO;
+    constexpr int LP = 32 / C;  // lanes per warp pass
+    static_assert(C <= 32, "row history too long for one warp");
+    const int sub = lid / C, j = lid % C;
+    for (int pass = wsel; pass * LP < NL; pass += nw) {
+        const int lane = pass * LP + sub;
+        const bool act = sub < LP && lane < NL;
+        float *row = j < CE ? sm + off_e(K, s) + lane * pe(K, s) + 4 * j
+                            : sm + off_o(K, s) + lane * po(K, s) + 4 * (j - CE);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (act) v = lds128(row + st_n(s));
+        __syncwarp();
+        if (act) *reinterpret_cast<float4 *>(row) = v;
+        __syncwarp();
     }
 }
 
 template <int K, int s> struct StageRun {
+    static constexpr int TI = K - 1 - s;
+    static constexpr int R = st_r(s);          // outputs per work item
+    static constexpr int RA = R < 4 ? 4 : R;   // outputs per aligned window (p0 % 4 == 0)
+    static constexpr int NSUB = RA / R;        // work items sharing one window (warp-uniform split)
+    static constexpr int WIN = NL * st_n(s) / RA;
+    static_assert(NSUB == 1 || WIN % 32 == 0, "sub-item index must be warp-uniform");
+
+    template <int Q0>
+    __device__ __forceinline__ static void item(float *sm, int lane, int p0, int nl, float *y, size_t ystride,
+                                                size_t yoff, size_t lane0) {
+        const float *E = sm + off_e(K, s);
+        const float *O = sm + off_o(K, s);
+        float out[R];
+        SplitItem<TI, RA, Q0, R>::run(E + lane * pe(K, s), O + lane * po(K, s), p0, out);
+        if constexpr (s == K - 1) {
+            if (lane < nl) {
+                float *dst = y + (lane0 + lane) * ystride + yoff + p0 + Q0;
+                if (R >= 4 && (((uintptr_t)dst) & 15) == 0) {
+#pragma unroll
+                    for (int j = 0; j < R / 4; j++)
+                        reinterpret_cast<float4 *>(dst)[j] =
+                            make_float4(out[4 * j], out[4 * j + 1], out[4 * j + 2], out[4 * j + 3]);
+                } else if (R == 2 && (((uintptr_t)dst) & 7) == 0) {
+                    *reinterpret_cast<float2 *>(dst) = make_float2(out[0], out[R - 1]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < R; j++) dst[j] = out[j];
+                }
+            }
+        } else {
+            float *En = sm + off_e(K, s + 1) + lane * pe(K, s + 1) + he(K, s + 1);
+            float *On = sm + off_o(K, s + 1) + lane * po(K, s + 1) + ho(K, s + 1);
+            put_split<R>(En, On, p0 + Q0, out);
+        }
+    }
+
+    // Warps that hold items of this stage: low-rate stages have fewer than NT items, and
+    // odd stages take the upper warps so that, over the CTAs of an SM, every scheduler gets
+    // work.  The other warps move the previous stage's row tails to the heads meanwhile.
+    static constexpr int ITEMS = WIN * NSUB;
+    static constexpr int NW = NT / 32;
+    static constexpr int NWA = ITEMS >= NT ? NW : (ITEMS + 31) / 32;
+    static constexpr int W0 = (s & 1) ? NW - NWA : 0;
+
     // runs stage s (1 <= s <= K-1) for one tile
     __device__ __forceinline__ static void run(float *sm, int tid, int nl, float *y, size_t ystride,
                                                size_t yoff, size_t lane0) {
-        constexpr int TI = K - 1 - s;
-        constexpr int R = st_r(s);
-        constexpr int ITEMS = NL * st_n(s) / R;
-        const float *E = sm + off_e(K, s);
-        const float *O = sm + off_o(K, s);
-        for (int idx = tid; idx < ITEMS; idx += NT) {
-            const int lane = idx % NL, p0 = (idx / NL) * R;
-            float out[R];
-            SplitItem<TI, R>::run(E + lane * pe(K, s), O + lane * po(K, s), p0, out);
-            if constexpr (s == K - 1) {
-                if (lane < nl) {
-                    float *dst = y + (lane0 + lane) * ystride + yoff + p0;
-                    if ((((uintptr_t)dst) & 15) == 0) {
-#pragma unroll
-                        for (int j = 0; j < R / 4; j++)
-                            reinterpret_cast<float4 *>(dst)[j] =
-                                make_float4(out[4 * j], out[4 * j + 1], out[4 * j + 2], out[4 * j + 3]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < R; j++) dst[j] = out[j];
-                    }
+        const int vt = tid - 32 * W0;
+        if (vt >= 0 && vt < 32 * NWA) {
+            for (int idx = vt; idx < ITEMS; idx += 32 * NWA) {
+                const int w = idx % WIN, sub = idx / WIN;
+                const int lane = w % NL, p0 = (w / NL) * RA;
+                if constexpr (NSUB == 1) {
+                    item<0>(sm, lane, p0, nl, y, ystride, yoff, lane0);
+                } else if constexpr (NSUB == 2) {
+                    if (sub == 0) item<0>(sm, lane, p0, nl, y, ystride, yoff, lane0);
+                    else item<R>(sm, lane, p0, nl, y, ystride, yoff, lane0);
+                } else {
+                    if (sub == 0) item<0>(sm, lane, p0, nl, y, ystride, yoff, lane0);
+                    else if (sub == 1) item<R>(sm, lane, p0, nl, y, ystride, yoff, lane0);
+                    else if (sub == 2) item<2 * R>(sm, lane, p0, nl, y, ystride, yoff, lane0);
+                    else item<3 * R>(sm, lane, p0, nl, y, ystride, yoff, lane0);
                 }
-            } else {
-                float *En = sm + off_e(K, s + 1) + lane * pe(K, s + 1) + he(K, s + 1);
-                float *On = sm + off_o(K, s + 1) + lane * po(K, s + 1) + ho(K, s + 1);
-                put_split<R>(En, On, p0, out);
             }
         }
-    }
-};
-
-// move the tail of a [hist | n new] row to its head; one thread per row, through registers
-template <int H, int N> __device__ __forceinline__ void carry_row(float *row) {
-    float t[H];
-#pragma unroll
-    for (int j = 0; j < H / 4; j++) {
-        float4 v = lds128(row + N + 4 * j);
-        t[4 * j] = v.x; t[4 * j + 1] = v.y; t[4 * j + 2] = v.z; t[4 * j + 3] = v.w;
-    }
-#pragma unroll
-    for (int j = 0; j < H / 4; j++)
-        reinterpret_cast<float4 *>(row)[j] = make_float4(t[4 * j], t[4 * j + 1], t[4 * j + 2], t[4 * j + 3]);
-}
-
-template <int K, int s> struct Carry {
-    __device__ __forceinline__ static void run(float *sm, int job, int lane) {
-        if constexpr (s < K) {
-            if (job == 2 * (s - 1)) carry_row<he(K, s), st_n(s)>(sm + off_e(K, s) + lane * pe(K, s));
-            else if (job == 2 * (s - 1) + 1) carry_row<ho(K, s), st_n(s)>(sm + off_o(K, s) + lane * po(K, s));
-            else Carry<K, s + 1>::run(sm, job, lane);
+        if constexpr (s >= 2) {  // rows s-1 were consumed in the previous phase
+            const int warp = tid >> 5;
+            if constexpr (NWA < NW) {
+                if (vt < 0 || vt >= 32 * NWA) carry_rows<K, s - 1>(sm, vt < 0 ? warp : warp - NWA, NW - NWA, tid & 31);
+            } else {
+                carry_rows<K, s - 1>(sm, warp, NW, tid & 31);
+            }
         }
     }
 };
 
 // ABI state <-> shared-memory histories (see header comment of include/idsp_b200.h)
 template <int K, int s, bool LOAD> struct StateIO {
+    // raw history lives at row[roff .. roff+HR): roff = 0 (head) on entry, TT (tail of the
+    // last tile) on exit
     __device__ __forceinline__ static void run(float *sm, float *st, size_t sstride, size_t lane0, int nl,
-                                               int tid, int rawbuf) {
+                                               int tid, int rawbuf, int roff) {
         if constexpr (s < K) {
             constexpr int M = st_m(K, s);
             constexpr int LEN = 2 * M - 1;
@@ -246,7 +310,7 @@ template <int K, int s, bool LOAD> struct StateIO {
                 float *p;
                 if constexpr (s == 0) {
                     constexpr int HR = raw_h(K);
-                    float *row = sm + (rawbuf * NL + lane) * raw_pitch(K);
+                    float *row = sm + (rawbuf * NL + lane) * raw_pitch(K) + roff;
                     p = w < M - 1 ? row + (HR - 2 * M + 2 + 2 * w) : row + (HR - 4 * M + 3 + 2 * (w - (M - 1)));
                 } else {
                     p = w < M - 1 ? sm + off_e(K, s) + lane * pe(K, s) + (he(K, s) - (M - 1) + w)
@@ -255,7 +319,7 @@ template <int K, int s, bool LOAD> struct StateIO {
                 if constexpr (LOAD) *p = stw[(size_t)w * sstride + lane];
                 else stw[(size_t)w * sstride + lane] = *p;
             }
-            StateIO<K, s + 1, LOAD>::run(sm, st, sstride, lane0, nl, tid, rawbuf);
+            StateIO<K, s + 1, LOAD>::run(sm, st, sstride, lane0, nl, tid, rawbuf, roff);
         }
     }
 };
@@ -284,18 +348,23 @@ hbf_dec_fast_kernel(float *st, const float *x, float *y, size_t n_out, size_t nt
         mbar_fence_init();
     }
     __syncthreads();
-    StateIO<K, 0, true>::run(sm, st, sstride, lane0, nl, tid, 0);
+    StateIO<K, 0, true>::run(sm, st, sstride, lane0, nl, tid, 0, 0);
     // generic-proxy writes above (zero fill) precede async-proxy (TMA) writes to the same rows
     fence_async_smem();
     __syncthreads();
 
+    // Tile t >= 1 is fetched together with the HR samples in front of it (they are in L2 from
+    // the previous tile), so the raw history never has to be copied between ring buffers;
+    // tile 0 takes its history from the ABI state (scattered into buffer 0 above).
     auto issue = [&](size_t tile) {  // executed by warp 0
         const int b = (int)(tile % S);
         const uint32_t bar = smem_u32(&bars[b]);
-        if ((tid & 31) == 0) mbar_expect_tx(bar, (uint32_t)(nl * TT * 4));
+        const uint32_t hist = tile ? HR : 0;
+        if ((tid & 31) == 0) mbar_expect_tx(bar, (uint32_t)(nl * (TT + hist) * 4));
         __syncwarp();
         if (tid < nl)
-            bulk_load_1d(smem_u32(sm + (b * NL + tid) * PR + HR), x + (lane0 + tid) * n_in + tile * TT, TT * 4, bar);
+            bulk_load_1d(smem_u32(sm + (b * NL + tid) * PR + HR - hist),
+                         x + (lane0 + tid) * n_in + tile * TT - hist, (TT + hist) * 4, bar);
     };
     if (tid < 32) {
 #pragma unroll
@@ -306,7 +375,7 @@ hbf_dec_fast_kernel(float *st, const float *x, float *y, size_t n_out, size_t nt
     for (size_t i = 0; i < ntiles; i++) {
         const int b = (int)(i % S);
         mbar_wait(smem_u32(&bars[b]), (uint32_t)((i / S) & 1));
-        // ---- stage 0: raw interleaved -> E_1 / O_1 (or -> y when K == 1)
+        // ---- phase 0: raw interleaved -> E_1 / O_1 (or -> y when K == 1)
         {
             const float *raw = sm + b * NL * PR;
             constexpr int ITEMS = NL * st_n(0) / R0;
@@ -333,41 +402,30 @@ hbf_dec_fast_kernel(float *st, const float *x, float *y, size_t n_out, size_t nt
                     put_split<R0>(En, On, p0, out);
                 }
             }
+            // rows K-1 of the previous tile (last read in its final phase, next written in phase K-2 >= 1)
+            if constexpr (K >= 3) {
+                if (i > 0) carry_rows<K, K - 1>(sm, tid >> 5, NT / 32, tid & 31);
+            }
         }
         __syncthreads();
-        // ---- raw history: tail of buffer b -> head of the next buffer, then refill buffer b
-        if (tid < 32) {
-            if (tid < NL) {
-                float *src = sm + (b * NL + tid) * PR;
-                float *dst = sm + (((b + 1) % S) * NL + tid) * PR;
-                float t[HR];
-#pragma unroll
-                for (int j = 0; j < HR / 4; j++) {
-                    float4 v = lds128(src + TT + 4 * j);
-                    t[4 * j] = v.x; t[4 * j + 1] = v.y; t[4 * j + 2] = v.z; t[4 * j + 3] = v.w;
-                }
-#pragma unroll
-                for (int j = 0; j < HR / 4; j++)
-                    reinterpret_cast<float4 *>(dst)[j] = make_float4(t[4 * j], t[4 * j + 1], t[4 * j + 2], t[4 * j + 3]);
-            }
-            __syncwarp();
-            if (i + S < ntiles) issue(i + S);
-        }
-        // ---- stages 1 .. K-1
+        // ---- raw buffer b is free again: refill it
+        if (tid < 32 && i + S < ntiles) issue(i + S);
+        // ---- phases 1 .. K-1 (phase s also carries rows s-1)
         if constexpr (K >= 2) { StageRun<K, 1>::run(sm, tid, nl, y, n_out, i * TO, lane0); __syncthreads(); }
         if constexpr (K >= 3) { StageRun<K, 2>::run(sm, tid, nl, y, n_out, i * TO, lane0); __syncthreads(); }
         if constexpr (K >= 4) { StageRun<K, 3>::run(sm, tid, nl, y, n_out, i * TO, lane0); __syncthreads(); }
         if constexpr (K >= 5) { StageRun<K, 4>::run(sm, tid, nl, y, n_out, i * TO, lane0); __syncthreads(); }
-        // ---- carry the E/O histories (one thread per row)
-        if constexpr (K >= 2) {
-            for (int idx = tid; idx < 2 * (K - 1) * NL; idx += NT) Carry<K, 1>::run(sm, idx / NL, idx % NL);
+        if constexpr (K == 2) {  // rows 1 are written again in the very next phase: carry them now
+            carry_rows<K, 1>(sm, tid >> 5, NT / 32, tid & 31);
+            __syncthreads();
         }
-        // also orders warp 0's raw-history copy before the next tile's stage 0
+    }
+    if constexpr (K >= 3) {
+        carry_rows<K, K - 1>(sm, tid >> 5, NT / 32, tid & 31);
         __syncthreads();
     }
-    // raw history of the stream now sits at the head of buffer (ntiles % S)
-    __syncthreads();
-    StateIO<K, 0, false>::run(sm, st, sstride, lane0, nl, tid, (int)(ntiles % S));
+    // the raw history of the stream is the tail of the last tile's buffer
+    StateIO<K, 0, false>::run(sm, st, sstride, lane0, nl, tid, (int)((ntiles - 1) % S), TT);
 }
 
 template <int K>
