@@ -1,30 +1,37 @@
-// hbf_fast.cuh -- shared-memory tiled HBF /2^K decimation cascade (f32, lane-major).
+// hbf_fast.cuh -- shared-memory tiled HBF /2^K decimation cascade (f32, lane-major),
+// packed f32x2 variant: every stage after the first runs on add/fma.rn.f32x2, two IEEE
+// round-to-nearest results per instruction, bit-identical to the scalar operations
+// (hbf_fast_scalar.cuh is the scalar variant with the same tiling; both are bit-exact).
 //
-// The FIR stages are time-parallel, so unlike the biquad kernels a lane is not tied
-// to one thread.  A CTA owns NL = 16 lanes (8 lane PAIRS) for the whole call and walks
-// the time axis in tiles of TT = 512 input samples per lane:
+// A CTA owns NL = 8 lanes for the whole call and walks the time axis in tiles of TT = 512
+// input samples per lane (4 CTAs of 128 threads per SM):
 //
-//   HBM --TMA 1-D bulk copy per lane row (2 KB), mbarrier complete_tx--> raw ring (S = 2)
-//   stage 0 : reads the interleaved raw stream of both lanes of a pair (scalar FP32) and
-//             writes de-interleaved even/odd rows for stage 1 with the two lanes of the
-//             pair PACKED side by side: element e of a pair row = (lane A, lane B)
-//   stage s : reads E_s / O_s, writes E_{s+1} / O_{s+1}, all in shared memory, all
-//             arithmetic as packed add.rn.f32x2 / mul.rn.f32x2 (FADD2/FMUL2: two IEEE
-//             round-to-nearest results per instruction, bit-identical to scalar ops;
-//             measured 2x the scalar FP32 rate on B200, tools/ubench.cu)
+//   HBM --TMA 1-D bulk copy per lane row (history + 2 KB), mbarrier complete_tx--> raw ring
+//   stage 0 : scalar FP32 on the interleaved raw stream.  A work item evaluates the same
+//             output positions in the FIRST and in the SECOND half of the tile and writes
+//             the two results side by side: element e of a row of stage 1 is the pair
+//             (first-half sample e, second-half sample e)
+//   stage s : packed arithmetic on those pairs: one instruction advances both halves of
+//             the tile; reads E_s / O_s, writes E_{s+1} / O_{s+1} (shared memory)
 //   stage K-1 : unpacks and writes the decimated output straight to HBM
 //
-// Work item = (lane pair, R consecutive outputs of one stage); items are spread over
-// the CTA's threads pair-fastest, so a quarter-warp touches 8 different rows whose
-// pitch is 4*odd floats -> every LDS.128 / STS.128 is bank-conflict free.  A thread
-// loads its whole window into registers with static indices (no shifting delay line)
-// and evaluates R outputs in exactly the reference's order:
+// Pairing two time halves of the SAME lane (instead of two lanes) keeps 8 rows per CTA, so a
+// quarter-warp still touches 8 different rows whose pitch is 4*odd floats: every LDS.128 /
+// STS.128 is bank-conflict free, and shared memory per CTA stays at 4 CTAs per SM.
+//
+// Row layout (elements = float2): lane .x of a row is the stream segment
+// [T0 - H, T0 + n/2), lane .y the segment [T0 + n/2 - H, T0 + n) (T0 = tile start, H = filter
+// history, n = new samples per tile).  The two segments overlap, so a producer writes the
+// last min(H, n/2) samples of the first half twice (.x main slot, .y history slot); the
+// carry between tiles is x'[i] = y[i + n/2] and, where H > n/2, y'[i] = y[i + n]
+// (the reference's copy_within, src/hbf.rs:183-184, on both segments at once).
+//
+// A thread loads its window into registers with static indices and evaluates R outputs in
+// exactly the reference's order:
 //   acc = ((w[2M-1]+w[0])*c0) + ((w[2M-2]+w[1])*c1) + ...  then  + even sample
-// (src/hbf.rs:46-68, :178-181), each op individually rounded -> bit-exact.
-// Each row keeps the history the next tile needs ([hist | tile]); after a tile the
-// tails are moved to the heads (the reference's copy_within, src/hbf.rs:183-184).
-// The ABI state (even/odd history per stage) is scattered into those heads at entry and
-// gathered back at exit, so calls can be chained like block() calls on the reference.
+// (src/hbf.rs:46-68, :178-181), each op individually rounded -> bit-exact.  The ABI state
+// (even/odd history per stage) is scattered into the row heads at entry and gathered back
+// at exit, so calls can be chained like block() calls on the reference.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -38,14 +45,25 @@
 namespace idsp {
 namespace hf {
 
-constexpr int NL = 16;      // lanes per CTA
-constexpr int NP = NL / 2;  // lane pairs per CTA
+constexpr int NL = 8;  // lanes per CTA
 #ifndef HF_NT
 #define HF_NT 128
 #endif
 constexpr int NT = HF_NT;  // threads per CTA
-constexpr int TT = 512;    // raw input samples per lane per tile
+#ifndef HF_TT
+#define HF_TT 512
+#endif
+constexpr int TT = HF_TT;  // raw input samples per lane per tile
 constexpr int S = 2;       // raw ring depth
+#ifndef HF_MINB
+#define HF_MINB 4
+#endif
+#ifndef HF_RLAST  // pair-outputs per item of a 23-tap stage
+#define HF_RLAST 4
+#endif
+#ifndef HF_ITEMS  // target number of items per packed stage (sets R)
+#define HF_ITEMS 64
+#endif
 
 __host__ __device__ constexpr int up2(int v) { return (v + 1) & ~1; }
 __host__ __device__ constexpr int up4(int v) { return (v + 3) & ~3; }
@@ -53,24 +71,28 @@ __host__ __device__ constexpr int up4(int v) { return (v + 3) & ~3; }
 __host__ __device__ constexpr int oddpitch(int v) { return (up4(v) / 4) % 2 ? up4(v) : up4(v) + 4; }
 __host__ __device__ constexpr int st_m(int K, int s) { return hbf_m(K - 1 - s); }
 __host__ __device__ constexpr int st_n(int s) { return TT >> (s + 1); }  // outputs per lane per tile
-// outputs per item: stage 0 (scalar, per lane) 8; packed stages n/16 clamped to [2, 8]
-__host__ __device__ constexpr int st_r(int s) {
-    return s == 0 ? 8 : (st_n(s) / 16 >= 8 ? 8 : (st_n(s) / 16 >= 2 ? st_n(s) / 16 : 2));
+__host__ __device__ constexpr int st_np(int s) { return st_n(s) / 2; }   // pair-outputs per lane per tile
+// outputs (stage 0: per half) / pair-outputs per work item
+__host__ __device__ constexpr int st_r(int K, int s) {
+    if (s == 0) return 8;
+    if (st_m(K, s) > 12) return HF_RLAST;
+    int r = NL * st_np(s) / HF_ITEMS;
+    return r > 8 ? 8 : (r < 2 ? 2 : r);
 }
 __host__ __device__ constexpr int raw_h(int K) { return up4(4 * st_m(K, 0) - 2); }
 __host__ __device__ constexpr int raw_pitch(int K) { return oddpitch(raw_h(K) + TT); }
-// packed rows (s >= 1): history in ELEMENTS (one element = 2 floats = both lanes of a pair)
+// packed rows (s >= 1): history in ELEMENTS (one element = 2 floats = both tile halves)
 __host__ __device__ constexpr int he(int K, int s) { return up2(st_m(K, s) - 1); }
 __host__ __device__ constexpr int ho(int K, int s) { return up2(2 * st_m(K, s) - 1); }
-__host__ __device__ constexpr int pe(int K, int s) { return oddpitch(2 * (he(K, s) + st_n(s))); }  // floats
-__host__ __device__ constexpr int po(int K, int s) { return oddpitch(2 * (ho(K, s) + st_n(s))); }
+__host__ __device__ constexpr int pe(int K, int s) { return oddpitch(2 * (he(K, s) + st_np(s))); }  // floats
+__host__ __device__ constexpr int po(int K, int s) { return oddpitch(2 * (ho(K, s) + st_np(s))); }
 // float offsets inside dynamic shared memory
 __host__ __device__ constexpr int off_e(int K, int s) {
     int o = S * NL * raw_pitch(K);
-    for (int i = 1; i < s; i++) o += NP * (pe(K, i) + po(K, i));
+    for (int i = 1; i < s; i++) o += NL * (pe(K, i) + po(K, i));
     return o;
 }
-__host__ __device__ constexpr int off_o(int K, int s) { return off_e(K, s) + NP * pe(K, s); }
+__host__ __device__ constexpr int off_o(int K, int s) { return off_e(K, s) + NL * pe(K, s); }
 __host__ __device__ constexpr int smem_floats(int K) { return off_e(K, K); }
 __host__ __device__ constexpr size_t smem_bytes(int K) { return (size_t)smem_floats(K) * 4 + S * 8; }
 // ABI state word offset of stage s (highest-rate stage first): sum of 3M-2
@@ -89,8 +111,7 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void *src, uint
 
 // 128-bit shared loads as explicit *volatile* PTX: ptxas narrows a plain `ld.shared.v4`
 // whose components are partly unused (windows over the interleaved stream) to scalar
-// LDS / LDS.64, and those are 4-8 way bank conflicted over rows of pitch 4*odd floats
-// (seen in profiles/r1_hbf_*: 147 M excess wavefronts).  `ld.volatile` keeps LDS.128.
+// LDS / LDS.64, and those are 4-8 way bank conflicted over rows of pitch 4*odd floats.
 __device__ __forceinline__ float4 lds128(const float *p) {
     float4 v;
     asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
@@ -98,7 +119,7 @@ __device__ __forceinline__ float4 lds128(const float *p) {
                  : "r"(smem_u32(p)));
     return v;
 }
-typedef unsigned long long f2;  // two packed f32: lo = lane A, hi = lane B
+typedef unsigned long long f2;  // two packed f32: lo = first tile half, hi = second tile half
 __device__ __forceinline__ void lds_2f2(const float *p, f2 &a, f2 &b) {
     asm volatile("ld.volatile.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(smem_u32(p)));
 }
@@ -133,7 +154,7 @@ __device__ __forceinline__ f2 mul2(f2 a, f2 b, f2 nz) {
     return r;
 }
 
-// One lane of the raw (interleaved) stage: outputs p0 .. p0+R-1 of lane row `row`
+// One half of a raw (interleaved) stage item: outputs p0 .. p0+R-1 of lane row `row`
 // (row[0..HR) = history, row[HR..] = tile).  Stream sample u[k] (k relative to the tile
 // start) sits at row[HR + k]; the window starts at row[2*p0] (16-byte aligned).
 template <int TI, int R> struct RawItem {
@@ -159,52 +180,96 @@ template <int TI, int R> struct RawItem {
     }
 };
 
-// One item of a packed stage: erow = [HE hist | n new] elements, orow = [HO hist | n new],
-// element = (lane A, lane B).  p0 (first output, even) is also the element offset of the
-// window inside the rows.
+// One item of a packed stage: erow = [HE hist | np new] elements, orow = [HO hist | np new],
+// element = (first half, second half).  p0 (first pair-output, even) is also the element
+// offset of the window inside the rows.  Long filters are evaluated in chunks of TC taps,
+// each chunk loading only the window pieces it is the first to need, so that the 23-tap
+// stage never holds its whole 2 x 48-register window at once.
 template <int TI, int R> struct PackedItem {
     static constexpr int M = HbfTaps<TI>::M;
     static constexpr int LEN = 2 * M - 1;
     static constexpr int HE = up2(M - 1), HO = up2(LEN);
     static constexpr int RE = HE - (M - 1), RO = HO - LEN;
     static constexpr int WO = up2(RO + R + 2 * M - 1), WE = up2(RE + R);
+    static constexpr int TC = M > 12 ? 12 : M;
+    static constexpr int NC = (M + TC - 1) / TC;
+    // does chunk c (taps [c*TC, min(M,(c+1)*TC))) read window piece j (elements 2j, 2j+1)?
+    __host__ __device__ static constexpr bool needs(int c, int j) {
+        const int i0 = c * TC, i1 = (c + 1) * TC < M ? (c + 1) * TC : M;
+        const int lo0 = RO + i0, lo1 = RO + i1 - 1 + R - 1;                          // ascending operand
+        const int hi0 = RO + 2 * M - 1 - (i1 - 1), hi1 = RO + 2 * M - 1 - i0 + R - 1;  // descending operand
+        const int e0 = 2 * j, e1 = 2 * j + 1;
+        return (e1 >= lo0 && e0 <= lo1) || (e1 >= hi0 && e0 <= hi1);
+    }
+    __host__ __device__ static constexpr int first_chunk(int j) {
+        for (int c = 0; c < NC; c++)
+            if (needs(c, j)) return c;
+        return NC;
+    }
     __device__ __forceinline__ static void run(const float *erow, const float *orow, int p0, f2 nz,
                                                f2 (&y)[R]) {
-        f2 wo[WO], we[WE];
+        f2 wo[WO], we[WE], acc[R];
 #pragma unroll
-        for (int j = 0; j < WO / 2; j++) lds_2f2(orow + 2 * p0 + 4 * j, wo[2 * j], wo[2 * j + 1]);
+        for (int c = 0; c < NC; c++) {
+#pragma unroll
+            for (int j = 0; j < WO / 2; j++)
+                if (first_chunk(j) == c) lds_2f2(orow + 2 * p0 + 4 * j, wo[2 * j], wo[2 * j + 1]);
+#pragma unroll
+            for (int q = 0; q < R; q++) {
+#pragma unroll
+                for (int i = c * TC; i < (c + 1) * TC && i < M; i++) {
+                    const float ci = HbfTaps<TI>::c(i);
+                    const f2 t = mul2(add2(wo[RO + q + 2 * M - 1 - i], wo[RO + q + i]), pk(ci, ci), nz);
+                    acc[q] = i == 0 ? t : add2(acc[q], t);
+                }
+            }
+        }
 #pragma unroll
         for (int j = 0; j < WE / 2; j++) lds_2f2(erow + 2 * p0 + 4 * j, we[2 * j], we[2 * j + 1]);
 #pragma unroll
-        for (int q = 0; q < R; q++) {
-            const float c0 = HbfTaps<TI>::c(0);
-            f2 acc = mul2(add2(wo[RO + q + 2 * M - 1], wo[RO + q]), pk(c0, c0), nz);
-#pragma unroll
-            for (int i = 1; i < M; i++) {
-                const float ci = HbfTaps<TI>::c(i);
-                acc = add2(acc, mul2(add2(wo[RO + q + 2 * M - 1 - i], wo[RO + q + i]), pk(ci, ci), nz));
-            }
-            y[q] = add2(acc, we[RE + q]);
-        }
+        for (int q = 0; q < R; q++) y[q] = add2(acc[q], we[RE + q]);
     }
 };
 
-// scatter R consecutive packed outputs (p0 multiple of R) into the next stage's E/O rows
-template <int R>
-__device__ __forceinline__ void put_packed(float *e_new, float *o_new, int p0, const f2 (&y)[R]) {
-    // e_new / o_new point at the first NEW element (past the history); output p goes to
-    // element p/2 of the even (p even) or odd (p odd) row, i.e. float offset p0 + ...
+// Scatter R consecutive pair-outputs (p0 multiple of R, R even) of stage s-1 into E_s / O_s.
+// e_row / o_row point at the row heads; H_E / H_O = history elements, NP = new elements per
+// tile.  Output p goes to element p/2 of the even (p even) or odd (p odd) row; first-half
+// results that are history of the second half are written a second time into lane .y.
+template <int R, int HE_, int HO_, int NP>
+__device__ __forceinline__ void put_packed(float *e_row, float *o_row, int p0, const f2 (&y)[R]) {
+    float *e_new = e_row + 2 * HE_ + p0, *o_new = o_row + 2 * HO_ + p0;  // element (p0/2) -> float offset p0
     if constexpr (R == 8) {
-        sts_2f2(e_new + p0, y[0], y[2]);
-        sts_2f2(e_new + p0 + 4, y[4], y[6]);
-        sts_2f2(o_new + p0, y[1], y[3]);
-        sts_2f2(o_new + p0 + 4, y[5], y[7]);
+        sts_2f2(e_new, y[0], y[2]);
+        sts_2f2(e_new + 4, y[4], y[6]);
+        sts_2f2(o_new, y[1], y[3]);
+        sts_2f2(o_new + 4, y[5], y[7]);
     } else if constexpr (R == 4) {
-        sts_2f2(e_new + p0, y[0], y[2]);
-        sts_2f2(o_new + p0, y[1], y[3]);
+        sts_2f2(e_new, y[0], y[2]);
+        sts_2f2(o_new, y[1], y[3]);
     } else {
-        sts_f2(e_new + p0, y[0]);
-        sts_f2(o_new + p0, y[1]);
+        static_assert(R == 2, "R must be 2, 4 or 8");
+        sts_f2(e_new, y[0]);
+        sts_f2(o_new, y[1]);
+    }
+    // u = element index inside the first half; it is also .y history element u + H - NP when >= 0
+    const int u0 = p0 / 2;
+    if (u0 + R / 2 > NP - HE_) {
+#pragma unroll
+        for (int q = 0; q < R; q += 2) {
+            const int i = u0 + q / 2 + HE_ - NP;
+            float a, b;
+            unpk(y[q], a, b);
+            if (i >= 0) e_row[2 * i + 1] = a;
+        }
+    }
+    if (u0 + R / 2 > NP - HO_) {
+#pragma unroll
+        for (int q = 1; q < R; q += 2) {
+            const int i = u0 + q / 2 + HO_ - NP;
+            float a, b;
+            unpk(y[q], a, b);
+            if (i >= 0) o_row[2 * i + 1] = a;
+        }
     }
 }
 
@@ -222,64 +287,91 @@ template <int R> __device__ __forceinline__ void store_out(float *dst, const flo
     }
 }
 
+// Carry one kind of row (E or O) of stage s for all NL lanes: x'[i] = y[i + NP] for i < H,
+// y'[i] = y[i + 2 NP] for i < H - NP.  A whole row is handled inside one warp (one 16-byte
+// piece = 2 elements per thread), everything is read before anything is written.
+template <int H, int NP, int PITCH>
+__device__ __forceinline__ void carry_kind(float *rows, int wsel, int nw, int lid) {
+    constexpr int C = H / 2;  // pieces per row head
+    static_assert(C <= 32 && H % 2 == 0 && NP % 2 == 0, "carry layout");
+    constexpr int LP = C > 16 ? 1 : C > 8 ? 2 : C > 4 ? 4 : 8;  // lanes per warp pass
+    constexpr int CP = 32 / LP;
+    const int sub = lid / CP, j = lid % CP;
+    for (int pass = wsel; pass * LP < NL; pass += nw) {
+        const int lane = pass * LP + sub;
+        const bool act = j < C && lane < NL;
+        float *head = rows + lane * PITCH + 4 * j;
+        float4 p1 = make_float4(0.f, 0.f, 0.f, 0.f), p2 = p1;
+        if (act) {
+            p1 = lds128(head + 2 * NP);
+            if (H > NP && 2 * j < H - NP) p2 = lds128(head + 4 * NP);
+        }
+        __syncwarp();
+        if (act) *reinterpret_cast<float4 *>(head) = make_float4(p1.y, p2.y, p1.w, p2.w);
+        __syncwarp();
+    }
+}
+template <int K, int s>
+__device__ __forceinline__ void carry_rows(float *sm, int wsel, int nw, int lid) {
+    carry_kind<he(K, s), st_np(s), pe(K, s)>(sm + off_e(K, s), wsel, nw, lid);
+    carry_kind<ho(K, s), st_np(s), po(K, s)>(sm + off_o(K, s), wsel, nw, lid);
+}
+
 template <int K, int s> struct StageRun {
+    static constexpr int TI = K - 1 - s;
+    static constexpr int R = st_r(K, s);
+    static constexpr int NP = st_np(s);
+    static constexpr int ITEMS = NL * NP / R;
+    // Warps that hold items of this stage; odd stages take the upper warps so that, over the
+    // CTAs of an SM, every scheduler gets work.  The other warps carry rows s-1 meanwhile.
+    static constexpr int NW = NT / 32;
+    static constexpr int NWA = ITEMS >= NT ? NW : (ITEMS + 31) / 32;
+    static constexpr int W0 = (s & 1) ? NW - NWA : 0;
+
     // runs packed stage s (1 <= s <= K-1) for one tile
     __device__ __forceinline__ static void run(float *sm, int tid, int nl, float *y, size_t ystride,
                                                size_t yoff, size_t lane0, f2 nz) {
-        constexpr int TI = K - 1 - s;
-        constexpr int R = st_r(s);
-        constexpr int ITEMS = NP * st_n(s) / R;
-        const float *E = sm + off_e(K, s);
-        const float *O = sm + off_o(K, s);
-        for (int idx = tid; idx < ITEMS; idx += NT) {
-            const int pr = idx % NP, p0 = (idx / NP) * R;
-            f2 out[R];
-            PackedItem<TI, R>::run(E + pr * pe(K, s), O + pr * po(K, s), p0, nz, out);
-            if constexpr (s == K - 1) {
-                float a[R], b[R];
+        const int vt = tid - 32 * W0;
+        if (vt >= 0 && vt < 32 * NWA) {
+            const float *E = sm + off_e(K, s);
+            const float *O = sm + off_o(K, s);
+            for (int idx = vt; idx < ITEMS; idx += 32 * NWA) {
+                const int lane = idx % NL, p0 = (idx / NL) * R;
+                f2 out[R];
+                PackedItem<TI, R>::run(E + lane * pe(K, s), O + lane * po(K, s), p0, nz, out);
+                if constexpr (s == K - 1) {
+                    float a[R], b[R];
 #pragma unroll
-                for (int q = 0; q < R; q++) unpk(out[q], a[q], b[q]);
-                if (2 * pr < nl) store_out<R>(y + (lane0 + 2 * pr) * ystride + yoff + p0, a);
-                if (2 * pr + 1 < nl) store_out<R>(y + (lane0 + 2 * pr + 1) * ystride + yoff + p0, b);
+                    for (int q = 0; q < R; q++) unpk(out[q], a[q], b[q]);
+                    if (lane < nl) {
+                        float *dst = y + (lane0 + lane) * ystride + yoff + p0;
+                        store_out<R>(dst, a);
+                        store_out<R>(dst + NP, b);
+                    }
+                } else {
+                    put_packed<R, he(K, s + 1), ho(K, s + 1), st_np(s + 1)>(
+                        sm + off_e(K, s + 1) + lane * pe(K, s + 1), sm + off_o(K, s + 1) + lane * po(K, s + 1), p0, out);
+                }
+            }
+        }
+        if constexpr (s >= 2) {  // rows s-1 were consumed in the previous phase
+            const int warp = tid >> 5;
+            if constexpr (NWA < NW) {
+                if (vt < 0 || vt >= 32 * NWA) carry_rows<K, s - 1>(sm, vt < 0 ? warp : warp - NWA, NW - NWA, tid & 31);
             } else {
-                float *En = sm + off_e(K, s + 1) + pr * pe(K, s + 1) + 2 * he(K, s + 1);
-                float *On = sm + off_o(K, s + 1) + pr * po(K, s + 1) + 2 * ho(K, s + 1);
-                put_packed<R>(En, On, p0, out);
+                carry_rows<K, s - 1>(sm, warp, NW, tid & 31);
             }
         }
     }
 };
 
-// move the tail of a [H hist | N new] row (in floats) to its head; one thread per row
-template <int H, int N> __device__ __forceinline__ void carry_row(float *row) {
-    float t[H];
-#pragma unroll
-    for (int j = 0; j < H / 4; j++) {
-        float4 v = lds128(row + N + 4 * j);
-        t[4 * j] = v.x; t[4 * j + 1] = v.y; t[4 * j + 2] = v.z; t[4 * j + 3] = v.w;
-    }
-#pragma unroll
-    for (int j = 0; j < H / 4; j++)
-        reinterpret_cast<float4 *>(row)[j] = make_float4(t[4 * j], t[4 * j + 1], t[4 * j + 2], t[4 * j + 3]);
-}
-
-template <int K, int s> struct Carry {
-    __device__ __forceinline__ static void run(float *sm, int job, int pr) {
-        if constexpr (s < K) {
-            if (job == 2 * (s - 1))
-                carry_row<2 * he(K, s), 2 * st_n(s)>(sm + off_e(K, s) + pr * pe(K, s));
-            else if (job == 2 * (s - 1) + 1)
-                carry_row<2 * ho(K, s), 2 * st_n(s)>(sm + off_o(K, s) + pr * po(K, s));
-            else
-                Carry<K, s + 1>::run(sm, job, pr);
-        }
-    }
-};
-
-// ABI state <-> shared-memory histories (see header comment of include/idsp_b200.h)
+// ABI state <-> shared-memory histories (see header comment of include/idsp_b200.h).
+// Raw history lives at row[roff .. roff+HR): roff = 0 (head) on entry, TT (tail of the last
+// tile) on exit.  Packed rows: word w of a history of Mh values is lane .x of head element
+// H - Mh + w and, on entry, also lane .y of element H - Mh + w - NP when that is >= 0.
 template <int K, int s, bool LOAD> struct StateIO {
     __device__ __forceinline__ static void run(float *sm, float *st, size_t sstride, size_t lane0, int nl,
-                                               int tid, int rawbuf) {
+                                               int tid, int rawbuf, int roff) {
         if constexpr (s < K) {
             constexpr int M = st_m(K, s);
             constexpr int LEN = 2 * M - 1;
@@ -288,30 +380,36 @@ template <int K, int s, bool LOAD> struct StateIO {
             for (int idx = tid; idx < WORDS * NL; idx += NT) {
                 const int lane = idx % NL, w = idx / NL;
                 if (lane >= nl) continue;
-                float *p;
                 if constexpr (s == 0) {
                     constexpr int HR = raw_h(K);
-                    float *row = sm + (rawbuf * NL + lane) * raw_pitch(K);
-                    p = w < M - 1 ? row + (HR - 2 * M + 2 + 2 * w) : row + (HR - 4 * M + 3 + 2 * (w - (M - 1)));
+                    float *row = sm + (rawbuf * NL + lane) * raw_pitch(K) + roff;
+                    float *p = w < M - 1 ? row + (HR - 2 * M + 2 + 2 * w) : row + (HR - 4 * M + 3 + 2 * (w - (M - 1)));
+                    if constexpr (LOAD) *p = stw[(size_t)w * sstride + lane];
+                    else stw[(size_t)w * sstride + lane] = *p;
                 } else {
-                    const int pr = lane >> 1, c = lane & 1;
-                    p = w < M - 1 ? sm + off_e(K, s) + pr * pe(K, s) + 2 * (he(K, s) - (M - 1) + w) + c
-                                  : sm + off_o(K, s) + pr * po(K, s) + 2 * (ho(K, s) - LEN + (w - (M - 1))) + c;
+                    constexpr int NP = st_np(s);
+                    float *row = w < M - 1 ? sm + off_e(K, s) + lane * pe(K, s) : sm + off_o(K, s) + lane * po(K, s);
+                    const int e = w < M - 1 ? he(K, s) - (M - 1) + w : ho(K, s) - LEN + (w - (M - 1));
+                    if constexpr (LOAD) {
+                        const float v = stw[(size_t)w * sstride + lane];
+                        row[2 * e] = v;
+                        if (e - NP >= 0) row[2 * (e - NP) + 1] = v;
+                    } else {
+                        stw[(size_t)w * sstride + lane] = row[2 * e];
+                    }
                 }
-                if constexpr (LOAD) *p = stw[(size_t)w * sstride + lane];
-                else stw[(size_t)w * sstride + lane] = *p;
             }
-            StateIO<K, s + 1, LOAD>::run(sm, st, sstride, lane0, nl, tid, rawbuf);
+            StateIO<K, s + 1, LOAD>::run(sm, st, sstride, lane0, nl, tid, rawbuf, roff);
         }
     }
 };
 
 template <int K>
-__global__ void __launch_bounds__(NT, 2)
+__global__ void __launch_bounds__(NT, HF_MINB)
 hbf_dec_fast_kernel(float *st, const float *x, float *y, size_t n_out, size_t ntiles, size_t lanes,
                     size_t sstride, f2 nz /* (-0.0f, -0.0f), see mul2() */) {
     constexpr int TI0 = K - 1;
-    constexpr int R0 = st_r(0);
+    constexpr int R0 = st_r(K, 0);
     constexpr int HR = raw_h(K);
     constexpr int PR = raw_pitch(K);
     constexpr int TO = TT >> K;
@@ -330,18 +428,23 @@ hbf_dec_fast_kernel(float *st, const float *x, float *y, size_t n_out, size_t nt
         mbar_fence_init();
     }
     __syncthreads();
-    StateIO<K, 0, true>::run(sm, st, sstride, lane0, nl, tid, 0);
+    StateIO<K, 0, true>::run(sm, st, sstride, lane0, nl, tid, 0, 0);
     // generic-proxy writes above (zero fill) precede async-proxy (TMA) writes to the same rows
     fence_async_smem();
     __syncthreads();
 
+    // Tile t >= 1 is fetched together with the HR samples in front of it (they are in L2 from
+    // the previous tile), so the raw history never has to be copied between ring buffers;
+    // tile 0 takes its history from the ABI state (scattered into buffer 0 above).
     auto issue = [&](size_t tile) {  // executed by warp 0
         const int b = (int)(tile % S);
         const uint32_t bar = smem_u32(&bars[b]);
-        if ((tid & 31) == 0) mbar_expect_tx(bar, (uint32_t)(nl * TT * 4));
+        const uint32_t hist = tile ? HR : 0;
+        if ((tid & 31) == 0) mbar_expect_tx(bar, (uint32_t)(nl * (TT + hist) * 4));
         __syncwarp();
         if (tid < nl)
-            bulk_load_1d(smem_u32(sm + (b * NL + tid) * PR + HR), x + (lane0 + tid) * n_in + tile * TT, TT * 4, bar);
+            bulk_load_1d(smem_u32(sm + (b * NL + tid) * PR + HR - hist),
+                         x + (lane0 + tid) * n_in + tile * TT - hist, (TT + hist) * 4, bar);
     };
     if (tid < 32) {
 #pragma unroll
@@ -352,10 +455,10 @@ hbf_dec_fast_kernel(float *st, const float *x, float *y, size_t n_out, size_t nt
     for (size_t i = 0; i < ntiles; i++) {
         const int b = (int)(i % S);
         mbar_wait(smem_u32(&bars[b]), (uint32_t)((i / S) & 1));
-        // ---- stage 0: raw interleaved (scalar FP32)
+        // ---- phase 0: raw interleaved stream (scalar FP32)
         {
             const float *raw = sm + b * NL * PR;
-            if constexpr (K == 1) {  // single stage: straight to HBM, one lane per item
+            if constexpr (K == 1) {  // single stage: straight to HBM
                 constexpr int ITEMS = NL * st_n(0) / R0;
                 for (int idx = tid; idx < ITEMS; idx += NT) {
                     const int lane = idx % NL, p0 = (idx / NL) * R0;
@@ -363,55 +466,44 @@ hbf_dec_fast_kernel(float *st, const float *x, float *y, size_t n_out, size_t nt
                     RawItem<TI0, R0>::run(raw + lane * PR, p0, out);
                     if (lane < nl) store_out<R0>(y + (lane0 + lane) * n_out + i * TO + p0, out);
                 }
-            } else {  // both lanes of a pair -> packed E_1 / O_1
-                constexpr int ITEMS = NP * st_n(0) / R0;
+            } else {  // same positions of both tile halves -> packed E_1 / O_1
+                constexpr int ITEMS = NL * st_np(0) / R0;
                 for (int idx = tid; idx < ITEMS; idx += NT) {
-                    const int pr = idx % NP, p0 = (idx / NP) * R0;
+                    const int lane = idx % NL, p0 = (idx / NL) * R0;
                     float a[R0], bb[R0];
-                    RawItem<TI0, R0>::run(raw + (2 * pr) * PR, p0, a);
-                    RawItem<TI0, R0>::run(raw + (2 * pr + 1) * PR, p0, bb);
+                    RawItem<TI0, R0>::run(raw + lane * PR, p0, a);
+                    RawItem<TI0, R0>::run(raw + lane * PR + TT / 2, p0, bb);
                     f2 out[R0];
 #pragma unroll
                     for (int q = 0; q < R0; q++) out[q] = pk(a[q], bb[q]);
-                    float *En = sm + off_e(K, 1) + pr * pe(K, 1) + 2 * he(K, 1);
-                    float *On = sm + off_o(K, 1) + pr * po(K, 1) + 2 * ho(K, 1);
-                    put_packed<R0>(En, On, p0, out);
+                    put_packed<R0, he(K, 1), ho(K, 1), st_np(1)>(sm + off_e(K, 1) + lane * pe(K, 1),
+                                                                 sm + off_o(K, 1) + lane * po(K, 1), p0, out);
+                }
+                // rows K-1 of the previous tile (last read in its final phase, next written in phase K-2 >= 1)
+                if constexpr (K >= 3) {
+                    if (i > 0) carry_rows<K, K - 1>(sm, tid >> 5, NT / 32, tid & 31);
                 }
             }
         }
         __syncthreads();
-        // ---- raw history: tail of buffer b -> head of the next buffer, then refill buffer b
-        if (tid < 32) {
-            if (tid < NL) {
-                float *src = sm + (b * NL + tid) * PR;
-                float *dst = sm + (((b + 1) % S) * NL + tid) * PR;
-                float t[HR];
-#pragma unroll
-                for (int j = 0; j < HR / 4; j++) {
-                    float4 v = lds128(src + TT + 4 * j);
-                    t[4 * j] = v.x; t[4 * j + 1] = v.y; t[4 * j + 2] = v.z; t[4 * j + 3] = v.w;
-                }
-#pragma unroll
-                for (int j = 0; j < HR / 4; j++)
-                    reinterpret_cast<float4 *>(dst)[j] = make_float4(t[4 * j], t[4 * j + 1], t[4 * j + 2], t[4 * j + 3]);
-            }
-            __syncwarp();
-            if (i + S < ntiles) issue(i + S);
-        }
-        // ---- packed stages 1 .. K-1
+        // ---- raw buffer b is free again: refill it
+        if (tid < 32 && i + S < ntiles) issue(i + S);
+        // ---- packed phases 1 .. K-1 (phase s also carries rows s-1)
         if constexpr (K >= 2) { StageRun<K, 1>::run(sm, tid, nl, y, n_out, i * TO, lane0, nz); __syncthreads(); }
         if constexpr (K >= 3) { StageRun<K, 2>::run(sm, tid, nl, y, n_out, i * TO, lane0, nz); __syncthreads(); }
         if constexpr (K >= 4) { StageRun<K, 3>::run(sm, tid, nl, y, n_out, i * TO, lane0, nz); __syncthreads(); }
         if constexpr (K >= 5) { StageRun<K, 4>::run(sm, tid, nl, y, n_out, i * TO, lane0, nz); __syncthreads(); }
-        // ---- carry the E/O histories (one thread per row)
-        if constexpr (K >= 2) {
-            for (int idx = tid; idx < 2 * (K - 1) * NP; idx += NT) Carry<K, 1>::run(sm, idx / NP, idx % NP);
+        if constexpr (K == 2) {  // rows 1 are written again in the very next phase: carry them now
+            carry_rows<K, 1>(sm, tid >> 5, NT / 32, tid & 31);
+            __syncthreads();
         }
-        // also orders warp 0's raw-history copy before the next tile's stage 0
+    }
+    if constexpr (K >= 3) {
+        carry_rows<K, K - 1>(sm, tid >> 5, NT / 32, tid & 31);
         __syncthreads();
     }
-    // raw history of the stream now sits at the head of buffer (ntiles % S)
-    StateIO<K, 0, false>::run(sm, st, sstride, lane0, nl, tid, (int)(ntiles % S));
+    // the raw history of the stream is the tail of the last tile's buffer
+    StateIO<K, 0, false>::run(sm, st, sstride, lane0, nl, tid, (int)((ntiles - 1) % S), TT);
 }
 
 template <int K>

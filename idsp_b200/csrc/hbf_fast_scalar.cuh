@@ -46,7 +46,10 @@ constexpr int NL = HFS_NL;  // lanes per CTA (multiple of 8)
 #define HFS_NT 128
 #endif
 constexpr int NT = HFS_NT;  // threads per CTA
-constexpr int TT = 512;   // raw input samples per lane per tile
+#ifndef HFS_TT
+#define HFS_TT 512
+#endif
+constexpr int TT = HFS_TT;  // raw input samples per lane per tile
 constexpr int S = 2;      // raw ring depth
 
 __host__ __device__ constexpr int up4(int v) { return (v + 3) & ~3; }
@@ -203,11 +206,12 @@ __device__ __forceinline__ void carry_rows(float *sm, int wsel, int nw, int lid)
     constexpr int LP = 32 / C;  // lanes per warp pass
     static_assert(C <= 32, "row history too long for one warp");
     const int sub = lid / C, j = lid % C;
-    for (int pass = wsel; pass * LP < NL; pass += nw) {
-        const int lane = pass * LP + sub;
+    const bool odd = j >= CE;
+    const int pitch = odd ? po(K, s) : pe(K, s);
+    int lane = wsel * LP + sub;
+    float *row = sm + (odd ? off_o(K, s) + 4 * (j - CE) : off_e(K, s) + 4 * j) + lane * pitch;
+    for (; lane - sub < NL; lane += nw * LP, row += nw * LP * pitch) {  // lane - sub is warp-uniform
         const bool act = sub < LP && lane < NL;
-        float *row = j < CE ? sm + off_e(K, s) + lane * pe(K, s) + 4 * j
-                            : sm + off_o(K, s) + lane * po(K, s) + 4 * (j - CE);
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (act) v = lds128(row + st_n(s));
         __syncwarp();
