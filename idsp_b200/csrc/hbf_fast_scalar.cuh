@@ -265,9 +265,13 @@ template <int K, int s> struct StageRun {
     static constexpr int NWA = ITEMS >= NT ? NW : (ITEMS + 31) / 32;
     static constexpr int W0 = (s & 1) ? NW - NWA : 0;
 
-    // runs stage s (1 <= s <= K-1) for one tile
+    static constexpr int NIDLE = 32 * (NW - NWA);  // threads without items in this phase
+
+    // runs stage s (1 <= s <= K-1) for one tile; `idle(gt, NIDLE)` is extra work for the
+    // threads of the warps that hold no items (after they carried rows s-1)
+    template <class F>
     __device__ __forceinline__ static void run(float *sm, int tid, int nl, float *y, size_t ystride,
-                                               size_t yoff, size_t lane0) {
+                                               size_t yoff, size_t lane0, F &&idle) {
         const int vt = tid - 32 * W0;
         if (vt >= 0 && vt < 32 * NWA) {
             for (int idx = vt; idx < ITEMS; idx += 32 * NWA) {
@@ -289,13 +293,24 @@ template <int K, int s> struct StageRun {
         if constexpr (s >= 2) {  // rows s-1 were consumed in the previous phase
             const int warp = tid >> 5;
             if constexpr (NWA < NW) {
-                if (vt < 0 || vt >= 32 * NWA) carry_rows<K, s - 1>(sm, vt < 0 ? warp : warp - NWA, NW - NWA, tid & 31);
+                if (vt < 0 || vt >= 32 * NWA) {
+                    const int iw = vt < 0 ? warp : warp - NWA;  // index among the idle warps
+                    carry_rows<K, s - 1>(sm, iw, NW - NWA, tid & 31);
+                    idle(32 * iw + (tid & 31), NIDLE);
+                }
             } else {
                 carry_rows<K, s - 1>(sm, warp, NW, tid & 31);
             }
         }
     }
+    __device__ __forceinline__ static void run(float *sm, int tid, int nl, float *y, size_t ystride,
+                                               size_t yoff, size_t lane0) {
+        run(sm, tid, nl, y, ystride, yoff, lane0, [](int, int) {});
+    }
 };
+
+// barrier among the `count` threads of the idle warps of a phase (id 1; id 0 is __syncthreads)
+__device__ __forceinline__ void bar_idle(int count) { asm volatile("bar.sync 1, %0;" ::"r"(count) : "memory"); }
 
 // ABI state <-> shared-memory histories (see header comment of include/idsp_b200.h)
 template <int K, int s, bool LOAD> struct StateIO {
@@ -376,52 +391,88 @@ hbf_dec_fast_kernel(float *st, const float *x, float *y, size_t n_out, size_t nt
             if ((size_t)b < ntiles) issue(b);
     }
 
-    for (size_t i = 0; i < ntiles; i++) {
-        const int b = (int)(i % S);
-        mbar_wait(smem_u32(&bars[b]), (uint32_t)((i / S) & 1));
-        // ---- phase 0: raw interleaved -> E_1 / O_1 (or -> y when K == 1)
-        {
-            const float *raw = sm + b * NL * PR;
-            constexpr int ITEMS = NL * st_n(0) / R0;
-            for (int idx = tid; idx < ITEMS; idx += NT) {
-                const int lane = idx % NL, p0 = (idx / NL) * R0;
-                float out[R0];
-                RawItem<TI0, R0>::run(raw + lane * PR, p0, out);
-                if constexpr (K == 1) {
-                    if (lane < nl) {
-                        float *dst = y + (lane0 + lane) * n_out + i * TO + p0;
-                        if ((((uintptr_t)dst) & 15) == 0) {
+    // stage 0 of tile `t`: items [c0, c1) spread over the `G` threads of a group (gt = index in it)
+    constexpr int ITEMS0 = NL * st_n(0) / R0;
+    auto stage0 = [&](size_t t, int c0, int c1, int gt, int G) {
+        const int b = (int)(t % S);
+        mbar_wait(smem_u32(&bars[b]), (uint32_t)((t / S) & 1));
+        const float *raw = sm + b * NL * PR;
+        for (int idx = c0 + gt; idx < c1; idx += G) {
+            const int lane = idx % NL, p0 = (idx / NL) * R0;
+            float out[R0];
+            RawItem<TI0, R0>::run(raw + lane * PR, p0, out);
+            if constexpr (K == 1) {
+                if (lane < nl) {
+                    float *dst = y + (lane0 + lane) * n_out + t * TO + p0;
+                    if ((((uintptr_t)dst) & 15) == 0) {
 #pragma unroll
-                            for (int j = 0; j < R0 / 4; j++)
-                                reinterpret_cast<float4 *>(dst)[j] =
-                                    make_float4(out[4 * j], out[4 * j + 1], out[4 * j + 2], out[4 * j + 3]);
-                        } else {
+                        for (int j = 0; j < R0 / 4; j++)
+                            reinterpret_cast<float4 *>(dst)[j] =
+                                make_float4(out[4 * j], out[4 * j + 1], out[4 * j + 2], out[4 * j + 3]);
+                    } else {
 #pragma unroll
-                            for (int j = 0; j < R0; j++) dst[j] = out[j];
-                        }
+                        for (int j = 0; j < R0; j++) dst[j] = out[j];
                     }
-                } else {
-                    float *En = sm + off_e(K, 1) + lane * pe(K, 1) + he(K, 1);
-                    float *On = sm + off_o(K, 1) + lane * po(K, 1) + ho(K, 1);
-                    put_split<R0>(En, On, p0, out);
                 }
+            } else {
+                float *En = sm + off_e(K, 1) + lane * pe(K, 1) + he(K, 1);
+                float *On = sm + off_o(K, 1) + lane * po(K, 1) + ho(K, 1);
+                put_split<R0>(En, On, p0, out);
             }
+        }
+    };
+
+    // K >= 4: the warps without items in the low-rate phases 2 and 3 run stage 0 of the NEXT tile
+    // there (its raw data is already in the ring), so in steady state there is no stage-0 phase,
+    // all warps are busy in every phase and a tile costs K-1 barriers.
+    constexpr bool PF = K >= 4 && StageRun<K, 2>::NIDLE > 0 && StageRun<K, 3>::NIDLE > 0 &&
+                        StageRun<K, 2>::NIDLE + StageRun<K, 3>::NIDLE >= ITEMS0;
+    if constexpr (PF) {
+        stage0(0, 0, ITEMS0, tid, NT);
+        __syncthreads();
+        if (tid < 32 && (size_t)S < ntiles) issue(S);
+    }
+    for (size_t i = 0; i < ntiles; i++) {
+        if constexpr (!PF) {
+            // ---- phase 0: raw interleaved -> E_1 / O_1 (or -> y when K == 1)
+            stage0(i, 0, ITEMS0, tid, NT);
             // rows K-1 of the previous tile (last read in its final phase, next written in phase K-2 >= 1)
             if constexpr (K >= 3) {
                 if (i > 0) carry_rows<K, K - 1>(sm, tid >> 5, NT / 32, tid & 31);
             }
-        }
-        __syncthreads();
-        // ---- raw buffer b is free again: refill it
-        if (tid < 32 && i + S < ntiles) issue(i + S);
-        // ---- phases 1 .. K-1 (phase s also carries rows s-1)
-        if constexpr (K >= 2) { StageRun<K, 1>::run(sm, tid, nl, y, n_out, i * TO, lane0); __syncthreads(); }
-        if constexpr (K >= 3) { StageRun<K, 2>::run(sm, tid, nl, y, n_out, i * TO, lane0); __syncthreads(); }
-        if constexpr (K >= 4) { StageRun<K, 3>::run(sm, tid, nl, y, n_out, i * TO, lane0); __syncthreads(); }
-        if constexpr (K >= 5) { StageRun<K, 4>::run(sm, tid, nl, y, n_out, i * TO, lane0); __syncthreads(); }
-        if constexpr (K == 2) {  // rows 1 are written again in the very next phase: carry them now
-            carry_rows<K, 1>(sm, tid >> 5, NT / 32, tid & 31);
             __syncthreads();
+            // ---- raw buffer b is free again: refill it
+            if (tid < 32 && i + S < ntiles) issue(i + S);
+            // ---- phases 1 .. K-1 (phase s also carries rows s-1)
+            if constexpr (K >= 2) { StageRun<K, 1>::run(sm, tid, nl, y, n_out, i * TO, lane0); __syncthreads(); }
+            if constexpr (K >= 3) { StageRun<K, 2>::run(sm, tid, nl, y, n_out, i * TO, lane0); __syncthreads(); }
+            if constexpr (K >= 4) { StageRun<K, 3>::run(sm, tid, nl, y, n_out, i * TO, lane0); __syncthreads(); }
+            if constexpr (K >= 5) { StageRun<K, 4>::run(sm, tid, nl, y, n_out, i * TO, lane0); __syncthreads(); }
+            if constexpr (K == 2) {  // rows 1 are written again in the very next phase: carry them now
+                carry_rows<K, 1>(sm, tid >> 5, NT / 32, tid & 31);
+                __syncthreads();
+            }
+        } else {
+            constexpr int H0 = StageRun<K, 2>::NIDLE < ITEMS0 ? StageRun<K, 2>::NIDLE : ITEMS0;  // items done in phase 2
+            const bool more = i + 1 < ntiles;
+            // ---- phase 1: stage 1, then rows K-1 of the previous tile (next written in phase K-2 >= 2)
+            StageRun<K, 1>::run(sm, tid, nl, y, n_out, i * TO, lane0);
+            if (i > 0) carry_rows<K, K - 1>(sm, tid >> 5, NT / 32, tid & 31);
+            __syncthreads();
+            // ---- phase 2: stage 2 | carry rows 1, then first part of stage 0 of tile i+1 (writes rows 1)
+            StageRun<K, 2>::run(sm, tid, nl, y, n_out, i * TO, lane0, [&](int gt, int G) {
+                bar_idle(G);  // every row-1 tail has been carried before any is overwritten
+                if (more) stage0(i + 1, 0, H0, gt, G);
+            });
+            __syncthreads();
+            // ---- phase 3: stage 3 | carry rows 2, rest of stage 0 of tile i+1
+            StageRun<K, 3>::run(sm, tid, nl, y, n_out, i * TO, lane0, [&](int gt, int G) {
+                if (more) stage0(i + 1, H0, ITEMS0, gt, G);
+            });
+            __syncthreads();
+            if constexpr (K >= 5) { StageRun<K, 4>::run(sm, tid, nl, y, n_out, i * TO, lane0); __syncthreads(); }
+            // ---- the raw buffer of tile i+1 is free again: refill it
+            if (tid < 32 && i + 1 + S < ntiles) issue(i + 1 + S);
         }
     }
     if constexpr (K >= 3) {
