@@ -375,21 +375,28 @@ hbf_dec_fast_kernel(float *st, const float *x, float *y, size_t n_out, size_t nt
     // Tile t >= 1 is fetched together with the HR samples in front of it (they are in L2 from
     // the previous tile), so the raw history never has to be copied between ring buffers;
     // tile 0 takes its history from the ABI state (scattered into buffer 0 above).
-    auto issue = [&](size_t tile) {  // executed by warp 0
-        const int b = (int)(tile % S);
-        const uint32_t bar = smem_u32(&bars[b]);
-        const uint32_t hist = tile ? HR : 0;
-        if ((tid & 31) == 0) mbar_expect_tx(bar, (uint32_t)(nl * (TT + hist) * 4));
-        __syncwarp();
-        if (tid < nl)
-            bulk_load_1d(smem_u32(sm + (b * NL + tid) * PR + HR - hist),
-                         x + (lane0 + tid) * n_in + tile * TT - hist, (TT + hist) * 4, bar);
-    };
-    if (tid < 32) {
+    // Executed by every warp: lane 0 of warp w issues the rows of lanes w*LPW .. (NL/NW rows each), so
+    // no warp is held up by a serial chain of NL bulk copies (complete_tx may precede the
+    // expect_tx of thread 0: the phase cannot complete before that arrival).
+    auto issue = [&](size_t tile) {
+        if ((tid & 31) == 0) {
+            constexpr int LPW = (NL + NT / 32 - 1) / (NT / 32);
+            const int b = (int)(tile % S);
+            const uint32_t bar = smem_u32(&bars[b]);
+            const uint32_t hist = tile ? HR : 0;
+            if (tid == 0) mbar_expect_tx(bar, (uint32_t)(nl * (TT + hist) * 4));
 #pragma unroll
-        for (int b = 0; b < S; b++)
-            if ((size_t)b < ntiles) issue(b);
-    }
+            for (int j = 0; j < LPW; j++) {
+                const int l = (tid >> 5) * LPW + j;
+                if (l < nl)
+                    bulk_load_1d(smem_u32(sm + (b * NL + l) * PR + HR - hist),
+                                 x + (lane0 + l) * n_in + tile * TT - hist, (TT + hist) * 4, bar);
+            }
+        }
+    };
+#pragma unroll
+    for (int b = 0; b < S; b++)
+        if ((size_t)b < ntiles) issue(b);
 
     // stage 0 of tile `t`: items [c0, c1) spread over the `G` threads of a group (gt = index in it)
     constexpr int ITEMS0 = NL * st_n(0) / R0;
@@ -430,7 +437,7 @@ hbf_dec_fast_kernel(float *st, const float *x, float *y, size_t n_out, size_t nt
     if constexpr (PF) {
         stage0(0, 0, ITEMS0, tid, NT);
         __syncthreads();
-        if (tid < 32 && (size_t)S < ntiles) issue(S);
+        if ((size_t)S < ntiles) issue(S);
     }
     for (size_t i = 0; i < ntiles; i++) {
         if constexpr (!PF) {
@@ -442,7 +449,7 @@ hbf_dec_fast_kernel(float *st, const float *x, float *y, size_t n_out, size_t nt
             }
             __syncthreads();
             // ---- raw buffer b is free again: refill it
-            if (tid < 32 && i + S < ntiles) issue(i + S);
+            if (i + S < ntiles) issue(i + S);
             // ---- phases 1 .. K-1 (phase s also carries rows s-1)
             if constexpr (K >= 2) { StageRun<K, 1>::run(sm, tid, nl, y, n_out, i * TO, lane0); __syncthreads(); }
             if constexpr (K >= 3) { StageRun<K, 2>::run(sm, tid, nl, y, n_out, i * TO, lane0); __syncthreads(); }
@@ -472,7 +479,7 @@ hbf_dec_fast_kernel(float *st, const float *x, float *y, size_t n_out, size_t nt
             __syncthreads();
             if constexpr (K >= 5) { StageRun<K, 4>::run(sm, tid, nl, y, n_out, i * TO, lane0); __syncthreads(); }
             // ---- the raw buffer of tile i+1 is free again: refill it
-            if (tid < 32 && i + 1 + S < ntiles) issue(i + 1 + S);
+            if (i + 1 + S < ntiles) issue(i + 1 + S);
         }
     }
     if constexpr (K >= 3) {
