@@ -51,6 +51,14 @@ def biquad_coeffs():
     return Biquad.from_ba6(Filter().critical_frequency(0.01).lowpass(), Q32(F_BITS))
 
 
+def host_threads():
+    """host cores this process may use (torchrun exports OMP_NUM_THREADS=1, so do not ask OpenMP)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def peak_hbm():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -212,7 +220,7 @@ def run_reference(args):
     import oracle as O
 
     O.build()
-    threads = O.max_threads()
+    threads = host_threads()
     wl = args.workload
     # per-step sample ~2 s of CPU work so K steps + W warm-up stay within minutes
     if wl == "biquad":
@@ -326,7 +334,7 @@ def run_lockin(args, rank, world, local):
     xs = xin[0].view(frames, lanes)[:, :sub].contiguous().cpu().numpy().reshape(-1)
     a0 = np.zeros(sub, np.int32)
     so = np.zeros((4, sub), np.int64)
-    want = O.lockin_lanes(LOCKIN_K, a0, step_t[:sub].cpu().numpy(), so, xs, sub, 0, nthreads=O.max_threads())
+    want = O.lockin_lanes(LOCKIN_K, a0, step_t[:sub].cpu().numpy(), so, xs, sub, 0, nthreads=host_threads())
     got = iq[0].view(frames, lanes, 2)[:, :sub].contiguous().cpu().numpy().reshape(-1)
     if not np.array_equal(got, want):
         raise SystemExit("bench: GPU lock-in output differs from the oracle -- refusing to report a number")
@@ -445,7 +453,7 @@ def run_biquad(args, rank, world, local):
         xs = xin[0].view(lanes, frames)[:sub].contiguous().cpu().numpy()
         got = yout[0].view(lanes, frames)[:sub].contiguous().cpu().numpy().reshape(-1)
     so = np.zeros((4, sub), np.int32)
-    want = O.biquad_lanes("df1", "i32", bq.ba, F_BITS, None, so, xs.reshape(-1), sub, layout, nthreads=O.max_threads())
+    want = O.biquad_lanes("df1", "i32", bq.ba, F_BITS, None, so, xs.reshape(-1), sub, layout, nthreads=host_threads())
     if not np.array_equal(got, want) or not np.array_equal(st.numpy()[:, :sub], so):
         raise SystemExit("bench: GPU output differs from the oracle -- refusing to report a number")
 
@@ -495,7 +503,7 @@ def run_biquad(args, rank, world, local):
     peak, peak_src = peak_hbm()
     per_launch_bytes = 8.0 * n  # 4 B read + 4 B written per sample; state/coeff traffic ~0
     achieved = per_launch_bytes * launches / (ms * 1e-3) / 1e9 if launches else 0.0
-    cpu_v, cpu_dt, cpu_sample = cpu_calibrated("biquad", O.max_threads(), args.cpu_seconds)
+    cpu_v, cpu_dt, cpu_sample = cpu_calibrated("biquad", host_threads(), args.cpu_seconds) if world == 1 else (None, None, "measured at N=1 only")
     line = {
         "metric": metric_name("biquad"), "value": value, "unit": "GSa/s", "n_gpus": world, "steps": steps,
         "warmup": args.warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
@@ -504,7 +512,7 @@ def run_biquad(args, rank, world, local):
                      "traffic": traffic_from_profiles("biquad_df1_i32_fm_bytes_per_launch"),
                      "peak_source": peak_src, "kernel": "tma_lanes_kernel<Df1Op<int,false,1>> (frame-major: 256-lane x 8-frame TMA boxes)" if layout == 0 else "tma_lanes_kernel<Df1Op<int,false,1>> (lane-major: swizzled 16-frame x 32-lane TMA boxes)",
                      "algorithmic_bytes_per_launch": per_launch_bytes},
-        "cpu_baseline": {"value": cpu_v, "unit": "GSa/s", "cores": O.max_threads(), "kind": "port",
+        "cpu_baseline": {"value": cpu_v, "unit": "GSa/s", "cores": host_threads(), "kind": "port",
                          "sample": cpu_sample, "seconds": cpu_dt},
         "e2e": {"value": e2e, "unit": "GSa/s", "h2d_bytes_per_step": 4 * ef * lanes, "d2h_bytes_per_step": 4 * ef * lanes,
                 "frames_per_step": ef, "steps": esteps, "api": "idsp_biquad_df1_i32_host (pinned host buffers)"},
@@ -552,7 +560,7 @@ def run_hbf(args, rank, world, local):
     sub = 32
     xs = xin[0].view(lanes_s, HBF_INPUTS)[:sub].contiguous().cpu().numpy().reshape(-1)
     so = np.zeros((O.hbf_dec_state_words(4), sub), np.float32)
-    want = O.hbf_dec_cascade_lanes(4, so, xs, sub, 1, nthreads=O.max_threads())
+    want = O.hbf_dec_cascade_lanes(4, so, xs, sub, 1, nthreads=host_threads())
     got = yout[0].view(lanes_s, n_out)[:sub].contiguous().cpu().numpy().reshape(-1)
     if not np.array_equal(got.view(np.uint32), want.view(np.uint32)):
         raise SystemExit("bench: GPU HBF output differs from the oracle -- refusing to report a number")
@@ -599,7 +607,7 @@ def run_hbf(args, rank, world, local):
     peak, peak_src = peak_hbm()
     per_launch_bytes = 4.25 * n_in
     achieved = per_launch_bytes * launches / (ms * 1e-3) / 1e9 if launches else 0.0
-    cpu_v, cpu_dt, cpu_sample = cpu_calibrated("hbf", O.max_threads(), args.cpu_seconds)
+    cpu_v, cpu_dt, cpu_sample = cpu_calibrated("hbf", host_threads(), args.cpu_seconds) if world == 1 else (None, None, "measured at N=1 only")
     line = {
         "metric": metric_name("hbf"), "value": value, "unit": "GSa/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -607,7 +615,7 @@ def run_hbf(args, rank, world, local):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic_from_profiles("hbf_dec16_f32_lm_bytes_per_launch"), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": per_launch_bytes},
-        "cpu_baseline": {"value": cpu_v, "unit": "GSa/s", "cores": O.max_threads(), "kind": "port",
+        "cpu_baseline": {"value": cpu_v, "unit": "GSa/s", "cores": host_threads(), "kind": "port",
                          "sample": cpu_sample, "seconds": cpu_dt},
         "e2e": {"value": e2e, "unit": "GSa/s", "h2d_bytes_per_step": 4 * el * HBF_INPUTS, "d2h_bytes_per_step": 4 * el * n_out,
                 "steps": esteps, "api": "idsp_hbf_dec_cascade_f32_host (pinned host buffers)"},

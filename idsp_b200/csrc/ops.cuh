@@ -312,6 +312,37 @@ __device__ __forceinline__ void cossin_dev(const uint32_t *lut, int32_t phase, i
     so = s;
 }
 
+// Same function on a pre-expanded table: entry i of the staged shared-memory table holds
+// c14 = ((lut & 0xffff) + 65536) << 14 and s15 = (lut >> 16) << 15, i.e. the two values the
+// reference forms before the interpolation (src/cossin.rs:44-60).  With d10 = dphi << 10,
+//   (s * dphi) >> 7 == (s15 * d10) >> 32   and   (c * dphi) >> 8 == (c14 * d10) >> 32
+// exactly (floor of the same rational; |d10| < 2^24, c14 < 2^31), so each correction is one
+// IMAD.HI and the unpack / shift instructions disappear.  Bit-exact with cossin_dev
+// (tests/test_gpu_nco.py sweeps it against the oracle).
+__device__ __forceinline__ void cossin_expand_lut(const uint32_t *lut, uint32_t *table, int tid, int nthreads) {
+    for (int i = tid; i < 128; i += nthreads) {
+        const uint32_t w = lut[i];
+        table[2 * i] = ((w & 0xffffu) + 65536u) << 14;
+        table[2 * i + 1] = (w >> 16) << 15;
+    }
+}
+__device__ __forceinline__ void cossin_dev_x(const uint32_t *table, int32_t phase, int32_t &co, int32_t &so) {
+    uint32_t octant = (uint32_t)phase;
+    if (octant & (1u << 29)) phase = ~phase;
+    const uint32_t ph = (((uint32_t)phase) << 3) >> 10;
+    const uint2 e = *reinterpret_cast<const uint2 *>(table + 2 * (ph >> 15));
+    const int32_t frac = (int32_t)(ph & 0x7fffu) - (1 << 14);
+    const int32_t d10 = ((frac * 51471) >> 6) & ~0x3ff;
+    int32_t c = (int32_t)e.x - __mulhi((int32_t)e.y, d10);
+    int32_t s = (int32_t)e.y + __mulhi((int32_t)e.x, d10);
+    octant ^= octant >> 1;
+    if (octant & (1u << 29)) { int32_t t = c; c = s; s = t; }
+    if (octant & (1u << 30)) c = -c;
+    if (octant & (1u << 31)) s = -s;
+    co = c;
+    so = s;
+}
+
 // --------------------------------------------------------------------------
 // atan2 (src/atan2.rs:7-82)
 // --------------------------------------------------------------------------
@@ -362,23 +393,31 @@ __device__ __forceinline__ int32_t sat_sub(int32_t a, int32_t b) {
     asm("sub.sat.s32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
     return r;
 }
+// a * b + c with a, b i32 and c i64: one IMAD.WIDE (the compiler turns an i64 product of a
+// sign-extended register and a kernel parameter into a 5-instruction 64x32 multiply)
+__device__ __forceinline__ int64_t mad_wide(int32_t a, int32_t b, int64_t c) {
+    int64_t r;
+    asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"(c));
+    return r;
+}
 template <int ORDER>
 __device__ __forceinline__ int32_t lowpass_step(int32_t k0, int32_t k1, int64_t &s0, int64_t &s1,
                                                 int32_t x) {
-    uint64_t d = (uint64_t)((int64_t)sat_sub(x, (int32_t)(s0 >> 32)) * (int64_t)k0);
+    // d = dx*k0 (+ (s1>>32)*k1); every `+= d` below is folded into multiply-adds, which is
+    // exact because i64 addition wraps (src/lowpass.rs:59-72 in release arithmetic)
+    const int32_t dx = sat_sub(x, (int32_t)(s0 >> 32));
     int32_t y;
     if constexpr (ORDER == 1) {
-        s0 = (int64_t)((uint64_t)s0 + d);
+        s0 = mad_wide(dx, k0, s0);
         y = (int32_t)(s0 >> 32);
-        s0 = (int64_t)((uint64_t)s0 + d);
+        s0 = mad_wide(dx, k0, s0);
     } else {
-        // (s1 >> 32) fits in i32: one IMAD.WIDE, same value mod 2^64 as the i64*i64 product
-        d += (uint64_t)((int64_t)(int32_t)(s1 >> 32) * (int64_t)k1);
-        s1 = (int64_t)((uint64_t)s1 + d);
+        const int32_t s1h = (int32_t)(s1 >> 32);
+        s1 = mad_wide(dx, k0, mad_wide(s1h, k1, s1));
         s0 = (int64_t)((uint64_t)s0 + (uint64_t)s1);
         y = (int32_t)(s0 >> 32);
         s0 = (int64_t)((uint64_t)s0 + (uint64_t)s1);
-        s1 = (int64_t)((uint64_t)s1 + d);
+        s1 = mad_wide(dx, k0, mad_wide(s1h, k1, s1));
     }
     return y;
 }
@@ -410,7 +449,7 @@ template <int ORDER, bool SMEM_LUT = false> struct LockinOp {
     using In = int32_t;
     using Out = int2;
     static constexpr bool TUNABLE = false;
-    static constexpr int SMEM_EXTRA_WORDS = SMEM_LUT ? 128 : 0;  // cossin LUT staged per CTA
+    static constexpr int SMEM_EXTRA_WORDS = SMEM_LUT ? 256 : 0;  // expanded cossin table staged per CTA
     struct Params {
         int32_t k[2];
         int32_t *accu_state;
@@ -422,8 +461,7 @@ template <int ORDER, bool SMEM_LUT = false> struct LockinOp {
     int64_t i0, i1, q0, q1;
     const uint32_t *lutp;
     __device__ __forceinline__ static void init_smem(const Params &p, uint32_t *extra, int tid, int nthreads) {
-        if constexpr (SMEM_LUT)
-            for (int i = tid; i < 128; i += nthreads) extra[i] = p.lut[i];
+        if constexpr (SMEM_LUT) cossin_expand_lut(p.lut, extra, tid, nthreads);
     }
     __device__ __forceinline__ void bind(const Params &p, const uint32_t *extra) { lutp = SMEM_LUT ? extra : p.lut; }
     __device__ __forceinline__ void load(const Params &p, size_t lane, size_t stride) {
@@ -445,7 +483,8 @@ template <int ORDER, bool SMEM_LUT = false> struct LockinOp {
     __device__ __forceinline__ int2 step(const Params &p, int32_t x) {
         ph += dph;
         int32_t c, s;
-        cossin_dev<SMEM_LUT>(lutp, (int32_t)ph, c, s);
+        if constexpr (SMEM_LUT) cossin_dev_x(lutp, (int32_t)ph, c, s);
+        else cossin_dev<false>(lutp, (int32_t)ph, c, s);
         int32_t mi = (int32_t)(((int64_t)c * (int64_t)x) >> 32);
         int32_t mq = (int32_t)(((int64_t)s * (int64_t)x) >> 32);
         int2 r;

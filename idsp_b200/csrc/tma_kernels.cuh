@@ -396,6 +396,34 @@ static int tma_launch_cfg(idsp_ctx *ctx, const typename Op::Params &p, const voi
     return IDSP_OK;
 }
 
+// Resident CTAs per SM of one frame-major configuration (cached) and the cost of its last,
+// partially filled wave: a CTA owns its lanes for the whole time axis, so with W waves of
+// CTAs the launch lasts ~ceil(W) rounds while doing W rounds of work.  Compute-bound ops pick
+// the configuration with the smallest ceil(W) / W (HBM-bound ops do not care).
+template <class Op, bool LM, int TF, int S, int O, int WPC, bool WIDE>
+static int tma_cfg_occupancy() {
+    static int occ = -1;
+    if (occ < 0) {
+        constexpr int BW = WIDE ? 32 * WPC : 32;
+        constexpr int OW = sizeof(typename Op::Out) / 4;
+        constexpr int NPIPE = WIDE ? 1 : WPC;
+        constexpr size_t smem = (size_t)NPIPE * (S + O * OW) * TF * BW * 4 + (size_t)NPIPE * S * 8 +
+                                (size_t)Op::SMEM_EXTRA_WORDS * 4;
+        auto kern = tma_lanes_kernel<Op, LM, TF, S, O, WPC, WIDE>;
+        int n = 0;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, WPC * 32, smem) != cudaSuccess || n < 1)
+            n = 1;
+        occ = n;
+    }
+    return occ;
+}
+static inline double tail_cost(size_t ctas, size_t sms, int occ) {
+    const double w = (double)ctas / (double)(sms * (size_t)occ);
+    const double full = (double)(size_t)w;
+    return (w > full ? full + 1.0 : full) / w;
+}
+
 template <class Op, int NBOX, int S, int O>
 static int tma_launch_lm(idsp_ctx *ctx, const typename Op::Params &p, const void *x, void *y,
                          size_t frames, size_t lanes, size_t sstride) {
@@ -461,9 +489,17 @@ static int tma_try_launch(idsp_ctx *ctx, const typename Op::Params &p, const typ
     if constexpr (OUT8) {
         // 4-byte in / 8-byte out (lock-in): 128-lane boxes (the 8-byte box row is 256 words)
         const size_t sms = (size_t)(ctx->sm_count > 0 ? ctx->sm_count : 148);
-        if ((lanes + 127) / 128 >= sms)
-            r = tma_launch_cfg<Op, false, 8, 4, 2, 4, true>(ctx, p, x, y, frames, lanes, sstride);
-        else
+        if ((lanes + 127) / 128 >= sms) {
+            // compute-bound: avoid a nearly empty last wave (131 072 lanes: 1024 CTAs fit in one
+            // wave with 3 load stages, 7 CTAs per SM, but need 1.15 waves with 4 stages, 6 per SM)
+            const size_t n4 = (lanes + 127) / 128;
+            const double c4 = tail_cost(n4, sms, tma_cfg_occupancy<Op, false, 8, 4, 2, 4, true>());
+            const double c3 = tail_cost(n4, sms, tma_cfg_occupancy<Op, false, 8, 3, 2, 4, true>());
+            if (c3 < 0.95 * c4)
+                r = tma_launch_cfg<Op, false, 8, 3, 2, 4, true>(ctx, p, x, y, frames, lanes, sstride);
+            else
+                r = tma_launch_cfg<Op, false, 8, 4, 2, 4, true>(ctx, p, x, y, frames, lanes, sstride);
+        } else
             r = tma_launch_cfg<Op, false, 8, 4, 2, 1>(ctx, p, x, y, frames, lanes, sstride);
     } else if (lm) {
 #ifdef IDSP_TUNE

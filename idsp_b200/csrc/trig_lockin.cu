@@ -9,8 +9,8 @@ using namespace idsp;
 // ---------------------------------------------------------------- memoryless maps
 // 4 phases per thread: one 16-byte load, two 16-byte stores.
 __global__ void __launch_bounds__(256) cossin_kernel(const int32_t *phase, int32_t *cs, size_t n) {
-    __shared__ uint32_t lut[128];
-    if (threadIdx.x < 128) lut[threadIdx.x] = g_cossin_lut[threadIdx.x];
+    __shared__ __align__(8) uint32_t lut[256];
+    cossin_expand_lut(g_cossin_lut, lut, threadIdx.x, blockDim.x);
     __syncthreads();
     const size_t n4 = n / 4;
     const bool vec = ((((uintptr_t)phase) | ((uintptr_t)cs)) & 15) == 0;
@@ -20,10 +20,10 @@ __global__ void __launch_bounds__(256) cossin_kernel(const int32_t *phase, int32
         for (; i < n4; i += stride) {
             int4 p = reinterpret_cast<const int4 *>(phase)[i];
             int4 a, b;
-            cossin_dev<true>(lut, p.x, a.x, a.y);
-            cossin_dev<true>(lut, p.y, a.z, a.w);
-            cossin_dev<true>(lut, p.z, b.x, b.y);
-            cossin_dev<true>(lut, p.w, b.z, b.w);
+            cossin_dev_x(lut, p.x, a.x, a.y);
+            cossin_dev_x(lut, p.y, a.z, a.w);
+            cossin_dev_x(lut, p.z, b.x, b.y);
+            cossin_dev_x(lut, p.w, b.z, b.w);
             reinterpret_cast<int4 *>(cs)[2 * i] = a;
             reinterpret_cast<int4 *>(cs)[2 * i + 1] = b;
         }
@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(256) cossin_kernel(const int32_t *phase, int32
     }
     for (; i < n; i += stride) {
         int32_t c, s;
-        cossin_dev<true>(lut, phase[i], c, s);
+        cossin_dev_x(lut, phase[i], c, s);
         cs[2 * i] = c;
         cs[2 * i + 1] = s;
     }
