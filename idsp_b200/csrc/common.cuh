@@ -13,7 +13,7 @@ struct idsp_ctx {
     cudaStream_t stream;
     bool own_stream;
     uint64_t launches;
-    int policy;  // 0 auto, 1 generic, 2 TMA
+    int policy;  // 0 auto, 1 generic, 2 TMA / tiled, 3 auto with the packed f32x2 HBF variant
     int sm_count;
     // host streaming (the *_host entry points): ring of device chunk buffers
     cudaStream_t s_h2d, s_d2h;

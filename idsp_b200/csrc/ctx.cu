@@ -121,7 +121,7 @@ extern "C" void idsp_b200_host_free(void *ptr) {
 extern "C" uint64_t idsp_b200_launch_count(const idsp_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 extern "C" int idsp_b200_set_kernel_policy(idsp_ctx *ctx, int policy) {
-    if (!ctx || policy < 0 || policy > 2) {
+    if (!ctx || policy < 0 || policy > 3) {
         idsp_set_error("idsp_b200_set_kernel_policy: bad argument");
         return IDSP_EINVAL;
     }

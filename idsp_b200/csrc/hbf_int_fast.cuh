@@ -100,6 +100,27 @@ template <int TI_, int R> struct IntItem {
     }
 };
 
+// Move the tails of the [hist | n new] input rows of stage s (all NL lanes) to their heads
+// (copy_within, src/hbf.rs:231).  One 16-byte piece per thread, a whole row inside one warp:
+// everything is read before anything is written (head and tail overlap when hist > n).
+template <int K, int s>
+__device__ __forceinline__ void carry_rows(float *sm, int warp, int lid) {
+    constexpr int C = hist(s) / 4;
+    constexpr int LP = 32 / C;  // lanes per warp pass
+    static_assert(C <= 32, "row history too long for one warp");
+    const int sub = lid / C, j = lid % C;
+    int lane = warp * LP + sub;
+    float *row = sm + off_u(K, s) + lane * pitch(K, s) + 4 * j;
+    for (; lane - sub < NL; lane += (NT / 32) * LP, row += (NT / 32) * LP * pitch(K, s)) {  // warp-uniform trip count
+        const bool act = sub < LP && lane < NL;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (act) v = lds128v(row + st_nin(K, s));
+        __syncwarp();
+        if (act) *reinterpret_cast<float4 *>(row) = v;
+        __syncwarp();
+    }
+}
+
 template <int K, int s> struct StageRun {
     __device__ __forceinline__ static void run(float *sm, int tid, int obuf) {
         constexpr int R = st_r(K, s);
@@ -112,28 +133,11 @@ template <int K, int s> struct StageRun {
             else dst = sm + off_u(K, s + 1) + lane * pitch(K, s + 1) + hist(s + 1) + 2 * n0;
             IntItem<s, R>::run(U + lane * pitch(K, s), n0, dst);
         }
+        // the input rows of the previous stage were consumed one barrier ago
+        if constexpr (s >= 1) carry_rows<K, s - 1>(sm, tid >> 5, tid & 31);
     }
 };
 
-template <int H, int N> __device__ __forceinline__ void carry_row(float *row) {
-    float t[H];
-#pragma unroll
-    for (int j = 0; j < H / 4; j++) {
-        float4 v = lds128v(row + N + 4 * j);
-        t[4 * j] = v.x; t[4 * j + 1] = v.y; t[4 * j + 2] = v.z; t[4 * j + 3] = v.w;
-    }
-#pragma unroll
-    for (int j = 0; j < H / 4; j++)
-        reinterpret_cast<float4 *>(row)[j] = make_float4(t[4 * j], t[4 * j + 1], t[4 * j + 2], t[4 * j + 3]);
-}
-template <int K, int s> struct Carry {
-    __device__ __forceinline__ static void run(float *sm, int job, int lane) {
-        if constexpr (s < K) {
-            if (job == s) carry_row<hist(s), st_nin(K, s)>(sm + off_u(K, s) + lane * pitch(K, s));
-            else Carry<K, s + 1>::run(sm, job, lane);
-        }
-    }
-};
 template <int K, int s, bool LOAD> struct StateIO {
     __device__ __forceinline__ static void run(float *sm, float *st, size_t sstride, size_t lane0, int nl, int tid) {
         if constexpr (s < K) {
@@ -188,6 +192,10 @@ hbf_int_fast_kernel(float *st, const float *x, float *y, size_t n_in, size_t nti
             if (v < NV) *reinterpret_cast<float4 *>(sm + off_u(K, 0) + plane * pitch(K, 0) + hist(0) + 4 * pvec) = nxt[j];
         }
         if (i + 1 < ntiles) fetch(i + 1);
+        // rows K-1 of the previous tile: last read in its final phase, next written by stage K-2
+        if constexpr (K >= 2) {
+            if (i > 0) carry_rows<K, K - 1>(sm, tid >> 5, tid & 31);
+        }
         // the staging buffer about to be refilled must have been drained by its bulk stores
         // (bulk async-groups are per thread: every issuing thread waits for its own)
         if (tid < nl) tma_wait_read<1>();
@@ -196,7 +204,7 @@ hbf_int_fast_kernel(float *st, const float *x, float *y, size_t n_in, size_t nti
         if constexpr (K >= 3) { StageRun<K, 1>::run(sm, tid, ob); __syncthreads(); }
         if constexpr (K >= 4) { StageRun<K, 2>::run(sm, tid, ob); __syncthreads(); }
         if constexpr (K >= 5) { StageRun<K, 3>::run(sm, tid, ob); __syncthreads(); }
-        StageRun<K, K - 1>::run(sm, tid, ob);  // -> staging
+        StageRun<K, K - 1>::run(sm, tid, ob);  // -> staging (and carries rows K-2)
         fence_async_smem();                    // writers make the staging rows visible to the async proxy
         __syncthreads();
         if (tid < nl) {
@@ -204,7 +212,13 @@ hbf_int_fast_kernel(float *st, const float *x, float *y, size_t n_in, size_t nti
                           TOUT * 4);
             tma_commit();
         }
-        for (int idx = tid; idx < K * NL; idx += NT) Carry<K, 0>::run(sm, idx / NL, idx % NL);
+        if constexpr (K == 1) {  // rows 0 are rewritten at the top of the next tile: carry them now
+            carry_rows<K, 0>(sm, tid >> 5, tid & 31);
+            __syncthreads();
+        }
+    }
+    if constexpr (K >= 2) {
+        carry_rows<K, K - 1>(sm, tid >> 5, tid & 31);
         __syncthreads();
     }
     if (tid < nl) tma_wait_read<0>();

@@ -78,7 +78,9 @@ uint64_t idsp_b200_launch_count(const idsp_ctx *ctx);
 int idsp_b200_host_alloc(void **ptr, size_t bytes);
 void idsp_b200_host_free(void *ptr);
 /* Kernel selection: 0 = automatic (default), 1 = force the generic LDG kernels,
- * 2 = force the TMA kernels (IDSP_EINVAL if the shape does not qualify). */
+ * 2 = force the TMA kernels (IDSP_EINVAL if the shape does not qualify),
+ * 3 = automatic, with the packed f32x2 variant of the tiled half-band decimator (bit-identical
+ * results; the scalar variant is the default because it measured faster). */
 int idsp_b200_set_kernel_policy(idsp_ctx *ctx, int policy);
 
 /* ------------------------------------------------------------------ iir::Biquad

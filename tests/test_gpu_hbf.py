@@ -198,13 +198,13 @@ def test_dec_cascade_tiled_kernel_streaming(oracle, k):
     R = 1 << k
     TO = 512 >> k
     lanes = 37
-    chunks = [2 * TO + 3, TO, 1, 3 * TO - 1]
+    chunks = [2 * TO + 3, TO, 1, 3 * TO - 1, 6 * TO + 2]
     n_out = sum(chunks)
     x = rng.uniform(-1, 1, (lanes, n_out, R)).astype(np.float32)
     so = np.zeros((oracle.hbf_dec_state_words(k), lanes), np.float32)
     want = oracle.hbf_dec_cascade_lanes(k, so, x.reshape(-1), lanes, 1).reshape(lanes, n_out)
     ctx = ib.default_context(0)
-    for policy in (0, 1):
+    for policy in (0, 1, 3):  # default tiled kernel, generic only, packed f32x2 tiled variant
         ctx.set_kernel_policy(policy)
         try:
             st = _dec_state(k)(lanes, DEV)
