@@ -113,6 +113,11 @@ __device__ __forceinline__ size_t fidx(int layout, size_t n, size_t lane, size_t
 
 // Generic thread-per-lane cascades (any shape / alignment). hbf_fast.cuh holds the
 // shared-memory tiled kernels used for the large aligned cases.
+// The delay lines live in registers as shift registers.  The main loops are unrolled over
+// UNR frames (about 64 high-rate samples) so that the shifts inside the body become register
+// renaming and only one real shift per delay line remains per iteration: with one frame per
+// iteration the 23-tap stage alone would spend 65 MOVs per 70 flops.
+__host__ __device__ constexpr int hbf_unroll(int K) { return K >= 6 ? 1 : (64 >> K) > 16 ? 16 : (64 >> K); }
 template <int K>
 __global__ void __launch_bounds__(128)
 hbf_dec_cascade_generic(float *st, const float *x, float *y, size_t n_begin, size_t n_out,
@@ -122,7 +127,18 @@ hbf_dec_cascade_generic(float *st, const float *x, float *y, size_t n_begin, siz
     if (lane >= lanes) return;
     DecCascadeRegs<K> c;
     c.load(st, sstride, lane);
-    for (size_t n = n_begin; n < n_out; n++) {
+    constexpr int UNR = hbf_unroll(K);
+    size_t n = n_begin;
+    for (; n + UNR <= n_out; n += UNR) {
+#pragma unroll
+        for (int u = 0; u < UNR; u++) {
+            float v[R];
+            size_t f = fidx(layout, n + u, lane, n_out, lanes);
+            load_frame<R>(x + f * R, v);
+            y[f] = c.push(v);
+        }
+    }
+    for (; n < n_out; n++) {
         float v[R];
         size_t f = fidx(layout, n, lane, n_out, lanes);
         load_frame<R>(x + f * R, v);
@@ -139,7 +155,18 @@ hbf_int_cascade_generic(float *st, const float *x, float *y, size_t n_begin, siz
     if (lane >= lanes) return;
     IntCascadeRegs<K> c;
     c.load(st, sstride, lane);
-    for (size_t n = n_begin; n < n_in; n++) {
+    constexpr int UNR = hbf_unroll(K);
+    size_t n = n_begin;
+    for (; n + UNR <= n_in; n += UNR) {
+#pragma unroll
+        for (int u = 0; u < UNR; u++) {
+            float v[R];
+            size_t f = fidx(layout, n + u, lane, n_in, lanes);
+            c.push(x[f], v);
+            store_frame<R>(y + f * R, v);
+        }
+    }
+    for (; n < n_in; n++) {
         float v[R];
         size_t f = fidx(layout, n, lane, n_in, lanes);
         c.push(x[f], v);
@@ -156,23 +183,24 @@ chain_generic(float *st, Df1Op<float, false>::Params bp, const float *x, float *
     size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (lane >= lanes) return;
     DecCascadeRegs<K> d;
-    IntCascadeRegs<K> u;
+    IntCascadeRegs<K> u_;
     Df1Op<float, false> b;
     d.load(st, sstride, lane);
-    u.load(st + (size_t)hbf_dec_words(K) * sstride, sstride, lane);
+    u_.load(st + (size_t)hbf_dec_words(K) * sstride, sstride, lane);
     bp.st = st + (size_t)(hbf_dec_words(K) + hbf_int_words(K)) * sstride;
     b.load(bp, lane, sstride);
+    // (one frame per iteration: unrolling this body pushes it past 255 registers and is slower)
     for (size_t n = 0; n < n_low; n++) {
         float v[R], o[R];
         size_t f = fidx(layout, n, lane, n_low, lanes);
         load_frame<R>(x + f * R, v);
-        u.push(d.push(v), o);
+        u_.push(d.push(v), o);
 #pragma unroll
         for (int j = 0; j < R; j++) o[j] = b.step(bp, o[j]);
         store_frame<R>(y + f * R, o);
     }
     d.store(st, sstride, lane);
-    u.store(st + (size_t)hbf_dec_words(K) * sstride, sstride, lane);
+    u_.store(st + (size_t)hbf_dec_words(K) * sstride, sstride, lane);
     b.store(bp, lane, sstride);
 }
 
