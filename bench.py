@@ -79,6 +79,35 @@ def traffic_from_profiles(key):
     return None
 
 
+def pcie_peak(dev, mb=256, reps=3):
+    """pinned-memory copy rates with both directions busy at once (what the e2e leg is bound by):
+    returns (h2d GB/s, d2h GB/s) measured with CUDA events on two streams"""
+    import torch
+
+    n = mb << 20
+    h_in = torch.empty(n, dtype=torch.uint8).pin_memory()
+    h_out = torch.empty(n, dtype=torch.uint8).pin_memory()
+    d_in = torch.empty(n, dtype=torch.uint8, device=dev)
+    d_out = torch.empty(n, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    best = [0.0, 0.0]
+    for _ in range(reps + 1):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        torch.cuda.synchronize()
+        with torch.cuda.stream(s1):
+            ev[0].record()
+            d_in.copy_(h_in, non_blocking=True)
+            ev[1].record()
+        with torch.cuda.stream(s2):
+            ev[2].record()
+            h_out.copy_(d_out, non_blocking=True)
+            ev[3].record()
+        torch.cuda.synchronize()
+        best[0] = max(best[0], n / (ev[0].elapsed_time(ev[1]) * 1e-3) / 1e9)
+        best[1] = max(best[1], n / (ev[2].elapsed_time(ev[3]) * 1e-3) / 1e9)
+    return best[0], best[1]
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
 
@@ -495,6 +524,7 @@ def run_biquad(args, rank, world, local):
     torch.cuda.synchronize()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, world, dev)
     e2e = world * ef * lanes * esteps / (e2e_ms * 1e-3) / 1e9
+    h2d_gbs, d2h_gbs = pcie_peak(dev)
 
     del xin, yout, xh, yh
     torch.cuda.empty_cache()
@@ -515,7 +545,9 @@ def run_biquad(args, rank, world, local):
         "cpu_baseline": {"value": cpu_v, "unit": "GSa/s", "cores": host_threads(), "kind": "port",
                          "sample": cpu_sample, "seconds": cpu_dt},
         "e2e": {"value": e2e, "unit": "GSa/s", "h2d_bytes_per_step": 4 * ef * lanes, "d2h_bytes_per_step": 4 * ef * lanes,
-                "frames_per_step": ef, "steps": esteps, "api": "idsp_biquad_df1_i32_host (pinned host buffers)"},
+                "frames_per_step": ef, "steps": esteps, "api": "idsp_biquad_df1_i32_host (pinned host buffers)",
+                "pcie_gbs": {"h2d": h2d_gbs, "d2h": d2h_gbs, "how": "256 MiB pinned copies, both directions at once"},
+                "bound": "PCIe: 4 B in + 4 B out per sample", "frac_of_pcie": (e2e / world) * 4.0 / min(h2d_gbs, d2h_gbs)},
         "gpu_launches": int(launches), "clocks": clocks, "parity_check": "first step == oracle on 64 lanes x all frames",
     }
     if layout == 1:
@@ -600,6 +632,7 @@ def run_hbf(args, rank, world, local):
     torch.cuda.synchronize()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, world, dev)
     e2e = world * el * HBF_INPUTS * esteps / (e2e_ms * 1e-3) / 1e9
+    h2d_gbs, d2h_gbs = pcie_peak(dev)
     del xin, yout, xh, yh
     torch.cuda.empty_cache()
     if rank != 0:
@@ -618,7 +651,9 @@ def run_hbf(args, rank, world, local):
         "cpu_baseline": {"value": cpu_v, "unit": "GSa/s", "cores": host_threads(), "kind": "port",
                          "sample": cpu_sample, "seconds": cpu_dt},
         "e2e": {"value": e2e, "unit": "GSa/s", "h2d_bytes_per_step": 4 * el * HBF_INPUTS, "d2h_bytes_per_step": 4 * el * n_out,
-                "steps": esteps, "api": "idsp_hbf_dec_cascade_f32_host (pinned host buffers)"},
+                "steps": esteps, "api": "idsp_hbf_dec_cascade_f32_host (pinned host buffers)",
+                "pcie_gbs": {"h2d": h2d_gbs, "d2h": d2h_gbs, "how": "256 MiB pinned copies, both directions at once"},
+                "bound": "PCIe: 4 B in + 0.25 B out per sample", "frac_of_pcie": (e2e / world) * 4.0 / h2d_gbs},
         "gpu_launches": int(launches), "clocks": clocks, "parity_check": "first step == oracle on 32 lanes",
     }
     return line

@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 static thread_local char g_err[512] = "";
@@ -131,7 +133,7 @@ extern "C" int idsp_b200_set_kernel_policy(idsp_ctx *ctx, int policy) {
 
 // ---------------------------------------------------------------------------
 // Host streaming: x/y/state live in host memory.  The frame (frame-major) or
-// lane (lane-major) axis is cut into chunks of ~64 MiB that rotate through a ring of
+// lane (lane-major) axis is cut into chunks of ~32 MiB that rotate through a ring of
 // IDSP_HOST_RING device buffers: the H2D copy of chunk i+1.. overlaps the kernel on
 // chunk i and the D2H copy of chunk i-1 (three streams, events), so both PCIe
 // directions stay busy.  If the caller's buffers are pinned (cudaHostAlloc /
@@ -205,7 +207,14 @@ int idsp_host_stream(idsp_ctx *ctx, const HostStreamSpec &spec, const void *x, v
     const size_t in_unit = other * spec.in_bytes_per_frame_lane;
     const size_t out_unit = other * spec.out_bytes_per_frame_lane;
     const size_t bigger = in_unit > out_unit ? in_unit : out_unit;
-    const size_t target = (size_t)64 << 20;  // ~64 MiB per chunk and direction
+    // chunk size per direction: small enough that the un-overlapped first H2D / last D2H are a
+    // few per cent of a call, large enough to keep PCIe efficient (IDSP_HOST_CHUNK_MB overrides)
+    static size_t chunk_mb = 0;
+    if (!chunk_mb) {
+        const char *e = getenv("IDSP_HOST_CHUNK_MB");
+        chunk_mb = e && atoi(e) > 0 ? (size_t)atoi(e) : 32;
+    }
+    const size_t target = chunk_mb << 20;
     size_t chunk = bigger ? target / bigger : n_axis;
     if (fm) {
         if (chunk > 512) chunk &= ~(size_t)511;  // whole tiles of the tiled kernels
