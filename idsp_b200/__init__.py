@@ -20,5 +20,6 @@ from .hbf import (  # noqa: F401
 )
 from .nco import Accu, Lockin, LockinState, Lowpass, LowpassState, atan2, cossin, sos, sos_clamp_wide  # noqa: F401
 from .coefficients import Filter  # noqa: F401
+from .cic import Cic, CicState, Decimator, Interpolator  # noqa: F401
 
 __version__ = "0.1.0"

@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libidsp_b200.so")
-SOURCES = ["ctx.cu", "biquad.cu", "hbf.cu", "trig_lockin.cu"]
+SOURCES = ["ctx.cu", "biquad.cu", "hbf.cu", "trig_lockin.cu", "cic.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -242,6 +242,21 @@ class Context:
                   lambda fn, p: fn(self._h, p["x"], p["y"], n))
         return pp
 
+    # ------------------------------------------------------------------ cic
+    def cic(self, decimate: bool, N: int, M: int, rate: int, state, x, out=None, *, lanes: int,
+            layout: int = FRAME_MAJOR):
+        R = rate + 1
+        nx = x.numel() if isinstance(x, torch.Tensor) else x.size
+        frames = nx // (lanes * (R if decimate else 1))
+        y = self._out_like(x, out, frames * lanes * (1 if decimate else R))
+        kind = {torch.int32: "i32", torch.int64: "i64"}.get(x.dtype) if isinstance(x, torch.Tensor) else \
+            {"int32": "i32", "int64": "i64"}.get(str(x.dtype))
+        if kind is None:
+            raise TypeError("Cic lanes: samples must be int32 or int64")
+        self._run(f"idsp_cic_{'dec' if decimate else 'int'}_{kind}", None, False, {"state": state, "x": x, "y": y},
+                  lambda fn, p: fn(self._h, N, M, rate, p["state"], p["x"], p["y"], frames, lanes, layout))
+        return y
+
     # ------------------------------------------------------------------ lowpass / lockin
     def lowpass(self, k: Sequence[int], state, x, out=None, *, lanes: int, layout: int = FRAME_MAJOR):
         order = len(k)

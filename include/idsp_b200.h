@@ -201,6 +201,25 @@ size_t idsp_chain_state_words(int log2_rate);
 int idsp_chain_f32(idsp_ctx *ctx, int log2_rate, const float ba[5], float *state,
                    const float *x, float *y, size_t n_low, size_t lanes, int layout);
 
+/* ------------------------------------------------------------------ cic::Cic
+ * `Cic<T, N, M>` src/cic.rs:13-200 (order N = 1..6, comb delay M = 1..3, rate = fast/slow - 1) under
+ * the chunk adapters of dsp-process/src/adapters.rs: `Decimator` (:154-222, `[T; rate+1] -> T`, the
+ * value of the frame's single tick) and `Interpolator` (:27-35, `T -> [T; rate+1]`).  Integer
+ * arithmetic wraps (wrapping_add / wrapping_sub in the decimator, release-mode `+=` / `-` in the
+ * interpolator).  State: SoA words of T, `state[w * lanes + lane]`, w = [index, zoh,
+ * combs[n][m] at 2 + n*M + m, integrators[n] at 2 + N*M + n]; all zero = `Cic::new(rate)`.
+ * Whole frames only, so `index` is 0 between calls (the adapters' one-tick-per-chunk contract).
+ * dec: x = frames * lanes * (rate+1) samples, y = frames * lanes; int: the reverse. */
+size_t idsp_cic_state_words(int N, int M);
+int idsp_cic_dec_i32(idsp_ctx *ctx, int N, int M, uint32_t rate, int32_t *state, const int32_t *x,
+                     int32_t *y, size_t frames, size_t lanes, int layout);
+int idsp_cic_dec_i64(idsp_ctx *ctx, int N, int M, uint32_t rate, int64_t *state, const int64_t *x,
+                     int64_t *y, size_t frames, size_t lanes, int layout);
+int idsp_cic_int_i32(idsp_ctx *ctx, int N, int M, uint32_t rate, int32_t *state, const int32_t *x,
+                     int32_t *y, size_t frames, size_t lanes, int layout);
+int idsp_cic_int_i64(idsp_ctx *ctx, int N, int M, uint32_t rate, int64_t *state, const int64_t *x,
+                     int64_t *y, size_t frames, size_t lanes, int layout);
+
 #ifdef __cplusplus
 }
 #endif

@@ -388,3 +388,45 @@ def chain_lanes(k, ba, st, x, lanes, layout=FRAME_MAJOR, nthreads=1):
     y = np.empty_like(x)
     lib().orc_chain_f32_lanes(C.c_int(k), _p(ba), _p(st), _p(x), _p(y), C.c_size_t(n_low), C.c_size_t(lanes), C.c_int(layout), C.c_int(nthreads))
     return y
+
+
+# ---------------------------------------------------------------- Cic<T,N,M> (src/cic.rs)
+def cic_state_words(N, M):
+    return 2 + N * M + N
+
+
+def _cic(kind_fn, N, M, rate, st, x, lanes, layout, nthreads, R_in, R_out):
+    dt = st.dtype
+    assert dt in (np.int32, np.int64) and st.shape == (cic_state_words(N, M), lanes)
+    x = _arr(x, dt)
+    frames = x.size // (lanes * R_in)
+    y = np.empty(frames * lanes * R_out, dt)
+    fn = getattr(lib(), f"orc_cic_{kind_fn}_{'i32' if dt == np.int32 else 'i64'}_lanes")
+    fn(C.c_int(N), C.c_int(M), C.c_uint32(rate), _p(st), _p(x), _p(y), C.c_size_t(frames), C.c_size_t(lanes),
+       C.c_int(layout), C.c_int(nthreads))
+    return y
+
+
+def cic_dec_lanes(N, M, rate, st, x, lanes, layout=FRAME_MAJOR, nthreads=1):
+    """Decimator(Cic::<T,N,M>::new(rate)): frames of rate+1 inputs -> 1 output; `st` updated in place."""
+    return _cic("dec", N, M, rate, st, x, lanes, layout, nthreads, rate + 1, 1)
+
+
+def cic_int_lanes(N, M, rate, st, x, lanes, layout=FRAME_MAJOR, nthreads=1):
+    """Interpolator(Cic::<T,N,M>::new(rate)): 1 input -> frames of rate+1 outputs."""
+    return _cic("int", N, M, rate, st, x, lanes, layout, nthreads, 1, rate + 1)
+
+
+def cic_gain(N, M, rate):
+    lib().orc_cic_gain.restype = C.c_int64
+    return int(lib().orc_cic_gain(C.c_int(N), C.c_int(M), C.c_uint32(rate)))
+
+
+def cic_gain_log2(N, M, rate):
+    lib().orc_cic_gain_log2.restype = C.c_uint32
+    return int(lib().orc_cic_gain_log2(C.c_int(N), C.c_int(M), C.c_uint32(rate)))
+
+
+def cic_response_length(N, rate):
+    lib().orc_cic_response_length.restype = C.c_size_t
+    return int(lib().orc_cic_response_length(C.c_int(N), C.c_uint32(rate)))

@@ -840,3 +840,128 @@ void orc_chain_f32_lanes(int k, const float ba[5], float *st, const float *x, fl
         free(ls);
     });
 }
+
+/* ------------------------------------------------------------------ */
+/* Cic<T, N, M> (src/cic.rs:13-200), SURVEY 8(f) rank 3.                */
+/* State words per lane (type T), ABI order:                            */
+/*   [0] index  [1] zoh  [2 + n*M + m] combs[n][m]  [2 + N*M + n] integrators[n]  */
+/* Integer adds wrap (decimator: wrapping_add/sub, cic.rs:183-197; the  */
+/* interpolator's `+=`/`-` wrap in release builds, cic.rs:156-170).     */
+/* ------------------------------------------------------------------ */
+#define ORC_CIC_MAXN 8
+#define ORC_CIC_MAXM 8
+size_t orc_cic_state_words(int N, int M) { return (size_t)(2 + N * M + N); }
+
+#define DEF_CIC(SUF, T, UT)                                                                         \
+    typedef struct {                                                                                \
+        uint32_t rate, index;                                                                       \
+        T zoh, combs[ORC_CIC_MAXN][ORC_CIC_MAXM], integ[ORC_CIC_MAXN];                              \
+    } cic_##SUF;                                                                                    \
+    static void cic_load_##SUF(cic_##SUF *c, int N, int M, uint32_t rate, const T *st, size_t stride, size_t l) { \
+        c->rate = rate;                                                                             \
+        c->index = (uint32_t)st[l];                                                                 \
+        c->zoh = st[stride + l];                                                                    \
+        for (int n = 0; n < N; n++)                                                                 \
+            for (int m = 0; m < M; m++) c->combs[n][m] = st[(size_t)(2 + n * M + m) * stride + l];  \
+        for (int n = 0; n < N; n++) c->integ[n] = st[(size_t)(2 + N * M + n) * stride + l];         \
+    }                                                                                               \
+    static void cic_store_##SUF(const cic_##SUF *c, int N, int M, T *st, size_t stride, size_t l) { \
+        st[l] = (T)c->index;                                                                        \
+        st[stride + l] = c->zoh;                                                                    \
+        for (int n = 0; n < N; n++)                                                                 \
+            for (int m = 0; m < M; m++) st[(size_t)(2 + n * M + m) * stride + l] = c->combs[n][m];  \
+        for (int n = 0; n < N; n++) st[(size_t)(2 + N * M + n) * stride + l] = c->integ[n];         \
+    }                                                                                               \
+    /* comb cascade, cic.rs:159-164 / :190-196 */                                                   \
+    static T cic_combs_##SUF(cic_##SUF *c, int N, int M, T x) {                                     \
+        for (int n = 0; n < N; n++) {                                                               \
+            T y = (T)((UT)x - (UT)c->combs[n][0]);                                                  \
+            for (int m = 0; m + 1 < M; m++) c->combs[n][m] = c->combs[n][m + 1];                    \
+            c->combs[n][M - 1] = x;                                                                 \
+            x = y;                                                                                  \
+        }                                                                                           \
+        return x;                                                                                   \
+    }                                                                                               \
+    /* Process<T, Option<T>> (decimator), cic.rs:176-200; returns 1 and *y on a tick */             \
+    static int cic_dec_step_##SUF(cic_##SUF *c, int N, int M, T x, T *y) {                          \
+        for (int n = 0; n < N; n++) {                                                               \
+            c->integ[n] = (T)((UT)c->integ[n] + (UT)x);                                             \
+            x = c->integ[n];                                                                        \
+        }                                                                                           \
+        if (c->index > 0) {                                                                         \
+            c->index -= 1;                                                                          \
+            return 0;                                                                               \
+        }                                                                                           \
+        c->index = c->rate;                                                                         \
+        c->zoh = cic_combs_##SUF(c, N, M, x);                                                       \
+        *y = c->zoh;                                                                                \
+        return 1;                                                                                   \
+    }                                                                                               \
+    /* Process<Option<T>, T> (interpolator), cic.rs:149-172 */                                      \
+    static T cic_int_step_##SUF(cic_##SUF *c, int N, int M, int some, T x) {                        \
+        if (some) {                                                                                 \
+            c->index = c->rate;                                                                     \
+            c->zoh = cic_combs_##SUF(c, N, M, x);                                                   \
+        } else {                                                                                    \
+            c->index -= 1;                                                                          \
+        }                                                                                           \
+        T v = c->zoh;                                                                               \
+        for (int n = 0; n < N; n++) {                                                               \
+            c->integ[n] = (T)((UT)c->integ[n] + (UT)v);                                             \
+            v = c->integ[n];                                                                        \
+        }                                                                                           \
+        return v;                                                                                   \
+    }                                                                                               \
+    /* Decimator adapter (dsp-process/src/adapters.rs:154-222): frames of R = rate+1 inputs,        \
+     * one output per frame = the value of the single tick (zoh) */                                 \
+    void orc_cic_dec_##SUF##_lanes(int N, int M, uint32_t rate, T *st, const T *x, T *y, size_t frames, \
+                                   size_t lanes, int layout, int nthreads) {                        \
+        const size_t R = (size_t)rate + 1;                                                          \
+        LANE_BLOCKS(lanes, nthreads, lo, hi, {                                                      \
+            for (size_t l = lo; l < hi; l++) {                                                      \
+                cic_##SUF c;                                                                        \
+                cic_load_##SUF(&c, N, M, rate, st, lanes, l);                                       \
+                for (size_t t = 0; t < frames; t++) {                                               \
+                    size_t f = layout == ORC_FRAME_MAJOR ? t * lanes + l : l * frames + t;          \
+                    T out = c.zoh;                                                                  \
+                    for (size_t j = 0; j < R; j++) {                                                \
+                        T v;                                                                        \
+                        if (cic_dec_step_##SUF(&c, N, M, x[f * R + j], &v)) out = v;                \
+                    }                                                                               \
+                    y[f] = out;                                                                     \
+                }                                                                                   \
+                cic_store_##SUF(&c, N, M, st, lanes, l);                                            \
+            }                                                                                       \
+        });                                                                                         \
+    }                                                                                               \
+    /* Interpolator adapter (adapters.rs:27-35): Some(x) then R-1 times None */                     \
+    void orc_cic_int_##SUF##_lanes(int N, int M, uint32_t rate, T *st, const T *x, T *y, size_t frames, \
+                                   size_t lanes, int layout, int nthreads) {                        \
+        const size_t R = (size_t)rate + 1;                                                          \
+        LANE_BLOCKS(lanes, nthreads, lo, hi, {                                                      \
+            for (size_t l = lo; l < hi; l++) {                                                      \
+                cic_##SUF c;                                                                        \
+                cic_load_##SUF(&c, N, M, rate, st, lanes, l);                                       \
+                for (size_t t = 0; t < frames; t++) {                                               \
+                    size_t f = layout == ORC_FRAME_MAJOR ? t * lanes + l : l * frames + t;          \
+                    for (size_t j = 0; j < R; j++) y[f * R + j] = cic_int_step_##SUF(&c, N, M, j == 0, x[f]); \
+                }                                                                                   \
+                cic_store_##SUF(&c, N, M, st, lanes, l);                                            \
+            }                                                                                       \
+        });                                                                                         \
+    }
+DEF_CIC(i32, int32_t, uint32_t)
+DEF_CIC(i64, int64_t, uint64_t)
+
+/* gain() = (M*(rate+1))^N (cic.rs:99-101), gain_log2() (cic.rs:107-109), response_length() (:112-114) */
+int64_t orc_cic_gain(int N, int M, uint32_t rate) {
+    uint64_t g = 1, b = (uint64_t)M * ((uint64_t)rate + 1);
+    for (int n = 0; n < N; n++) g *= b;
+    return (int64_t)g;
+}
+uint32_t orc_cic_gain_log2(int N, int M, uint32_t rate) {
+    uint32_t v = (uint32_t)M * rate + (uint32_t)(M - 1);
+    uint32_t lz = v ? (uint32_t)__builtin_clz(v) : 32u;
+    return (32u - lz) * (uint32_t)N;
+}
+size_t orc_cic_response_length(int N, uint32_t rate) { return (size_t)rate * (size_t)N; }

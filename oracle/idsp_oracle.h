@@ -160,6 +160,22 @@ void orc_chain_f32_lanes(int log2_rate, const float ba[5], float *st, const floa
                          int nthreads);
 
 int orc_max_threads(void);
+
+/* ---- Cic<T,N,M> (src/cic.rs:13-200) with the Decimator / Interpolator adapters
+ * (dsp-process/src/adapters.rs:27-35, :154-222); state words [index, zoh, combs[N][M], integrators[N]] */
+size_t orc_cic_state_words(int N, int M);
+void orc_cic_dec_i32_lanes(int N, int M, uint32_t rate, int32_t *st, const int32_t *x, int32_t *y,
+                           size_t frames, size_t lanes, int layout, int nthreads);
+void orc_cic_dec_i64_lanes(int N, int M, uint32_t rate, int64_t *st, const int64_t *x, int64_t *y,
+                           size_t frames, size_t lanes, int layout, int nthreads);
+void orc_cic_int_i32_lanes(int N, int M, uint32_t rate, int32_t *st, const int32_t *x, int32_t *y,
+                           size_t frames, size_t lanes, int layout, int nthreads);
+void orc_cic_int_i64_lanes(int N, int M, uint32_t rate, int64_t *st, const int64_t *x, int64_t *y,
+                           size_t frames, size_t lanes, int layout, int nthreads);
+int64_t orc_cic_gain(int N, int M, uint32_t rate);
+uint32_t orc_cic_gain_log2(int N, int M, uint32_t rate);
+size_t orc_cic_response_length(int N, uint32_t rate);
+
 #ifdef __cplusplus
 }
 #endif
