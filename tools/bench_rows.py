@@ -113,6 +113,19 @@ def main():
             add(f"a14 HbfInt x{R} cascade f32 {lname}", "hbf.rs:476-512", hl * n_out * R, 4 + 4 / R,
                 lambda: Lanes(HbfIntCascade(k)).block(sint, y, x, layout))
             del x, y
+        # CIC /16 and x16, cubic (src/cic.rs PERF_N = 3, PERF_R = 16, PERF_D = 1)
+        from idsp_b200 import Cic, CicState
+        for kind in ("i32", "i64"):
+            cl, cf, R = 65536, (256 if args.quick else 1024), 16
+            xh = rnd(kind, cl * cf * R)
+            yl = torch.empty(cl * cf, dtype=TDT[kind], device=DEV)
+            sz = xh.element_size()
+            cd, ci = CicState.default(3, 1, kind, cl, DEV), CicState.default(3, 1, kind, cl, DEV)
+            add(f"f3 Cic<3> /16 decimator {kind} {lname}", "cic.rs:176-200", cl * cf * R, sz + sz / R,
+                lambda: Lanes(Cic(3, 1, 15).decimate()).block(cd, xh, yl, layout))
+            add(f"f3 Cic<3> x16 interpolator {kind} {lname}", "cic.rs:149-172", cl * cf * R, sz + sz / R,
+                lambda: Lanes(Cic(3, 1, 15).interpolate()).block(ci, yl, xh, layout))
+            del xh, yl
     n = 1 << (24 if args.quick else 28)
     ph = rnd("i32", n)
     cs = torch.empty(2 * n, dtype=torch.int32, device=DEV)
