@@ -18,7 +18,9 @@ from .hbf import (  # noqa: F401
     HbfDecCascade, HbfInt, HbfInt2, HbfInt4, HbfInt8, HbfInt16, HbfInt32, HbfIntCascade,
     OddAntiSymmetric, OddSymmetric, hbf_dec_response_length, hbf_int_response_length, hbf_taps,
 )
-from .nco import Accu, Lockin, LockinState, Lowpass, LowpassState, atan2, cossin, sos, sos_clamp_wide  # noqa: F401
+from .nco import (  # noqa: F401
+    PLL, Accu, Lockin, LockinState, Lowpass, LowpassState, PLLState, atan2, cossin, sos, sos_clamp_wide,
+)
 from .coefficients import Filter  # noqa: F401
 from .cic import Cic, CicState, Decimator, Interpolator  # noqa: F401
 

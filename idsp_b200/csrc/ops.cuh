@@ -494,4 +494,62 @@ template <int ORDER, bool SMEM_LUT = false> struct LockinOp {
     }
 };
 
+// --------------------------------------------------------------------------
+// PLL (src/pll.rs:88-108): type-2 sampled-phase PLL, wrapping 32/64-bit integer math, with the
+// ClampWrap phase-error clamp (src/unwrap.rs:166-194, overflowing_sub :73-81).  SURVEY 8(f) rank 4.
+// State words (i32): [x0, clamp, z0, y0, f0 lo, f0 hi, f lo, f hi, y].
+// --------------------------------------------------------------------------
+struct PllOp : OpHooks {
+    using In = int32_t;
+    using Out = int32_t;
+    struct Params {
+        int32_t ba[3];
+        int32_t *st;
+    };
+    int32_t x0, clamp, z0, y0, y;
+    int64_t f0, f;
+    __device__ __forceinline__ void load(const Params &p, size_t lane, size_t stride) {
+        x0 = p.st[lane];
+        clamp = p.st[stride + lane];
+        z0 = p.st[2 * stride + lane];
+        y0 = p.st[3 * stride + lane];
+        f0 = (int64_t)((uint64_t)(uint32_t)p.st[4 * stride + lane] | ((uint64_t)(uint32_t)p.st[5 * stride + lane] << 32));
+        f = (int64_t)((uint64_t)(uint32_t)p.st[6 * stride + lane] | ((uint64_t)(uint32_t)p.st[7 * stride + lane] << 32));
+        y = p.st[8 * stride + lane];
+    }
+    __device__ __forceinline__ void store(const Params &p, size_t lane, size_t stride) const {
+        p.st[lane] = x0;
+        p.st[stride + lane] = clamp;
+        p.st[2 * stride + lane] = z0;
+        p.st[3 * stride + lane] = y0;
+        p.st[4 * stride + lane] = (int32_t)(uint32_t)f0;
+        p.st[5 * stride + lane] = (int32_t)(f0 >> 32);
+        p.st[6 * stride + lane] = (int32_t)(uint32_t)f;
+        p.st[7 * stride + lane] = (int32_t)(f >> 32);
+        p.st[8 * stride + lane] = y;
+    }
+    __device__ __forceinline__ int32_t step(const Params &p, int32_t x) {
+        y = (int32_t)((uint32_t)y + (uint32_t)(int32_t)(f >> 32));  // oscillator, frequency() = f >> 32
+        const int32_t t = (int32_t)((uint32_t)x + (uint32_t)y);     // phase error before the clamp
+        const int32_t delta = (int32_t)((uint32_t)t - (uint32_t)x0);
+        const int wrap = (int)(delta >= 0) - (int)(t >= x0);        // Ordering of the two bools
+        x0 = t;
+        const int c = clamp + wrap;
+        clamp = (c > 0) - (c < 0);
+        const int32_t o = clamp < 0 ? INT32_MIN : (clamp > 0 ? INT32_MAX : t);
+        const int32_t zn = o >> 1;
+        const int32_t yn = (int32_t)((uint32_t)zn + (uint32_t)z0);  // Nyquist zero
+        z0 = zn;
+        // lead-lag with a wide state: f0 += b0*y0 + b1*y0' + a1*hi(f0) + ((a1 * lo(f0)) >> 32)
+        int64_t acc = mad_wide(p.ba[0], yn, f0);
+        acc = mad_wide(p.ba[1], y0, acc);
+        acc = mad_wide(p.ba[2], (int32_t)(f0 >> 32), acc);
+        acc = (int64_t)((uint64_t)acc + (uint64_t)(((int64_t)p.ba[2] * (int64_t)(uint32_t)f0) >> 32));
+        f0 = acc;
+        y0 = yn;
+        f = (int64_t)((uint64_t)f + (uint64_t)f0);  // DC pole
+        return y;
+    }
+};
+
 }  // namespace idsp

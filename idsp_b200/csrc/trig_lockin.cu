@@ -213,3 +213,21 @@ extern "C" int idsp_lockin_i32_host(idsp_ctx *ctx, int order, const int32_t *k,
                               lanes, layout);
         });
 }
+
+// ---------------------------------------------------------------- PLL
+extern "C" int idsp_pll_i32(idsp_ctx *ctx, const int32_t *ba, int32_t *state, const int32_t *x, int32_t *y,
+                            size_t frames, size_t lanes, int layout) {
+    int r = idsp_use_device(ctx);
+    if (r) return r;
+    IDSP_CHECK_ARG(ba != nullptr, "ba is null");
+    IDSP_CHECK_ARG(layout == IDSP_FRAME_MAJOR || layout == IDSP_LANE_MAJOR,
+                   "layout must be 0 (frame-major) or 1 (lane-major)");
+    if (frames == 0 || lanes == 0) return IDSP_OK;
+    IDSP_CHECK_ARG(state && x && y, "state/x/y must not be null");
+    PllOp::Params p;
+    p.ba[0] = ba[0];
+    p.ba[1] = ba[1];
+    p.ba[2] = ba[2];
+    p.st = state;
+    return launch_lanes_best<PllOp>(ctx, p, x, y, frames, lanes, lanes, layout);
+}

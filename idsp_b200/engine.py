@@ -242,6 +242,15 @@ class Context:
                   lambda fn, p: fn(self._h, p["x"], p["y"], n))
         return pp
 
+    # ------------------------------------------------------------------ pll
+    def pll(self, ba: Sequence[int], state, x, out=None, *, lanes: int, layout: int = FRAME_MAJOR):
+        b = np.asarray(ba, np.int32).reshape(3)
+        frames = (x.numel() if isinstance(x, torch.Tensor) else x.size) // lanes
+        y = self._out_like(x, out)
+        self._run("idsp_pll_i32", None, False, {"state": state, "x": x, "y": y},
+                  lambda fn, p: fn(self._h, C.c_void_p(b.ctypes.data), p["state"], p["x"], p["y"], frames, lanes, layout))
+        return y
+
     # ------------------------------------------------------------------ cic
     def cic(self, decimate: bool, N: int, M: int, rate: int, state, x, out=None, *, lanes: int,
             layout: int = FRAME_MAJOR):

@@ -120,3 +120,56 @@ class Lockin:
     def block(self, state: LockinState, accu: Accu, x, iq, layout: int = FRAME_MAJOR):
         ctx = default_context(_dev_of(x))
         ctx.lockin(self.lowpass.k, accu.state, accu.step, state.words, x, iq, lanes=state.lanes, layout=layout)
+
+
+class PLLState(LaneState):
+    """``PLLState`` (src/pll.rs:60-86) per lane as i32 words
+    [clamp.x0, clamp.clamp, z0, y0, f0 lo, f0 hi, f lo, f hi, y]; all zero == ``default()``."""
+
+    DTYPE = np.int32
+
+    @classmethod
+    def default(cls, lanes: int = 1, device=None):
+        return cls(LaneState._alloc(9, lanes, np.int32, device))
+
+    def phase(self):
+        """``PLLState::phase()`` (src/pll.rs:76-78)"""
+        return self.numpy()[8]
+
+    def frequency(self):
+        """``PLLState::frequency()`` = ``(f >> 32) as i32`` (src/pll.rs:81-83)"""
+        return self.numpy()[7]
+
+
+class PLL(_Proc):
+    """``PLL { ba: [Q32<32>; 3] }`` (src/pll.rs:33-38) with raw coefficient bits."""
+
+    def __init__(self, ba):
+        self.ba = [int(v) for v in ba]
+        if len(self.ba) != 3:
+            raise ValueError("PLL.ba has three coefficients")
+
+    @staticmethod
+    def _q32(v: np.float32) -> int:
+        """f32 -> Q32<32>: (v * 2^32).round() as i32, saturating (num_traits_impl.rs:30-45)"""
+        s = np.float32(v) * np.float32(4294967296.0)
+        s = np.float32(np.copysign(np.floor(np.abs(s) + np.float32(0.5)), s))  # round half away from zero
+        if np.isnan(s):
+            return 0
+        return int(max(-(1 << 31), min((1 << 31) - 1, int(s))))
+
+    @classmethod
+    def from_zpk(cls, zero, pole, gain):
+        """src/pll.rs:41-46 (f32 arithmetic)"""
+        z, p, k = np.float32(zero), np.float32(pole), np.float32(gain)
+        return cls([cls._q32(k), cls._q32(-k * z), cls._q32(-(np.float32(1.0) - p))])
+
+    @classmethod
+    def from_bandwidth(cls, bw, split=4.0):
+        """src/pll.rs:51-57 (f32 arithmetic)"""
+        bw, split = np.float32(bw), np.float32(split)
+        a = bw * np.float32(2.0) * np.float32(np.pi)
+        return cls.from_zpk(np.float32(1.0) - a / split, np.float32(1.0) - a * split, -a * a * split)
+
+    def _block(self, ctx, state, x, y, layout):
+        ctx.pll(self.ba, state.words, x, y, lanes=state.lanes, layout=layout)

@@ -220,6 +220,15 @@ int idsp_cic_int_i32(idsp_ctx *ctx, int N, int M, uint32_t rate, int32_t *state,
 int idsp_cic_int_i64(idsp_ctx *ctx, int N, int M, uint32_t rate, int64_t *state, const int64_t *x,
                      int64_t *y, size_t frames, size_t lanes, int layout);
 
+/* ------------------------------------------------------------------ pll::PLL
+ * `SplitProcess<W<i32>, W<i32>, PLLState> for PLL` src/pll.rs:88-108 (phase clamp: `ClampWrap`,
+ * src/unwrap.rs:166-194).  ba = the three raw `Q32<32>` lead-lag coefficients (`PLL::ba`, e.g. from
+ * `PLL::from_bandwidth`, src/pll.rs:41-57); x = input phase, y = output phase estimate (`state.y`).
+ * State: SoA i32 words [clamp.x0, clamp.clamp (-1|0|1), z0, y0, f0 lo, f0 hi, f lo, f hi, y];
+ * `PLLState::frequency()` is word 7.  All arithmetic wraps, bit-exact. */
+int idsp_pll_i32(idsp_ctx *ctx, const int32_t *ba, int32_t *state, const int32_t *x, int32_t *y,
+                 size_t frames, size_t lanes, int layout);
+
 #ifdef __cplusplus
 }
 #endif

@@ -430,3 +430,24 @@ def cic_gain_log2(N, M, rate):
 def cic_response_length(N, rate):
     lib().orc_cic_response_length.restype = C.c_size_t
     return int(lib().orc_cic_response_length(C.c_int(N), C.c_uint32(rate)))
+
+
+# ---------------------------------------------------------------- PLL (src/pll.rs)
+PLL_WORDS = 9
+
+
+def pll_from_bandwidth(bw, split=4.0):
+    ba = np.zeros(3, np.int32)
+    lib().orc_pll_from_bandwidth(C.c_float(bw), C.c_float(split), _p(ba))
+    return ba
+
+
+def pll_lanes(ba, st, x, lanes, layout=FRAME_MAJOR, nthreads=1):
+    """PLL::process over lanes; st int32 [9, lanes] updated in place; returns y (output phase)."""
+    ba = _arr(ba, np.int32)
+    x = _arr(x, np.int32)
+    assert st.dtype == np.int32 and st.shape == (PLL_WORDS, lanes)
+    y = np.empty_like(x)
+    lib().orc_pll_i32_lanes(_p(ba), _p(st), _p(x), _p(y), C.c_size_t(x.size // lanes), C.c_size_t(lanes),
+                            C.c_int(layout), C.c_int(nthreads))
+    return y

@@ -965,3 +965,77 @@ uint32_t orc_cic_gain_log2(int N, int M, uint32_t rate) {
     return (32u - lz) * (uint32_t)N;
 }
 size_t orc_cic_response_length(int N, uint32_t rate) { return (size_t)rate * (size_t)N; }
+
+/* ------------------------------------------------------------------ */
+/* PLL (src/pll.rs:33-108), SURVEY 8(f) rank 4.  All math is wrapping   */
+/* 32/64-bit integer.  State words per lane (i32), ABI order:           */
+/*   [0] clamp.x0  [1] clamp.clamp (-1,0,1)  [2] z0  [3] y0             */
+/*   [4] f0 lo  [5] f0 hi  [6] f lo  [7] f hi  [8] y                    */
+/* ------------------------------------------------------------------ */
+/* f32 -> Q32<32>: (v * 2^32).round() as i32, f32 arithmetic, saturating cast
+ * (dsp-fixedpoint/src/num_traits_impl.rs:30-45) */
+static int32_t q32_32_from_f32(float v) {
+    float s = roundf(v * 4294967296.0f);
+    if (s != s) return 0;
+    if (s >= 2147483648.0f) return INT32_MAX;
+    if (s <= -2147483648.0f) return INT32_MIN;
+    return (int32_t)s;
+}
+/* PLL::from_bandwidth / from_zpk (src/pll.rs:41-57), f32 arithmetic like the reference */
+void orc_pll_from_bandwidth(float bw, float split, int32_t ba[3]) {
+    float a = bw * 2.0f * 3.14159274101257324f; /* core::f32::consts::PI */
+    float z = 1.0f - a / split;
+    float p = 1.0f - a * split;
+    float k = -a * a * split;
+    ba[0] = q32_32_from_f32(k);
+    ba[1] = q32_32_from_f32(-k * z);
+    ba[2] = q32_32_from_f32(-(1.0f - p));
+}
+typedef struct {
+    int32_t x0, clamp, z0, y0;
+    int64_t f0, f;
+    int32_t y;
+} pll_state;
+/* SplitProcess<W<i32>, W<i32>, PLLState> for PLL (src/pll.rs:88-108) with ClampWrap
+ * (src/unwrap.rs:166-194) and overflowing_sub (src/unwrap.rs:73-81) */
+static int32_t pll_step(const int32_t ba[3], pll_state *s, int32_t x) {
+    s->y = (int32_t)((uint32_t)s->y + (uint32_t)(int32_t)(s->f >> 32));
+    int32_t t = (int32_t)((uint32_t)x + (uint32_t)s->y);
+    int32_t delta = (int32_t)((uint32_t)t - (uint32_t)s->x0);
+    int a = delta >= 0, b = t >= s->x0;
+    int wrap = a > b ? 1 : (a < b ? -1 : 0);
+    s->x0 = t;
+    int c = s->clamp + wrap;
+    s->clamp = c > 0 ? 1 : (c < 0 ? -1 : 0);
+    int32_t o = s->clamp < 0 ? INT32_MIN : (s->clamp > 0 ? INT32_MAX : t);
+    int32_t z0 = o >> 1;
+    int32_t y0 = (int32_t)((uint32_t)z0 + (uint32_t)s->z0);
+    s->z0 = z0;
+    uint64_t acc = (uint64_t)((int64_t)ba[0] * y0) + (uint64_t)((int64_t)ba[1] * s->y0) +
+                   (uint64_t)((int64_t)ba[2] * (int32_t)(s->f0 >> 32));
+    acc += (uint64_t)(((int64_t)ba[2] * (int64_t)(uint32_t)s->f0) >> 32);
+    s->f0 = (int64_t)((uint64_t)s->f0 + acc);
+    s->y0 = y0;
+    s->f = (int64_t)((uint64_t)s->f + (uint64_t)s->f0);
+    return s->y;
+}
+void orc_pll_i32_lanes(const int32_t ba[3], int32_t *st, const int32_t *x, int32_t *y, size_t frames,
+                       size_t lanes, int layout, int nthreads) {
+    LANE_BLOCKS(lanes, nthreads, lo, hi, {
+        for (size_t l = lo; l < hi; l++) {
+            pll_state s;
+            s.x0 = st[l]; s.clamp = st[lanes + l]; s.z0 = st[2 * lanes + l]; s.y0 = st[3 * lanes + l];
+            s.f0 = (int64_t)((uint64_t)(uint32_t)st[4 * lanes + l] | ((uint64_t)(uint32_t)st[5 * lanes + l] << 32));
+            s.f = (int64_t)((uint64_t)(uint32_t)st[6 * lanes + l] | ((uint64_t)(uint32_t)st[7 * lanes + l] << 32));
+            s.y = st[8 * lanes + l];
+            for (size_t t = 0; t < frames; t++) {
+                size_t i = layout == ORC_FRAME_MAJOR ? t * lanes + l : l * frames + t;
+                y[i] = pll_step(ba, &s, x[i]);
+            }
+            st[l] = s.x0; st[lanes + l] = s.clamp; st[2 * lanes + l] = s.z0; st[3 * lanes + l] = s.y0;
+            st[4 * lanes + l] = (int32_t)(uint32_t)s.f0; st[5 * lanes + l] = (int32_t)(s.f0 >> 32);
+            st[6 * lanes + l] = (int32_t)(uint32_t)s.f; st[7 * lanes + l] = (int32_t)(s.f >> 32);
+            st[8 * lanes + l] = s.y;
+        }
+    });
+}

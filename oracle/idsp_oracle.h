@@ -176,6 +176,12 @@ int64_t orc_cic_gain(int N, int M, uint32_t rate);
 uint32_t orc_cic_gain_log2(int N, int M, uint32_t rate);
 size_t orc_cic_response_length(int N, uint32_t rate);
 
+/* ---- PLL (src/pll.rs:33-108, ClampWrap src/unwrap.rs:166-194); state words (i32):
+ * [x0, clamp, z0, y0, f0 lo, f0 hi, f lo, f hi, y]; frequency() = f hi */
+void orc_pll_from_bandwidth(float bw, float split, int32_t ba[3]);
+void orc_pll_i32_lanes(const int32_t ba[3], int32_t *st /*[9][lanes]*/, const int32_t *x, int32_t *y,
+                       size_t frames, size_t lanes, int layout, int nthreads);
+
 #ifdef __cplusplus
 }
 #endif

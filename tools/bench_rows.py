@@ -113,6 +113,12 @@ def main():
             add(f"a14 HbfInt x{R} cascade f32 {lname}", "hbf.rs:476-512", hl * n_out * R, 4 + 4 / R,
                 lambda: Lanes(HbfIntCascade(k)).block(sint, y, x, layout))
             del x, y
+        from idsp_b200 import PLL, PLLState
+        xp, yp = rnd("i32", lanes * frames), torch.empty(lanes * frames, dtype=torch.int32, device=DEV)
+        sp = PLLState.default(lanes, DEV)
+        add(f"f4 PLL i32 {lname}", "pll.rs:88-108", lanes * frames, 8,
+            lambda: Lanes(PLL.from_bandwidth(1e-2, 4.0)).block(sp, xp, yp, layout))
+        del xp, yp
         # CIC /16 and x16, cubic (src/cic.rs PERF_N = 3, PERF_R = 16, PERF_D = 1)
         from idsp_b200 import Cic, CicState
         for kind in ("i32", "i64"):
