@@ -126,15 +126,22 @@ static int cascade_impl(idsp_ctx *ctx, const T *ba, int F, int nsec, T *state, c
     do {                                                                             \
         typename CascadeOp<T, N>::Params p;                                          \
         for (int s = 0; s < N; s++)                                                  \
-            for (int i = 0; i < 5; i++) p.ba[s][i] = s < nsec ? ba[5 * s + i] : T(0); \
+            for (int i = 0; i < 5; i++) p.ba[s][i] = ba[5 * s + i];                    \
         p.F = F;                                                                     \
         p.nsec = nsec;                                                               \
         p.st = state;                                                                \
         return launch_lanes_best<CascadeOp<T, N>>(ctx, p, x, y, frames, lanes, sstride, layout); \
     } while (0)
-    if (nsec <= 2) GO(2);
-    if (nsec <= 4) GO(4);
-    GO(IDSP_MAX_SECTIONS);
+    switch (nsec) {
+        case 1: GO(1);
+        case 2: GO(2);
+        case 3: GO(3);
+        case 4: GO(4);
+        case 5: GO(5);
+        case 6: GO(6);
+        case 7: GO(7);
+        default: GO(8);
+    }
 #undef GO
 }
 

@@ -8,6 +8,7 @@
 // arithmetic shifts, per-op rounded floats, no FMA: the library is compiled with
 // -fmad=false).  Reference file:line is cited at each Op.
 #pragma once
+#include <type_traits>
 #include <stdint.h>
 
 #include "tables.cuh"
@@ -39,6 +40,13 @@ struct OpHooks {
     template <class P> __device__ __forceinline__ void bind(const P &, const uint32_t *) {}
 };
 
+// a * b + c with a, b i32 and c i64: one IMAD.WIDE (the compiler turns an i64 product of a
+// sign-extended register and a kernel parameter into a 5-instruction 64x32 multiply)
+__device__ __forceinline__ int64_t mad_wide(int32_t a, int32_t b, int64_t c) {
+    int64_t r;
+    asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"(c));
+    return r;
+}
 // num_traits::clamp (src/iir/biquad.rs:400): `<`/`>` compares so NaN passes through
 template <class T> __device__ __forceinline__ T clamp_nt(T v, T lo, T hi) {
     return v < lo ? lo : (v > hi ? hi : v);
@@ -125,44 +133,45 @@ template <class T, bool CLAMP, int MODE = 0> struct Df1Op {
 };
 
 // Cascade<[Biquad;N]> on DirectForm<T,N> (src/iir/biquad.rs:339-364)
-template <class T, int NMAX> struct CascadeOp : OpHooks {
+template <class T, int N> struct CascadeOp : OpHooks {
+    // exactly N sections (the entry point dispatches on nsec): every index below is static, so
+    // the 2 + 2N delay values stay in registers
     using In = T;
     using Out = T;
+    static constexpr bool FAST = std::is_same<T, int32_t>::value;  // i32: the entry point routes 0 <= F < 32 here
     struct Params {
-        T ba[NMAX][5];
+        T ba[N][5];
         int F;
         int nsec;
         T *st;
     };
-    T d[2 + 2 * NMAX];  // [x0,x1,y[0][0],y[0][1],...]
+    T d[2 + 2 * N];  // [x0,x1,y[0][0],y[0][1],...]
     __device__ __forceinline__ void load(const Params &p, size_t lane, size_t stride) {
 #pragma unroll
-        for (int w = 0; w < 2 + 2 * NMAX; w++)
-            if (w < 2 + 2 * p.nsec) d[w] = p.st[(size_t)w * stride + lane];
+        for (int w = 0; w < 2 + 2 * N; w++) d[w] = p.st[(size_t)w * stride + lane];
     }
     __device__ __forceinline__ void store(const Params &p, size_t lane, size_t stride) const {
 #pragma unroll
-        for (int w = 0; w < 2 + 2 * NMAX; w++)
-            if (w < 2 + 2 * p.nsec) p.st[(size_t)w * stride + lane] = d[w];
+        for (int w = 0; w < 2 + 2 * N; w++) p.st[(size_t)w * stride + lane] = d[w];
     }
     __device__ __forceinline__ T step(const Params &p, T x0) {
 #pragma unroll
-        for (int s = 0; s < NMAX; s++) {
-            if (s < p.nsec) {
-                T y0 = Sos<T>::eval(p.ba[s], p.F, x0, d[2 * s], d[2 * s + 1], d[2 * s + 2],
-                                    d[2 * s + 3]);
-                d[2 * s + 1] = d[2 * s];
-                d[2 * s] = x0;
-                x0 = y0;
+        for (int s = 0; s < N; s++) {
+            T y0;
+            if constexpr (FAST) {
+                if (p.F >= 0 && p.F < 32)  // uniform
+                    y0 = SosI32Fast::eval(p.ba[s], p.F, x0, d[2 * s], d[2 * s + 1], d[2 * s + 2], d[2 * s + 3]);
+                else
+                    y0 = Sos<T>::eval(p.ba[s], p.F, x0, d[2 * s], d[2 * s + 1], d[2 * s + 2], d[2 * s + 3]);
+            } else {
+                y0 = Sos<T>::eval(p.ba[s], p.F, x0, d[2 * s], d[2 * s + 1], d[2 * s + 2], d[2 * s + 3]);
             }
+            d[2 * s + 1] = d[2 * s];
+            d[2 * s] = x0;
+            x0 = y0;
         }
-#pragma unroll
-        for (int s = 0; s < NMAX; s++) {
-            if (s == p.nsec - 1) {
-                d[2 * s + 3] = d[2 * s + 2];
-                d[2 * s + 2] = x0;
-            }
-        }
+        d[2 * N + 1] = d[2 * N];
+        d[2 * N] = x0;
         return x0;
     }
 };
@@ -270,12 +279,15 @@ template <bool CLAMP> struct Df1DitherOp : OpHooks {
         p.st[4 * stride + lane] = (int32_t)e;
     }
     __device__ __forceinline__ int32_t step(const Params &p, int32_t x0) {
-        uint64_t acc = (uint64_t)e + (uint64_t)((int64_t)p.ba[0] * x0) +
-                       (uint64_t)((int64_t)p.ba[1] * x1) + (uint64_t)((int64_t)p.ba[2] * x2) +
-                       (uint64_t)((int64_t)p.ba[3] * y1) + (uint64_t)((int64_t)p.ba[4] * y2);
-        acc <<= (32 - p.F);
-        e = p.F == 0 ? 0u : ((uint32_t)acc) >> (32 - p.F);
-        int32_t y0 = (int32_t)((int64_t)acc >> 32);
+        // acc <<= 32 - F; e = (acc as u32) >> (32 - F); y0 = (acc >> 32) as i32   (biquad.rs:520-526)
+        // == y0 = bits [F, F+32) of acc (one funnel shift), e = low F bits of acc (0 <= F < 32)
+        int64_t acc = mad_wide(p.ba[0], x0, (int64_t)(uint64_t)e);
+        acc = mad_wide(p.ba[1], x1, acc);
+        acc = mad_wide(p.ba[2], x2, acc);
+        acc = mad_wide(p.ba[3], y1, acc);
+        acc = mad_wide(p.ba[4], y2, acc);
+        e = (uint32_t)acc & ((1u << p.F) - 1u);
+        int32_t y0 = (int32_t)__funnelshift_r((uint32_t)acc, (uint32_t)((uint64_t)acc >> 32), (uint32_t)p.F);
         x2 = x1;
         x1 = x0;
         y2 = y1;
@@ -391,13 +403,6 @@ __device__ __forceinline__ int32_t atan2_dev(int32_t y, int32_t x) {
 __device__ __forceinline__ int32_t sat_sub(int32_t a, int32_t b) {
     int32_t r;
     asm("sub.sat.s32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
-    return r;
-}
-// a * b + c with a, b i32 and c i64: one IMAD.WIDE (the compiler turns an i64 product of a
-// sign-extended register and a kernel parameter into a 5-instruction 64x32 multiply)
-__device__ __forceinline__ int64_t mad_wide(int32_t a, int32_t b, int64_t c) {
-    int64_t r;
-    asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"(c));
     return r;
 }
 template <int ORDER>
