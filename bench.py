@@ -557,6 +557,41 @@ def run_biquad(args, rank, world, local):
     return line
 
 
+def verify_full_job(args, rank, local):
+    """--full: replay the whole 1e7-frame job on a lane subset with the CPU oracle (same cyclic ring
+    of input blocks, state carried from the very first frame) and compare the FINAL filter state
+    and the last output block bit for bit."""
+    import torch
+
+    import oracle as O
+    from idsp_b200 import DirectForm1, Lanes
+
+    dev = f"cuda:{local}"
+    bq = biquad_coeffs()
+    cfg = Lanes(bq)
+    lanes, frames, nring, sub = BIQUAD_LANES, args.frames, args.ring, 64
+    n = lanes * frames
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(2 + rank)
+    xin = [torch.randint(-(1 << 28), 1 << 28, (n,), dtype=torch.int32, device=dev, generator=gen) for _ in range(nring)]
+    y = torch.empty(n, dtype=torch.int32, device=dev)
+    st = DirectForm1.default("i32", lanes, dev)
+    steps = (TOTAL_FRAMES + frames - 1) // frames
+    for i in range(steps):
+        cfg.block(st, xin[i % nring], y, 0)
+    torch.cuda.synchronize()
+    xs = [x.view(frames, lanes)[:, :sub].contiguous().cpu().numpy().reshape(-1) for x in xin]
+    so = np.zeros((4, sub), np.int32)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        want = O.biquad_lanes("df1", "i32", bq.ba, F_BITS, None, so, xs[i % nring], sub, 0, nthreads=host_threads())
+    cpu_s = time.perf_counter() - t0
+    got = y.view(frames, lanes)[:, :sub].contiguous().cpu().numpy().reshape(-1)
+    ok = bool(np.array_equal(got, want) and np.array_equal(st.numpy()[:, :sub], so))
+    return {"lanes_checked": sub, "frames": steps * frames, "final_state_and_last_block_bit_exact": ok,
+            "cpu_replay_seconds": cpu_s}
+
+
 def run_hbf(args, rank, world, local):
     import torch
 
@@ -686,6 +721,10 @@ def main():
     rank, world, local = dist_setup(args.gpus)
     if args.workload == "biquad":
         line = run_biquad(args, rank, world, local)
+        if args.full and line is not None and not args.profile:
+            line["full_job"]["verify"] = verify_full_job(args, rank, local)
+            if not line["full_job"]["verify"]["final_state_and_last_block_bit_exact"]:
+                raise SystemExit("bench --full: final state differs from the oracle")
         if not (args.no_extra or args.profile or args.full):
             # secondary headline (BASELINE configs[2]) measured in the same run, same contract
             import copy
