@@ -19,7 +19,7 @@ from .hbf import (  # noqa: F401
     OddAntiSymmetric, OddSymmetric, hbf_dec_response_length, hbf_int_response_length, hbf_taps,
 )
 from .nco import (  # noqa: F401
-    PLL, Accu, Lockin, LockinState, Lowpass, LowpassState, PLLState, atan2, cossin, sos, sos_clamp_wide,
+    PLL, Accu, FmDiscriminator, FmDiscState, Lockin, LockinState, Lowpass, LowpassState, PLLState, atan2, cossin, sos, sos_clamp_wide,
 )
 from .coefficients import Filter  # noqa: F401
 from .cic import Cic, CicState, Decimator, Interpolator  # noqa: F401

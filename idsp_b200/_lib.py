@@ -61,6 +61,7 @@ def _signatures():
     sig["idsp_lowpass_i32"] = ([_c_p, _i, _c_p, _c_p, _c_p, _c_p] + lanes_tail, _i)
     for n in ("idsp_lockin_i32", "idsp_lockin_i32_host"):
         sig[n] = ([_c_p, _i, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p] + lanes_tail, _i)
+    sig["idsp_fm_disc_i32"] = ([_c_p, C.c_int32, _c_p, _i, _c_p, _c_p, _c_p] + lanes_tail, _i)
     sig["idsp_pll_i32"] = ([_c_p, _c_p, _c_p, _c_p, _c_p] + lanes_tail, _i)
     # ctx, N, M, rate, state, x, y, frames, lanes, layout
     sig["idsp_cic_state_words"] = ([_i, _i], _sz)

@@ -557,4 +557,62 @@ struct PllOp : OpHooks {
     }
 };
 
+// --------------------------------------------------------------------------
+// FM discriminator graph of examples/fm_disc.rs:26-48, fused:
+//   z = x * prev.into_bits().conj()   Complex<Q32<32>> * Complex<i32> (src/complex.rs:117-134):
+//                                     wide products, one late `>> 32` per component
+//   d = z.arg() - carrier             atan2(im, re) (src/complex.rs:254-256), wrapping
+//   y = Biquad<Q32<F>> DF1 (d)        src/iir/biquad.rs:366-383
+// The first sample of a stream (no previous sample) gives d = 0.
+// State words (i32): [has_prev, prev.re, prev.im, x1, x2, y1, y2].
+// --------------------------------------------------------------------------
+struct FmDiscOp : OpHooks {
+    using In = int2;   // Complex<Q32<32>> as raw (re, im)
+    using Out = int32_t;
+    struct Params {
+        int32_t carrier;
+        int32_t ba[5];
+        int F;
+        int32_t *st;
+    };
+    int32_t has, pre, pim, x1, x2, y1, y2;
+    __device__ __forceinline__ void load(const Params &p, size_t lane, size_t stride) {
+        has = p.st[lane];
+        pre = p.st[stride + lane];
+        pim = p.st[2 * stride + lane];
+        x1 = p.st[3 * stride + lane];
+        x2 = p.st[4 * stride + lane];
+        y1 = p.st[5 * stride + lane];
+        y2 = p.st[6 * stride + lane];
+    }
+    __device__ __forceinline__ void store(const Params &p, size_t lane, size_t stride) const {
+        p.st[lane] = has;
+        p.st[stride + lane] = pre;
+        p.st[2 * stride + lane] = pim;
+        p.st[3 * stride + lane] = x1;
+        p.st[4 * stride + lane] = x2;
+        p.st[5 * stride + lane] = y1;
+        p.st[6 * stride + lane] = y2;
+    }
+    __device__ __forceinline__ int32_t step(const Params &p, int2 x) {
+        int32_t d = 0;
+        if (has) {
+            const int32_t cim = (int32_t)(0u - (uint32_t)pim);  // conj() of the i32 bits (wrapping neg)
+            const int64_t re = (int64_t)((uint64_t)((int64_t)x.x * pre) - (uint64_t)((int64_t)x.y * cim));
+            const int64_t im = (int64_t)((uint64_t)((int64_t)x.x * cim) + (uint64_t)((int64_t)x.y * pre));
+            d = (int32_t)((uint32_t)atan2_dev((int32_t)(im >> 32), (int32_t)(re >> 32)) - (uint32_t)p.carrier);
+        }
+        has = 1;
+        pre = x.x;
+        pim = x.y;
+        const int32_t y0 = (p.F >= 0 && p.F < 32) ? SosI32Fast::eval(p.ba, p.F, d, x1, x2, y1, y2)
+                                                  : Sos<int32_t>::eval(p.ba, p.F, d, x1, x2, y1, y2);
+        x2 = x1;
+        x1 = d;
+        y2 = y1;
+        y1 = y0;
+        return y0;
+    }
+};
+
 }  // namespace idsp

@@ -231,3 +231,23 @@ extern "C" int idsp_pll_i32(idsp_ctx *ctx, const int32_t *ba, int32_t *state, co
     p.st = state;
     return launch_lanes_best<PllOp>(ctx, p, x, y, frames, lanes, lanes, layout);
 }
+
+// ---------------------------------------------------------------- FM discriminator
+extern "C" int idsp_fm_disc_i32(idsp_ctx *ctx, int32_t carrier, const int32_t *ba, int F, int32_t *state,
+                                const int32_t *x, int32_t *y, size_t frames, size_t lanes, int layout) {
+    int r = idsp_use_device(ctx);
+    if (r) return r;
+    IDSP_CHECK_ARG(ba != nullptr, "ba is null");
+    IDSP_CHECK_ARG(F > -32 && F < 64, "F out of range");
+    IDSP_CHECK_ARG(layout == IDSP_FRAME_MAJOR || layout == IDSP_LANE_MAJOR,
+                   "layout must be 0 (frame-major) or 1 (lane-major)");
+    if (frames == 0 || lanes == 0) return IDSP_OK;
+    IDSP_CHECK_ARG(state && x && y, "state/x/y must not be null");
+    IDSP_CHECK_ARG((((uintptr_t)x) & 7) == 0, "x (re, im pairs) must be 8-byte aligned");
+    FmDiscOp::Params p;
+    p.carrier = carrier;
+    for (int i = 0; i < 5; i++) p.ba[i] = ba[i];
+    p.F = F;
+    p.st = state;
+    return launch_lanes<FmDiscOp>(ctx, p, (const int2 *)x, y, frames, lanes, lanes, layout);
+}

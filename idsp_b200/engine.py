@@ -242,6 +242,17 @@ class Context:
                   lambda fn, p: fn(self._h, p["x"], p["y"], n))
         return pp
 
+    # ------------------------------------------------------------------ fm discriminator
+    def fm_disc(self, carrier: int, ba: Sequence[int], F: int, state, x, out=None, *, lanes: int,
+                layout: int = FRAME_MAJOR):
+        b = np.asarray(ba, np.int32).reshape(5)
+        frames = (x.numel() if isinstance(x, torch.Tensor) else x.size) // (2 * lanes)
+        y = self._out_like(x, out, frames * lanes)
+        car = int(carrier) - (1 << 32) if int(carrier) >= (1 << 31) else int(carrier)
+        self._run("idsp_fm_disc_i32", None, False, {"state": state, "x": x, "y": y},
+                  lambda fn, p: fn(self._h, car, C.c_void_p(b.ctypes.data), F, p["state"], p["x"], p["y"], frames, lanes, layout))
+        return y
+
     # ------------------------------------------------------------------ pll
     def pll(self, ba: Sequence[int], state, x, out=None, *, lanes: int, layout: int = FRAME_MAJOR):
         b = np.asarray(ba, np.int32).reshape(3)

@@ -173,3 +173,29 @@ class PLL(_Proc):
 
     def _block(self, ctx, state, x, y, layout):
         ctx.pll(self.ba, state.words, x, y, lanes=state.lanes, layout=layout)
+
+
+class FmDiscState(LaneState):
+    """State of the fused FM discriminator graph per lane, i32 words
+    [has_prev, prev.re, prev.im, x1, x2, y1, y2] (``Option<Complex<Q32<32>>>`` + ``DirectForm1<i32>``)."""
+
+    DTYPE = np.int32
+
+    @classmethod
+    def default(cls, lanes: int = 1, device=None):
+        return cls(LaneState._alloc(7, lanes, np.int32, device))
+
+
+class FmDiscriminator(_Proc):
+    """``(FmDiscriminator{carrier} * Biquad<Q32<F>>).minor()`` of examples/fm_disc.rs:26-48:
+    X = Complex<Q32<32>> as (re, im) i32 pairs -> Y = i32."""
+
+    def __init__(self, carrier: int, deemph):
+        self.carrier = int(carrier)
+        self.deemph = deemph  # iir.Biquad with an i32 Q format
+
+    def widths(self):
+        return 2, 1
+
+    def _block(self, ctx, state, x, y, layout):
+        ctx.fm_disc(self.carrier, self.deemph.ba, self.deemph.fmt.F, state.words, x, y, lanes=state.lanes, layout=layout)

@@ -229,6 +229,16 @@ int idsp_cic_int_i64(idsp_ctx *ctx, int N, int M, uint32_t rate, int64_t *state,
 int idsp_pll_i32(idsp_ctx *ctx, const int32_t *ba, int32_t *state, const int32_t *x, int32_t *y,
                  size_t frames, size_t lanes, int layout);
 
+/* ------------------------------------------------------------------ FM discriminator
+ * The fixed-point core of examples/fm_disc.rs:26-48 fused into one pass per lane:
+ * `z = x * prev.into_bits().conj()` (`Complex<Q32<32>> * Complex<i32>`, src/complex.rs:117-134),
+ * `d = z.arg() - carrier` (src/complex.rs:254-256, wrapping), `y = Biquad<Q32<F>>` DF1 of d
+ * (src/iir/biquad.rs:366-383, ba = 5 raw coefficients).  x = frames * lanes (re, im) i32 pairs,
+ * y = frames * lanes.  State: SoA i32 words [has_prev, prev.re, prev.im, x1, x2, y1, y2];
+ * all zero = `Split::new(FmDiscriminator{..}, None)` * `DirectForm1::default()`. */
+int idsp_fm_disc_i32(idsp_ctx *ctx, int32_t carrier, const int32_t *ba, int F, int32_t *state,
+                     const int32_t *x, int32_t *y, size_t frames, size_t lanes, int layout);
+
 #ifdef __cplusplus
 }
 #endif

@@ -451,3 +451,20 @@ def pll_lanes(ba, st, x, lanes, layout=FRAME_MAJOR, nthreads=1):
     lib().orc_pll_i32_lanes(_p(ba), _p(st), _p(x), _p(y), C.c_size_t(x.size // lanes), C.c_size_t(lanes),
                             C.c_int(layout), C.c_int(nthreads))
     return y
+
+
+# ---------------------------------------------------------------- FM discriminator (examples/fm_disc.rs)
+FM_DISC_WORDS = 7
+
+
+def fm_disc_lanes(carrier, ba, F, st, x, lanes, layout=FRAME_MAJOR, nthreads=1):
+    """x: int32 (re, im) pairs, frames*lanes*2 values; st int32 [7, lanes] updated in place."""
+    ba = _arr(ba, np.int32)
+    x = _arr(x, np.int32)
+    assert st.dtype == np.int32 and st.shape == (FM_DISC_WORDS, lanes)
+    frames = x.size // (2 * lanes)
+    y = np.empty(frames * lanes, np.int32)
+    car = int(carrier) - (1 << 32) if int(carrier) >= (1 << 31) else int(carrier)
+    lib().orc_fm_disc_i32_lanes(C.c_int32(car), _p(ba), C.c_int(F), _p(st), _p(x), _p(y), C.c_size_t(frames),
+                                C.c_size_t(lanes), C.c_int(layout), C.c_int(nthreads))
+    return y

@@ -1039,3 +1039,35 @@ void orc_pll_i32_lanes(const int32_t ba[3], int32_t *st, const int32_t *x, int32
         }
     });
 }
+
+/* ------------------------------------------------------------------ */
+/* FM discriminator graph, examples/fm_disc.rs:26-48: */
+/* z = x * prev.into_bits().conj() (src/complex.rs:117-134: wide products, */
+/* `.as_()` = >> 32), d = atan2(z.im, z.re) - carrier (src/complex.rs:254),*/
+/* y = Biquad<Q32<F>> DF1 (src/iir/biquad.rs:366-383).                     */
+/* State words (i32): [has_prev, prev.re, prev.im, x1, x2, y1, y2].        */
+/* ------------------------------------------------------------------ */
+void orc_fm_disc_i32_lanes(int32_t carrier, const int32_t ba[5], int F, int32_t *st, const int32_t *x,
+                           int32_t *y, size_t frames, size_t lanes, int layout, int nthreads) {
+    make_tables();
+    LANE_BLOCKS(lanes, nthreads, lo, hi, {
+        for (size_t l = lo; l < hi; l++) {
+            int32_t has = st[l], pre = st[lanes + l], pim = st[2 * lanes + l];
+            int32_t s[4] = {st[3 * lanes + l], st[4 * lanes + l], st[5 * lanes + l], st[6 * lanes + l]};
+            for (size_t t = 0; t < frames; t++) {
+                size_t i = layout == ORC_FRAME_MAJOR ? t * lanes + l : l * frames + t;
+                int32_t xre = x[2 * i], xim = x[2 * i + 1], d = 0;
+                if (has) {
+                    int32_t cim = (int32_t)(0u - (uint32_t)pim);
+                    int64_t re = (int64_t)((uint64_t)((int64_t)xre * pre) - (uint64_t)((int64_t)xim * cim));
+                    int64_t im = (int64_t)((uint64_t)((int64_t)xre * cim) + (uint64_t)((int64_t)xim * pre));
+                    d = (int32_t)((uint32_t)orc_atan2((int32_t)(im >> 32), (int32_t)(re >> 32)) - (uint32_t)carrier);
+                }
+                has = 1; pre = xre; pim = xim;
+                orc_biquad_df1_i32(ba, F, NULL, s, &d, &y[i], 1);
+            }
+            st[l] = has; st[lanes + l] = pre; st[2 * lanes + l] = pim;
+            st[3 * lanes + l] = s[0]; st[4 * lanes + l] = s[1]; st[5 * lanes + l] = s[2]; st[6 * lanes + l] = s[3];
+        }
+    });
+}

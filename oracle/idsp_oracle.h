@@ -182,6 +182,11 @@ void orc_pll_from_bandwidth(float bw, float split, int32_t ba[3]);
 void orc_pll_i32_lanes(const int32_t ba[3], int32_t *st /*[9][lanes]*/, const int32_t *x, int32_t *y,
                        size_t frames, size_t lanes, int layout, int nthreads);
 
+/* ---- FM discriminator graph (examples/fm_disc.rs:26-48): x = (re, im) i32 pairs; state words (i32)
+ * [has_prev, prev.re, prev.im, x1, x2, y1, y2] */
+void orc_fm_disc_i32_lanes(int32_t carrier, const int32_t ba[5], int F, int32_t *st, const int32_t *x,
+                           int32_t *y, size_t frames, size_t lanes, int layout, int nthreads);
+
 #ifdef __cplusplus
 }
 #endif

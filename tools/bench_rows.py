@@ -113,6 +113,14 @@ def main():
             add(f"a14 HbfInt x{R} cascade f32 {lname}", "hbf.rs:476-512", hl * n_out * R, 4 + 4 / R,
                 lambda: Lanes(HbfIntCascade(k)).block(sint, y, x, layout))
             del x, y
+        from idsp_b200 import FmDiscriminator, FmDiscState
+        xc = rnd("i32", 2 * lanes * frames)
+        yd = torch.empty(lanes * frames, dtype=torch.int32, device=DEV)
+        sf = FmDiscState.default(lanes, DEV)
+        fd = FmDiscriminator(0x19341234, Biquad.from_ba6(lp, Q("i32", 30)))
+        add(f"f4 FM discriminator graph i32 {lname}", "examples/fm_disc.rs:26-48", lanes * frames, 12,
+            lambda: Lanes(fd).block(sf, xc, yd, layout))
+        del xc, yd
         from idsp_b200 import PLL, PLLState
         xp, yp = rnd("i32", lanes * frames), torch.empty(lanes * frames, dtype=torch.int32, device=DEV)
         sp = PLLState.default(lanes, DEV)
