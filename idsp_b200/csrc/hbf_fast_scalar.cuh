@@ -229,14 +229,19 @@ template <int K, int s> struct StageRun {
     static_assert(NSUB == 1 || WIN % 32 == 0, "sub-item index must be warp-uniform");
 
     template <int Q0>
+    // y is lane-major (row stride `ystride`) when ylanes == 0, else frame-major with `ylanes` lanes
     __device__ __forceinline__ static void item(float *sm, int lane, int p0, int nl, float *y, size_t ystride,
-                                                size_t yoff, size_t lane0) {
+                                                size_t yoff, size_t lane0, size_t ylanes) {
         const float *E = sm + off_e(K, s);
         const float *O = sm + off_o(K, s);
         float out[R];
         SplitItem<TI, RA, Q0, R>::run(E + lane * pe(K, s), O + lane * po(K, s), p0, out);
         if constexpr (s == K - 1) {
-            if (lane < nl) {
+            if (lane < nl && ylanes) {
+                float *dst = y + (yoff + p0 + Q0) * ylanes + lane0 + lane;
+#pragma unroll
+                for (int j = 0; j < R; j++) dst[(size_t)j * ylanes] = out[j];
+            } else if (lane < nl) {
                 float *dst = y + (lane0 + lane) * ystride + yoff + p0 + Q0;
                 if (R >= 4 && (((uintptr_t)dst) & 15) == 0) {
 #pragma unroll
@@ -271,22 +276,22 @@ template <int K, int s> struct StageRun {
     // threads of the warps that hold no items (after they carried rows s-1)
     template <class F>
     __device__ __forceinline__ static void run(float *sm, int tid, int nl, float *y, size_t ystride,
-                                               size_t yoff, size_t lane0, F &&idle) {
+                                               size_t yoff, size_t lane0, size_t ylanes, F &&idle) {
         const int vt = tid - 32 * W0;
         if (vt >= 0 && vt < 32 * NWA) {
             for (int idx = vt; idx < ITEMS; idx += 32 * NWA) {
                 const int w = idx % WIN, sub = idx / WIN;
                 const int lane = w % NL, p0 = (w / NL) * RA;
                 if constexpr (NSUB == 1) {
-                    item<0>(sm, lane, p0, nl, y, ystride, yoff, lane0);
+                    item<0>(sm, lane, p0, nl, y, ystride, yoff, lane0, ylanes);
                 } else if constexpr (NSUB == 2) {
-                    if (sub == 0) item<0>(sm, lane, p0, nl, y, ystride, yoff, lane0);
-                    else item<R>(sm, lane, p0, nl, y, ystride, yoff, lane0);
+                    if (sub == 0) item<0>(sm, lane, p0, nl, y, ystride, yoff, lane0, ylanes);
+                    else item<R>(sm, lane, p0, nl, y, ystride, yoff, lane0, ylanes);
                 } else {
-                    if (sub == 0) item<0>(sm, lane, p0, nl, y, ystride, yoff, lane0);
-                    else if (sub == 1) item<R>(sm, lane, p0, nl, y, ystride, yoff, lane0);
-                    else if (sub == 2) item<2 * R>(sm, lane, p0, nl, y, ystride, yoff, lane0);
-                    else item<3 * R>(sm, lane, p0, nl, y, ystride, yoff, lane0);
+                    if (sub == 0) item<0>(sm, lane, p0, nl, y, ystride, yoff, lane0, ylanes);
+                    else if (sub == 1) item<R>(sm, lane, p0, nl, y, ystride, yoff, lane0, ylanes);
+                    else if (sub == 2) item<2 * R>(sm, lane, p0, nl, y, ystride, yoff, lane0, ylanes);
+                    else item<3 * R>(sm, lane, p0, nl, y, ystride, yoff, lane0, ylanes);
                 }
             }
         }
@@ -304,8 +309,8 @@ template <int K, int s> struct StageRun {
         }
     }
     __device__ __forceinline__ static void run(float *sm, int tid, int nl, float *y, size_t ystride,
-                                               size_t yoff, size_t lane0) {
-        run(sm, tid, nl, y, ystride, yoff, lane0, [](int, int) {});
+                                               size_t yoff, size_t lane0, size_t ylanes) {
+        run(sm, tid, nl, y, ystride, yoff, lane0, ylanes, [](int, int) {});
     }
 };
 
@@ -343,10 +348,24 @@ template <int K, int s, bool LOAD> struct StateIO {
     }
 };
 
-template <int K>
+// 16-byte asynchronous copy global -> shared (LDGSTS, L1 bypassed) and its mbarrier hook
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive(uint32_t bar) {  // arrives when this thread's copies landed
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// FM = false: x, y lane-major (x rows of n_in floats).  FM = true (K >= 2): frame-major,
+// x[t][lane][2^K], y[t][lane]: the per-lane rows of a tile are gathered with 16-byte LDGSTS
+// copies (8 lanes x 4 pieces of one frame per warp instruction = 512 contiguous bytes of HBM,
+// 8 different shared-memory rows per quarter-warp), every thread arriving on the tile's mbarrier.
+template <int K, bool FM>
 __global__ void __launch_bounds__(NT, HFS_MINB)
 hbf_dec_fast_kernel(float *st, const float *x, float *y, size_t n_out, size_t ntiles, size_t lanes,
                     size_t sstride) {
+    static_assert(!FM || K >= 2, "frame-major frames must be at least 16 bytes");
+    const size_t ylanes = FM ? lanes : 0;
     constexpr int TI0 = K - 1;
     constexpr int R0 = st_r(0);
     constexpr int HR = raw_h(K);
@@ -363,7 +382,7 @@ hbf_dec_fast_kernel(float *st, const float *x, float *y, size_t n_out, size_t nt
     for (int i = tid; i < smem_floats(K); i += NT) sm[i] = 0.f;
     if (tid == 0) {
 #pragma unroll
-        for (int b = 0; b < S; b++) mbar_init(smem_u32(&bars[b]), 1);
+        for (int b = 0; b < S; b++) mbar_init(smem_u32(&bars[b]), FM ? NT : 1);
         mbar_fence_init();
     }
     __syncthreads();
@@ -379,11 +398,25 @@ hbf_dec_fast_kernel(float *st, const float *x, float *y, size_t n_out, size_t nt
     // no warp is held up by a serial chain of NL bulk copies (complete_tx may precede the
     // expect_tx of thread 0: the phase cannot complete before that arrival).
     auto issue = [&](size_t tile) {
-        if ((tid & 31) == 0) {
+        const int b = (int)(tile % S);
+        const uint32_t bar = smem_u32(&bars[b]);
+        const uint32_t hist = tile ? HR : 0;
+        if constexpr (FM) {
+            constexpr int R = 1 << K;  // floats per frame and lane
+            // piece q = 4 consecutive stream samples of one lane, counted from the start of the history
+            const int npieces = (int)(NL * (TT + hist) / 4);
+            const size_t s0 = tile * TT - hist;  // stream position of piece 0
+            float *row0 = sm + b * NL * PR + HR - hist;
+            for (int c = tid; c < npieces; c += NT) {
+                const int l = c % NL, q = c / NL;
+                const size_t sp = s0 + 4 * (size_t)q;
+                if (l < nl)
+                    cp_async16(smem_u32(row0 + l * PR + 4 * q),
+                               x + ((sp / R) * lanes + lane0 + l) * R + (sp % R));
+            }
+            cp_async_arrive(bar);
+        } else if ((tid & 31) == 0) {
             constexpr int LPW = (NL + NT / 32 - 1) / (NT / 32);
-            const int b = (int)(tile % S);
-            const uint32_t bar = smem_u32(&bars[b]);
-            const uint32_t hist = tile ? HR : 0;
             if (tid == 0) mbar_expect_tx(bar, (uint32_t)(nl * (TT + hist) * 4));
 #pragma unroll
             for (int j = 0; j < LPW; j++) {
@@ -451,10 +484,10 @@ hbf_dec_fast_kernel(float *st, const float *x, float *y, size_t n_out, size_t nt
             // ---- raw buffer b is free again: refill it
             if (i + S < ntiles) issue(i + S);
             // ---- phases 1 .. K-1 (phase s also carries rows s-1)
-            if constexpr (K >= 2) { StageRun<K, 1>::run(sm, tid, nl, y, n_out, i * TO, lane0); __syncthreads(); }
-            if constexpr (K >= 3) { StageRun<K, 2>::run(sm, tid, nl, y, n_out, i * TO, lane0); __syncthreads(); }
-            if constexpr (K >= 4) { StageRun<K, 3>::run(sm, tid, nl, y, n_out, i * TO, lane0); __syncthreads(); }
-            if constexpr (K >= 5) { StageRun<K, 4>::run(sm, tid, nl, y, n_out, i * TO, lane0); __syncthreads(); }
+            if constexpr (K >= 2) { StageRun<K, 1>::run(sm, tid, nl, y, n_out, i * TO, lane0, ylanes); __syncthreads(); }
+            if constexpr (K >= 3) { StageRun<K, 2>::run(sm, tid, nl, y, n_out, i * TO, lane0, ylanes); __syncthreads(); }
+            if constexpr (K >= 4) { StageRun<K, 3>::run(sm, tid, nl, y, n_out, i * TO, lane0, ylanes); __syncthreads(); }
+            if constexpr (K >= 5) { StageRun<K, 4>::run(sm, tid, nl, y, n_out, i * TO, lane0, ylanes); __syncthreads(); }
             if constexpr (K == 2) {  // rows 1 are written again in the very next phase: carry them now
                 carry_rows<K, 1>(sm, tid >> 5, NT / 32, tid & 31);
                 __syncthreads();
@@ -463,21 +496,21 @@ hbf_dec_fast_kernel(float *st, const float *x, float *y, size_t n_out, size_t nt
             constexpr int H0 = StageRun<K, 2>::NIDLE < ITEMS0 ? StageRun<K, 2>::NIDLE : ITEMS0;  // items done in phase 2
             const bool more = i + 1 < ntiles;
             // ---- phase 1: stage 1, then rows K-1 of the previous tile (next written in phase K-2 >= 2)
-            StageRun<K, 1>::run(sm, tid, nl, y, n_out, i * TO, lane0);
+            StageRun<K, 1>::run(sm, tid, nl, y, n_out, i * TO, lane0, ylanes);
             if (i > 0) carry_rows<K, K - 1>(sm, tid >> 5, NT / 32, tid & 31);
             __syncthreads();
             // ---- phase 2: stage 2 | carry rows 1, then first part of stage 0 of tile i+1 (writes rows 1)
-            StageRun<K, 2>::run(sm, tid, nl, y, n_out, i * TO, lane0, [&](int gt, int G) {
+            StageRun<K, 2>::run(sm, tid, nl, y, n_out, i * TO, lane0, ylanes, [&](int gt, int G) {
                 bar_idle(G);  // every row-1 tail has been carried before any is overwritten
                 if (more) stage0(i + 1, 0, H0, gt, G);
             });
             __syncthreads();
             // ---- phase 3: stage 3 | carry rows 2, rest of stage 0 of tile i+1
-            StageRun<K, 3>::run(sm, tid, nl, y, n_out, i * TO, lane0, [&](int gt, int G) {
+            StageRun<K, 3>::run(sm, tid, nl, y, n_out, i * TO, lane0, ylanes, [&](int gt, int G) {
                 if (more) stage0(i + 1, H0, ITEMS0, gt, G);
             });
             __syncthreads();
-            if constexpr (K >= 5) { StageRun<K, 4>::run(sm, tid, nl, y, n_out, i * TO, lane0); __syncthreads(); }
+            if constexpr (K >= 5) { StageRun<K, 4>::run(sm, tid, nl, y, n_out, i * TO, lane0, ylanes); __syncthreads(); }
             // ---- the raw buffer of tile i+1 is free again: refill it
             if (i + 1 + S < ntiles) issue(i + 1 + S);
         }
@@ -490,10 +523,10 @@ hbf_dec_fast_kernel(float *st, const float *x, float *y, size_t n_out, size_t nt
     StateIO<K, 0, false>::run(sm, st, sstride, lane0, nl, tid, (int)((ntiles - 1) % S), TT);
 }
 
-template <int K>
+template <int K, bool FM>
 static int launch(idsp_ctx *ctx, float *st, const float *x, float *y, size_t n_out, size_t ntiles,
                   size_t lanes, size_t sstride) {
-    auto kern = hbf_dec_fast_kernel<K>;
+    auto kern = hbf_dec_fast_kernel<K, FM>;
     IDSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(K)));
     unsigned grid = (unsigned)((lanes + NL - 1) / NL);
     kern<<<grid, NT, smem_bytes(K), ctx->stream>>>(st, x, y, n_out, ntiles, lanes, sstride);
@@ -509,18 +542,30 @@ static int launch(idsp_ctx *ctx, float *st, const float *x, float *y, size_t n_o
 static int hbf_dec_fast_try_scalar(idsp_ctx *ctx, int k, float *state, const float *x, float *y, size_t n_out,
                             size_t lanes, size_t sstride, int layout, size_t *done) {
     *done = 0;
-    if (ctx->policy == 1 || layout != IDSP_LANE_MAJOR) return IDSP_HBF_FAST_NOT_APPLICABLE;
+    const bool fm = layout == IDSP_FRAME_MAJOR;
+    // frame-major: /2 frames are 8 bytes (no 16-byte pieces); /32 measured faster on the generic
+    // thread-per-lane kernel (946 vs 823 GSa/s), whose 128-byte frames already coalesce well
+    if (ctx->policy == 1 || (fm && (k < 2 || (k > 4 && ctx->policy != 2)))) return IDSP_HBF_FAST_NOT_APPLICABLE;
     const size_t TO = (size_t)hfs::TT >> k;
     const size_t ntiles = n_out / TO;
     const bool ok = ntiles >= 1 && (((uintptr_t)x) & 15) == 0 && ((n_out << k) % 4) == 0;
     if (!ok) return IDSP_HBF_FAST_NOT_APPLICABLE;
     int r;
-    switch (k) {
-        case 1: r = hfs::launch<1>(ctx, state, x, y, n_out, ntiles, lanes, sstride); break;
-        case 2: r = hfs::launch<2>(ctx, state, x, y, n_out, ntiles, lanes, sstride); break;
-        case 3: r = hfs::launch<3>(ctx, state, x, y, n_out, ntiles, lanes, sstride); break;
-        case 4: r = hfs::launch<4>(ctx, state, x, y, n_out, ntiles, lanes, sstride); break;
-        default: r = hfs::launch<5>(ctx, state, x, y, n_out, ntiles, lanes, sstride); break;
+    if (fm) {
+        switch (k) {
+            case 2: r = hfs::launch<2, true>(ctx, state, x, y, n_out, ntiles, lanes, sstride); break;
+            case 3: r = hfs::launch<3, true>(ctx, state, x, y, n_out, ntiles, lanes, sstride); break;
+            case 4: r = hfs::launch<4, true>(ctx, state, x, y, n_out, ntiles, lanes, sstride); break;
+            default: r = hfs::launch<5, true>(ctx, state, x, y, n_out, ntiles, lanes, sstride); break;
+        }
+    } else {
+        switch (k) {
+            case 1: r = hfs::launch<1, false>(ctx, state, x, y, n_out, ntiles, lanes, sstride); break;
+            case 2: r = hfs::launch<2, false>(ctx, state, x, y, n_out, ntiles, lanes, sstride); break;
+            case 3: r = hfs::launch<3, false>(ctx, state, x, y, n_out, ntiles, lanes, sstride); break;
+            case 4: r = hfs::launch<4, false>(ctx, state, x, y, n_out, ntiles, lanes, sstride); break;
+            default: r = hfs::launch<5, false>(ctx, state, x, y, n_out, ntiles, lanes, sstride); break;
+        }
     }
     if (r == IDSP_OK) *done = ntiles * TO;
     return r;

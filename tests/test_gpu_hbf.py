@@ -190,19 +190,21 @@ def test_chain_vs_oracle(oracle, k):
         assert_bits_equal(to_np(st), so)
 
 
+@pytest.mark.parametrize("layout", [1, 0])
 @pytest.mark.parametrize("k", [1, 2, 3, 4, 5])
-def test_dec_cascade_tiled_kernel_streaming(oracle, k):
-    """lane-major: the tiled TMA kernel + generic tail, state carried across ragged calls,
-    == one oracle pass; also the generic-only path (policy 1) gives the same bits"""
+def test_dec_cascade_tiled_kernel_streaming(oracle, k, layout):
+    """the tiled kernel (lane-major: TMA rows; frame-major: LDGSTS gathers, k >= 2) + generic tail,
+    state carried across ragged calls, == one oracle pass; also the generic-only path (policy 1) and
+    the packed f32x2 variant (policy 3) give the same bits"""
     rng = np.random.default_rng(60 + k)
     R = 1 << k
     TO = 512 >> k
     lanes = 37
     chunks = [2 * TO + 3, TO, 1, 3 * TO - 1, 6 * TO + 2]
     n_out = sum(chunks)
-    x = rng.uniform(-1, 1, (lanes, n_out, R)).astype(np.float32)
+    x = rng.uniform(-1, 1, (n_out, lanes, R)).astype(np.float32)  # [frames, lanes, R]
     so = np.zeros((oracle.hbf_dec_state_words(k), lanes), np.float32)
-    want = oracle.hbf_dec_cascade_lanes(k, so, x.reshape(-1), lanes, 1).reshape(lanes, n_out)
+    want = oracle.hbf_dec_cascade_lanes(k, so, layout_flat(x, 1), lanes, 1).reshape(lanes, n_out).T
     ctx = ib.default_context(0)
     for policy in (0, 1, 3):  # default tiled kernel, generic only, packed f32x2 tiled variant
         ctx.set_kernel_policy(policy)
@@ -210,12 +212,11 @@ def test_dec_cascade_tiled_kernel_streaming(oracle, k):
             st = _dec_state(k)(lanes, DEV)
             outs, a = [], 0
             for c in chunks:
-                xc = np.ascontiguousarray(x[:, a:a + c]).reshape(-1)
                 y = torch.empty(lanes * c, dtype=torch.float32, device=DEV)
-                Lanes(HbfDecCascade(k)).block(st, to_dev(xc), y, 1)
-                outs.append(to_np(y).reshape(lanes, c))
+                Lanes(HbfDecCascade(k)).block(st, to_dev(layout_flat(x[a:a + c], layout)), y, layout)
+                outs.append(to_np(y).reshape(c, lanes) if layout == 0 else to_np(y).reshape(lanes, c).T)
                 a += c
-            assert_bits_equal(np.concatenate(outs, axis=1), want, f"k={k} policy={policy}")
+            assert_bits_equal(np.concatenate(outs, axis=0), want, f"k={k} policy={policy} layout={layout}")
             assert_bits_equal(st.numpy(), so, "state")
         finally:
             ctx.set_kernel_policy(0)
