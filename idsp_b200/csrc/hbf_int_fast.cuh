@@ -155,12 +155,16 @@ template <int K, int s, bool LOAD> struct StateIO {
     }
 };
 
-template <int K>
+// FM = false: x, y lane-major.  FM = true (K >= 2): frame-major x[t][lane], y[t][lane][2^K]: the
+// input tile is prefetched element-wise and the staged output rows leave as 16-byte pieces
+// (8 lanes x 4 pieces of one frame per warp store = up to 512 contiguous bytes of HBM).
+template <int K, bool FM>
 __global__ void __launch_bounds__(NT, 4)
 hbf_int_fast_kernel(float *st, const float *x, float *y, size_t n_in, size_t ntiles, size_t lanes, size_t sstride) {
+    static_assert(!FM || K >= 2, "frame-major frames must be at least 16 bytes");
     constexpr int TI = ti(K);
-    constexpr int NV = NL * TI / 4;            // float4 loads per input tile
-    constexpr int NVT = (NV + NT - 1) / NT;    // ... per thread
+    constexpr int NV = FM ? NL * TI : NL * TI / 4;  // loads per input tile (floats if FM, float4 else)
+    constexpr int NVT = (NV + NT - 1) / NT;         // ... per thread
     extern __shared__ __align__(128) float sm[];
     const int tid = threadIdx.x;
     const size_t lane0 = (size_t)blockIdx.x * NL;
@@ -172,14 +176,20 @@ hbf_int_fast_kernel(float *st, const float *x, float *y, size_t n_in, size_t nti
     StateIO<K, 0, true>::run(sm, st, sstride, lane0, nl, tid);
 
     // input prefetch (the input is 1/2^K of the traffic): float4 v = tid + j*NT of the tile
-    float4 nxt[NVT];
+    float4 nxt[NVT];  // FM uses .x only
     auto fetch = [&](size_t tile) {
 #pragma unroll
         for (int j = 0; j < NVT; j++) {
-            const int v = tid + j * NT, plane = v / (TI / 4), pvec = v % (TI / 4);
-            nxt[j] = (v < NV && plane < nl)
-                         ? *reinterpret_cast<const float4 *>(x + (lane0 + plane) * n_in + tile * TI + 4 * pvec)
-                         : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int v = tid + j * NT;
+            if constexpr (FM) {
+                const int plane = v % NL, t = v / NL;  // lane-fastest: 8 lanes of a frame are contiguous
+                nxt[j].x = (v < NV && plane < nl) ? x[(tile * TI + t) * lanes + lane0 + plane] : 0.f;
+            } else {
+                const int plane = v / (TI / 4), pvec = v % (TI / 4);
+                nxt[j] = (v < NV && plane < nl)
+                             ? *reinterpret_cast<const float4 *>(x + (lane0 + plane) * n_in + tile * TI + 4 * pvec)
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         }
     };
     if (ntiles) fetch(0);
@@ -188,8 +198,14 @@ hbf_int_fast_kernel(float *st, const float *x, float *y, size_t n_in, size_t nti
         const int ob = (int)(i & 1);
 #pragma unroll
         for (int j = 0; j < NVT; j++) {
-            const int v = tid + j * NT, plane = v / (TI / 4), pvec = v % (TI / 4);
-            if (v < NV) *reinterpret_cast<float4 *>(sm + off_u(K, 0) + plane * pitch(K, 0) + hist(0) + 4 * pvec) = nxt[j];
+            const int v = tid + j * NT;
+            if constexpr (FM) {
+                const int plane = v % NL, t = v / NL;
+                if (v < NV) sm[off_u(K, 0) + plane * pitch(K, 0) + hist(0) + t] = nxt[j].x;
+            } else {
+                const int plane = v / (TI / 4), pvec = v % (TI / 4);
+                if (v < NV) *reinterpret_cast<float4 *>(sm + off_u(K, 0) + plane * pitch(K, 0) + hist(0) + 4 * pvec) = nxt[j];
+            }
         }
         if (i + 1 < ntiles) fetch(i + 1);
         // rows K-1 of the previous tile: last read in its final phase, next written by stage K-2
@@ -198,16 +214,28 @@ hbf_int_fast_kernel(float *st, const float *x, float *y, size_t n_in, size_t nti
         }
         // the staging buffer about to be refilled must have been drained by its bulk stores
         // (bulk async-groups are per thread: every issuing thread waits for its own)
-        if (tid < nl) tma_wait_read<1>();
+        if constexpr (!FM) {
+            if (tid < nl) tma_wait_read<1>();
+        }
         __syncthreads();
         if constexpr (K >= 2) { StageRun<K, 0>::run(sm, tid, ob); __syncthreads(); }
         if constexpr (K >= 3) { StageRun<K, 1>::run(sm, tid, ob); __syncthreads(); }
         if constexpr (K >= 4) { StageRun<K, 2>::run(sm, tid, ob); __syncthreads(); }
         if constexpr (K >= 5) { StageRun<K, 3>::run(sm, tid, ob); __syncthreads(); }
         StageRun<K, K - 1>::run(sm, tid, ob);  // -> staging (and carries rows K-2)
-        fence_async_smem();                    // writers make the staging rows visible to the async proxy
+        if constexpr (!FM) fence_async_smem();  // writers make the staging rows visible to the async proxy
         __syncthreads();
-        if (tid < nl) {
+        if constexpr (FM) {
+            constexpr int R = 1 << K;
+            const float *stg = sm + off_out(K) + ob * NL * OUT_PITCH;
+            for (int c = tid; c < NL * TOUT / 4; c += NT) {
+                const int l = c % NL, q = c / NL;  // piece q = output samples 4q .. 4q+3 of lane l's tile
+                if (l < nl) {
+                    const float4 v = lds128v(stg + l * OUT_PITCH + 4 * q);
+                    *reinterpret_cast<float4 *>(y + ((i * TI + (4 * q) / R) * lanes + lane0 + l) * R + (4 * q) % R) = v;
+                }
+            }
+        } else if (tid < nl) {
             bulk_store_1d(y + (lane0 + tid) * n_out + i * TOUT, smem_u32(sm + off_out(K) + (ob * NL + tid) * OUT_PITCH),
                           TOUT * 4);
             tma_commit();
@@ -221,14 +249,16 @@ hbf_int_fast_kernel(float *st, const float *x, float *y, size_t n_in, size_t nti
         carry_rows<K, K - 1>(sm, tid >> 5, tid & 31);
         __syncthreads();
     }
-    if (tid < nl) tma_wait_read<0>();
+    if constexpr (!FM) {
+        if (tid < nl) tma_wait_read<0>();
+    }
     StateIO<K, 0, false>::run(sm, st, sstride, lane0, nl, tid);
 }
 
-template <int K>
+template <int K, bool FM>
 static int launch(idsp_ctx *ctx, float *st, const float *x, float *y, size_t n_in, size_t ntiles, size_t lanes,
                   size_t sstride) {
-    auto kern = hbf_int_fast_kernel<K>;
+    auto kern = hbf_int_fast_kernel<K, FM>;
     IDSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(K)));
     unsigned grid = (unsigned)((lanes + NL - 1) / NL);
     kern<<<grid, NT, smem_bytes(K), ctx->stream>>>(st, x, y, n_in, ntiles, lanes, sstride);
@@ -243,18 +273,30 @@ static int launch(idsp_ctx *ctx, float *st, const float *x, float *y, size_t n_i
 static int hbf_int_fast_try(idsp_ctx *ctx, int k, float *state, const float *x, float *y, size_t n_in,
                             size_t lanes, size_t sstride, int layout, size_t *done) {
     *done = 0;
-    if (ctx->policy == 1 || layout != IDSP_LANE_MAJOR) return IDSP_HBF_FAST_NOT_APPLICABLE;
+    const bool fm = layout == IDSP_FRAME_MAJOR;
+    // frame-major: x2 frames are 8 bytes (no 16-byte pieces); x32 measured faster on the generic
+    // thread-per-lane kernel (714 vs 560 GSa/s)
+    if (ctx->policy == 1 || (fm && (k < 2 || (k > 4 && ctx->policy != 2)))) return IDSP_HBF_FAST_NOT_APPLICABLE;
     const size_t TI = (size_t)hfi::TOUT >> k;
     const size_t ntiles = n_in / TI;
-    const bool ok = ntiles >= 1 && ((((uintptr_t)x) | ((uintptr_t)y)) & 15) == 0 && (n_in % 4) == 0;
+    const bool ok = ntiles >= 1 && ((((uintptr_t)x) | ((uintptr_t)y)) & 15) == 0 && (fm || (n_in % 4) == 0);
     if (!ok) return IDSP_HBF_FAST_NOT_APPLICABLE;
     int r;
-    switch (k) {
-        case 1: r = hfi::launch<1>(ctx, state, x, y, n_in, ntiles, lanes, sstride); break;
-        case 2: r = hfi::launch<2>(ctx, state, x, y, n_in, ntiles, lanes, sstride); break;
-        case 3: r = hfi::launch<3>(ctx, state, x, y, n_in, ntiles, lanes, sstride); break;
-        case 4: r = hfi::launch<4>(ctx, state, x, y, n_in, ntiles, lanes, sstride); break;
-        default: r = hfi::launch<5>(ctx, state, x, y, n_in, ntiles, lanes, sstride); break;
+    if (fm) {
+        switch (k) {
+            case 2: r = hfi::launch<2, true>(ctx, state, x, y, n_in, ntiles, lanes, sstride); break;
+            case 3: r = hfi::launch<3, true>(ctx, state, x, y, n_in, ntiles, lanes, sstride); break;
+            case 4: r = hfi::launch<4, true>(ctx, state, x, y, n_in, ntiles, lanes, sstride); break;
+            default: r = hfi::launch<5, true>(ctx, state, x, y, n_in, ntiles, lanes, sstride); break;
+        }
+    } else {
+        switch (k) {
+            case 1: r = hfi::launch<1, false>(ctx, state, x, y, n_in, ntiles, lanes, sstride); break;
+            case 2: r = hfi::launch<2, false>(ctx, state, x, y, n_in, ntiles, lanes, sstride); break;
+            case 3: r = hfi::launch<3, false>(ctx, state, x, y, n_in, ntiles, lanes, sstride); break;
+            case 4: r = hfi::launch<4, false>(ctx, state, x, y, n_in, ntiles, lanes, sstride); break;
+            default: r = hfi::launch<5, false>(ctx, state, x, y, n_in, ntiles, lanes, sstride); break;
+        }
     }
     if (r == IDSP_OK) *done = ntiles * TI;
     return r;

@@ -222,19 +222,21 @@ def test_dec_cascade_tiled_kernel_streaming(oracle, k, layout):
             ctx.set_kernel_policy(0)
 
 
+@pytest.mark.parametrize("layout", [1, 0])
 @pytest.mark.parametrize("k", [1, 2, 3, 4, 5])
-def test_int_cascade_tiled_kernel_streaming(oracle, k):
-    """lane-major x2^k: tiled kernel (TMA bulk stores) + generic tail, ragged calls with carried
-    state == one oracle pass; the generic-only path (policy 1) gives the same bits"""
+def test_int_cascade_tiled_kernel_streaming(oracle, k, layout):
+    """x2^k: tiled kernel (lane-major: TMA bulk stores; frame-major: 16-byte piece stores, k >= 2) +
+    generic tail, ragged calls with carried state == one oracle pass; the generic-only path
+    (policy 1) gives the same bits"""
     rng = np.random.default_rng(70 + k)
     R = 1 << k
     TI = 512 >> k
     lanes = 21
-    chunks = [2 * TI + 4, TI, 4, 3 * TI - 4, 5]
+    chunks = [2 * TI + 4, TI, 4, 3 * TI - 4, 5, 4 * TI]
     n_in = sum(chunks)
-    x = rng.uniform(-1, 1, (lanes, n_in)).astype(np.float32)
+    x = rng.uniform(-1, 1, (n_in, lanes)).astype(np.float32)  # [frames, lanes]
     so = np.zeros((oracle.hbf_int_state_words(k), lanes), np.float32)
-    want = oracle.hbf_int_cascade_lanes(k, so, x.reshape(-1), lanes, 1).reshape(lanes, n_in * R)
+    want = oracle.hbf_int_cascade_lanes(k, so, layout_flat(x, 1), lanes, 1).reshape(lanes, n_in, R).transpose(1, 0, 2)
     ctx = ib.default_context(0)
     for policy in (0, 1):
         ctx.set_kernel_policy(policy)
@@ -242,12 +244,12 @@ def test_int_cascade_tiled_kernel_streaming(oracle, k):
             st = _int_state(k)(lanes, DEV)
             outs, a = [], 0
             for c in chunks:
-                xc = np.ascontiguousarray(x[:, a:a + c]).reshape(-1)
                 y = torch.empty(lanes * c * R, dtype=torch.float32, device=DEV)
-                Lanes(HbfIntCascade(k)).block(st, to_dev(xc), y, 1)
-                outs.append(to_np(y).reshape(lanes, c * R))
+                Lanes(HbfIntCascade(k)).block(st, to_dev(layout_flat(x[a:a + c], layout)), y, layout)
+                yy = to_np(y)
+                outs.append(yy.reshape(c, lanes, R) if layout == 0 else yy.reshape(lanes, c, R).transpose(1, 0, 2))
                 a += c
-            assert_bits_equal(np.concatenate(outs, axis=1), want, f"k={k} policy={policy}")
+            assert_bits_equal(np.concatenate(outs, axis=0), want, f"k={k} policy={policy} layout={layout}")
             assert_bits_equal(st.numpy(), so, "state")
         finally:
             ctx.set_kernel_policy(0)
