@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """bench.py -- headline benchmark of the lane engine (BASELINE.json metric: GSa/s).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload biquad|hbf] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload biquad|hbf|lockin|chain|plumbing] [--full] [--impl reference]
 
 Workloads (BASELINE.json `configs`):
   biquad (default, configs[1]): 65 536-lane i32 iir::Biquad DF1, Q30 Butterworth lowpass
@@ -445,6 +445,59 @@ def run_chain(args, rank, world, local):
     }
 
 
+def run_plumbing(args, rank, world, local):
+    """configs[0]: 1-lane f32 iir::Biquad DF2T lowpass over 1e6 white-noise samples.  The reference
+    crate cannot be built here, so its scalar loop is the C port on ONE host core; the same stream
+    then goes through the C ABI on the GPU (one lane = one thread: pure latency, plumbing only) and
+    must produce the same bits."""
+    import hashlib
+
+    import torch
+
+    import oracle as O
+    from idsp_b200 import Biquad, DirectForm2Transposed, Filter, Lanes
+
+    n = 1_000_000
+    bq = Biquad.from_ba6(Filter().critical_frequency(0.01).lowpass(), "f32")
+    x = np.random.default_rng(1).standard_normal(n).astype(np.float32)
+    st = np.zeros(2, np.float32)
+    O.biquad_df2t("f32", bq.ba, None, st.copy(), x[:1000])
+    t0 = time.perf_counter()
+    reps = max(1, args.steps // 10)
+    for _ in range(reps):
+        s = st.copy()
+        want = O.biquad_df2t("f32", bq.ba, None, s, x)
+    cpu_s = (time.perf_counter() - t0) / reps
+    dev = f"cuda:{local}"
+    xd = torch.from_numpy(x).to(dev)
+    yd = torch.empty_like(xd)
+    sd = DirectForm2Transposed.default("f32", 1, dev)
+    Lanes(bq).block(sd, xd, yd)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sd = DirectForm2Transposed.default("f32", 1, dev)
+    e0.record()
+    Lanes(bq).block(sd, xd, yd)
+    e1.record()
+    torch.cuda.synchronize()
+    got = yd.cpu().numpy()
+    same = bool(np.array_equal(got.view(np.uint32), want.view(np.uint32)))
+    if not same:
+        raise SystemExit("bench plumbing: GPU output differs from the CPU port")
+    if rank != 0:
+        return None
+    return {
+        "metric": "MSa/s, 1-lane f32 iir::Biquad DF2T lowpass, 1e6 white-noise samples", "value": n / cpu_s / 1e6, "unit": "MSa/s",
+        "n_gpus": world, "steps": reps, "warmup": 1, "ms_per_step": cpu_s * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[0]: 1-lane f32 Biquad DF2T lowpass f0=0.01, 1e6 N(0,1) samples (seed 1), host CPU, 1 core"},
+        "cpu_baseline": {"value": n / cpu_s / 1e6, "unit": "MSa/s", "cores": 1, "kind": "port", "sample": "the whole 1e6-sample stream"},
+        "gpu_one_lane": {"value": n / (e0.elapsed_time(e1) * 1e-3) / 1e6, "unit": "MSa/s",
+                         "note": "one lane = one GPU thread: latency bound by construction; parity only"},
+        "checksum_sha256": hashlib.sha256(want.tobytes()).hexdigest(), "gpu_bits_equal_cpu": same,
+    }
+
+
 def run_biquad(args, rank, world, local):
     import torch
 
@@ -700,7 +753,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="biquad", choices=["biquad", "hbf", "lockin", "chain"])
+    ap.add_argument("--workload", default="biquad", choices=["biquad", "hbf", "lockin", "chain", "plumbing"])
     ap.add_argument("--frames", type=int, default=16384, help="frames per step (biquad)")
     ap.add_argument("--ring", type=int, default=3, help="distinct resident input blocks")
     ap.add_argument("--full", action="store_true", help="run the whole 1e7-frame job (biquad)")
@@ -738,6 +791,8 @@ def main():
         line = run_hbf(args, rank, world, local)
     elif args.workload == "lockin":
         line = run_lockin(args, rank, world, local)
+    elif args.workload == "plumbing":
+        line = run_plumbing(args, rank, world, local)
     else:
         line = run_chain(args, rank, world, local)
     if line is not None:
