@@ -671,17 +671,23 @@ def run_hbf(args, rank, world, local):
     yout = [torch.empty(lanes_s * n_out, dtype=torch.float32, device=dev) for _ in range(2)]
     states = [HbfDec16(lanes_s, dev) for _ in range(2)]
 
+    hl = args.hbf_layout  # x: lane-major [lane][65536] or frame-major [4096 frames][lane][16]
+
     def step(i):
         states[i % 2].words.zero_()
-        cfg.block(states[i % 2], xin[i % nring], yout[i % 2], 1)
+        cfg.block(states[i % 2], xin[i % nring], yout[i % 2], hl)
 
     step(0)
     torch.cuda.synchronize()
     sub = 32
-    xs = xin[0].view(lanes_s, HBF_INPUTS)[:sub].contiguous().cpu().numpy().reshape(-1)
+    if hl == 1:
+        xs = xin[0].view(lanes_s, HBF_INPUTS)[:sub].contiguous().cpu().numpy().reshape(-1)
+        got = yout[0].view(lanes_s, n_out)[:sub].contiguous().cpu().numpy().reshape(-1)
+    else:
+        xs = xin[0].view(n_out, lanes_s, 16)[:, :sub].contiguous().cpu().numpy().reshape(-1)
+        got = yout[0].view(n_out, lanes_s)[:, :sub].contiguous().cpu().numpy().reshape(-1)
     so = np.zeros((O.hbf_dec_state_words(4), sub), np.float32)
-    want = O.hbf_dec_cascade_lanes(4, so, xs, sub, 1, nthreads=host_threads())
-    got = yout[0].view(lanes_s, n_out)[:sub].contiguous().cpu().numpy().reshape(-1)
+    want = O.hbf_dec_cascade_lanes(4, so, xs, sub, hl, nthreads=host_threads())
     if not np.array_equal(got.view(np.uint32), want.view(np.uint32)):
         raise SystemExit("bench: GPU HBF output differs from the oracle -- refusing to report a number")
     for i in range(args.warmup):
@@ -729,12 +735,15 @@ def run_hbf(args, rank, world, local):
     per_launch_bytes = 4.25 * n_in
     achieved = per_launch_bytes * launches / (ms * 1e-3) / 1e9 if launches else 0.0
     cpu_v, cpu_dt, cpu_sample = cpu_calibrated("hbf", host_threads(), args.cpu_seconds) if world == 1 else (None, None, "measured at N=1 only")
+    cfg_h = hbf_config(args)
+    if hl == 0:
+        cfg_h["workload"] = cfg_h["workload"].replace("lane-major", "frame-major ([[f32;16]; lanes] per frame)")
     line = {
         "metric": metric_name("hbf"), "value": value, "unit": "GSa/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": hbf_config(args),
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg_h,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic_from_profiles("hbf_dec16_f32_lm_bytes_per_launch"), "peak_source": peak_src,
+                     "traffic": traffic_from_profiles("hbf_dec16_f32_lm_bytes_per_launch") if hl == 1 else None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": per_launch_bytes},
         "cpu_baseline": {"value": cpu_v, "unit": "GSa/s", "cores": host_threads(), "kind": "port",
                          "sample": cpu_sample, "seconds": cpu_dt},
@@ -761,10 +770,13 @@ def main():
     ap.add_argument("--e2e-frames", type=int, default=2048)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
-    ap.add_argument("--layout", type=int, default=0, choices=[0, 1], help="biquad: 0 frame-major (default), 1 lane-major")
+    ap.add_argument("--layout", type=int, default=None, choices=[0, 1],
+                    help="0 frame-major, 1 lane-major (default: biquad 0, hbf 1)")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary (hbf) measurement of the default run")
     ap.add_argument("--profile", action="store_true", help="profiling run: skip the CPU baseline and e2e legs")
     args = ap.parse_args()
+    args.hbf_layout = 1 if args.layout is None else args.layout
+    args.layout = 0 if args.layout is None else args.layout
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.full:
         args.steps = (TOTAL_FRAMES + args.frames - 1) // args.frames
