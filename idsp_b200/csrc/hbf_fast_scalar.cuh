@@ -352,19 +352,21 @@ template <int K, int s, bool LOAD> struct StateIO {
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cp_async_arrive(uint32_t bar) {  // arrives when this thread's copies landed
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-// FM = false: x, y lane-major (x rows of n_in floats).  FM = true (K >= 2): frame-major,
-// x[t][lane][2^K], y[t][lane]: the per-lane rows of a tile are gathered with 16-byte LDGSTS
+// FM = false: x, y lane-major (x rows of n_in floats).  FM = true: frame-major,
+// x[t][lane][2^K], y[t][lane]: the per-lane rows of a tile are gathered with 16-byte (/2: 8-byte) LDGSTS
 // copies (8 lanes x 4 pieces of one frame per warp instruction = 512 contiguous bytes of HBM,
 // 8 different shared-memory rows per quarter-warp), every thread arriving on the tile's mbarrier.
 template <int K, bool FM>
 __global__ void __launch_bounds__(NT, HFS_MINB)
 hbf_dec_fast_kernel(float *st, const float *x, float *y, size_t n_out, size_t ntiles, size_t lanes,
                     size_t sstride) {
-    static_assert(!FM || K >= 2, "frame-major frames must be at least 16 bytes");
     const size_t ylanes = FM ? lanes : 0;
     constexpr int TI0 = K - 1;
     constexpr int R0 = st_r(0);
@@ -402,17 +404,20 @@ hbf_dec_fast_kernel(float *st, const float *x, float *y, size_t n_out, size_t nt
         const uint32_t bar = smem_u32(&bars[b]);
         const uint32_t hist = tile ? HR : 0;
         if constexpr (FM) {
-            constexpr int R = 1 << K;  // floats per frame and lane
-            // piece q = 4 consecutive stream samples of one lane, counted from the start of the history
-            const int npieces = (int)(NL * (TT + hist) / 4);
+            constexpr int R = 1 << K;            // floats per frame and lane
+            constexpr int PF_ = R >= 4 ? 4 : 2;  // floats per piece: 16 bytes, or the whole 8-byte frame of /2
+            // piece q = PF_ consecutive stream samples of one lane, counted from the start of the history
+            const int npieces = (int)(NL * (TT + hist) / PF_);
             const size_t s0 = tile * TT - hist;  // stream position of piece 0
             float *row0 = sm + b * NL * PR + HR - hist;
             for (int c = tid; c < npieces; c += NT) {
                 const int l = c % NL, q = c / NL;
-                const size_t sp = s0 + 4 * (size_t)q;
-                if (l < nl)
-                    cp_async16(smem_u32(row0 + l * PR + 4 * q),
-                               x + ((sp / R) * lanes + lane0 + l) * R + (sp % R));
+                const size_t sp = s0 + PF_ * (size_t)q;
+                if (l < nl) {
+                    const float *src = x + ((sp / R) * lanes + lane0 + l) * R + (sp % R);
+                    if constexpr (PF_ == 4) cp_async16(smem_u32(row0 + l * PR + PF_ * q), src);
+                    else cp_async8(smem_u32(row0 + l * PR + PF_ * q), src);
+                }
             }
             cp_async_arrive(bar);
         } else if ((tid & 31) == 0) {
@@ -442,7 +447,11 @@ hbf_dec_fast_kernel(float *st, const float *x, float *y, size_t n_out, size_t nt
             float out[R0];
             RawItem<TI0, R0>::run(raw + lane * PR, p0, out);
             if constexpr (K == 1) {
-                if (lane < nl) {
+                if (lane < nl && FM) {
+                    float *dst = y + (t * TO + p0) * lanes + lane0 + lane;
+#pragma unroll
+                    for (int j = 0; j < R0; j++) dst[(size_t)j * lanes] = out[j];
+                } else if (lane < nl) {
                     float *dst = y + (lane0 + lane) * n_out + t * TO + p0;
                     if ((((uintptr_t)dst) & 15) == 0) {
 #pragma unroll
@@ -543,16 +552,16 @@ static int hbf_dec_fast_try_scalar(idsp_ctx *ctx, int k, float *state, const flo
                             size_t lanes, size_t sstride, int layout, size_t *done) {
     *done = 0;
     const bool fm = layout == IDSP_FRAME_MAJOR;
-    // frame-major: /2 frames are 8 bytes (no 16-byte pieces); /32 measured faster on the generic
-    // thread-per-lane kernel (946 vs 823 GSa/s), whose 128-byte frames already coalesce well
-    if (ctx->policy == 1 || (fm && (k < 2 || (k > 4 && ctx->policy != 2)))) return IDSP_HBF_FAST_NOT_APPLICABLE;
+    // frame-major /32 measured faster on the generic thread-per-lane kernel (946 vs 823 GSa/s), whose 128-byte frames already coalesce well
+    if (ctx->policy == 1 || (fm && k > 4 && ctx->policy != 2)) return IDSP_HBF_FAST_NOT_APPLICABLE;
     const size_t TO = (size_t)hfs::TT >> k;
     const size_t ntiles = n_out / TO;
-    const bool ok = ntiles >= 1 && (((uintptr_t)x) & 15) == 0 && ((n_out << k) % 4) == 0;
+    const bool ok = ntiles >= 1 && (((uintptr_t)x) & 15) == 0 && (fm || ((n_out << k) % 4) == 0);
     if (!ok) return IDSP_HBF_FAST_NOT_APPLICABLE;
     int r;
     if (fm) {
         switch (k) {
+            case 1: r = hfs::launch<1, true>(ctx, state, x, y, n_out, ntiles, lanes, sstride); break;
             case 2: r = hfs::launch<2, true>(ctx, state, x, y, n_out, ntiles, lanes, sstride); break;
             case 3: r = hfs::launch<3, true>(ctx, state, x, y, n_out, ntiles, lanes, sstride); break;
             case 4: r = hfs::launch<4, true>(ctx, state, x, y, n_out, ntiles, lanes, sstride); break;

@@ -155,13 +155,12 @@ template <int K, int s, bool LOAD> struct StateIO {
     }
 };
 
-// FM = false: x, y lane-major.  FM = true (K >= 2): frame-major x[t][lane], y[t][lane][2^K]: the
-// input tile is prefetched element-wise and the staged output rows leave as 16-byte pieces
+// FM = false: x, y lane-major.  FM = true: frame-major x[t][lane], y[t][lane][2^K]: the
+// input tile is prefetched element-wise and the staged output rows leave as 16-byte (x2: 8-byte) pieces
 // (8 lanes x 4 pieces of one frame per warp store = up to 512 contiguous bytes of HBM).
 template <int K, bool FM>
 __global__ void __launch_bounds__(NT, 4)
 hbf_int_fast_kernel(float *st, const float *x, float *y, size_t n_in, size_t ntiles, size_t lanes, size_t sstride) {
-    static_assert(!FM || K >= 2, "frame-major frames must be at least 16 bytes");
     constexpr int TI = ti(K);
     constexpr int NV = FM ? NL * TI : NL * TI / 4;  // loads per input tile (floats if FM, float4 else)
     constexpr int NVT = (NV + NT - 1) / NT;         // ... per thread
@@ -227,12 +226,17 @@ hbf_int_fast_kernel(float *st, const float *x, float *y, size_t n_in, size_t nti
         __syncthreads();
         if constexpr (FM) {
             constexpr int R = 1 << K;
+            constexpr int PF_ = R >= 4 ? 4 : 2;  // floats per piece: 16 bytes, or the 8-byte frame of x2
             const float *stg = sm + off_out(K) + ob * NL * OUT_PITCH;
-            for (int c = tid; c < NL * TOUT / 4; c += NT) {
-                const int l = c % NL, q = c / NL;  // piece q = output samples 4q .. 4q+3 of lane l's tile
+            for (int c = tid; c < NL * TOUT / PF_; c += NT) {
+                const int l = c % NL, q = c / NL;  // piece q = output samples PF_*q .. of lane l's tile
                 if (l < nl) {
-                    const float4 v = lds128v(stg + l * OUT_PITCH + 4 * q);
-                    *reinterpret_cast<float4 *>(y + ((i * TI + (4 * q) / R) * lanes + lane0 + l) * R + (4 * q) % R) = v;
+                    float *dst = y + ((i * TI + (PF_ * q) / R) * lanes + lane0 + l) * R + (PF_ * q) % R;
+                    if constexpr (PF_ == 4) {
+                        *reinterpret_cast<float4 *>(dst) = lds128v(stg + l * OUT_PITCH + PF_ * q);
+                    } else {
+                        *reinterpret_cast<float2 *>(dst) = *reinterpret_cast<const float2 *>(stg + l * OUT_PITCH + PF_ * q);
+                    }
                 }
             }
         } else if (tid < nl) {
@@ -274,9 +278,8 @@ static int hbf_int_fast_try(idsp_ctx *ctx, int k, float *state, const float *x, 
                             size_t lanes, size_t sstride, int layout, size_t *done) {
     *done = 0;
     const bool fm = layout == IDSP_FRAME_MAJOR;
-    // frame-major: x2 frames are 8 bytes (no 16-byte pieces); x32 measured faster on the generic
-    // thread-per-lane kernel (714 vs 560 GSa/s)
-    if (ctx->policy == 1 || (fm && (k < 2 || (k > 4 && ctx->policy != 2)))) return IDSP_HBF_FAST_NOT_APPLICABLE;
+    // frame-major x32 measured faster on the generic thread-per-lane kernel (714 vs 560 GSa/s)
+    if (ctx->policy == 1 || (fm && k > 4 && ctx->policy != 2)) return IDSP_HBF_FAST_NOT_APPLICABLE;
     const size_t TI = (size_t)hfi::TOUT >> k;
     const size_t ntiles = n_in / TI;
     const bool ok = ntiles >= 1 && ((((uintptr_t)x) | ((uintptr_t)y)) & 15) == 0 && (fm || (n_in % 4) == 0);
@@ -284,6 +287,7 @@ static int hbf_int_fast_try(idsp_ctx *ctx, int k, float *state, const float *x, 
     int r;
     if (fm) {
         switch (k) {
+            case 1: r = hfi::launch<1, true>(ctx, state, x, y, n_in, ntiles, lanes, sstride); break;
             case 2: r = hfi::launch<2, true>(ctx, state, x, y, n_in, ntiles, lanes, sstride); break;
             case 3: r = hfi::launch<3, true>(ctx, state, x, y, n_in, ntiles, lanes, sstride); break;
             case 4: r = hfi::launch<4, true>(ctx, state, x, y, n_in, ntiles, lanes, sstride); break;
