@@ -21,6 +21,9 @@ struct idsp_ctx {
     size_t dev_in_bytes, dev_out_bytes;
     void *dev_state;
     size_t dev_state_bytes;
+    // scratch for entry points that compose several kernels (stream-ordered reuse)
+    void *dev_scratch;
+    size_t dev_scratch_bytes;
     cudaEvent_t ev_h2d[IDSP_HOST_RING], ev_k[IDSP_HOST_RING], ev_d2h[IDSP_HOST_RING];
 };
 
@@ -53,6 +56,10 @@ void idsp_set_error(const char *fmt, ...);
             return IDSP_ECUDA;                                                       \
         }                                                                            \
     } while (0)
+
+// grows ctx->dev_scratch to at least `bytes` (ctx.cu); the previous buffer is released only after
+// the work queued on the ctx stream has finished
+int idsp_scratch(idsp_ctx *ctx, size_t bytes, void **ptr);
 
 static inline int idsp_use_device(idsp_ctx *ctx) {
     if (!ctx) {

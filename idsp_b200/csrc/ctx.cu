@@ -81,10 +81,31 @@ static void free_staging(idsp_ctx *c) {
     }
     if (c->dev_state) cudaFree(c->dev_state);
     c->dev_state = nullptr;
-    c->dev_in_bytes = c->dev_out_bytes = c->dev_state_bytes = 0;
+    if (c->dev_scratch) cudaFree(c->dev_scratch);
+    c->dev_scratch = nullptr;
+    c->dev_in_bytes = c->dev_out_bytes = c->dev_state_bytes = c->dev_scratch_bytes = 0;
     if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
     if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
     c->s_h2d = c->s_d2h = nullptr;
+}
+
+int idsp_scratch(idsp_ctx *ctx, size_t bytes, void **ptr) {
+    if (ctx->dev_scratch_bytes < bytes) {
+        if (ctx->dev_scratch) {
+            IDSP_CUDA(cudaStreamSynchronize(ctx->stream));  // queued kernels may still use the old buffer
+            cudaFree(ctx->dev_scratch);
+            ctx->dev_scratch = nullptr;
+            ctx->dev_scratch_bytes = 0;
+        }
+        cudaError_t e = cudaMalloc(&ctx->dev_scratch, bytes);
+        if (e != cudaSuccess) {
+            idsp_set_error("cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+            return IDSP_ENOMEM;
+        }
+        ctx->dev_scratch_bytes = bytes;
+    }
+    *ptr = ctx->dev_scratch;
+    return IDSP_OK;
 }
 
 extern "C" void idsp_b200_free(idsp_ctx *ctx) {

@@ -430,6 +430,23 @@ extern "C" int idsp_chain_f32(idsp_ctx *ctx, int log2_rate, const float ba[5], f
     HBF_COMMON_CHECK(n_low);
     IDSP_CHECK_ARG(ba != nullptr, "ba is null");
     IDSP_CHECK_ARG(log2_rate >= 1 && log2_rate <= 5, "log2_rate must be 1..5");
+    // Few lanes, lane-major: the fused thread-per-lane kernel would leave most SMs idle (one thread
+    // per lane, ~200 registers of delay lines).  Run the three bit-identical pieces instead: the two
+    // FIR cascades are time-parallel (tiled kernels, 8 lanes per CTA), only the biquad recurrence is
+    // serial per lane.  The low-rate stream goes through ctx scratch, the biquad runs in place on y.
+    // Measured cross-over on B200: composed wins up to 2^14 lanes (profiles/r1_bench_chain.json).
+    if (layout == IDSP_LANE_MAJOR && ctx->policy != 1 && lanes <= 16384) {
+        void *low = nullptr;
+        int r = idsp_scratch(ctx, n_low * lanes * sizeof(float), &low);
+        if (r) return r;
+        const size_t wd = (size_t)hbf_dec_words(log2_rate), wi = (size_t)hbf_int_words(log2_rate);
+        r = hbf_dec_cascade_dev(ctx, log2_rate, state, x, (float *)low, n_low, lanes, lanes, layout);
+        if (r) return r;
+        r = idsp_hbf_int_cascade_f32(ctx, log2_rate, state + wd * lanes, (const float *)low, y, n_low, lanes, layout);
+        if (r) return r;
+        return idsp_biquad_df1_f32(ctx, ba, 0, nullptr, state + (wd + wi) * lanes, y, y, n_low << log2_rate, lanes,
+                                   layout);
+    }
     Df1Op<float, false>::Params bp;
     for (int i = 0; i < 5; i++) bp.ba[i] = ba[i];
     bp.F = 0;
