@@ -353,8 +353,10 @@ int hbf_dec_cascade_dev(idsp_ctx *ctx, int k, float *state, const float *x, floa
         const char *e = getenv("IDSP_HBF_VARIANT");
         variant = (e && e[0] == 'p') ? 1 : 0;
     }
-    int fr = (variant == 1 || ctx->policy == 3) ? hbf_dec_fast_try(ctx, k, state, x, y, n_out, lanes, sstride, layout, &done)
-                          : hbf_dec_fast_try_scalar(ctx, k, state, x, y, n_out, lanes, sstride, layout, &done);
+    int fr = IDSP_HBF_FAST_NOT_APPLICABLE;
+    if (variant == 1 || ctx->policy == 3) fr = hbf_dec_fast_try(ctx, k, state, x, y, n_out, lanes, sstride, layout, &done);
+    if (fr == IDSP_HBF_FAST_NOT_APPLICABLE)  // the packed variant is lane-major only
+        fr = hbf_dec_fast_try_scalar(ctx, k, state, x, y, n_out, lanes, sstride, layout, &done);
     if (fr != IDSP_HBF_FAST_NOT_APPLICABLE && fr != IDSP_OK) return fr;
     if (fr == IDSP_HBF_FAST_NOT_APPLICABLE && ctx->policy == 2 && layout == IDSP_LANE_MAJOR) {
         idsp_set_error("tiled HBF kernel forced but shape/alignment does not qualify");

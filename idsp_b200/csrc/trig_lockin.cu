@@ -42,6 +42,17 @@ __global__ void __launch_bounds__(256) atan2_kernel(const int32_t *xy, int32_t *
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (vec) {
+        for (; i + stride < n2; i += 2 * stride) {  // two 16-byte loads in flight per thread
+            const int4 v0 = reinterpret_cast<const int4 *>(xy)[i];
+            const int4 v1 = reinterpret_cast<const int4 *>(xy)[i + stride];
+            int2 r0, r1;
+            r0.x = atan2_dev(v0.y, v0.x);
+            r0.y = atan2_dev(v0.w, v0.z);
+            r1.x = atan2_dev(v1.y, v1.x);
+            r1.y = atan2_dev(v1.w, v1.z);
+            reinterpret_cast<int2 *>(p)[i] = r0;
+            reinterpret_cast<int2 *>(p)[i + stride] = r1;
+        }
         for (; i < n2; i += stride) {
             int4 v = reinterpret_cast<const int4 *>(xy)[i];
             int2 r;
