@@ -40,7 +40,27 @@ unsafe extern "C" {
     ) -> c_int;
     pub fn idsp_cossin_i32_host(ctx: *mut idsp_ctx, phase: *const i32, cs: *mut i32, n: usize) -> c_int;
     pub fn idsp_atan2_i32_host(ctx: *mut idsp_ctx, xy: *const i32, p: *mut i32, n: usize) -> c_int;
-    // ... one declaration per symbol of include/idsp_b200.h
+    /// replaces `Lockin<Lowpass<N>>` fed by an `Accu` (src/lockin.rs:30-39); device pointers
+    pub fn idsp_lockin_i32(
+        ctx: *mut idsp_ctx, order: c_int, k: *const i32, accu_state: *mut i32, accu_step: *const i32,
+        lp_state: *mut i64, x: *const i32, iq: *mut i32, frames: usize, lanes: usize, layout: c_int,
+    ) -> c_int;
+    /// replaces `Split::stateful(Cic::<i64, N, M>::new(rate)).decimate()` (src/cic.rs:176-200)
+    pub fn idsp_cic_dec_i64(
+        ctx: *mut idsp_ctx, n: c_int, m: c_int, rate: u32, state: *mut i64, x: *const i64, y: *mut i64,
+        frames: usize, lanes: usize, layout: c_int,
+    ) -> c_int;
+    /// replaces `PLL::process` (src/pll.rs:88-108); ba = raw `Q32<32>` bits
+    pub fn idsp_pll_i32(
+        ctx: *mut idsp_ctx, ba: *const i32, state: *mut i32, x: *const i32, y: *mut i32,
+        frames: usize, lanes: usize, layout: c_int,
+    ) -> c_int;
+    /// replaces the graph of examples/fm_disc.rs:26-48
+    pub fn idsp_fm_disc_i32(
+        ctx: *mut idsp_ctx, carrier: i32, ba: *const i32, f: c_int, state: *mut i32, x: *const i32,
+        y: *mut i32, frames: usize, lanes: usize, layout: c_int,
+    ) -> c_int;
+    // ... one declaration per remaining symbol of include/idsp_b200.h (same pattern)
 }
 
 /// Owns a device context (one CUDA stream); `!Sync`, mirrors `&mut` exclusivity.
