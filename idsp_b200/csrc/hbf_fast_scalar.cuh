@@ -435,6 +435,30 @@ hbf_dec_fast_kernel(float *st, const float *x, float *y, size_t n_out, size_t nt
 #pragma unroll
     for (int b = 0; b < S; b++)
         if ((size_t)b < ntiles) issue(b);
+    // steady state (tile >= S >= 1, lane-major): source / destination of this warp's rows are kept in
+    // registers, so a refill is one multiply-add per pointer plus the copy itself
+    constexpr int LPW_ = (NL + NT / 32 - 1) / (NT / 32);
+    const float *isrc[LPW_];
+    uint32_t idst[LPW_];
+#pragma unroll
+    for (int j = 0; j < LPW_; j++) {
+        const int l = (tid >> 5) * LPW_ + j;
+        isrc[j] = x + (lane0 + (l < nl ? l : 0)) * n_in - HR;
+        idst[j] = smem_u32(sm + l * PR);
+    }
+    auto refill = [&](size_t tile) {
+        if constexpr (FM) {
+            issue(tile);
+        } else if ((tid & 31) == 0) {
+            const uint32_t b = (uint32_t)(tile % S);
+            const uint32_t bar = smem_u32(&bars[b]);
+            if (tid == 0) mbar_expect_tx(bar, (uint32_t)(nl * (TT + HR) * 4));
+#pragma unroll
+            for (int j = 0; j < LPW_; j++)
+                if ((tid >> 5) * LPW_ + j < nl)
+                    bulk_load_1d(idst[j] + b * (uint32_t)(NL * PR * 4), isrc[j] + tile * TT, (TT + HR) * 4, bar);
+        }
+    };
 
     // stage 0 of tile `t`: items [c0, c1) spread over the `G` threads of a group (gt = index in it)
     constexpr int ITEMS0 = NL * st_n(0) / R0;
@@ -479,7 +503,7 @@ hbf_dec_fast_kernel(float *st, const float *x, float *y, size_t n_out, size_t nt
     if constexpr (PF) {
         stage0(0, 0, ITEMS0, tid, NT);
         __syncthreads();
-        if ((size_t)S < ntiles) issue(S);
+        if ((size_t)S < ntiles) refill(S);
     }
     for (size_t i = 0; i < ntiles; i++) {
         if constexpr (!PF) {
@@ -491,7 +515,7 @@ hbf_dec_fast_kernel(float *st, const float *x, float *y, size_t n_out, size_t nt
             }
             __syncthreads();
             // ---- raw buffer b is free again: refill it
-            if (i + S < ntiles) issue(i + S);
+            if (i + S < ntiles) refill(i + S);
             // ---- phases 1 .. K-1 (phase s also carries rows s-1)
             if constexpr (K >= 2) { StageRun<K, 1>::run(sm, tid, nl, y, n_out, i * TO, lane0, ylanes); __syncthreads(); }
             if constexpr (K >= 3) { StageRun<K, 2>::run(sm, tid, nl, y, n_out, i * TO, lane0, ylanes); __syncthreads(); }
@@ -521,7 +545,7 @@ hbf_dec_fast_kernel(float *st, const float *x, float *y, size_t n_out, size_t nt
             __syncthreads();
             if constexpr (K >= 5) { StageRun<K, 4>::run(sm, tid, nl, y, n_out, i * TO, lane0, ylanes); __syncthreads(); }
             // ---- the raw buffer of tile i+1 is free again: refill it
-            if (i + 1 + S < ntiles) issue(i + 1 + S);
+            if (i + 1 + S < ntiles) refill(i + 1 + S);
         }
     }
     if constexpr (K >= 3) {
