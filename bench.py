@@ -109,7 +109,9 @@ def pcie_peak(dev, mb=256, reps=3):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled while the GPU runs the timed workload.  A reader
+    thread collects the lines, so the caller can keep the GPU busy until enough samples exist
+    (nvidia-smi needs ~0.1-0.5 s to start on an 8-GPU box, longer than a short timed region)."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -118,27 +120,42 @@ class ClockSampler:
     def __init__(self, index):
         self.index = index
         self.proc = None
+        self.lines = []
+        self.thread = None
 
     def start(self):
+        import threading
+
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
+            return
+
+        def reader():
+            for line in self.proc.stdout:
+                self.lines.append(line)
+
+        self.thread = threading.Thread(target=reader, daemon=True)
+        self.thread.start()
+
+    def count(self):
+        return len(self.lines)
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
         self.proc.terminate()
         try:
-            out, _ = self.proc.communicate(timeout=5)
+            self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-            out = ""
+        if self.thread:
+            self.thread.join(timeout=2)
         sm, mx, reasons = [], [], set()
-        for line in out.splitlines():
+        for line in self.lines:
             f = [s.strip() for s in line.split(",")]
             if len(f) < 8:
                 continue
@@ -154,6 +171,20 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def keep_busy_until_sampled(sampler, step, min_samples=3, max_seconds=2.0):
+    """after the timed region: keep running (untimed) steps of the same workload until the clock
+    sampler has seen the GPU under this load at least `min_samples` times"""
+    import torch
+
+    t0 = time.perf_counter()
+    i = 0
+    while sampler.proc and sampler.count() < min_samples and time.perf_counter() - t0 < max_seconds:
+        for _ in range(8):
+            step(i)
+            i += 1
+        torch.cuda.synchronize()
+
+
 def dist_setup(n_gpus):
     import torch
 
@@ -164,7 +195,19 @@ def dist_setup(n_gpus):
         import torch.distributed as dist
 
         torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+        # NCCL writes its version banner to stdout when the communicator is created; stdout must
+        # carry the one JSON line only, so fd 1 points at stderr until the first collective is done
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     else:
         torch.cuda.set_device(local)
     return rank, world, local
@@ -322,9 +365,11 @@ def time_steps(step, steps, warmup, world, local, ctx, dev):
         step(i)
     e1.record()
     torch.cuda.synchronize()
+    launches = ctx.launches - l0
+    keep_busy_until_sampled(sampler, step)
     clocks = sampler.stop()
     barrier(world)
-    return max_over_ranks(e0.elapsed_time(e1), world, dev), ctx.launches - l0, clocks
+    return max_over_ranks(e0.elapsed_time(e1), world, dev), launches, clocks
 
 
 LOCKIN_LANES_TOTAL = 1_048_576
@@ -551,10 +596,11 @@ def run_biquad(args, rank, world, local):
         step(i)
     e1.record()
     torch.cuda.synchronize()
+    launches = ctx.launches - l0
+    keep_busy_until_sampled(sampler, step)
     clocks = sampler.stop()
     barrier(world)
     ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
-    launches = ctx.launches - l0
     value = world * n * steps / (ms * 1e-3) / 1e9
 
     if args.profile:
@@ -702,10 +748,11 @@ def run_hbf(args, rank, world, local):
         step(i)
     e1.record()
     torch.cuda.synchronize()
+    launches = ctx.launches - l0
+    keep_busy_until_sampled(sampler, step)
     clocks = sampler.stop()
     barrier(world)
     ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
-    launches = ctx.launches - l0
     value = world * n_in * args.steps / (ms * 1e-3) / 1e9
 
     if args.profile:
