@@ -50,16 +50,34 @@ def build(force: bool = False, verbose: bool = False, out: str = OUT) -> str:
         cmd += [f"-D{d}"]
     if os.environ.get("IDSP_TUNE"):  # tile-shape sweep builds (tools/sweep_biquad.py)
         cmd += ["-DIDSP_TUNE"]
-    cmd += ["-ccbin", "g++", "-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd += ["-ccbin", "g++"]
     env = dict(os.environ)
     env.pop("CC", None)
     env.pop("CXX", None)
-    res = subprocess.run(cmd, cwd=CSRC, env=env, capture_output=True, text=True)
+    # one nvcc per translation unit, in parallel, then one link step
+    objdir = os.path.join(HERE, "build", os.path.splitext(os.path.basename(out))[0])
+    os.makedirs(objdir, exist_ok=True)
+    compile_flags = [f for f in cmd if f not in ("-shared", "-cudart", "static")]
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        procs.append((src, obj, subprocess.Popen(compile_flags + ["-c", "-o", obj, os.path.join(CSRC, src)], cwd=CSRC, env=env,
+                                                 stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    log, failed = "", False
+    for src, obj, pr in procs:
+        o, _ = pr.communicate()
+        log += o
+        failed |= pr.returncode != 0
+    if failed:
+        sys.stderr.write(log)
+        raise RuntimeError("nvcc failed building libidsp_b200.so")
+    res = subprocess.run([nvcc, "-shared", "-cudart", "static", "-ccbin", "g++", "-o", out] + [o for _, o, _ in procs],
+                         cwd=CSRC, env=env, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("nvcc failed building libidsp_b200.so")
+        raise RuntimeError("nvcc failed linking libidsp_b200.so")
     if verbose:
-        sys.stderr.write(res.stdout + res.stderr)
+        sys.stderr.write(log + res.stdout + res.stderr)
     return out
 
 

@@ -170,6 +170,177 @@ cic_int_kernel(CicParams<T> p, const T *x, T *y, size_t frames, size_t lanes, si
     c.store(p, lane, sstride);
 }
 
+// ---------------------------------------------------------------- warp-cooperative variants
+// A warp owns 32 lanes and moves tiles of 128 bytes per lane (8 pieces of 16 bytes = 8/P frames,
+// P = (rate+1)*sizeof(T)/16 in {1,2,4,8}) with fully coalesced 16-byte accesses: frame-major data is
+// one contiguous 32 x P-piece block per frame, lane-major data 128 contiguous bytes per lane.  The
+// tile is transposed through shared memory with the piece index XOR-swizzled by (lane & 7), so both
+// the cooperative side (consecutive pieces) and the per-lane side (thread = lane, same piece) are
+// bank-conflict free.  The next tile is prefetched into registers while the current one is consumed.
+// Instantiated for the usual comb delay M = 1 (other M use the direct kernels above).
+constexpr int CIC_WPB = 4;  // warps per block
+
+template <class T, int P, bool FM>
+__device__ __forceinline__ const T *cic_piece_ptr(const T *x, int c, size_t t0, size_t lane0, size_t frames,
+                                                   size_t lanes, int &lane, int &q) {
+    constexpr int FT = 8 / P;                   // frames per tile
+    constexpr int EPP = 16 / (int)sizeof(T);    // elements per piece
+    constexpr int R = P * EPP;                  // rate + 1
+    int f, j;
+    if (FM) {  // memory order of a frame block: [lane][P]
+        f = c / (32 * P);
+        lane = (c % (32 * P)) / P;
+        j = c % P;
+    } else {   // 128 contiguous bytes per lane: [lane][FT][P]
+        lane = c / 8;
+        f = (c % 8) / P;
+        j = c % P;
+    }
+    (void)FT;
+    q = f * P + j;
+    const size_t frame = t0 + f;
+    const size_t fi = FM ? frame * lanes + lane0 + lane : (lane0 + lane) * frames + frame;
+    return x + fi * R + (size_t)j * EPP;
+}
+
+template <class T, int N, int M, int P, bool FM>
+__global__ void __launch_bounds__(CIC_WPB * 32)
+cic_dec_coop_kernel(CicParams<T> p, const T *x, T *y, size_t frames, size_t lanes, size_t sstride) {
+    using UT = typename std::make_unsigned<T>::type;
+    constexpr int FT = 8 / P, EPP = 16 / (int)sizeof(T);
+    __shared__ int4 tile[CIC_WPB][32 * 8];
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    const size_t lane0 = ((size_t)blockIdx.x * CIC_WPB + w) * 32;
+    if (lane0 >= lanes) return;
+    const int nl = (int)((lanes - lane0) < 32 ? (lanes - lane0) : 32);
+    const bool active = l < nl;
+    CicRegs<T, N, M> c;
+    if (active) c.load(p, lane0 + l, sstride);
+    const size_t ntiles = frames / FT;
+    int4 pre[8];
+    auto fetch = [&](size_t tile_i) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            int lane, q;
+            const T *src = cic_piece_ptr<T, P, FM>(x, l + 32 * k, tile_i * FT, lane0, frames, lanes, lane, q);
+            pre[k] = lane < nl ? *reinterpret_cast<const int4 *>(src) : make_int4(0, 0, 0, 0);
+        }
+    };
+    if (ntiles) fetch(0);
+    for (size_t ti = 0; ti < ntiles; ti++) {
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            int lane, q;
+            cic_piece_ptr<T, P, FM>(x, l + 32 * k, 0, 0, frames, lanes, lane, q);
+            tile[w][lane * 8 + (q ^ (lane & 7))] = pre[k];
+        }
+        __syncwarp();
+        if (ti + 1 < ntiles) fetch(ti + 1);
+        if (active) {
+#pragma unroll
+            for (int f = 0; f < FT; f++) {
+#pragma unroll
+                for (int j = 0; j < P; j++) {
+                    const int4 v = tile[w][l * 8 + ((f * P + j) ^ (l & 7))];
+                    UT e[EPP];
+                    unpack16<UT>(v, e);
+#pragma unroll
+                    for (int k = 0; k < EPP; k++) c.dec_step(p.rate, e[k]);
+                }
+                const size_t frame = ti * FT + f;
+                y[FM ? frame * lanes + lane0 + l : (lane0 + l) * frames + frame] = (T)c.zoh;
+            }
+        }
+    }
+    // frames that do not fill a tile
+    if (active) {
+        constexpr int R = P * EPP;
+        for (size_t frame = ntiles * FT; frame < frames; frame++) {
+            const size_t fi = FM ? frame * lanes + lane0 + l : (lane0 + l) * frames + frame;
+            for (int j = 0; j < R; j++) c.dec_step(p.rate, (UT)x[fi * R + j]);
+            y[fi] = (T)c.zoh;
+        }
+        c.store(p, lane0 + l, sstride);
+    }
+}
+
+template <class T, int N, int M, int P, bool FM>
+__global__ void __launch_bounds__(CIC_WPB * 32)
+cic_int_coop_kernel(CicParams<T> p, const T *x, T *y, size_t frames, size_t lanes, size_t sstride) {
+    using UT = typename std::make_unsigned<T>::type;
+    constexpr int FT = 8 / P, EPP = 16 / (int)sizeof(T);
+    __shared__ int4 tile[CIC_WPB][32 * 8];
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    const size_t lane0 = ((size_t)blockIdx.x * CIC_WPB + w) * 32;
+    if (lane0 >= lanes) return;
+    const int nl = (int)((lanes - lane0) < 32 ? (lanes - lane0) : 32);
+    const bool active = l < nl;
+    CicRegs<T, N, M> c;
+    if (active) c.load(p, lane0 + l, sstride);
+    const size_t ntiles = frames / FT;
+    for (size_t ti = 0; ti < ntiles; ti++) {
+        __syncwarp();
+        if (active) {
+#pragma unroll
+            for (int f = 0; f < FT; f++) {
+                const size_t frame = ti * FT + f;
+                const UT xin = (UT)x[FM ? frame * lanes + lane0 + l : (lane0 + l) * frames + frame];
+#pragma unroll
+                for (int j = 0; j < P; j++) {
+                    UT e[EPP];
+#pragma unroll
+                    for (int k = 0; k < EPP; k++) e[k] = c.int_step(p.rate, j == 0 && k == 0, xin);
+                    tile[w][l * 8 + ((f * P + j) ^ (l & 7))] = pack16<UT>(e);
+                }
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            int lane, q;
+            const T *dst = cic_piece_ptr<T, P, FM>(y, l + 32 * k, ti * FT, lane0, frames, lanes, lane, q);
+            if (lane < nl) *reinterpret_cast<int4 *>(const_cast<T *>(dst)) = tile[w][lane * 8 + (q ^ (lane & 7))];
+        }
+    }
+    if (active) {
+        constexpr int R = P * EPP;
+        for (size_t frame = ntiles * FT; frame < frames; frame++) {
+            const size_t fi = FM ? frame * lanes + lane0 + l : (lane0 + l) * frames + frame;
+            const UT xin = (UT)x[fi];
+            for (int j = 0; j < R; j++) y[fi * R + j] = (T)c.int_step(p.rate, j == 0, xin);
+        }
+        c.store(p, lane0 + l, sstride);
+    }
+}
+
+template <class T, bool DEC, int N, int M>
+static bool cic_launch_coop(idsp_ctx *ctx, const CicParams<T> &p, const T *x, T *y, size_t frames, size_t lanes,
+                            int layout) {
+    const size_t bytes = ((size_t)p.rate + 1) * sizeof(T);
+    if (bytes != 16 && bytes != 32 && bytes != 64 && bytes != 128) return false;
+    const unsigned grid = (unsigned)((lanes + 32 * CIC_WPB - 1) / (32 * CIC_WPB));
+    const bool fm = layout == IDSP_FRAME_MAJOR;
+#define COOP(PP)                                                                                                    \
+    do {                                                                                                            \
+        if (DEC) {                                                                                                  \
+            if (fm) cic_dec_coop_kernel<T, N, M, PP, true><<<grid, 32 * CIC_WPB, 0, ctx->stream>>>(p, x, y, frames, lanes, lanes); \
+            else cic_dec_coop_kernel<T, N, M, PP, false><<<grid, 32 * CIC_WPB, 0, ctx->stream>>>(p, x, y, frames, lanes, lanes);   \
+        } else {                                                                                                    \
+            if (fm) cic_int_coop_kernel<T, N, M, PP, true><<<grid, 32 * CIC_WPB, 0, ctx->stream>>>(p, x, y, frames, lanes, lanes); \
+            else cic_int_coop_kernel<T, N, M, PP, false><<<grid, 32 * CIC_WPB, 0, ctx->stream>>>(p, x, y, frames, lanes, lanes);   \
+        }                                                                                                           \
+    } while (0)
+    switch (bytes) {
+        case 16: COOP(1); break;
+        case 32: COOP(2); break;
+        case 64: COOP(4); break;
+        default: COOP(8); break;
+    }
+#undef COOP
+    return true;
+}
+
 template <class T, bool DEC>
 int cic_launch(idsp_ctx *ctx, int N, int M, uint32_t rate, T *state, const T *x, T *y, size_t frames, size_t lanes,
                int layout) {
@@ -187,6 +358,7 @@ int cic_launch(idsp_ctx *ctx, int N, int M, uint32_t rate, T *state, const T *x,
     const unsigned grid = (unsigned)((lanes + 127) / 128);
 #define GO(NN, MM)                                                                                                  \
     case NN * 8 + MM:                                                                                               \
+        if (MM == 1 && vec && ctx->policy != 1 && cic_launch_coop<T, DEC, NN, 1>(ctx, p, x, y, frames, lanes, layout)) break; \
         if (DEC) cic_dec_kernel<T, NN, MM><<<grid, 128, 0, ctx->stream>>>(p, x, y, frames, lanes, lanes, layout, vec); \
         else cic_int_kernel<T, NN, MM><<<grid, 128, 0, ctx->stream>>>(p, x, y, frames, lanes, lanes, layout, vec);    \
         break;
