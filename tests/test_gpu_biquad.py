@@ -67,7 +67,7 @@ def test_kat_clamp_identity_hold():
 
 
 # ------------------------------------------------------------------ DF1 all types / layouts / shapes
-SHAPES = [(1, 1), (1, 37), (33, 1), (100, 33), (64, 128), (17, 260), (130, 96)]  # (frames, lanes)
+SHAPES = [(1, 1), (1, 37), (33, 1), (100, 33), (64, 128), (17, 260), (130, 96), (400, 70)]  # (frames, lanes); 400 frames = several 128-byte tiles + a tail for every sample size
 
 
 @pytest.mark.parametrize("kind", ["i8", "i16", "i32", "i64", "f32", "f64"])
