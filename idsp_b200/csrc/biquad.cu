@@ -24,6 +24,24 @@ template <class T> static bool f_ok(int F) {
     } while (0)
 
 // ------------------------------------------------------------------ DF1
+// i16 frame-major: 2 adjacent lanes share a 32-bit word, so the rows go through the frame-major TMA
+// kernels as words (PackedOp, 794 -> 870 GSa/s); everything else takes the generic lane kernels
+// (i8 packed four to a word leaves too few warps per SM at 65 536 lanes: 912 -> 722, not used).
+template <class Op>
+static int launch_packed_or_lanes(idsp_ctx *ctx, const typename Op::Params &p, const typename Op::In *x,
+                                  typename Op::Out *y, size_t frames, size_t lanes, size_t sstride, int layout) {
+    if constexpr (sizeof(typename Op::In) == 2 && std::is_integral<typename Op::In>::value) {
+        constexpr size_t P = 4 / sizeof(typename Op::In);
+        if (layout == IDSP_FRAME_MAJOR && lanes % (4 * P) == 0 && frames >= 16 &&
+            (((uintptr_t)x | (uintptr_t)y) & 15) == 0) {
+            int tr = tma_try_launch<PackedOp<Op>>(ctx, p, reinterpret_cast<const int32_t *>(x),
+                                                  reinterpret_cast<int32_t *>(y), frames, lanes / P, sstride, layout);
+            if (tr != IDSP_TMA_NOT_APPLICABLE) return tr;
+        }
+    }
+    return launch_lanes<Op>(ctx, p, x, y, frames, lanes, sstride, layout);
+}
+
 template <class T>
 static int df1_impl(idsp_ctx *ctx, const T *ba, int F, const T *clamp, T *state, const T *x,
                     T *y, size_t frames, size_t lanes, size_t sstride, int layout) {
@@ -35,14 +53,14 @@ static int df1_impl(idsp_ctx *ctx, const T *ba, int F, const T *clamp, T *state,
         p.mn = clamp[1];
         p.mx = clamp[2];
         p.st = state;
-        return launch_lanes<Df1Op<T, true>>(ctx, p, x, y, frames, lanes, sstride, layout);
+        return launch_packed_or_lanes<Df1Op<T, true>>(ctx, p, x, y, frames, lanes, sstride, layout);
     }
     typename Df1Op<T, false>::Params p;
     for (int i = 0; i < 5; i++) p.ba[i] = ba[i];
     p.F = F;
     p.u = p.mn = p.mx = T(0);
     p.st = state;
-    return launch_lanes<Df1Op<T, false>>(ctx, p, x, y, frames, lanes, sstride, layout);
+    return launch_packed_or_lanes<Df1Op<T, false>>(ctx, p, x, y, frames, lanes, sstride, layout);
 }
 
 // i32 specialisation: funnel-shift fast path for 0 <= F < 32 and the TMA-pipelined kernels

@@ -35,6 +35,7 @@ template <> struct is_float<double> { static constexpr bool value = true; };
 // Defaults of the optional Op hooks used by the TMA kernels (tma_kernels.cuh)
 struct OpHooks {
     static constexpr bool TUNABLE = false;
+    static constexpr bool HEAVY = false;  // compute-bound: lane-major TMA kernels trade tile size for resident warps
     static constexpr int SMEM_EXTRA_WORDS = 0;
     template <class P> __device__ __forceinline__ static void init_smem(const P &, uint32_t *, int, int) {}
     template <class P> __device__ __forceinline__ void bind(const P &, const uint32_t *) {}
@@ -95,6 +96,7 @@ template <class T, bool CLAMP, int MODE = 0> struct Df1Op {
     using In = T;
     using Out = T;
     static constexpr bool TUNABLE = true;  // tuning builds sweep tile shapes for this Op
+    static constexpr bool HEAVY = false;
     static constexpr int SMEM_EXTRA_WORDS = 0;
     struct Params {
         T ba[5];
@@ -132,6 +134,37 @@ template <class T, bool CLAMP, int MODE = 0> struct Df1Op {
     }
 };
 
+// P = 4 / sizeof(T) adjacent lanes of a 1- or 2-byte Op packed into one 32-bit word: lets the
+// frame-major TMA kernels (4-byte samples) carry i8 / i16 lanes, one word = P lanes of one frame,
+// and gives every thread P independent recurrences.  `lane` counts words, state stays SoA per lane.
+template <class Op> struct PackedOp : OpHooks {
+    using T = typename Op::In;
+    using UT = typename Wide<T>::UT;
+    static_assert(sizeof(T) < 4 && sizeof(typename Op::Out) == sizeof(T), "1- or 2-byte samples");
+    static constexpr int P = 4 / (int)sizeof(T);
+    using In = int32_t;
+    using Out = int32_t;
+    using Params = typename Op::Params;
+    Op op[P];
+    __device__ __forceinline__ void load(const Params &p, size_t word, size_t stride) {
+#pragma unroll
+        for (int k = 0; k < P; k++) op[k].load(p, word * P + k, stride);
+    }
+    __device__ __forceinline__ void store(const Params &p, size_t word, size_t stride) const {
+#pragma unroll
+        for (int k = 0; k < P; k++) op[k].store(p, word * P + k, stride);
+    }
+    __device__ __forceinline__ int32_t step(const Params &p, int32_t w) {
+        uint32_t r = 0;
+#pragma unroll
+        for (int k = 0; k < P; k++) {
+            const T o = op[k].step(p, (T)(UT)((uint32_t)w >> (8 * sizeof(T) * k)));
+            r |= (uint32_t)(UT)o << (8 * sizeof(T) * k);
+        }
+        return (int32_t)r;
+    }
+};
+
 // Cascade<[Biquad;N]> on DirectForm<T,N> (src/iir/biquad.rs:339-364)
 template <class T, int N> struct CascadeOp : OpHooks {
     // exactly N sections (the entry point dispatches on nsec): every index below is static, so
@@ -139,6 +172,7 @@ template <class T, int N> struct CascadeOp : OpHooks {
     using In = T;
     using Out = T;
     static constexpr bool FAST = std::is_same<T, int32_t>::value;  // i32: the entry point routes 0 <= F < 32 here
+    static constexpr bool HEAVY = N >= 2;
     struct Params {
         T ba[N][5];
         int F;
@@ -454,6 +488,7 @@ template <int ORDER, bool SMEM_LUT = false> struct LockinOp {
     using In = int32_t;
     using Out = int2;
     static constexpr bool TUNABLE = false;
+    static constexpr bool HEAVY = true;
     static constexpr int SMEM_EXTRA_WORDS = SMEM_LUT ? 256 : 0;  // expanded cossin table staged per CTA
     struct Params {
         int32_t k[2];
@@ -507,6 +542,7 @@ template <int ORDER, bool SMEM_LUT = false> struct LockinOp {
 struct PllOp : OpHooks {
     using In = int32_t;
     using Out = int32_t;
+    static constexpr bool HEAVY = true;
     struct Params {
         int32_t ba[3];
         int32_t *st;

@@ -107,7 +107,8 @@ tma_lanes_kernel(typename Op::Params p, const __grid_constant__ CUtensorMap mx,
     static_assert(!LM || TF == 16, "lane-major tiles are 16 frames (64B swizzle)");
     static_assert(!(WIDE && LM), "wide boxes are frame-major only");
     constexpr int OW = sizeof(Out) / 4;             // output words per sample (Complex<i32> = 2)
-    static_assert(!LM || OW == 1, "8-byte outputs are frame-major only");
+    // lane-major 8-byte outputs: the output tile is [32 lanes][16 frames x 2 words] = 128-byte rows
+    // written with the 128-byte TMA swizzle (chunk index XOR (l & 7))
     constexpr int BW = WIDE ? 32 * WPC : 32;        // box width in lanes
     constexpr int TILE_WORDS = TF * BW;
     constexpr uint32_t TILE_BYTES = TILE_WORDS * 4;
@@ -183,7 +184,22 @@ tma_lanes_kernel(typename Op::Params p, const __grid_constant__ CUtensorMap mx,
             const int sw = (l >> 1) & 3;
             const uint4 *rin = reinterpret_cast<const uint4 *>(tin + l * 16);
             uint4 *rout = reinterpret_cast<uint4 *>(tout + l * 16);
-            if (nvalid == TF) {
+            if constexpr (OW == 2) {
+                uint4 *rout8 = reinterpret_cast<uint4 *>(tout + l * 32);
+                const int sw8 = l & 7;
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    if (c * 4 < nvalid) {  // frames % 4 == 0: whole chunks are valid or not
+                        const uint4 v = rin[c ^ sw];
+                        const Out r0 = op.step(p, Bits32<In>::from(v.x));
+                        const Out r1 = op.step(p, Bits32<In>::from(v.y));
+                        const Out r2 = op.step(p, Bits32<In>::from(v.z));
+                        const Out r3 = op.step(p, Bits32<In>::from(v.w));
+                        rout8[(2 * c) ^ sw8] = make_uint4((uint32_t)r0.x, (uint32_t)r0.y, (uint32_t)r1.x, (uint32_t)r1.y);
+                        rout8[(2 * c + 1) ^ sw8] = make_uint4((uint32_t)r2.x, (uint32_t)r2.y, (uint32_t)r3.x, (uint32_t)r3.y);
+                    }
+                }
+            } else if (nvalid == TF) {
 #pragma unroll
                 for (int c = 0; c < 4; c++) {
                     uint4 v = rin[c ^ sw];
@@ -234,7 +250,7 @@ tma_lanes_kernel(typename Op::Params p, const __grid_constant__ CUtensorMap mx,
         sync_pipe();
         if (leader) {
             if (LM)
-                tma_store_2d(&my, smem_u32(tout), (int)(i * TF), (int)box0);
+                tma_store_2d(&my, smem_u32(tout), (int)(i * TF * OW), (int)box0);
             else
                 tma_store_2d(&my, smem_u32(tout), (int)(box0 * OW), (int)(i * TF));
             tma_commit();
@@ -378,7 +394,8 @@ static int tma_launch_cfg(idsp_ctx *ctx, const typename Op::Params &p, const voi
     static_assert(BW * OW <= 256, "TMA box dimension limit");
     if (LM) {
         ok = make_map_2d(&mx, x, frames, lanes, TF, 32, CU_TENSOR_MAP_SWIZZLE_64B) &&
-             make_map_2d(&my, y, frames, lanes, TF, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+             make_map_2d(&my, y, frames * OW, lanes, TF * OW, 32,
+                         OW == 2 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
     } else {
         ok = make_map_2d(&mx, x, lanes, frames, BW, TF, CU_TENSOR_MAP_SWIZZLE_NONE) &&
              make_map_2d(&my, y, lanes * OW, frames, BW * OW, TF, CU_TENSOR_MAP_SWIZZLE_NONE);
@@ -446,6 +463,12 @@ static int tma_launch_lm(idsp_ctx *ctx, const typename Op::Params &p, const void
 template <class Op>
 static int tma_launch_lm_auto(idsp_ctx *ctx, const typename Op::Params &p, const void *x, void *y,
                               size_t frames, size_t lanes, size_t sstride) {
+    if constexpr (Op::HEAVY) {
+        // compute-bound ops: 12 KB (128-byte rows) or 8 KB (64-byte rows) per warp instead of 40 KB, so
+        // 18..28 warps are resident per SM instead of 5 (Cascade<4> i32 128 -> 316 GSa/s, PLL 324 -> 515)
+        if (frames >= 128) return tma_launch_lm<Op, 1, 2, 1>(ctx, p, x, y, frames, lanes, sstride);
+        return tma_launch_cfg<Op, true, 16, 3, 1, 1>(ctx, p, x, y, frames, lanes, sstride);
+    }
     if (frames >= 128) return tma_launch_lm<Op, 2, 3, 2>(ctx, p, x, y, frames, lanes, sstride);
     return tma_launch_cfg<Op, true, 16, 4, 2, 1>(ctx, p, x, y, frames, lanes, sstride);
 }
@@ -474,9 +497,8 @@ static int tma_try_launch(idsp_ctx *ctx, const typename Op::Params &p, const typ
     constexpr bool OUT8 = sizeof(typename Op::Out) == 8;
     if (ctx->policy == 1) return IDSP_TMA_NOT_APPLICABLE;
     const bool lm = layout == IDSP_LANE_MAJOR;
-    if (OUT8 && lm) return IDSP_TMA_NOT_APPLICABLE;
     bool ok = (((uintptr_t)x | (uintptr_t)y) & 15) == 0 && frames >= 16 &&
-              frames < (1ull << 31) && lanes < (1ull << 31) &&
+              frames < (1ull << 30) && lanes < (1ull << 30) &&
               (lm ? (frames % 4 == 0) : (lanes % 4 == 0));
     if (!ok) {
         if (ctx->policy == 2) {
@@ -489,7 +511,11 @@ static int tma_try_launch(idsp_ctx *ctx, const typename Op::Params &p, const typ
     if constexpr (OUT8) {
         // 4-byte in / 8-byte out (lock-in): 128-lane boxes (the 8-byte box row is 256 words)
         const size_t sms = (size_t)(ctx->sm_count > 0 ? ctx->sm_count : 148);
-        if ((lanes + 127) / 128 >= sms) {
+        if (lm) {
+            // one warp per CTA, 64-byte input rows / 128-byte output rows, 10 KB per warp: the op
+            // is ALU-bound, so resident warps count for more than long DRAM bursts
+            r = tma_launch_cfg<Op, true, 16, 3, 1, 1>(ctx, p, x, y, frames, lanes, sstride);
+        } else if ((lanes + 127) / 128 >= sms) {
             // compute-bound: avoid a nearly empty last wave (131 072 lanes: 1024 CTAs fit in one
             // wave with 3 load stages, 7 CTAs per SM, but need 1.15 waves with 4 stages, 6 per SM)
             const size_t n4 = (lanes + 127) / 128;

@@ -67,7 +67,7 @@ def test_kat_clamp_identity_hold():
 
 
 # ------------------------------------------------------------------ DF1 all types / layouts / shapes
-SHAPES = [(1, 1), (1, 37), (33, 1), (100, 33), (64, 128), (17, 260), (130, 96), (400, 70)]  # (frames, lanes); 400 frames = several 128-byte tiles + a tail for every sample size
+SHAPES = [(1, 1), (1, 37), (33, 1), (100, 33), (64, 128), (17, 260), (130, 96), (400, 70), (50, 272)]  # (frames, lanes); 400 frames = several 128-byte tiles + a tail for every sample size
 
 
 @pytest.mark.parametrize("kind", ["i8", "i16", "i32", "i64", "f32", "f64"])
@@ -219,8 +219,7 @@ def test_cascade_vs_oracle(oracle, kind, nsec):
         secs.append(Biquad.from_ba6(ba6, Q(kind, BITS[kind] - 3) if kind in BITS else kind))
     ba = np.stack([s.ba for s in secs])
     F = secs[0].F
-    for layout in (0, 1):
-        frames, lanes = 77, 45
+    for layout, (frames, lanes) in [(l, s) for l in (0, 1) for s in ((77, 45), (76, 40))]:  # 76x40: TMA tiles in both layouts
         x = rand_samples(rng, kind, frames * lanes, (BITS[kind] - 6) if kind in BITS else None)
         so = np.zeros((2 + 2 * nsec, lanes), NP[kind])
         want = oracle.biquad_lanes("cascade", kind, ba, F, None, so, x, lanes, layout, nsec=nsec)

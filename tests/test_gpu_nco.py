@@ -77,7 +77,7 @@ def test_lowpass_model_vectors():
 def test_lockin_vs_oracle(oracle, order, layout):
     rng = np.random.default_rng(4 + order)
     k = [67465188] if order == 1 else [1048576, -94906265]
-    for frames, lanes in [(50, 70), (128, 128), (3, 1)]:
+    for frames, lanes in [(50, 70), (128, 128), (3, 1), (52, 37), (16, 64)]:  # 52x37, 16x64: lane-major TMA tiles (frames % 4 == 0) with ragged tile / lane edges
         x = rng.integers(-(1 << 30), 1 << 30, frames * lanes).astype(np.int32)
         a0 = rng.integers(-(1 << 31), 1 << 31, lanes).astype(np.int32)
         step = rng.integers(-(1 << 31), 1 << 31, lanes).astype(np.int32)

@@ -57,7 +57,7 @@ def test_converge_narrow_on_gpu():
 
 
 @pytest.mark.parametrize("layout", [0, 1])
-@pytest.mark.parametrize("lanes,frames", [(1, 300), (37, 211), (256, 128), (1000, 64)])
+@pytest.mark.parametrize("lanes,frames", [(1, 300), (37, 211), (256, 128), (1000, 64), (64, 132)])
 def test_pll_vs_oracle(oracle, layout, lanes, frames):
     rng = np.random.default_rng(lanes + frames)
     ba = oracle.pll_from_bandwidth(3e-3, 4.0)

@@ -6,6 +6,7 @@ entry point, algorithmic bytes / CUDA-event time vs the measured HBM copy peak.
 """
 import argparse
 import json
+import re
 import os
 import sys
 
@@ -48,14 +49,19 @@ def timeit(fn, reps):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--only", default=None, help="regex: time only the rows whose name matches (e.g. under ncu)")
+    ap.add_argument("--reps", type=int, default=None)
     args = ap.parse_args()
     peak, src = peak_hbm()
     lanes = 65536
     frames = 1024 if args.quick else 4096
-    reps = 3 if args.quick else 10
+    reps = args.reps or (3 if args.quick else 10)
+    only = re.compile(args.only) if args.only else None
     rows = []
 
     def add(name, ref, samples, bytes_per_sample, fn):
+        if only and not only.search(name):
+            return
         ms = timeit(fn, reps)
         gbs = samples * bytes_per_sample / ms / 1e6
         rows.append({"row": name, "reference": ref, "GSa/s": samples / ms / 1e6, "GB/s": gbs, "frac_of_peak": gbs / peak,
