@@ -35,6 +35,25 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _deps(path: str, seen=None) -> set:
+    """the source file plus, transitively, every `#include "..."` found next to it or under include/"""
+    seen = set() if seen is None else seen
+    if path in seen or not os.path.exists(path):
+        return seen
+    seen.add(path)
+    for line in open(path, errors="replace"):
+        line = line.strip()
+        if line.startswith("#include \""):
+            name = line.split('"')[1]
+            for base in (os.path.dirname(path), CSRC, os.path.join(HERE, "..", "include")):
+                cand = os.path.normpath(os.path.join(base, name))
+                if os.path.exists(cand):
+                    _deps(cand, seen)
+                    break
+    seen.add(os.path.abspath(__file__))
+    return seen
+
+
 def build(force: bool = False, verbose: bool = False, out: str = OUT) -> str:
     if out == OUT and not force and not _stale():
         return OUT
@@ -59,15 +78,28 @@ def build(force: bool = False, verbose: bool = False, out: str = OUT) -> str:
     os.makedirs(objdir, exist_ok=True)
     compile_flags = [f for f in cmd if f not in ("-shared", "-cudart", "static")]
     procs = []
+    sig = " ".join(compile_flags)
+    sigfile = os.path.join(objdir, "flags.txt")
+    same_flags = os.path.exists(sigfile) and open(sigfile).read() == sig
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        if same_flags and not force and os.path.exists(obj) and all(
+                os.path.getmtime(d) <= os.path.getmtime(obj) for d in _deps(os.path.join(CSRC, src))):
+            procs.append((src, obj, None))  # object is newer than the source and every header it includes
+            continue
         procs.append((src, obj, subprocess.Popen(compile_flags + ["-c", "-o", obj, os.path.join(CSRC, src)], cwd=CSRC, env=env,
                                                  stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log, failed = "", False
     for src, obj, pr in procs:
+        if pr is None:
+            continue
         o, _ = pr.communicate()
         log += o
         failed |= pr.returncode != 0
+        if pr.returncode != 0 and os.path.exists(obj):
+            os.remove(obj)
+    if not failed:
+        open(sigfile, "w").write(sig)
     if failed:
         sys.stderr.write(log)
         raise RuntimeError("nvcc failed building libidsp_b200.so")

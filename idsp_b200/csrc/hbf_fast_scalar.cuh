@@ -63,6 +63,9 @@ __host__ __device__ constexpr int st_n(int s) { return TT >> (s + 1); }  // outp
 #ifndef HFS_R0
 #define HFS_R0 16
 #endif
+#ifndef HFS_R0_K1
+#define HFS_R0_K1 8
+#endif
 #ifndef HFS_BAL
 #define HFS_BAL 0
 #endif
@@ -369,7 +372,9 @@ hbf_dec_fast_kernel(float *st, const float *x, float *y, size_t n_out, size_t nt
                     size_t sstride) {
     const size_t ylanes = FM ? lanes : 0;
     constexpr int TI0 = K - 1;
-    constexpr int R0 = st_r(0);
+    // /2 runs the 23-tap stage on the raw stream: 16 outputs per item need a 124-float window and spill
+    // (96 bytes of stack, reloaded on the refill path); 8 outputs per item fit in registers
+    constexpr int R0 = K == 1 ? HFS_R0_K1 : st_r(0);
     constexpr int HR = raw_h(K);
     constexpr int PR = raw_pitch(K);
     constexpr int TO = TT >> K;

@@ -19,8 +19,7 @@ namespace idsp {
 // lookup tables (build.rs:9-69) in global memory, read through L1 (__ldg)
 // --------------------------------------------------------------------------
 __device__ const uint32_t g_cossin_lut[128] = IDSP_COSSIN_TABLE_INIT;
-__device__ const uint32_t g_divi_base[16] = IDSP_ATAN2_DIVI_BASE_INIT;
-__device__ const int32_t g_divi_slope[16] = IDSP_ATAN2_DIVI_SLOPE_INIT;
+__device__ const uint2 g_divi_tab[16] = IDSP_ATAN2_DIVI_PAIR_INIT;  // (base, slope bits), build.rs:46-69
 
 template <class T> struct Wide;
 template <> struct Wide<int8_t> { using A = int16_t; using UA = uint16_t; using UT = uint8_t; };
@@ -392,43 +391,62 @@ __device__ __forceinline__ void cossin_dev_x(const uint32_t *table, int32_t phas
 // --------------------------------------------------------------------------
 // atan2 (src/atan2.rs:7-82)
 // --------------------------------------------------------------------------
+// Written branch-free and with explicit 32x32 -> 64 / high-word multiplies so that (a) one call is
+// ~50 instead of ~80 SASS instructions (the compiler expands the reference's mixed signed / unsigned
+// i64 products into multi-instruction sequences) and (b) the unrolled frame loops of the lane kernels
+// can interleave several independent calls (a branch per call serialises them).  Bit-exact with the
+// straightforward transcription (tests/test_gpu_nco.py sweeps it against the oracle).
 __device__ __forceinline__ uint32_t mul_q31(uint32_t x, uint32_t y) {
-    return (uint32_t)(((uint64_t)x * (uint64_t)y) >> 31);
+    const uint64_t p = (uint64_t)x * (uint64_t)y;  // IMAD.WIDE.U32
+    return __funnelshift_r((uint32_t)p, (uint32_t)(p >> 32), 31);
 }
-__device__ __forceinline__ uint32_t divi_dev(uint32_t y, uint32_t x) {
-    if (x == 0) return 0;
-    int shift = __clz((int)x);
+// 16 x (base, slope) reciprocal seeds, one 8-byte load per lookup: global (__ldg) or staged in shared memory
+template <bool SMEM_TAB>
+__device__ __forceinline__ uint32_t divi_dev(const uint2 *tab, uint32_t y, uint32_t x) {
+    const uint32_t x_in = x;  // x == 0 (then y == 0 too): the reference returns 0 early (atan2.rs:16-18)
+    const int shift = __clz((int)x);
     y <<= shift;
     x <<= shift;
-    const int FRAC_BITS = 31 - IDSP_ATAN2_DIVI_DEPTH;
-    uint32_t rem = x & ((1u << FRAC_BITS) - 1);
-    uint32_t idx = (x << 1) >> (1 + FRAC_BITS);
-    uint32_t base = __ldg(g_divi_base + idx);
-    int32_t slope = __ldg(g_divi_slope + idx);
-    uint32_t step = (uint32_t)(((int64_t)slope * (int64_t)rem) >> FRAC_BITS);
-    uint32_t r0 = base + step;
-    return mul_q31(y, mul_q31(r0, 0u - mul_q31(x, r0)));
+    constexpr int FRAC_BITS = 31 - IDSP_ATAN2_DIVI_DEPTH;
+    const uint32_t rem = x & ((1u << FRAC_BITS) - 1);
+    const uint32_t idx = (x << 1) >> (1 + FRAC_BITS);
+    const uint2 e = SMEM_TAB ? tab[idx] : __ldg(tab + idx);
+    // (slope as i64 * rem as i64) >> FRAC_BITS: rem < 2^27, so one signed IMAD.WIDE and a funnel shift
+    const int64_t sp = mad_wide((int32_t)e.y, (int32_t)rem, 0);
+    const uint32_t step = __funnelshift_r((uint32_t)sp, (uint32_t)((uint64_t)sp >> 32), FRAC_BITS);
+    const uint32_t r0 = e.x + step;
+    const uint32_t q = mul_q31(y, mul_q31(r0, 0u - mul_q31(x, r0)));
+    return x_in ? q : 0u;
 }
 __device__ __forceinline__ uint32_t atani_dev(uint32_t x) {
     const int32_t ATANI[6] = {0x0517c2cd, -0x06c6496b, 0x0fbdb021,
                               -0x25b32e0a, 0x43b34c81, -0x3bc823dd};
-    int32_t x2 = (int32_t)(((int64_t)(uint64_t)x * (int64_t)(uint64_t)x) >> 32);
+    // ((x as i64 * x as i64) >> 32) as i32: the same bits as the unsigned high word
+    const int32_t x2 = (int32_t)__umulhi(x, x);
     int32_t r = 0;
 #pragma unroll
     for (int i = 5; i >= 0; i--) {
-        r = (int32_t)(((int64_t)r * (int64_t)x2) >> 32);  // Q32<32>*Q32<32>, ops.rs:145-153
+        r = __mulhi(r, x2);  // Q32<32>*Q32<32> = (i64 product) >> 32, ops.rs:145-153: signed high word
         r = (int32_t)((uint32_t)r + (uint32_t)ATANI[i]);
     }
     return (uint32_t)(((int64_t)r * (int64_t)(uint64_t)x) >> 28);
 }
-__device__ __forceinline__ int32_t sat_neg(int32_t a) { return a == INT32_MIN ? INT32_MAX : -a; }
-__device__ __forceinline__ int32_t atan2_dev(int32_t y, int32_t x) {
+__device__ __forceinline__ int32_t sat_neg(int32_t a) {  // saturating_neg: 0 - a, saturated
+    int32_t r;
+    asm("sub.sat.s32 %0, 0, %1;" : "=r"(r) : "r"(a));
+    return r;
+}
+template <bool SMEM_TAB>
+__device__ __forceinline__ int32_t atan2_dev_t(const uint2 *tab, int32_t y, int32_t x) {
     uint32_t k = 0;
     if (y < 0) { y = sat_neg(y); k ^= 0xffffffffu; }
     if (x < 0) { x = sat_neg(x); k ^= 0xffffffffu >> 1; }
     if (y > x) { int32_t t = y; y = x; x = t; k ^= 0xffffffffu >> 2; }
-    uint32_t r = atani_dev(divi_dev((uint32_t)y, (uint32_t)x));
+    uint32_t r = atani_dev(divi_dev<SMEM_TAB>(tab, (uint32_t)y, (uint32_t)x));
     return (int32_t)(r ^ k);
+}
+__device__ __forceinline__ int32_t atan2_dev(int32_t y, int32_t x) {
+    return atan2_dev_t<false>(g_divi_tab, y, x);
 }
 
 // --------------------------------------------------------------------------
@@ -631,13 +649,13 @@ struct FmDiscOp : OpHooks {
         p.st[6 * stride + lane] = y2;
     }
     __device__ __forceinline__ int32_t step(const Params &p, int2 x) {
-        int32_t d = 0;
-        if (has) {
-            const int32_t cim = (int32_t)(0u - (uint32_t)pim);  // conj() of the i32 bits (wrapping neg)
-            const int64_t re = (int64_t)((uint64_t)((int64_t)x.x * pre) - (uint64_t)((int64_t)x.y * cim));
-            const int64_t im = (int64_t)((uint64_t)((int64_t)x.x * cim) + (uint64_t)((int64_t)x.y * pre));
-            d = (int32_t)((uint32_t)atan2_dev((int32_t)(im >> 32), (int32_t)(re >> 32)) - (uint32_t)p.carrier);
-        }
+        // evaluated unconditionally and selected (no branch: the unrolled frame loop interleaves the
+        // discriminators of several samples, only the biquad below is a recurrence)
+        const int32_t cim = (int32_t)(0u - (uint32_t)pim);  // conj() of the i32 bits (wrapping neg)
+        const int64_t re = (int64_t)((uint64_t)((int64_t)x.x * pre) - (uint64_t)((int64_t)x.y * cim));
+        const int64_t im = (int64_t)((uint64_t)((int64_t)x.x * cim) + (uint64_t)((int64_t)x.y * pre));
+        const int32_t dd = (int32_t)((uint32_t)atan2_dev((int32_t)(im >> 32), (int32_t)(re >> 32)) - (uint32_t)p.carrier);
+        const int32_t d = has ? dd : 0;
         has = 1;
         pre = x.x;
         pim = x.y;

@@ -37,6 +37,10 @@ __global__ void __launch_bounds__(256) cossin_kernel(const int32_t *phase, int32
     }
 }
 __global__ void __launch_bounds__(256) atan2_kernel(const int32_t *xy, int32_t *p, size_t n) {
+    __shared__ uint2 tab[16];  // reciprocal seeds staged per CTA (LDS.64 instead of a global load per call)
+    if (threadIdx.x < 16) tab[threadIdx.x] = g_divi_tab[threadIdx.x];
+    __syncthreads();
+    auto atan2_dev = [&](int32_t y, int32_t x) { return atan2_dev_t<true>(tab, y, x); };
     const size_t n2 = n / 2;
     const bool vec = ((((uintptr_t)xy) & 15) | (((uintptr_t)p) & 7)) == 0;
     const size_t stride = (size_t)gridDim.x * blockDim.x;

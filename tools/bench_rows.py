@@ -51,6 +51,7 @@ def main():
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--only", default=None, help="regex: time only the rows whose name matches (e.g. under ncu)")
     ap.add_argument("--reps", type=int, default=None)
+    ap.add_argument("--hbf-in", type=int, default=8192, help="high-rate samples per lane and call of the HBF rows")
     args = ap.parse_args()
     peak, src = peak_hbm()
     lanes = 65536
@@ -107,9 +108,9 @@ def main():
         del x, y, iq
         # hbf cascades: 262144 lanes (config 3 shape, fewer frames)
         hl = 65536 if args.quick else 262144
-        n_out = 512
         for k in (1, 2, 3, 4, 5):
             R = 1 << k
+            n_out = args.hbf_in >> k  # same high-rate stream length per lane for every rate (state I/O amortised alike)
             x = rnd("f32", hl * n_out * R)
             y = torch.empty(hl * n_out, dtype=torch.float32, device=DEV)
             sdec = _dec_state(k)(hl, DEV)
