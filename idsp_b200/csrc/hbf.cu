@@ -437,6 +437,35 @@ extern "C" int idsp_chain_f32(idsp_ctx *ctx, int log2_rate, const float ba[5], f
     // FIR cascades are time-parallel (tiled kernels, 8 lanes per CTA), only the biquad recurrence is
     // serial per lane.  The low-rate stream goes through ctx scratch, the biquad runs in place on y.
     // Measured cross-over on B200: composed wins up to 2^14 lanes (profiles/r1_bench_chain.json).
+    // Lane-major, whole tiles, up to 2^17 lanes: tiled decimator -> low-rate scratch -> tiled interpolator
+    // with the biquad fused as a fifth warp (hbf_int_fast_body.cuh): two passes, 4.25 + 4.25 bytes per sample.
+    // Measured on B200 against the alternatives (GSa/s at 2^10 / 2^12 / 2^14 / 2^16 / 2^18 lanes, 2^30 samples):
+    // three kernels 44 / 145 / 276 / - / -, thread-per-lane fused - / - / - / 320 / 353, this path with 8-lane
+    // tiles 86 / 243 / 250 / 271 / 245 and with 16-lane tiles 71 / 221 / 313 / 337 / 304.  Short streams
+    // (fewer than 8 tiles per call) and more lanes stay on the single-pass thread-per-lane kernel.
+    const bool wide = lanes > 8192;
+    const size_t tile_low = hbf_int_bq_tile(log2_rate, wide);
+    if (layout == IDSP_LANE_MAJOR && ctx->policy != 1 && n_low % tile_low == 0 && n_low >= 8 * tile_low &&
+        (lanes <= 131072 || ctx->policy == 2) && ((((uintptr_t)x) | ((uintptr_t)y)) & 15) == 0) {
+        void *low = nullptr;
+        int r = idsp_scratch(ctx, n_low * lanes * sizeof(float), &low);
+        if (r) return r;
+        const size_t wd = (size_t)hbf_dec_words(log2_rate), wi = (size_t)hbf_int_words(log2_rate);
+        r = hbf_dec_cascade_dev(ctx, log2_rate, state, x, (float *)low, n_low, lanes, lanes, layout);
+        if (r) return r;
+        Df1Op<float, false>::Params bq;
+        for (int i = 0; i < 5; i++) bq.ba[i] = ba[i];
+        bq.F = 0;
+        bq.u = bq.mn = bq.mx = 0.f;
+        bq.st = state + (wd + wi) * lanes;
+        r = hbf_int_bq_fast_try(ctx, log2_rate, state + wd * lanes, (const float *)low, y, n_low, lanes, lanes, bq, wide);
+        if (r != IDSP_HBF_FAST_NOT_APPLICABLE) return r;
+        // (not reached: the scratch buffer is aligned) the three-kernel composition
+        r = idsp_hbf_int_cascade_f32(ctx, log2_rate, state + wd * lanes, (const float *)low, y, n_low, lanes, layout);
+        if (r) return r;
+        return idsp_biquad_df1_f32(ctx, ba, 0, nullptr, state + (wd + wi) * lanes, y, y, n_low << log2_rate, lanes,
+                                   layout);
+    }
     if (layout == IDSP_LANE_MAJOR && ctx->policy != 1 && lanes <= 16384) {
         void *low = nullptr;
         int r = idsp_scratch(ctx, n_low * lanes * sizeof(float), &low);

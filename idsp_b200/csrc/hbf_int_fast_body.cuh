@@ -1,0 +1,302 @@
+// hbf_int_fast_body.cuh -- body of the tiled interpolator, included by hbf_int_fast.cuh once per tile shape
+// (HFI_NS = namespace, HFI_NL = lanes per CTA, HFI_TOUT = output samples per lane and tile).  No include guard.
+namespace idsp {
+namespace HFI_NS {
+
+constexpr int NL = HFI_NL;      // lanes per CTA
+constexpr int NT = 128;         // threads per CTA (FIR warps)
+constexpr int TOUT = HFI_TOUT;  // output samples per lane per tile
+
+__host__ __device__ constexpr int up4(int v) { return (v + 3) & ~3; }
+__host__ __device__ constexpr int oddpitch(int v) { return (up4(v) / 4) % 2 ? up4(v) : up4(v) + 4; }
+// stage s of a x2^K cascade uses TAPS[s] (lowest rate first, src/hbf.rs:503-512)
+__host__ __device__ constexpr int st_m(int s) { return hbf_m(s); }
+__host__ __device__ constexpr int ti(int K) { return TOUT >> K; }                 // inputs per tile
+__host__ __device__ constexpr int st_nin(int K, int s) { return ti(K) << s; }      // inputs of stage s per tile
+__host__ __device__ constexpr int st_r(int K, int s) {                             // inputs per item
+    return st_nin(K, s) / 16 >= 8 ? 8 : 4;
+}
+__host__ __device__ constexpr int hist(int s) { return up4(2 * st_m(s) - 1); }
+__host__ __device__ constexpr int pitch(int K, int s) { return oddpitch(hist(s) + st_nin(K, s)); }
+__host__ __device__ constexpr int off_u(int K, int s) {  // float offset of stage s's input rows
+    int o = 0;
+    for (int i = 0; i < s; i++) o += NL * pitch(K, i);
+    return o;
+}
+constexpr int OUT_PITCH = oddpitch(TOUT);
+__host__ __device__ constexpr int off_out(int K) { return off_u(K, K); }
+__host__ __device__ constexpr int smem_floats(int K) { return off_out(K) + 2 * NL * OUT_PITCH; }
+__host__ __device__ constexpr size_t smem_bytes(int K) { return (size_t)smem_floats(K) * 4; }
+__host__ __device__ constexpr int st_word(int s) {  // ABI state word offset of stage s
+    int w = 0;
+    for (int i = 0; i < s; i++) w += 2 * st_m(i) - 1;
+    return w;
+}
+
+
+// One item: inputs n0 .. n0+R-1 of row `row` = [H hist | n new]; writes 2R outputs to dst
+template <int TI_, int R> struct IntItem {
+    static constexpr int M = HbfTaps<TI_>::M;
+    static constexpr int LEN = 2 * M - 1;
+    static constexpr int H = up4(LEN);
+    static constexpr int RO = H - LEN;
+    static constexpr int W = up4(RO + R + LEN);
+    __device__ __forceinline__ static void run(const float *row, int n0, float *dst) {
+        float w[W];
+#pragma unroll
+        for (int j = 0; j < W / 4; j++) {
+            float4 v = lds128v(row + n0 + 4 * j);
+            w[4 * j] = v.x; w[4 * j + 1] = v.y; w[4 * j + 2] = v.z; w[4 * j + 3] = v.w;
+        }
+        float o[2 * R];
+#pragma unroll
+        for (int q = 0; q < R; q++) {
+            // window of input n0+q: w[RO+q .. RO+q+2M-1]
+            float acc = (w[RO + q + 2 * M - 1] + w[RO + q]) * HbfTaps<TI_>::c(0);
+#pragma unroll
+            for (int i = 1; i < M; i++)
+                acc = acc + (w[RO + q + 2 * M - 1 - i] + w[RO + q + i]) * HbfTaps<TI_>::c(i);
+            o[2 * q] = acc;
+            o[2 * q + 1] = w[RO + q + M];
+        }
+#pragma unroll
+        for (int j = 0; j < 2 * R / 4; j++)
+            reinterpret_cast<float4 *>(dst)[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+    }
+};
+
+// Move the tails of the [hist | n new] input rows of stage s (all NL lanes) to their heads
+// (copy_within, src/hbf.rs:231).  One 16-byte piece per thread, a whole row inside one warp:
+// everything is read before anything is written (head and tail overlap when hist > n).
+template <int K, int s>
+__device__ __forceinline__ void carry_rows(float *sm, int warp, int lid) {
+    constexpr int C = hist(s) / 4;
+    constexpr int LP = 32 / C;  // lanes per warp pass
+    static_assert(C <= 32, "row history too long for one warp");
+    const int sub = lid / C, j = lid % C;
+    int lane = warp * LP + sub;
+    float *row = sm + off_u(K, s) + lane * pitch(K, s) + 4 * j;
+    for (; lane - sub < NL; lane += (NT / 32) * LP, row += (NT / 32) * LP * pitch(K, s)) {  // warp-uniform trip count
+        const bool act = sub < LP && lane < NL;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (act) v = lds128v(row + st_nin(K, s));
+        __syncwarp();
+        if (act) *reinterpret_cast<float4 *>(row) = v;
+        __syncwarp();
+    }
+}
+
+template <int K, int s> struct StageRun {
+    __device__ __forceinline__ static void run(float *sm, int tid, int obuf) {
+        constexpr int R = st_r(K, s);
+        constexpr int ITEMS = NL * st_nin(K, s) / R;
+        const float *U = sm + off_u(K, s);
+        for (int idx = tid; idx < ITEMS; idx += NT) {
+            const int lane = idx % NL, n0 = (idx / NL) * R;
+            float *dst;
+            if constexpr (s == K - 1) dst = sm + off_out(K) + (obuf * NL + lane) * OUT_PITCH + 2 * n0;
+            else dst = sm + off_u(K, s + 1) + lane * pitch(K, s + 1) + hist(s + 1) + 2 * n0;
+            IntItem<s, R>::run(U + lane * pitch(K, s), n0, dst);
+        }
+        // the input rows of the previous stage were consumed one barrier ago
+        if constexpr (s >= 1) carry_rows<K, s - 1>(sm, tid >> 5, tid & 31);
+    }
+};
+
+template <int K, int s, bool LOAD> struct StateIO {
+    __device__ __forceinline__ static void run(float *sm, float *st, size_t sstride, size_t lane0, int nl, int tid) {
+        if constexpr (s < K) {
+            constexpr int LEN = 2 * st_m(s) - 1;
+            float *stw = st + (size_t)st_word(s) * sstride + lane0;
+            for (int idx = tid; idx < LEN * NL; idx += NT) {
+                const int lane = idx % NL, w = idx / NL;
+                if (lane >= nl) continue;
+                float *p = sm + off_u(K, s) + lane * pitch(K, s) + (hist(s) - LEN + w);
+                if constexpr (LOAD) *p = stw[(size_t)w * sstride + lane];
+                else stw[(size_t)w * sstride + lane] = *p;
+            }
+            StateIO<K, s + 1, LOAD>::run(sm, st, sstride, lane0, nl, tid);
+        }
+    }
+};
+
+// FM = false: x, y lane-major.  FM = true: frame-major x[t][lane], y[t][lane][2^K]: the
+// input tile is prefetched element-wise and the staged output rows leave as 16-byte (x2: 8-byte) pieces
+// (8 lanes x 4 pieces of one frame per warp store = up to 512 contiguous bytes of HBM).
+// BQ = true (lane-major only): a fifth warp runs an iir::Biquad DF1 f32 (src/iir/biquad.rs:366-383) over every
+// staged output tile in place before it is stored -- one thread per lane, the recurrence is serial in
+// time -- while the four FIR warps already compute the next tile (HbfInt -> Biquad of the config-5 chain
+// without a second pass over HBM).
+template <int K, bool FM, bool BQ = false>
+__global__ void __launch_bounds__(NT + (BQ ? 32 : 0), BQ ? HFI_BQ_MINB : 4)
+hbf_int_fast_kernel(float *st, const float *x, float *y, size_t n_in, size_t ntiles, size_t lanes, size_t sstride,
+                    Df1Op<float, false>::Params bq) {
+    static_assert(!(BQ && FM), "the fused biquad variant is lane-major");
+    constexpr int NTA = NT + (BQ ? 32 : 0);
+    auto fir_sync = [&]() {
+        if constexpr (BQ) nbar_sync(1, NT);
+        else __syncthreads();
+    };
+    constexpr int TI = ti(K);
+    constexpr int NV = FM ? NL * TI : NL * TI / 4;  // loads per input tile (floats if FM, float4 else)
+    constexpr int NVT = (NV + NT - 1) / NT;         // ... per thread
+    extern __shared__ __align__(128) float sm[];
+    const int tid = threadIdx.x;
+    const size_t lane0 = (size_t)blockIdx.x * NL;
+    const int nl = (int)((lanes - lane0) < (size_t)NL ? (lanes - lane0) : (size_t)NL);
+    const size_t n_out = n_in << K;  // row stride of y in floats
+
+    for (int i = tid; i < smem_floats(K); i += NTA) sm[i] = 0.f;
+    __syncthreads();
+    if constexpr (BQ) {
+        if (tid >= NT) {
+            // ---- the biquad warp: thread j owns lane j of the CTA (NL <= 32).  The recurrence is a chain
+            // of dependent FP32 operations, so its cost per tile does not depend on how many of the 32
+            // threads are in use: more lanes per CTA (hfi16) make it cheaper per sample.
+            static_assert(NL <= 32, "one biquad warp");
+            const int j = tid - NT;
+            const bool act = j < nl && j < NL;
+            Df1Op<float, false> op;
+            op.x1 = op.x2 = op.y1 = op.y2 = 0.f;
+            if (act) op.load(bq, lane0 + j, sstride);
+            for (size_t i = 0; i < ntiles; i++) {
+                const int ob = (int)(i & 1);
+                nbar_sync(2 + ob, NTA);  // tile i is staged
+                if (act) {
+                    float *row = sm + off_out(K) + (ob * NL + j) * OUT_PITCH;
+                    float4 v0 = lds128v(row), v1 = lds128v(row + 4);  // loads run two pieces ahead of the chain
+#pragma unroll 4
+                    for (int q = 0; q < TOUT / 4; q++) {
+                        float4 v = v0;
+                        v0 = v1;
+                        if (q + 2 < TOUT / 4) v1 = lds128v(row + 4 * (q + 2));
+                        v.x = op.step(bq, v.x);
+                        v.y = op.step(bq, v.y);
+                        v.z = op.step(bq, v.z);
+                        v.w = op.step(bq, v.w);
+                        *reinterpret_cast<float4 *>(row + 4 * q) = v;
+                    }
+                    fence_async_smem();
+                    bulk_store_1d(y + (lane0 + j) * n_out + i * TOUT, smem_u32(row), TOUT * 4);
+                    tma_commit();
+                    tma_wait_read<0>();  // the FIR warps are one tile ahead: this wait is off their path
+                }
+                __syncwarp();
+                if (i + 2 < ntiles) nbar_arrive(4 + ob, NTA);  // buffer ob may be refilled (tile i + 2)
+            }
+            if (act) op.store(bq, lane0 + j, sstride);
+            return;
+        }
+    }
+    StateIO<K, 0, true>::run(sm, st, sstride, lane0, nl, tid);
+
+    // input prefetch (the input is 1/2^K of the traffic): float4 v = tid + j*NT of the tile
+    float4 nxt[NVT];  // FM uses .x only
+    auto fetch = [&](size_t tile) {
+#pragma unroll
+        for (int j = 0; j < NVT; j++) {
+            const int v = tid + j * NT;
+            if constexpr (FM) {
+                const int plane = v % NL, t = v / NL;  // lane-fastest: 8 lanes of a frame are contiguous
+                nxt[j].x = (v < NV && plane < nl) ? x[(tile * TI + t) * lanes + lane0 + plane] : 0.f;
+            } else {
+                const int plane = v / (TI / 4), pvec = v % (TI / 4);
+                nxt[j] = (v < NV && plane < nl)
+                             ? *reinterpret_cast<const float4 *>(x + (lane0 + plane) * n_in + tile * TI + 4 * pvec)
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    };
+    if (ntiles) fetch(0);
+
+    for (size_t i = 0; i < ntiles; i++) {
+        const int ob = (int)(i & 1);
+#pragma unroll
+        for (int j = 0; j < NVT; j++) {
+            const int v = tid + j * NT;
+            if constexpr (FM) {
+                const int plane = v % NL, t = v / NL;
+                if (v < NV) sm[off_u(K, 0) + plane * pitch(K, 0) + hist(0) + t] = nxt[j].x;
+            } else {
+                const int plane = v / (TI / 4), pvec = v % (TI / 4);
+                if (v < NV) *reinterpret_cast<float4 *>(sm + off_u(K, 0) + plane * pitch(K, 0) + hist(0) + 4 * pvec) = nxt[j];
+            }
+        }
+        if (i + 1 < ntiles) fetch(i + 1);
+        // rows K-1 of the previous tile: last read in its final phase, next written by stage K-2
+        if constexpr (K >= 2) {
+            if (i > 0) carry_rows<K, K - 1>(sm, tid >> 5, tid & 31);
+        }
+        // the staging buffer about to be refilled must have been drained by its bulk stores
+        // (bulk async-groups are per thread: every issuing thread waits for its own)
+        if constexpr (!FM && !BQ) {
+            if (tid < nl) tma_wait_read<1>();
+        }
+        fir_sync();
+        if constexpr (K >= 2) { StageRun<K, 0>::run(sm, tid, ob); fir_sync(); }
+        if constexpr (K >= 3) { StageRun<K, 1>::run(sm, tid, ob); fir_sync(); }
+        if constexpr (K >= 4) { StageRun<K, 2>::run(sm, tid, ob); fir_sync(); }
+        if constexpr (K >= 5) { StageRun<K, 3>::run(sm, tid, ob); fir_sync(); }
+        if constexpr (BQ) {
+            if (i >= 2) nbar_sync(4 + ob, NTA);  // the biquad warp has stored tile i - 2 out of this buffer
+        }
+        StageRun<K, K - 1>::run(sm, tid, ob);  // -> staging (and carries rows K-2)
+        if constexpr (BQ) {
+            nbar_arrive(2 + ob, NTA);  // hand the staged tile to the biquad warp
+            fir_sync();
+            if constexpr (K == 1) {
+                carry_rows<K, 0>(sm, tid >> 5, tid & 31);
+                fir_sync();
+            }
+            continue;
+        }
+        if constexpr (!FM) fence_async_smem();  // writers make the staging rows visible to the async proxy
+        __syncthreads();
+        if constexpr (FM) {
+            constexpr int R = 1 << K;
+            constexpr int PF_ = R >= 4 ? 4 : 2;  // floats per piece: 16 bytes, or the 8-byte frame of x2
+            const float *stg = sm + off_out(K) + ob * NL * OUT_PITCH;
+            for (int c = tid; c < NL * TOUT / PF_; c += NT) {
+                const int l = c % NL, q = c / NL;  // piece q = output samples PF_*q .. of lane l's tile
+                if (l < nl) {
+                    float *dst = y + ((i * TI + (PF_ * q) / R) * lanes + lane0 + l) * R + (PF_ * q) % R;
+                    if constexpr (PF_ == 4) {
+                        *reinterpret_cast<float4 *>(dst) = lds128v(stg + l * OUT_PITCH + PF_ * q);
+                    } else {
+                        *reinterpret_cast<float2 *>(dst) = *reinterpret_cast<const float2 *>(stg + l * OUT_PITCH + PF_ * q);
+                    }
+                }
+            }
+        } else if (tid < nl) {
+            bulk_store_1d(y + (lane0 + tid) * n_out + i * TOUT, smem_u32(sm + off_out(K) + (ob * NL + tid) * OUT_PITCH),
+                          TOUT * 4);
+            tma_commit();
+        }
+        if constexpr (K == 1) {  // rows 0 are rewritten at the top of the next tile: carry them now
+            carry_rows<K, 0>(sm, tid >> 5, tid & 31);
+            __syncthreads();
+        }
+    }
+    if constexpr (K >= 2) {
+        carry_rows<K, K - 1>(sm, tid >> 5, tid & 31);
+        fir_sync();
+    }
+    if constexpr (!FM && !BQ) {
+        if (tid < nl) tma_wait_read<0>();
+    }
+    StateIO<K, 0, false>::run(sm, st, sstride, lane0, nl, tid);
+}
+
+template <int K, bool FM, bool BQ = false>
+static int launch(idsp_ctx *ctx, float *st, const float *x, float *y, size_t n_in, size_t ntiles, size_t lanes,
+                  size_t sstride, const Df1Op<float, false>::Params &bq = Df1Op<float, false>::Params()) {
+    auto kern = hbf_int_fast_kernel<K, FM, BQ>;
+    IDSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(K)));
+    unsigned grid = (unsigned)((lanes + NL - 1) / NL);
+    kern<<<grid, NT + (BQ ? 32 : 0), smem_bytes(K), ctx->stream>>>(st, x, y, n_in, ntiles, lanes, sstride, bq);
+    IDSP_LAUNCHED(ctx);
+    return IDSP_OK;
+}
+
+}  // namespace HFI_NS
+}  // namespace idsp

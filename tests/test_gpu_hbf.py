@@ -190,6 +190,48 @@ def test_chain_vs_oracle(oracle, k):
         assert_bits_equal(to_np(st), so)
 
 
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5])
+def test_chain_tiled_fused_biquad_streaming(oracle, k):
+    """config 5, lane-major, whole tiles: tiled decimator -> tiled interpolator with the biquad warp
+    (two passes); state carried over calls of 8, 1, 9 and 11 tiles and a ragged call (the short and
+    ragged ones run on the other kernels), ragged lane count, == the oracle called the same way"""
+    from idsp_b200 import Biquad, Filter
+    rng = np.random.default_rng(70 + k)
+    ba = Biquad.from_ba6(Filter().critical_frequency(0.05).lowpass(), "f32").ba
+    R = 1 << k
+    TI = 512 >> k
+    W = oracle.hbf_dec_state_words(k) + oracle.hbf_int_state_words(k) + 4
+    ctx = ib.default_context(0)
+    for lanes in (50, 8, 3):
+        so = np.zeros((W, lanes), np.float32)
+        st = torch.zeros((W, lanes), dtype=torch.float32, device=DEV)
+        for n_low in (8 * TI, TI, 9 * TI, TI + 5, 11 * TI):  # >= 8 tiles: fused path; fewer / ragged: the other kernels
+            x = rng.uniform(-1, 1, n_low * lanes * R).astype(np.float32)
+            want = oracle.chain_lanes(k, ba, so, x, lanes, 1)
+            y = ctx.chain(k, ba, st, to_dev(x), lanes=lanes, layout=1)
+            assert_bits_equal(to_np(y), want, f"k={k} lanes={lanes} n_low={n_low}")
+            assert_bits_equal(to_np(st), so, f"state k={k} lanes={lanes} n_low={n_low}")
+
+
+@pytest.mark.parametrize("k", [2, 4, 5])
+def test_chain_tiled_fused_biquad_many_lanes(oracle, k):
+    """above 8192 lanes the fused path uses 16-lane x 256-output tiles (ragged last CTA: 8200 = 512 * 16 + 8)"""
+    from idsp_b200 import Biquad, Filter
+    rng = np.random.default_rng(90 + k)
+    ba = Biquad.from_ba6(Filter().critical_frequency(0.05).lowpass(), "f32").ba
+    R, lanes = 1 << k, 8200
+    W = oracle.hbf_dec_state_words(k) + oracle.hbf_int_state_words(k) + 4
+    ctx = ib.default_context(0)
+    so = np.zeros((W, lanes), np.float32)
+    st = torch.zeros((W, lanes), dtype=torch.float32, device=DEV)
+    for n_low in (8 * (256 >> k), 9 * (256 >> k)):
+        x = rng.uniform(-1, 1, n_low * lanes * R).astype(np.float32)
+        want = oracle.chain_lanes(k, ba, so, x, lanes, 1)
+        y = ctx.chain(k, ba, st, to_dev(x), lanes=lanes, layout=1)
+        assert_bits_equal(to_np(y), want, f"k={k} n_low={n_low}")
+        assert_bits_equal(to_np(st), so, f"state k={k} n_low={n_low}")
+
+
 @pytest.mark.parametrize("layout", [1, 0])
 @pytest.mark.parametrize("k", [1, 2, 3, 4, 5])
 def test_dec_cascade_tiled_kernel_streaming(oracle, k, layout):

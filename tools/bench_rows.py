@@ -70,6 +70,7 @@ def main():
         print(f"{name:46s} {samples / ms / 1e6:9.1f} GSa/s {gbs:8.1f} GB/s {100 * gbs / peak:5.1f}%", flush=True)
 
     lp = Filter().critical_frequency(0.01).lowpass()
+    ctx0 = ib.default_context(0)
     for layout, lname in ((0, "frame-major"), (1, "lane-major")):
         for kind in ("i8", "i16", "i32", "i64", "f32", "f64"):
             fmt = Q(kind, BITS[kind] - 2) if kind in BITS else kind
@@ -120,6 +121,18 @@ def main():
             add(f"a14 HbfInt x{R} cascade f32 {lname}", "hbf.rs:476-512", hl * n_out * R, 4 + 4 / R,
                 lambda: Lanes(HbfIntCascade(k)).block(sint, y, x, layout))
             del x, y
+        if layout == 1:  # config 5 chain at 65 536 lanes x 16 384 samples
+            from idsp_b200.hbf import _dec_state as _ds, _int_state as _is  # noqa: F401
+            import oracle as _O  # state word counts only (test infrastructure is fine in a bench tool)
+            cl, cn = 65536, 1024
+            W = _O.hbf_dec_state_words(4) + _O.hbf_int_state_words(4) + 4
+            xc5 = rnd("f32", cl * cn * 16)
+            yc5 = torch.empty_like(xc5)
+            stc = torch.zeros((W, cl), dtype=torch.float32, device=DEV)
+            bac = np.asarray(Biquad.from_ba6(Filter().critical_frequency(0.05).lowpass(), "f32").ba)
+            add(f"cfg5 chain HbfDec16->HbfInt16->Biquad f32 {lname}", "hbf.rs:385-512, biquad.rs:366-383", cl * cn * 16, 8,
+                lambda: ctx0.chain(4, bac, stc, xc5, yc5, lanes=cl, layout=1))
+            del xc5, yc5
         from idsp_b200 import FmDiscriminator, FmDiscState
         xc = rnd("i32", 2 * lanes * frames)
         yd = torch.empty(lanes * frames, dtype=torch.int32, device=DEV)
