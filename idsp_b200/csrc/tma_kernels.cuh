@@ -482,6 +482,9 @@ static int tma_launch_fm_auto(idsp_ctx *ctx, const typename Op::Params &p, const
                               size_t frames, size_t lanes, size_t sstride) {
     const size_t sms = (size_t)(ctx->sm_count > 0 ? ctx->sm_count : 148);
     auto ctas = [&](size_t wpc) { return (lanes + 32 * wpc - 1) / (32 * wpc); };
+    // compute-bound ops: independent per-warp pipelines of 16-frame tiles (no CTA-wide barrier per tile);
+    // Cascade<4> i32 276 -> 302 GSa/s, PLL 455 -> 487 against the wide boxes that serve the HBM-bound ops
+    if constexpr (Op::HEAVY) return tma_launch_cfg<Op, false, 16, 4, 2, 1>(ctx, p, x, y, frames, lanes, sstride);
     if (ctas(8) >= sms) return tma_launch_cfg<Op, false, 8, 4, 2, 8, true>(ctx, p, x, y, frames, lanes, sstride);
     if (ctas(4) >= sms) return tma_launch_cfg<Op, false, 8, 4, 2, 4, true>(ctx, p, x, y, frames, lanes, sstride);
     if (ctas(2) >= sms) return tma_launch_cfg<Op, false, 8, 4, 2, 2, true>(ctx, p, x, y, frames, lanes, sstride);

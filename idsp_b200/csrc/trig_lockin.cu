@@ -7,27 +7,37 @@
 using namespace idsp;
 
 // ---------------------------------------------------------------- memoryless maps
-// 4 phases per thread: one 16-byte load, two 16-byte stores.
+// 2 phases per thread: one 8-byte load and ONE 16-byte store, so a warp store covers 512 contiguous
+// bytes (with 4 phases per thread the two 16-byte stores of a thread interleave with its neighbours'
+// and every 32-byte sector is written in two halves); two such pairs in flight per thread.
 __global__ void __launch_bounds__(256) cossin_kernel(const int32_t *phase, int32_t *cs, size_t n) {
     __shared__ __align__(8) uint32_t lut[256];
     cossin_expand_lut(g_cossin_lut, lut, threadIdx.x, blockDim.x);
     __syncthreads();
-    const size_t n4 = n / 4;
-    const bool vec = ((((uintptr_t)phase) | ((uintptr_t)cs)) & 15) == 0;
+    const size_t n2 = n / 2;
+    const bool vec = ((((uintptr_t)phase) & 7) | (((uintptr_t)cs) & 15)) == 0;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (vec) {
-        for (; i < n4; i += stride) {
-            int4 p = reinterpret_cast<const int4 *>(phase)[i];
+        for (; i + stride < n2; i += 2 * stride) {
+            const int2 p = reinterpret_cast<const int2 *>(phase)[i];
+            const int2 q = reinterpret_cast<const int2 *>(phase)[i + stride];
             int4 a, b;
             cossin_dev_x(lut, p.x, a.x, a.y);
             cossin_dev_x(lut, p.y, a.z, a.w);
-            cossin_dev_x(lut, p.z, b.x, b.y);
-            cossin_dev_x(lut, p.w, b.z, b.w);
-            reinterpret_cast<int4 *>(cs)[2 * i] = a;
-            reinterpret_cast<int4 *>(cs)[2 * i + 1] = b;
+            cossin_dev_x(lut, q.x, b.x, b.y);
+            cossin_dev_x(lut, q.y, b.z, b.w);
+            reinterpret_cast<int4 *>(cs)[i] = a;
+            reinterpret_cast<int4 *>(cs)[i + stride] = b;
         }
-        i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+        for (; i < n2; i += stride) {
+            const int2 p = reinterpret_cast<const int2 *>(phase)[i];
+            int4 a;
+            cossin_dev_x(lut, p.x, a.x, a.y);
+            cossin_dev_x(lut, p.y, a.z, a.w);
+            reinterpret_cast<int4 *>(cs)[i] = a;
+        }
+        i = n2 * 2 + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     }
     for (; i < n; i += stride) {
         int32_t c, s;
@@ -82,7 +92,7 @@ extern "C" int idsp_cossin_i32(idsp_ctx *ctx, const int32_t *phase, int32_t *cs,
     if (r) return r;
     if (n == 0) return IDSP_OK;
     IDSP_CHECK_ARG(phase && cs, "phase/cs must not be null");
-    cossin_kernel<<<map_grid(ctx, (n + 3) / 4), 256, 0, ctx->stream>>>(phase, cs, n);
+    cossin_kernel<<<map_grid(ctx, (n + 1) / 2), 256, 0, ctx->stream>>>(phase, cs, n);
     IDSP_LAUNCHED(ctx);
     return IDSP_OK;
 }
