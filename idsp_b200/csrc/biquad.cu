@@ -1,4 +1,6 @@
 // biquad.cu -- C-ABI entry points of the iir::Biquad family (include/idsp_b200.h).
+#include <string.h>
+
 #include "common.cuh"
 #include "ops.cuh"
 #include "lane_kernels.cuh"
@@ -148,7 +150,17 @@ static int cascade_impl(idsp_ctx *ctx, const T *ba, int F, int nsec, T *state, c
         p.F = F;                                                                     \
         p.nsec = nsec;                                                               \
         p.st = state;                                                                \
-        return launch_lanes_best<CascadeOp<T, N>>(ctx, p, x, y, frames, lanes, sstride, layout); \
+        if constexpr (std::is_same<T, int32_t>::value) {                             \
+            /* i32: 0 <= F < 32 takes the funnel-shift ops on the TMA kernels, other F the generic ones */ \
+            if (F >= 0 && F < 32) {                                                  \
+                typename CascadeOp<T, N, 1>::Params q;                               \
+                memcpy(&q, &p, sizeof(q));                                           \
+                return launch_lanes_best<CascadeOp<T, N, 1>>(ctx, q, x, y, frames, lanes, sstride, layout); \
+            }                                                                        \
+            return launch_lanes<CascadeOp<T, N>>(ctx, p, x, y, frames, lanes, sstride, layout); \
+        } else {                                                                     \
+            return launch_lanes_best<CascadeOp<T, N>>(ctx, p, x, y, frames, lanes, sstride, layout); \
+        }                                                                            \
     } while (0)
     switch (nsec) {
         case 1: GO(1);

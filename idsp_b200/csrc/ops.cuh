@@ -165,12 +165,14 @@ template <class Op> struct PackedOp : OpHooks {
 };
 
 // Cascade<[Biquad;N]> on DirectForm<T,N> (src/iir/biquad.rs:339-364)
-template <class T, int N> struct CascadeOp : OpHooks {
+template <class T, int N, int MODE = 0> struct CascadeOp : OpHooks {
     // exactly N sections (the entry point dispatches on nsec): every index below is static, so
-    // the 2 + 2N delay values stay in registers
+    // the 2 + 2N delay values stay in registers.  MODE 1 (i32, 0 <= F < 32, chosen by the entry point):
+    // funnel-shift quantiser with no per-section test of F -- a branch per section, even a uniform one,
+    // keeps the scheduler from overlapping the sections of consecutive samples.
     using In = T;
     using Out = T;
-    static constexpr bool FAST = std::is_same<T, int32_t>::value;  // i32: the entry point routes 0 <= F < 32 here
+    static_assert(MODE == 0 || std::is_same<T, int32_t>::value, "MODE 1 is the i32 fast path");
     static constexpr bool HEAVY = N >= 2;
     struct Params {
         T ba[N][5];
@@ -191,14 +193,10 @@ template <class T, int N> struct CascadeOp : OpHooks {
 #pragma unroll
         for (int s = 0; s < N; s++) {
             T y0;
-            if constexpr (FAST) {
-                if (p.F >= 0 && p.F < 32)  // uniform
-                    y0 = SosI32Fast::eval(p.ba[s], p.F, x0, d[2 * s], d[2 * s + 1], d[2 * s + 2], d[2 * s + 3]);
-                else
-                    y0 = Sos<T>::eval(p.ba[s], p.F, x0, d[2 * s], d[2 * s + 1], d[2 * s + 2], d[2 * s + 3]);
-            } else {
+            if constexpr (MODE == 1)
+                y0 = SosI32Fast::eval(p.ba[s], p.F, x0, d[2 * s], d[2 * s + 1], d[2 * s + 2], d[2 * s + 3]);
+            else
                 y0 = Sos<T>::eval(p.ba[s], p.F, x0, d[2 * s], d[2 * s + 1], d[2 * s + 2], d[2 * s + 3]);
-            }
             d[2 * s + 1] = d[2 * s];
             d[2 * s] = x0;
             x0 = y0;
@@ -620,6 +618,7 @@ struct PllOp : OpHooks {
 // The first sample of a stream (no previous sample) gives d = 0.
 // State words (i32): [has_prev, prev.re, prev.im, x1, x2, y1, y2].
 // --------------------------------------------------------------------------
+template <int MODE = 0>  // MODE 1: 0 <= F < 32 (funnel-shift quantiser, no test of F per sample)
 struct FmDiscOp : OpHooks {
     using In = int2;   // Complex<Q32<32>> as raw (re, im)
     using Out = int32_t;
@@ -659,8 +658,8 @@ struct FmDiscOp : OpHooks {
         has = 1;
         pre = x.x;
         pim = x.y;
-        const int32_t y0 = (p.F >= 0 && p.F < 32) ? SosI32Fast::eval(p.ba, p.F, d, x1, x2, y1, y2)
-                                                  : Sos<int32_t>::eval(p.ba, p.F, d, x1, x2, y1, y2);
+        const int32_t y0 = MODE == 1 ? SosI32Fast::eval(p.ba, p.F, d, x1, x2, y1, y2)
+                                     : Sos<int32_t>::eval(p.ba, p.F, d, x1, x2, y1, y2);
         x2 = x1;
         x1 = d;
         y2 = y1;

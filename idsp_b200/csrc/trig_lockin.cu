@@ -269,10 +269,18 @@ extern "C" int idsp_fm_disc_i32(idsp_ctx *ctx, int32_t carrier, const int32_t *b
     if (frames == 0 || lanes == 0) return IDSP_OK;
     IDSP_CHECK_ARG(state && x && y, "state/x/y must not be null");
     IDSP_CHECK_ARG((((uintptr_t)x) & 7) == 0, "x (re, im pairs) must be 8-byte aligned");
-    FmDiscOp::Params p;
+    if (F >= 0 && F < 32) {
+        FmDiscOp<1>::Params p;
+        p.carrier = carrier;
+        for (int i = 0; i < 5; i++) p.ba[i] = ba[i];
+        p.F = F;
+        p.st = state;
+        return launch_lanes<FmDiscOp<1>>(ctx, p, (const int2 *)x, y, frames, lanes, lanes, layout);
+    }
+    FmDiscOp<0>::Params p;
     p.carrier = carrier;
     for (int i = 0; i < 5; i++) p.ba[i] = ba[i];
     p.F = F;
     p.st = state;
-    return launch_lanes<FmDiscOp>(ctx, p, (const int2 *)x, y, frames, lanes, lanes, layout);
+    return launch_lanes<FmDiscOp<0>>(ctx, p, (const int2 *)x, y, frames, lanes, lanes, layout);
 }
