@@ -97,6 +97,34 @@ def test_df1_vs_oracle(oracle, kind, layout, clamp):
         assert_bits_equal(st.numpy(), so, "state")
 
 
+@pytest.mark.parametrize("kind", ["i8", "i16", "i32", "i64"])
+def test_df1_fractional_bits_sweep(oracle, kind):
+    """every quantiser variant: F = 0, the usual range, the top of it, beyond the sample width and negative
+    (generic-shift kernels), with full-scale raw coefficients and samples so the wide accumulator wraps
+    and every carry of the i64 (i128 accumulator) chain is exercised"""
+    bits = BITS[kind]
+    rng = np.random.default_rng(bits)
+    frames, lanes = 48, 64
+    info = np.iinfo(NP[kind])
+    for F in (0, 1, bits // 2, bits - 2, bits - 1, bits, bits + 3, 2 * bits - 1, -1, -(bits - 1)):
+        for clamp in (None, [3, int(info.min) // 3, int(info.max) // 5]):
+            ba = rng.integers(info.min, info.max, 5, dtype=NP[kind], endpoint=True)
+            x = rng.integers(info.min, info.max, frames * lanes, dtype=NP[kind], endpoint=True)
+            x[:8] = [info.min, info.max, -1, 0, 1, info.min, info.min, info.max]
+            st0 = rng.integers(info.min, info.max, (4, lanes), dtype=NP[kind], endpoint=True)
+            for layout in (0, 1):
+                so = st0.copy()
+                want = oracle.biquad_lanes("df1", kind, ba, F, clamp, so, x, lanes, layout)
+                st = DirectForm1(to_dev(st0), kind)
+                y = torch.empty_like(to_dev(x))
+                bq = Biquad(ba, Q(kind, F))
+                if clamp is not None:
+                    bq = BiquadClamp(bq, *clamp)
+                Lanes(bq).block(st, to_dev(x), y, layout)
+                assert_bits_equal(to_np(y), want, f"{kind} F={F} clamp={clamp is not None} layout={layout}")
+                assert_bits_equal(st.numpy(), so, f"state {kind} F={F}")
+
+
 @pytest.mark.parametrize("kind", ["i32", "f32"])
 @pytest.mark.parametrize("layout", [0, 1])
 @pytest.mark.parametrize("policy", [1, 2])
