@@ -75,14 +75,15 @@ def scatter_lanes(flat: Optional[torch.Tensor], frames: int, lanes: int, layout:
     if world == 1:
         out.copy_(parts[0])
         return out
-    # blocks may differ in size: point-to-point sends (NCCL groups them over NVLink)
+    # blocks may differ in size: one batch of point-to-point operations (NCCL runs them as a single
+    # grouped launch over NVLink / NVSwitch)
     if rank == src:
-        reqs = [dist.isend(parts[r], r, group=group) for r in range(world) if r != src]
+        ops = [dist.P2POp(dist.isend, parts[r], r, group) for r in range(world) if r != src]
         out.copy_(parts[src])
-        for q in reqs:
-            q.wait()
     else:
-        dist.recv(out, src, group=group)
+        ops = [dist.P2POp(dist.irecv, out, src, group)]
+    for q in dist.batch_isend_irecv(ops):
+        q.wait()
     return out
 
 
@@ -92,14 +93,15 @@ def gather_lanes(part: torch.Tensor, frames: int, lanes: int, layout: int, width
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     blocks = all_blocks(world, lanes)
     if rank != dst:
-        dist.send(part, dst, group=group)
+        for q in dist.batch_isend_irecv([dist.P2POp(dist.isend, part, dst, group)]):
+            q.wait()
         return None
     full = torch.empty(frames * lanes * width, dtype=part.dtype, device=part.device)
+    bufs = [part if r == dst else torch.empty(frames * (b - a) * width, dtype=part.dtype, device=part.device)
+            for r, (a, b) in enumerate(blocks)]
+    ops = [dist.P2POp(dist.irecv, bufs[r], r, group) for r in range(world) if r != dst]
+    for q in (dist.batch_isend_irecv(ops) if ops else []):
+        q.wait()
     for r, (a, b) in enumerate(blocks):
-        if r == dst:
-            buf = part
-        else:
-            buf = torch.empty(frames * (b - a) * width, dtype=part.dtype, device=part.device)
-            dist.recv(buf, r, group=group)
-        unshard_into(full, buf, frames, lanes, a, b, layout, width)
+        unshard_into(full, bufs[r], frames, lanes, a, b, layout, width)
     return full
