@@ -143,6 +143,55 @@ extern "C" void idsp_b200_host_free(void *ptr) {
 
 extern "C" uint64_t idsp_b200_launch_count(const idsp_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+// ---------------------------------------------------------------------------
+// Peer memory (CUDA IPC): a plain cudaMalloc allocation (exportable, unlike a sub-block of a caching
+// allocator), its handle, and the importing side.  Opening enables peer access lazily.
+// ---------------------------------------------------------------------------
+static_assert(sizeof(cudaIpcMemHandle_t) == IDSP_IPC_HANDLE_BYTES, "handle size");
+extern "C" int idsp_b200_malloc(idsp_ctx *ctx, size_t bytes, void **ptr) {
+    int r = idsp_use_device(ctx);
+    if (r) return r;
+    IDSP_CHECK_ARG(ptr != nullptr, "ptr is null");
+    *ptr = nullptr;
+    cudaError_t e = cudaMalloc(ptr, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+        idsp_set_error("cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+        return IDSP_ENOMEM;
+    }
+    return IDSP_OK;
+}
+extern "C" int idsp_b200_mfree(idsp_ctx *ctx, void *ptr) {
+    int r = idsp_use_device(ctx);
+    if (r) return r;
+    if (ptr) IDSP_CUDA(cudaFree(ptr));
+    return IDSP_OK;
+}
+extern "C" int idsp_b200_ipc_export(idsp_ctx *ctx, const void *ptr, unsigned char handle[IDSP_IPC_HANDLE_BYTES]) {
+    int r = idsp_use_device(ctx);
+    if (r) return r;
+    IDSP_CHECK_ARG(ptr != nullptr && handle != nullptr, "ptr/handle is null");
+    cudaIpcMemHandle_t h;
+    IDSP_CUDA(cudaIpcGetMemHandle(&h, const_cast<void *>(ptr)));
+    memcpy(handle, &h, sizeof(h));
+    return IDSP_OK;
+}
+extern "C" int idsp_b200_ipc_open(idsp_ctx *ctx, const unsigned char handle[IDSP_IPC_HANDLE_BYTES], void **ptr) {
+    int r = idsp_use_device(ctx);
+    if (r) return r;
+    IDSP_CHECK_ARG(ptr != nullptr && handle != nullptr, "ptr/handle is null");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    *ptr = nullptr;
+    IDSP_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return IDSP_OK;
+}
+extern "C" int idsp_b200_ipc_close(idsp_ctx *ctx, void *ptr) {
+    int r = idsp_use_device(ctx);
+    if (r) return r;
+    if (ptr) IDSP_CUDA(cudaIpcCloseMemHandle(ptr));
+    return IDSP_OK;
+}
+
 extern "C" int idsp_b200_set_kernel_policy(idsp_ctx *ctx, int policy) {
     if (!ctx || policy < 0 || policy > 3) {
         idsp_set_error("idsp_b200_set_kernel_policy: bad argument");

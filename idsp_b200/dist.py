@@ -6,6 +6,9 @@ slice of the SoA state; coefficients are tiny and replicated.  There is no colle
 inside the computation.  NCCL (or gloo in the CPU tests) is used only at the edges:
 `scatter_lanes` hands lane blocks of a root-resident buffer to the ranks,
 `gather_lanes` collects outputs, both for either layout of dsp-process/src/view.rs.
+`PeerBuffer` is the fused form of the gather: the root's result buffer is mapped into every
+process (CUDA IPC), and each rank passes its lane block of it as the output of its kernel, whose
+stores then travel over NVLink / NVSwitch from the kernel's own epilogue.
 """
 from __future__ import annotations
 
@@ -14,7 +17,10 @@ from typing import List, Optional, Tuple
 import torch
 import torch.distributed as dist
 
-from .engine import FRAME_MAJOR, LANE_MAJOR
+import ctypes as C
+
+from . import _lib
+from .engine import FRAME_MAJOR, LANE_MAJOR, PeerView, default_context
 
 
 def lane_block(rank: int, world: int, lanes: int, align: int = 32) -> Tuple[int, int]:
@@ -105,3 +111,61 @@ def gather_lanes(part: torch.Tensor, frames: int, lanes: int, layout: int, width
     for r, (a, b) in enumerate(blocks):
         unshard_into(full, bufs[r], frames, lanes, a, b, layout, width)
     return full
+
+
+class PeerBuffer:
+    """A device buffer owned by rank `owner` and mapped into every process of the group.
+
+    All ranks call the constructor (collective: the 64-byte handle of ``idsp_b200_ipc_export`` is
+    broadcast).  ``view(offset, numel)`` gives the range as a kernel output (`PeerView`); on the
+    owner ``tensor()`` is a torch view of the whole buffer.  ``close()`` is collective too.
+    Lane-major results are the natural fit: the lane block [lo, hi) of a [lanes][frames * width]
+    buffer is the contiguous range starting at lo * frames * width."""
+
+    def __init__(self, numel: int, dtype: torch.dtype, device: int, owner: int = 0, group=None):
+        self.numel, self.dtype, self.device, self.owner, self.group = int(numel), dtype, int(device), owner, group
+        self.rank = dist.get_rank(group)
+        self._ctx = default_context(self.device)
+        self._L = _lib.lib()
+        self.itemsize = torch.empty(0, dtype=dtype).element_size()
+        p = C.c_void_p()
+        handle = [None]
+        if self.rank == owner:
+            _lib.check(self._L.idsp_b200_malloc(self._ctx._h, self.numel * self.itemsize, C.byref(p)))
+            buf = (C.c_ubyte * 64)()
+            _lib.check(self._L.idsp_b200_ipc_export(self._ctx._h, p, buf))
+            handle = [bytes(buf)]
+        dist.broadcast_object_list(handle, src=owner, group=group)
+        if self.rank != owner:
+            buf = (C.c_ubyte * 64).from_buffer_copy(handle[0])
+            _lib.check(self._L.idsp_b200_ipc_open(self._ctx._h, buf, C.byref(p)))
+        self.ptr = p.value
+
+    def view(self, offset: int, numel: int) -> PeerView:
+        assert 0 <= offset and offset + numel <= self.numel
+        return PeerView(self.ptr + offset * self.itemsize, numel, self.dtype)
+
+    def tensor(self) -> torch.Tensor:
+        """the owner's torch view of the buffer (no copy)"""
+        assert self.rank == self.owner, "only the owning rank has a local view"
+
+        class _Iface:
+            pass
+
+        o = _Iface()
+        typestr = {torch.int32: "<i4", torch.float32: "<f4", torch.int64: "<i8", torch.float64: "<f8",
+                   torch.int16: "<i2", torch.int8: "|i1"}[self.dtype]
+        o.__cuda_array_interface__ = {"shape": (self.numel,), "typestr": typestr, "data": (self.ptr, False), "version": 2}
+        self._keep = o
+        return torch.as_tensor(o, device=f"cuda:{self.device}")
+
+    def close(self) -> None:
+        """collective: importers unmap first, then the owner frees"""
+        if self.ptr is None:
+            return
+        if self.rank != self.owner:
+            _lib.check(self._L.idsp_b200_ipc_close(self._ctx._h, C.c_void_p(self.ptr)))
+        dist.barrier(group=self.group)
+        if self.rank == self.owner:
+            _lib.check(self._L.idsp_b200_mfree(self._ctx._h, C.c_void_p(self.ptr)))
+        self.ptr = None

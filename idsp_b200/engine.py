@@ -44,13 +44,26 @@ def _small(values, kind):
     return (ct * len(vals))(*vals)
 
 
+class PeerView:
+    """A range of device memory given by address (e.g. a lane block inside a buffer another process
+    owns, mapped with ``idsp_b200_ipc_open``): accepted wherever an output device tensor is."""
+
+    def __init__(self, ptr: int, numel: int, dtype: torch.dtype):
+        self.ptr, self._numel, self.dtype = int(ptr), int(numel), dtype
+
+    def numel(self) -> int:
+        return self._numel
+
+
 def _is_dev(a) -> bool:
-    return isinstance(a, torch.Tensor) and a.is_cuda
+    return isinstance(a, PeerView) or (isinstance(a, torch.Tensor) and a.is_cuda)
 
 
 def _ptr(a):
     if a is None:
         return None
+    if isinstance(a, PeerView):
+        return C.c_void_p(a.ptr)
     if isinstance(a, torch.Tensor):
         if not a.is_contiguous():
             raise ValueError("tensor must be contiguous")
@@ -129,7 +142,7 @@ class Context:
             raise ValueError(f"{name}: mix of device tensors and host arrays")
         if all_dev:
             for a in arrays.values():
-                if a is not None and a.device.index != self.device:
+                if a is not None and not isinstance(a, PeerView) and a.device.index != self.device:
                     raise ValueError(f"{name}: tensor on {a.device}, ctx on cuda:{self.device}")
             _lib.check(call(getattr(self._L, name), {k: _ptr(v) for k, v in arrays.items()}))
             return

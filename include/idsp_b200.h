@@ -77,6 +77,20 @@ uint64_t idsp_b200_launch_count(const idsp_ctx *ctx);
  * works too but is staged by the driver. */
 int idsp_b200_host_alloc(void **ptr, size_t bytes);
 void idsp_b200_host_free(void *ptr);
+/* Peer memory for the multi-GPU edges (one process per GPU).  Lanes shard with no collective inside the
+ * computation (dsp-process/src/compose.rs:472-475), so the only exchange is handing results to the rank
+ * that wants them.  A rank can let its kernels write there directly: the owner allocates a device buffer
+ * and exports a 64-byte handle (cudaIpcMemHandle_t), every other process opens the handle and passes
+ * the mapped pointer (plus its lane-block offset) as the `y` of any entry point above -- the stores then
+ * go over NVLink / NVSwitch from the kernel's epilogue, i.e. the gather is fused into the producer.
+ * In the lane-major layout a contiguous lane block of the result is a contiguous range of the buffer.
+ * The exporter must keep the allocation alive until every importer has closed it. */
+#define IDSP_IPC_HANDLE_BYTES 64
+int idsp_b200_malloc(idsp_ctx *ctx, size_t bytes, void **ptr);
+int idsp_b200_mfree(idsp_ctx *ctx, void *ptr);
+int idsp_b200_ipc_export(idsp_ctx *ctx, const void *ptr, unsigned char handle[IDSP_IPC_HANDLE_BYTES]);
+int idsp_b200_ipc_open(idsp_ctx *ctx, const unsigned char handle[IDSP_IPC_HANDLE_BYTES], void **ptr);
+int idsp_b200_ipc_close(idsp_ctx *ctx, void *ptr);
 /* Kernel selection: 0 = automatic (default), 1 = force the generic LDG kernels,
  * 2 = force the TMA kernels (IDSP_EINVAL if the shape does not qualify),
  * 3 = automatic, with the packed f32x2 variant of the tiled half-band decimator (bit-identical

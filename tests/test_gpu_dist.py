@@ -113,3 +113,95 @@ def test_scatter_lockin_gather_nccl(layout, frames, lanes_per_gpu):
         p.join(300)
         assert p.exitcode == 0
     assert list(ok) == [1] * world
+
+
+def _worker_peer(rank, world, port, frames, lanes, ok, out_path):
+    """lane-major lock-in whose output goes straight into rank 0's buffer (CUDA IPC peer stores from the
+    kernel epilogue) vs the same kernel followed by an NCCL gather"""
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = f"cuda:{rank}"
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(dev))
+    try:
+        from idsp_b200 import Accu, Lockin, LockinState, Lowpass
+        from idsp_b200.dist import PeerBuffer, gather_lanes, lane_block, scatter_lanes
+
+        layout = 1
+        x = a0 = step = None
+        if rank == 0:
+            rng = np.random.default_rng(5)
+            xn = rng.integers(-(1 << 30), 1 << 30, frames * lanes).astype(np.int32)
+            a0n = rng.integers(-(1 << 31), 1 << 31, lanes).astype(np.int32)
+            stn = rng.integers(-(1 << 31), 1 << 31, lanes).astype(np.int32)
+            x, a0, step = (torch.from_numpy(v).to(dev) for v in (xn, a0n, stn))
+        lo, hi = lane_block(rank, world, lanes)
+        xs = scatter_lanes(x, frames, lanes, layout, dtype=torch.int32, device=dev)
+        a0s = scatter_lanes(a0, 1, lanes, 0, dtype=torch.int32, device=dev)
+        sts = scatter_lanes(step, 1, lanes, 0, dtype=torch.int32, device=dev)
+        buf = PeerBuffer(2 * frames * lanes, torch.int32, rank, owner=0)
+        mine = buf.view(2 * frames * lo, 2 * frames * (hi - lo))
+        local = torch.empty(2 * xs.numel(), dtype=torch.int32, device=dev)
+        lock = Lockin(Lowpass(K))
+
+        def run(out):
+            lock.block(LockinState.default(2, hi - lo, dev), Accu(a0s.clone(), sts), xs, out, layout)
+
+        run(local)
+        gather_lanes(local, frames, lanes, layout, width=2)  # warm-up of both paths
+        run(mine)
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        run(local)
+        full = gather_lanes(local, frames, lanes, layout, width=2)
+        torch.cuda.synchronize()
+        dist.barrier()
+        t1 = time.perf_counter()
+        run(mine)
+        torch.cuda.synchronize()
+        dist.barrier()
+        t2 = time.perf_counter()
+        if rank == 0:
+            import oracle as O
+
+            O.build()
+            ao = a0n.copy()
+            so = np.zeros((4, lanes), np.int64)
+            want = O.lockin_lanes(K, ao, stn, so, xn, lanes, layout, nthreads=8)
+            assert np.array_equal(full.cpu().numpy(), want), "NCCL-gathered output differs from the oracle"
+            assert np.array_equal(buf.tensor().cpu().numpy(), want), "peer-stored output differs from the oracle"
+            n = frames * lanes
+            line = (f"world={world} lane-major lanes={lanes} frames={frames}: kernel + NCCL gather {n / (t1 - t0) / 1e9:.1f} GSa/s, "
+                    f"kernel storing into rank 0's buffer over NVLink {n / (t2 - t1) / 1e9:.1f} GSa/s, both bit-exact")
+            print(line, flush=True)
+            if out_path:
+                with open(out_path, "a") as f:
+                    f.write(line + "\n")
+        buf.close()
+        ok[rank] = 1
+    finally:
+        dist.destroy_process_group()
+
+
+def test_lockin_stores_into_root_buffer_over_nvlink():
+    """SURVEY 8(e) fused form: the result tiles leave the kernel epilogue for the root's buffer"""
+    world = min(torch.cuda.device_count(), 8)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs")
+    frames, lanes = 2048, 131072 * world
+    ctx = mp.get_context("spawn")
+    ok = ctx.Array("i", [0] * world)
+    port = _free_port()
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    out_path = os.path.join(out, "dist_nccl.log") if os.path.isdir(out) else None
+    procs = [ctx.Process(target=_worker_peer, args=(r, world, port, frames, lanes, ok, out_path)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    assert list(ok) == [1] * world
