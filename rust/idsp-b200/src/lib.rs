@@ -28,6 +28,13 @@ unsafe extern "C" {
     pub fn idsp_b200_free(ctx: *mut idsp_ctx);
     pub fn idsp_b200_sync(ctx: *mut idsp_ctx) -> c_int;
     pub fn idsp_b200_last_error() -> *const c_char;
+    // peer memory (multi-GPU edges): the owner exports a device buffer, the other processes map it and
+    // pass their lane block of it as the `y` of a kernel (stores over NVLink from the kernel epilogue)
+    pub fn idsp_b200_malloc(ctx: *mut idsp_ctx, bytes: usize, ptr: *mut *mut c_void) -> c_int;
+    pub fn idsp_b200_mfree(ctx: *mut idsp_ctx, ptr: *mut c_void) -> c_int;
+    pub fn idsp_b200_ipc_export(ctx: *mut idsp_ctx, ptr: *const c_void, handle: *mut [u8; 64]) -> c_int;
+    pub fn idsp_b200_ipc_open(ctx: *mut idsp_ctx, handle: *const [u8; 64], ptr: *mut *mut c_void) -> c_int;
+    pub fn idsp_b200_ipc_close(ctx: *mut idsp_ctx, ptr: *mut c_void) -> c_int;
     /// replaces `Biquad<Q32<F>>::process` looped by `Lanes` (src/iir/biquad.rs:366-383)
     pub fn idsp_biquad_df1_i32_host(
         ctx: *mut idsp_ctx, ba: *const i32, f: c_int, clamp: *const i32, state: *mut i32,
