@@ -122,10 +122,9 @@ def main():
                 lambda: Lanes(HbfIntCascade(k)).block(sint, y, x, layout))
             del x, y
         if layout == 1:  # config 5 chain at 65 536 lanes x 16 384 samples
-            from idsp_b200.hbf import _dec_state as _ds, _int_state as _is  # noqa: F401
-            import oracle as _O  # state word counts only (test infrastructure is fine in a bench tool)
+            from idsp_b200 import _lib as _l
             cl, cn = 65536, 1024
-            W = _O.hbf_dec_state_words(4) + _O.hbf_int_state_words(4) + 4
+            W = int(_l.lib().idsp_chain_state_words(4))
             xc5 = rnd("f32", cl * cn * 16)
             yc5 = torch.empty_like(xc5)
             stc = torch.zeros((W, cl), dtype=torch.float32, device=DEV)
