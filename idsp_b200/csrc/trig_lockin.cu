@@ -19,9 +19,18 @@ __global__ void __launch_bounds__(256) cossin_kernel(const int32_t *phase, int32
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (vec) {
+        // software pipeline: the loads of the next pair are issued before the current pair is converted
+        int2 p = make_int2(0, 0), q = make_int2(0, 0);
+        if (i + stride < n2) {
+            p = reinterpret_cast<const int2 *>(phase)[i];
+            q = reinterpret_cast<const int2 *>(phase)[i + stride];
+        }
         for (; i + stride < n2; i += 2 * stride) {
-            const int2 p = reinterpret_cast<const int2 *>(phase)[i];
-            const int2 q = reinterpret_cast<const int2 *>(phase)[i + stride];
+            int2 pn = p, qn = q;
+            if (i + 3 * stride < n2) {
+                pn = reinterpret_cast<const int2 *>(phase)[i + 2 * stride];
+                qn = reinterpret_cast<const int2 *>(phase)[i + 3 * stride];
+            }
             int4 a, b;
             cossin_dev_x(lut, p.x, a.x, a.y);
             cossin_dev_x(lut, p.y, a.z, a.w);
@@ -29,6 +38,8 @@ __global__ void __launch_bounds__(256) cossin_kernel(const int32_t *phase, int32
             cossin_dev_x(lut, q.y, b.z, b.w);
             reinterpret_cast<int4 *>(cs)[i] = a;
             reinterpret_cast<int4 *>(cs)[i + stride] = b;
+            p = pn;
+            q = qn;
         }
         for (; i < n2; i += stride) {
             const int2 p = reinterpret_cast<const int2 *>(phase)[i];
@@ -56,9 +67,20 @@ __global__ void __launch_bounds__(256) atan2_kernel(const int32_t *xy, int32_t *
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (vec) {
-        for (; i + stride < n2; i += 2 * stride) {  // two 16-byte loads in flight per thread
-            const int4 v0 = reinterpret_cast<const int4 *>(xy)[i];
-            const int4 v1 = reinterpret_cast<const int4 *>(xy)[i + stride];
+        // two 16-byte loads in flight per thread, software pipelined: the next pair is requested before the
+        // current one is converted (the conversion is ~240 instructions long, and without this the warps
+        // sit on the long scoreboard at the top of every iteration)
+        int4 v0 = make_int4(0, 0, 0, 0), v1 = v0;
+        if (i + stride < n2) {
+            v0 = reinterpret_cast<const int4 *>(xy)[i];
+            v1 = reinterpret_cast<const int4 *>(xy)[i + stride];
+        }
+        for (; i + stride < n2; i += 2 * stride) {
+            int4 n0 = v0, n1 = v1;
+            if (i + 3 * stride < n2) {
+                n0 = reinterpret_cast<const int4 *>(xy)[i + 2 * stride];
+                n1 = reinterpret_cast<const int4 *>(xy)[i + 3 * stride];
+            }
             int2 r0, r1;
             r0.x = atan2_dev(v0.y, v0.x);
             r0.y = atan2_dev(v0.w, v0.z);
@@ -66,6 +88,8 @@ __global__ void __launch_bounds__(256) atan2_kernel(const int32_t *xy, int32_t *
             r1.y = atan2_dev(v1.w, v1.z);
             reinterpret_cast<int2 *>(p)[i] = r0;
             reinterpret_cast<int2 *>(p)[i + stride] = r1;
+            v0 = n0;
+            v1 = n1;
         }
         for (; i < n2; i += stride) {
             int4 v = reinterpret_cast<const int4 *>(xy)[i];
