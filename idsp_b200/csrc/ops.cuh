@@ -35,6 +35,7 @@ template <> struct is_float<double> { static constexpr bool value = true; };
 struct OpHooks {
     static constexpr bool TUNABLE = false;
     static constexpr bool HEAVY = false;  // compute-bound: lane-major TMA kernels trade tile size for resident warps
+    static constexpr bool LM_SMALL = false;  // in between: fewer lane-major stages of the same tile
     static constexpr int SMEM_EXTRA_WORDS = 0;
     template <class P> __device__ __forceinline__ static void init_smem(const P &, uint32_t *, int, int) {}
     template <class P> __device__ __forceinline__ void bind(const P &, const uint32_t *) {}
@@ -96,6 +97,7 @@ template <class T, bool CLAMP, int MODE = 0> struct Df1Op {
     using Out = T;
     static constexpr bool TUNABLE = true;  // tuning builds sweep tile shapes for this Op
     static constexpr bool HEAVY = false;
+    static constexpr bool LM_SMALL = false;
     static constexpr int SMEM_EXTRA_WORDS = 0;
     struct Params {
         T ba[5];
@@ -288,6 +290,7 @@ template <bool CLAMP> struct Df1WideOp : OpHooks {
 template <bool CLAMP> struct Df1DitherOp : OpHooks {
     using In = int32_t;
     using Out = int32_t;
+    static constexpr bool LM_SMALL = true;
     struct Params {
         int32_t ba[5];
         int F;
@@ -480,6 +483,7 @@ __device__ __forceinline__ int32_t lowpass_step(int32_t k0, int32_t k1, int64_t 
 template <int ORDER> struct LowpassOp : OpHooks {
     using In = int32_t;
     using Out = int32_t;
+    static constexpr bool LM_SMALL = true;
     struct Params {
         int32_t k[2];
         int64_t *st;
@@ -506,6 +510,7 @@ template <int ORDER, bool SMEM_LUT = false> struct LockinOp {
     using Out = int2;
     static constexpr bool TUNABLE = false;
     static constexpr bool HEAVY = true;
+    static constexpr bool LM_SMALL = false;
     static constexpr int SMEM_EXTRA_WORDS = SMEM_LUT ? 256 : 0;  // expanded cossin table staged per CTA
     struct Params {
         int32_t k[2];

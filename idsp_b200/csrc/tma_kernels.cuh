@@ -469,6 +469,11 @@ static int tma_launch_lm_auto(idsp_ctx *ctx, const typename Op::Params &p, const
         if (frames >= 128) return tma_launch_lm<Op, 1, 2, 1>(ctx, p, x, y, frames, lanes, sstride);
         return tma_launch_cfg<Op, true, 16, 3, 1, 1>(ctx, p, x, y, frames, lanes, sstride);
     }
+    // ops with 64-bit state arithmetic between HBM- and compute-bound: 2 load + 1 store stage of the same
+    // 256-byte rows (24 KB, 9 warps per SM instead of 5): Lowpass<2> 557 -> 656 GSa/s, Lowpass<1> 657 -> 679
+    if constexpr (Op::LM_SMALL) {
+        if (frames >= 128) return tma_launch_lm<Op, 2, 2, 1>(ctx, p, x, y, frames, lanes, sstride);
+    }
     if (frames >= 128) return tma_launch_lm<Op, 2, 3, 2>(ctx, p, x, y, frames, lanes, sstride);
     return tma_launch_cfg<Op, true, 16, 4, 2, 1>(ctx, p, x, y, frames, lanes, sstride);
 }
