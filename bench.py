@@ -19,6 +19,8 @@ Workloads (BASELINE.json `configs`):
 `roofline`: algorithmic bytes per launch / average launch duration vs MEASURED_PEAKS.json.
 `cpu_baseline`: the CPU oracle (a C port of the reference; the Rust crate cannot be built in
            this image) timed on the host cores on a bounded sample of the same workload.
+`extra`  : the default N = 1 run also measures configs[2] (hbf), configs[3] (lock-in) and configs[4] (chain sweep)
+           in the same process and attaches their lines (a failure there is recorded, never raised).
 `--impl reference`: times that CPU path alone and prints the same JSON line with impl=reference.
 N > 1: one process per GPU (torchrun), lanes sharded, no data-path collective ("weak" scaling:
 every rank runs the full 65 536-lane workload on its own lane block).
@@ -846,6 +848,22 @@ def main():
             extra = run_hbf(a2, rank, world, local)
             if line is not None and extra is not None:
                 line["extra"] = {"hbf_dec16_f32": {k: extra[k] for k in ("metric", "value", "unit", "steps", "ms_per_step", "dtype", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "parity_check")}}
+            # BASELINE configs[3] and configs[4] in the same run (N = 1 only, short; a failure here must not
+            # cost the headline line, so it is recorded instead of raised)
+            if world == 1 and line is not None:
+                import torch
+
+                line.setdefault("extra", {})
+                for name, fn, keys in (("lockin_i32", run_lockin, ("metric", "value", "unit", "steps", "ms_per_step", "dtype", "config", "roofline", "gpu_launches", "parity_check")),
+                                       ("chain_f32", run_chain, ("metric", "value", "unit", "dtype", "config", "sweep", "roofline", "parity_check"))):
+                    try:
+                        torch.cuda.empty_cache()
+                        a3 = copy.copy(args)
+                        a3.steps = min(args.steps, 24)
+                        res = fn(a3, rank, world, local)
+                        line["extra"][name] = {k: res[k] for k in keys}
+                    except (Exception, SystemExit) as e:  # noqa: BLE001
+                        line["extra"][name] = {"error": f"{type(e).__name__}: {e}"[:300]}
     elif args.workload == "hbf":
         line = run_hbf(args, rank, world, local)
     elif args.workload == "lockin":
