@@ -67,3 +67,13 @@ def test_block_length_mismatch_is_an_error():
         Biquad.identity(Q32(30)).block(st, np.zeros(4, np.int32), np.zeros(6, np.int32))
     with pytest.raises(ValueError):
         Biquad.identity(Q32(30)).block(st, np.zeros(3, np.int32), np.zeros(3, np.int32))
+
+
+def test_peer_view_is_a_device_output():
+    """a range of another process's buffer (idsp_b200_ipc_open) is passed to the kernels by address"""
+    import torch
+
+    from idsp_b200.engine import PeerView, _is_dev, _ptr
+
+    v = PeerView(0x7F0000001000, 64, torch.int32)
+    assert _is_dev(v) and v.numel() == 64 and _ptr(v).value == 0x7F0000001000

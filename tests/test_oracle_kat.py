@@ -251,6 +251,11 @@ def test_cossin_tables(oracle):
     b = [int(v) for v in re.findall(r"(\d+)u", src.split("IDSP_ATAN2_DIVI_BASE_INIT {")[1].split("}")[0])]
     s = [int(v) for v in re.findall(r"(-?\d+)", src.split("IDSP_ATAN2_DIVI_SLOPE_INIT {")[1].split("}")[0])]
     assert b == [int(v) for v in base] and s == [int(v) for v in slope]
+    # the (base, slope bits) pairs the kernels load (one 8-byte entry per lookup) hold the same values
+    pairs = re.findall(r"\{(\d+)u, 0x([0-9a-f]{8})u\}", src.split("IDSP_ATAN2_DIVI_PAIR_INIT {")[1])
+    assert len(pairs) == 16
+    assert [int(p[0]) for p in pairs] == b
+    assert [int(p[1], 16) - (1 << 32) if int(p[1], 16) >= 1 << 31 else int(p[1], 16) for p in pairs] == s
 
 
 def test_cossin_error_bounds(oracle):
