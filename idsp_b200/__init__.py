@@ -16,12 +16,13 @@ from .iir import (  # noqa: F401
 from .hbf import (  # noqa: F401
     EvenAntiSymmetric, EvenSymmetric, HbfDec, HbfDec2, HbfDec4, HbfDec8, HbfDec16, HbfDec32,
     HbfDecCascade, HbfInt, HbfInt2, HbfInt4, HbfInt8, HbfInt16, HbfInt32, HbfIntCascade,
-    OddAntiSymmetric, OddSymmetric, hbf_dec_response_length, hbf_int_response_length, hbf_taps,
+    OddAntiSymmetric, OddSymmetric, hbf_dec_response_length, hbf_int_response_length, hbf_taps, hbf_taps_98,
 )
 from .nco import (  # noqa: F401
     PLL, Accu, FmDiscriminator, FmDiscState, Lockin, LockinState, Lowpass, LowpassState, PLLState, atan2, cossin, sos, sos_clamp_wide,
 )
-from .coefficients import Filter  # noqa: F401
+from .coefficients import Filter, FilterError, WebAudio  # noqa: F401
+from . import pid  # noqa: F401
 from .cic import Cic, CicState, Decimator, Interpolator  # noqa: F401
 
 __version__ = "0.1.0"

@@ -72,10 +72,64 @@ def _signatures():
     sig["idsp_cic_state_words"] = ([_i, _i], _sz)
     for n in ("idsp_cic_dec_i32", "idsp_cic_dec_i64", "idsp_cic_int_i32", "idsp_cic_int_i64"):
         sig[n] = ([_c_p, _i, _i, C.c_uint32, _c_p, _c_p, _c_p] + lanes_tail, _i)
+    sig["idsp_b200_last_kernel"] = ([_c_p], C.c_char_p)
+    # ctx, order, k, lp_state, xp | xlo, iq, frames, lanes, layout
+    for n in ("idsp_lockin_phase_i32", "idsp_lockin_lo_i32"):
+        sig[n] = ([_c_p, _i, _c_p, _c_p, _c_p, _c_p] + lanes_tail, _i)
+    # caller-supplied tap sets: ctx, nstages, taps**, M*, state, x, y, n, lanes, layout
+    sig["idsp_hbf_cascade_state_words"] = ([_i, _i, _c_p], _sz)
+    for n in ("idsp_hbf_dec_cascade_taps_f32", "idsp_hbf_int_cascade_taps_f32"):
+        sig[n] = ([_c_p, _i, _c_p, _c_p, _c_p, _c_p, _c_p] + lanes_tail, _i)
+    sig["idsp_hbf_taps_98"] = ([_i, C.POINTER(_i)], C.POINTER(C.c_float))
+    sig["idsp_chain_f32_host"] = sig["idsp_chain_f32"]
+    # multi-GPU edges
+    sig["idsp_b200_comm_unique_id"] = ([_c_p], _i)
+    sig["idsp_b200_comm_init"] = ([_c_p, _i, _i, _c_p, C.POINTER(_c_p)], _i)
+    sig["idsp_b200_comm_free"] = ([_c_p], _i)
+    sig["idsp_b200_comm_rank"] = ([_c_p], _i)
+    sig["idsp_b200_comm_size"] = ([_c_p], _i)
+    sig["idsp_b200_nccl_version"] = ([], _i)
+    sig["idsp_b200_lane_block"] = ([_sz, _i, _i, _sz, C.POINTER(_sz), C.POINTER(_sz)], _i)
+    for n in ("idsp_scatter_lanes", "idsp_gather_lanes"):
+        sig[n] = ([_c_p, _c_p, _c_p, _sz, _sz, _sz, _i, _i], _i)
+    sig["idsp_broadcast"] = ([_c_p, _c_p, _sz, _i], _i)
+    # coefficient builders (host side)
+    for s_, ft in (("f64", C.c_double), ("f32", C.c_float)):
+        sig[f"idsp_filter_default_{s_}"] = ([_c_p], None)
+        sig[f"idsp_filter_validate_{s_}"] = ([_c_p], _i)
+        sig[f"idsp_filter_build_{s_}"] = ([_c_p, _i, _c_p], _i)
+        sig[f"idsp_biquad_from_ba6_{s_}"] = ([_c_p, _i, _i, _c_p], _i)
+        sig[f"idsp_biquad_from_ba5_{s_}"] = ([_c_p, _i, _i, _c_p], _i)
+        sig[f"idsp_filter_build_biquad_{s_}"] = ([_c_p, _i, _i, _i, _c_p], _i)
+        sig[f"idsp_pid_default_{s_}"] = ([_c_p], None)
+        sig[f"idsp_pid_validate_{s_}"] = ([_c_p, ft], _i)
+        sig[f"idsp_pid_build_{s_}"] = ([_c_p, ft, _i, _i, _c_p], _i)
+    sig["idsp_biquad_from_zpk_f64"] = ([_c_p, _i, _c_p, _i, C.c_double, _i, _i, _c_p], _i)
     return sig
 
 
 SIGNATURES = _signatures()
+
+
+class FilterF64(C.Structure):
+    _fields_ = [("frequency", C.c_double), ("gain", C.c_double), ("shelf", C.c_double),
+                ("shape_kind", C.c_int), ("shape", C.c_double)]
+
+
+class FilterF32(C.Structure):
+    _fields_ = [("frequency", C.c_float), ("gain", C.c_float), ("shelf", C.c_float),
+                ("shape_kind", C.c_int), ("shape", C.c_float)]
+
+
+class PidF64(C.Structure):
+    _fields_ = [("order", C.c_int), ("gain", C.c_double * 5), ("limit", C.c_double * 5)]
+
+
+class PidF32(C.Structure):
+    _fields_ = [("order", C.c_int), ("gain", C.c_float * 5), ("limit", C.c_float * 5)]
+
+
+KIND_CODE = {"i8": 0, "i16": 1, "i32": 2, "i64": 3, "f32": 4, "f64": 5}
 
 _lib = None
 

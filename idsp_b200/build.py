@@ -13,14 +13,14 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libidsp_b200.so")
-SOURCES = ["ctx.cu", "biquad.cu", "hbf.cu", "trig_lockin.cu", "cic.cu"]
+SOURCES = ["ctx.cu", "biquad.cu", "hbf.cu", "trig_lockin.cu", "cic.cu", "comm.cu", "coeff.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     # bit-exact float parity with the reference: no FMA contraction, no FTZ, IEEE div/sqrt
     "-fmad=false", "-ftz=false", "-prec-div=true", "-prec-sqrt=true",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off", "-shared",
     "-cudart", "static",
 ]
 
@@ -103,7 +103,7 @@ def build(force: bool = False, verbose: bool = False, out: str = OUT) -> str:
     if failed:
         sys.stderr.write(log)
         raise RuntimeError("nvcc failed building libidsp_b200.so")
-    res = subprocess.run([nvcc, "-shared", "-cudart", "static", "-ccbin", "g++", "-o", out] + [o for _, o, _ in procs],
+    res = subprocess.run([nvcc, "-shared", "-cudart", "static", "-ccbin", "g++", "-o", out] + [o for _, o, _ in procs] + ["-ldl"],
                          cwd=CSRC, env=env, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

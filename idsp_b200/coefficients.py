@@ -1,12 +1,25 @@
 """Host-side biquad coefficient builder: mirror of ``idsp::iir::coefficients::Filter``
-(src/iir/coefficients.rs:17-40, 111-527; audio-EQ-cookbook formulas).  Pure host
-math in f64 -- it feeds raw coefficients to the C ABI, it is not part of the
-device hot path.
+(src/iir/coefficients.rs:17-40, 111-527; audio-EQ-cookbook formulas).  Host math only --
+it feeds raw coefficients to the C ABI, it is not part of the device hot path.
+
+Two implementations that must agree: the f64 formulas below (pure Python, libm through
+``math``) and the C ABI builders ``idsp_filter_build_{f64,f32}`` (``idsp_b200/csrc/coeff.cu``),
+which also carry the reference's f32 flavour (``Filter<f32>``: every intermediate rounded to
+f32).  ``Filter(dtype="f32")`` routes through the C ABI.
 """
 from __future__ import annotations
 
+import ctypes as C
 import math
 from dataclasses import dataclass, field
+
+# coefficients::Type (coefficients.rs:44-66), the order of the C ABI's idsp_filter_type_t
+TYPES = ("lowpass", "highpass", "bandpass", "allpass", "notch", "peaking", "lowshelf", "highshelf", "iho")
+_SHAPES = {"q": 0, "bandwidth": 1, "slope": 2}
+
+
+class FilterError(ValueError):
+    """``iir::Error`` (src/iir/error.rs:5-16): the message is ``Variant(field)``"""
 
 
 @dataclass
@@ -21,6 +34,75 @@ class Filter:
     gain: float = 1.0
     shelf: float = 1.0
     shape: Shape = field(default_factory=Shape)
+    dtype: str = "f64"  # the reference's Filter<f64> or Filter<f32>
+
+    # ---- C ABI route (both widths; the only route for f32)
+    def _c_struct(self):
+        from . import _lib
+
+        st = (_lib.FilterF32 if self.dtype == "f32" else _lib.FilterF64)()
+        st.frequency, st.gain, st.shelf = self.frequency, self.gain, self.shelf
+        st.shape_kind, st.shape = _SHAPES[self.shape.kind], self.shape.value
+        return st
+
+    def build_c(self, typ: str):
+        """``Filter::build(typ)`` through ``idsp_filter_build_{f64,f32}``"""
+        from . import _lib
+
+        L = _lib.lib()
+        st = self._c_struct()
+        out = ((C.c_float if self.dtype == "f32" else C.c_double) * 6)()
+        fn = L.idsp_filter_build_f32 if self.dtype == "f32" else L.idsp_filter_build_f64
+        _lib.check(fn(C.byref(st), TYPES.index(typ), out))
+        v = list(out)
+        return [v[0:3], v[3:6]]
+
+    def validate(self):
+        """``Filter::validate`` (coefficients.rs:241-265); raises FilterError(``Variant(field)``)"""
+        f, g, a = self.frequency, self.gain, self.shelf
+        fin = math.isfinite
+        if not fin(f):
+            raise FilterError("NonFinite(frequency)")
+        if f < 0.0 or f > math.pi:
+            raise FilterError("OutOfRange(frequency)")
+        if not fin(g) or g <= 0.0:
+            raise FilterError("NonPositive(gain)")
+        if not fin(a) or a <= 0.0:
+            raise FilterError("NonPositive(shelf)")
+        k, v = self.shape.kind, self.shape.value
+        name = {"q": "q", "bandwidth": "bandwidth", "slope": "slope"}[k]
+        if not fin(v):
+            raise FilterError(f"NonFinite({name})")
+        if k != "bandwidth" and v <= 0.0:
+            raise FilterError(f"NonPositive({name})")
+
+    def build(self, typ: str):
+        """``Filter::build(typ)`` (coefficients.rs:466-479): ``[[b0,b1,b2],[a0,a1,a2]]``"""
+        if typ not in TYPES:
+            raise ValueError(f"type must be one of {TYPES}")
+        if self.dtype == "f32":
+            return self.build_c(typ)
+        return getattr(self, typ)()
+
+    def try_build(self, typ: str):
+        self.validate()
+        return self.build(typ)
+
+    def build_biquad(self, typ: str, fmt):
+        """``Filter::build_biquad::<C>(typ)`` (coefficients.rs:481-487)"""
+        from .iir import Biquad
+
+        return Biquad.from_ba6(self.build(typ), fmt, src=self.dtype)
+
+    def try_build_biquad(self, typ: str, fmt):
+        self.validate()
+        return self.build_biquad(typ, fmt)
+
+    def build_clamped(self, typ: str, fmt):
+        """``Filter::build_clamped`` (coefficients.rs:499-505): default clamp (u = 0, MIN, MAX)"""
+        from .iir import BiquadClamp
+
+        return BiquadClamp(self.build_biquad(typ, fmt))
 
     # builder methods (coefficients.rs:111-238)
     def set_frequency(self, critical_frequency, sample_frequency):
@@ -126,3 +208,35 @@ class Filter:
         return [[s * self.gain * (sp1 + sm1 * fcos + tsa), -2.0 * s * self.gain * (sm1 + sp1 * fcos),
                  s * self.gain * (sp1 + sm1 * fcos - tsa)],
                 [sp1 - sm1 * fcos + tsa, 2.0 * (sm1 - sp1 * fcos), sp1 - sm1 * fcos - tsa]]
+
+    def iho(self):
+        """I/HO: notch, integrating below, flat ``shelf`` gain above (coefficients.rs:451-464)"""
+        fcos, alpha = self._fcos_alpha()
+        fsin = 0.5 * math.sin(self.frequency)
+        a = (1.0 + fcos) / (2.0 * self.shelf)
+        return [[self.gain * (1.0 + alpha), -2.0 * self.gain * fcos, self.gain * (1.0 - alpha)],
+                [a + fsin, -2.0 * a, a - fsin]]
+
+
+@dataclass
+class WebAudio:
+    """``coefficients::WebAudio`` (coefficients.rs:68-86, 529-560): WebAudio-style parametrisation"""
+
+    typ: str = "lowpass"
+    frequency_hz: float = 350.0
+    sample_rate_hz: float = 48e3
+    detune_cents: float = 0.0
+    q: float = 1.0
+    gain_db: float = 0.0
+
+    def filter(self) -> Filter:
+        f = Filter()
+        f.set_frequency(self.frequency_hz * 2.0 ** (self.detune_cents / 1200.0), self.sample_rate_hz)
+        f.q(self.q)
+        if self.typ in ("peaking", "lowshelf", "highshelf"):
+            f.shelf_db(self.gain_db)
+        return f
+
+    def build(self):
+        return self.filter().build(self.typ)
+

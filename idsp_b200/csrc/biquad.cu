@@ -41,7 +41,7 @@ static int launch_packed_or_lanes(idsp_ctx *ctx, const typename Op::Params &p, c
             if (tr != IDSP_TMA_NOT_APPLICABLE) return tr;
         }
     }
-    return launch_lanes<Op>(ctx, p, x, y, frames, lanes, sstride, layout);
+    return launch_lanes_best<Op>(ctx, p, x, y, frames, lanes, sstride, layout);  // 8-byte samples: TMA kernels
 }
 
 template <class T>
@@ -115,6 +115,11 @@ int df1_impl<float>(idsp_ctx *ctx, const float *ba, int F, const float *clamp, f
     if (clamp) GO(Df1Op<float, true, 0>);
     GO(Df1Op<float, false, 0>);
 #undef GO
+}
+
+int idsp_df1_f32_strided(idsp_ctx *ctx, const float *ba, float *state, const float *x, float *y, size_t frames,
+                         size_t lanes, size_t sstride, int layout) {
+    return df1_impl<float>(ctx, ba, 0, nullptr, state, x, y, frames, lanes, sstride, layout);
 }
 
 template <class T>

@@ -338,6 +338,7 @@ static bool cic_launch_coop(idsp_ctx *ctx, const CicParams<T> &p, const T *x, T 
         default: COOP(8); break;
     }
 #undef COOP
+    IDSP_KERNEL_FAMILY(ctx, "cic warp-cooperative tiles");
     return true;
 }
 
@@ -356,6 +357,7 @@ int cic_launch(idsp_ctx *ctx, int N, int M, uint32_t rate, T *state, const T *x,
     const T *wide = DEC ? x : y;  // the rate+1 wide side
     const int vec = ((R * sizeof(T)) % 16 == 0 && (((uintptr_t)wide) & 15) == 0) ? 1 : 0;
     const unsigned grid = (unsigned)((lanes + 127) / 128);
+    IDSP_KERNEL_FAMILY(ctx, "cic thread-per-lane");
 #define GO(NN, MM)                                                                                                  \
     case NN * 8 + MM:                                                                                               \
         if (MM == 1 && vec && ctx->policy != 1 && cic_launch_coop<T, DEC, NN, 1>(ctx, p, x, y, frames, lanes, layout)) break; \

@@ -15,6 +15,7 @@ struct idsp_ctx {
     uint64_t launches;
     int policy;  // 0 auto, 1 generic, 2 TMA / tiled, 3 auto with the packed f32x2 HBF variant
     int sm_count;
+    const char *last_kernel;  // family of the most recent launch (idsp_b200_last_kernel)
     // host streaming (the *_host entry points): ring of device chunk buffers
     cudaStream_t s_h2d, s_d2h;
     void *dev_in[IDSP_HOST_RING], *dev_out[IDSP_HOST_RING];
@@ -47,6 +48,7 @@ void idsp_set_error(const char *fmt, ...);
     } while (0)
 
 // after a kernel launch
+#define IDSP_KERNEL_FAMILY(ctx, name) ((ctx)->last_kernel = (name))
 #define IDSP_LAUNCHED(ctx)                                                           \
     do {                                                                             \
         (ctx)->launches++;                                                           \
@@ -73,6 +75,10 @@ static inline int idsp_use_device(idsp_ctx *ctx) {
     }
     return IDSP_OK;
 }
+
+// f32 DF1 biquad on a lane block of a larger SoA state (biquad.cu; used by the chain composition in hbf.cu)
+int idsp_df1_f32_strided(idsp_ctx *ctx, const float *ba, float *state, const float *x, float *y, size_t frames,
+                         size_t lanes, size_t sstride, int layout);
 
 // Host streaming helper (ctx.cu): cuts the frame axis (frame-major) or the lane axis
 // (lane-major) into chunks [a0, a0+an) and runs `launch(dev_blobs, dev_x, dev_y, a0, an)`

@@ -142,6 +142,9 @@ extern "C" void idsp_b200_host_free(void *ptr) {
 }
 
 extern "C" uint64_t idsp_b200_launch_count(const idsp_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" const char *idsp_b200_last_kernel(const idsp_ctx *ctx) {
+    return ctx && ctx->last_kernel ? ctx->last_kernel : "";
+}
 
 // ---------------------------------------------------------------------------
 // Peer memory (CUDA IPC): a plain cudaMalloc allocation (exportable, unlike a sub-block of a caching

@@ -4,7 +4,6 @@
 #include "common.cuh"
 #include "hbf_stages.cuh"
 #include "ops.cuh"
-#include "hbf_fast.cuh"
 #include "hbf_fast_scalar.cuh"
 #include "hbf_int_fast.cuh"
 
@@ -80,7 +79,13 @@ template <> struct IntCascadeRegs<0> {
     __device__ __forceinline__ void push(float x, float *out) { out[0] = x; }
 };
 
-template <int R> __device__ __forceinline__ void load_frame(const float *p, float *v) {
+// vec != 0: the frame is 16-byte (R >= 4) / 8-byte (R == 2) aligned; otherwise scalar accesses
+template <int R> __device__ __forceinline__ void load_frame(const float *p, float *v, int vec) {
+    if (!vec) {
+#pragma unroll
+        for (int j = 0; j < R; j++) v[j] = p[j];
+        return;
+    }
     if constexpr (R >= 4) {
 #pragma unroll
         for (int j = 0; j < R / 4; j++) {
@@ -94,7 +99,12 @@ template <int R> __device__ __forceinline__ void load_frame(const float *p, floa
         v[0] = p[0];
     }
 }
-template <int R> __device__ __forceinline__ void store_frame(float *p, const float *v) {
+template <int R> __device__ __forceinline__ void store_frame(float *p, const float *v, int vec) {
+    if (!vec) {
+#pragma unroll
+        for (int j = 0; j < R; j++) p[j] = v[j];
+        return;
+    }
     if constexpr (R >= 4) {
 #pragma unroll
         for (int j = 0; j < R / 4; j++)
@@ -121,7 +131,7 @@ __host__ __device__ constexpr int hbf_unroll(int K) { return K >= 6 ? 1 : (64 >>
 template <int K>
 __global__ void __launch_bounds__(128)
 hbf_dec_cascade_generic(float *st, const float *x, float *y, size_t n_begin, size_t n_out,
-                        size_t lanes, size_t sstride, int layout) {
+                        size_t lanes, size_t sstride, int layout, int vec) {
     constexpr int R = 1 << K;
     size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (lane >= lanes) return;
@@ -134,14 +144,14 @@ hbf_dec_cascade_generic(float *st, const float *x, float *y, size_t n_begin, siz
         for (int u = 0; u < UNR; u++) {
             float v[R];
             size_t f = fidx(layout, n + u, lane, n_out, lanes);
-            load_frame<R>(x + f * R, v);
+            load_frame<R>(x + f * R, v, vec);
             y[f] = c.push(v);
         }
     }
     for (; n < n_out; n++) {
         float v[R];
         size_t f = fidx(layout, n, lane, n_out, lanes);
-        load_frame<R>(x + f * R, v);
+        load_frame<R>(x + f * R, v, vec);
         y[f] = c.push(v);
     }
     c.store(st, sstride, lane);
@@ -149,7 +159,7 @@ hbf_dec_cascade_generic(float *st, const float *x, float *y, size_t n_begin, siz
 template <int K>
 __global__ void __launch_bounds__(128)
 hbf_int_cascade_generic(float *st, const float *x, float *y, size_t n_begin, size_t n_in,
-                        size_t lanes, size_t sstride, int layout) {
+                        size_t lanes, size_t sstride, int layout, int vec) {
     constexpr int R = 1 << K;
     size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (lane >= lanes) return;
@@ -163,14 +173,14 @@ hbf_int_cascade_generic(float *st, const float *x, float *y, size_t n_begin, siz
             float v[R];
             size_t f = fidx(layout, n + u, lane, n_in, lanes);
             c.push(x[f], v);
-            store_frame<R>(y + f * R, v);
+            store_frame<R>(y + f * R, v, vec);
         }
     }
     for (; n < n_in; n++) {
         float v[R];
         size_t f = fidx(layout, n, lane, n_in, lanes);
         c.push(x[f], v);
-        store_frame<R>(y + f * R, v);
+        store_frame<R>(y + f * R, v, vec);
     }
     c.store(st, sstride, lane);
 }
@@ -178,7 +188,7 @@ hbf_int_cascade_generic(float *st, const float *x, float *y, size_t n_begin, siz
 template <int K>
 __global__ void __launch_bounds__(128)
 chain_generic(float *st, Df1Op<float, false>::Params bp, const float *x, float *y, size_t n_low,
-              size_t lanes, size_t sstride, int layout) {
+              size_t lanes, size_t sstride, int layout, int vec) {
     constexpr int R = 1 << K;
     size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (lane >= lanes) return;
@@ -193,11 +203,11 @@ chain_generic(float *st, Df1Op<float, false>::Params bp, const float *x, float *
     for (size_t n = 0; n < n_low; n++) {
         float v[R], o[R];
         size_t f = fidx(layout, n, lane, n_low, lanes);
-        load_frame<R>(x + f * R, v);
+        load_frame<R>(x + f * R, v, vec);
         u_.push(d.push(v), o);
 #pragma unroll
         for (int j = 0; j < R; j++) o[j] = b.step(bp, o[j]);
-        store_frame<R>(y + f * R, o);
+        store_frame<R>(y + f * R, o, vec);
     }
     d.store(st, sstride, lane);
     u_.store(st + (size_t)hbf_dec_words(K) * sstride, sstride, lane);
@@ -210,6 +220,12 @@ struct TapsParam {
     int M;
 };
 #define GEN_CH 8
+// element offset (in frames of the stage) of frame `o` of `lane`: lane-major rows are contiguous; frame-major
+// data may carry J frames of the stage per ABI frame and lane (the stages of a cascade: [f32; 2J] frames)
+__device__ __forceinline__ size_t fidx2(int layout, size_t o, size_t lane, size_t n, size_t lanes, size_t J) {
+    if (layout != IDSP_FRAME_MAJOR) return lane * n + o;
+    return J == 1 ? o * lanes + lane : ((o / J) * lanes + lane) * J + (o % J);
+}
 // hbf.rs:46-68 window sum for runtime M
 __device__ __forceinline__ float window_sum(const TapsParam &tp, const float *w, int odd, int sym) {
     const int M = tp.M;
@@ -223,9 +239,10 @@ __device__ __forceinline__ float window_sum(const TapsParam &tp, const float *w,
     if (odd && sym) acc = acc + w[M];
     return acc;
 }
+// Any M <= IDSP_HBF_MAX_M: the windows are indexed dynamically (local memory).  Unaligned-safe: scalar accesses.
 __global__ void __launch_bounds__(128)
 hbf_dec_single(TapsParam tp, float *st, const float *x, float *y, size_t n_out, size_t lanes,
-               size_t sstride, int layout) {
+               size_t sstride, int layout, size_t J) {
     size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (lane >= lanes) return;
     const int M = tp.M, LEN = 2 * M - 1;
@@ -235,12 +252,12 @@ hbf_dec_single(TapsParam tp, float *st, const float *x, float *y, size_t n_out, 
     for (size_t o = 0; o < n_out; o += GEN_CH) {
         int c = (int)((n_out - o) < GEN_CH ? (n_out - o) : GEN_CH);
         for (int i = 0; i < c; i++) {
-            float2 p = *reinterpret_cast<const float2 *>(x + 2 * fidx(layout, o + i, lane, n_out, lanes));
-            ev[M - 1 + i] = p.x;
-            od[LEN + i] = p.y;
+            const float *p = x + 2 * fidx2(layout, o + i, lane, n_out, lanes, J);
+            ev[M - 1 + i] = p[0];
+            od[LEN + i] = p[1];
         }
         for (int i = 0; i < c; i++)
-            y[fidx(layout, o + i, lane, n_out, lanes)] = window_sum(tp, od + i, 0, 1) + ev[i];
+            y[fidx2(layout, o + i, lane, n_out, lanes, J)] = window_sum(tp, od + i, 0, 1) + ev[i];
         for (int i = 0; i < M - 1; i++) ev[i] = ev[i + c];
         for (int i = 0; i < LEN; i++) od[i] = od[i + c];
     }
@@ -249,7 +266,7 @@ hbf_dec_single(TapsParam tp, float *st, const float *x, float *y, size_t n_out, 
 }
 __global__ void __launch_bounds__(128)
 hbf_int_single(TapsParam tp, float *st, const float *x, float *y, size_t n_in, size_t lanes,
-               size_t sstride, int layout) {
+               size_t sstride, int layout, size_t J) {
     size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (lane >= lanes) return;
     const int M = tp.M, LEN = 2 * M - 1;
@@ -257,13 +274,109 @@ hbf_int_single(TapsParam tp, float *st, const float *x, float *y, size_t n_in, s
     for (int i = 0; i < LEN; i++) xs[i] = st[(size_t)i * sstride + lane];
     for (size_t o = 0; o < n_in; o += GEN_CH) {
         int c = (int)((n_in - o) < GEN_CH ? (n_in - o) : GEN_CH);
-        for (int i = 0; i < c; i++) xs[LEN + i] = x[fidx(layout, o + i, lane, n_in, lanes)];
+        for (int i = 0; i < c; i++) xs[LEN + i] = x[fidx2(layout, o + i, lane, n_in, lanes, J)];
         for (int i = 0; i < c; i++) {
-            float2 r = make_float2(window_sum(tp, xs + i, 0, 1), xs[M + i]);
-            *reinterpret_cast<float2 *>(y + 2 * fidx(layout, o + i, lane, n_in, lanes)) = r;
+            float *q = y + 2 * fidx2(layout, o + i, lane, n_in, lanes, J);
+            q[0] = window_sum(tp, xs + i, 0, 1);
+            q[1] = xs[M + i];
         }
         for (int i = 0; i < LEN; i++) xs[i] = xs[i + c];
     }
+    for (int i = 0; i < LEN; i++) st[(size_t)i * sstride + lane] = xs[i];
+}
+// The tap counts of the reference's published designs (HBF_TAPS: 23, 10, 5, 4, 3; HBF_TAPS_98: 15, 6, 3, 3, 2)
+// get the same kernels with M as a template parameter: every window index is static, so the delay
+// lines live in registers (shifts become renaming inside the unrolled chunk) and the taps are read
+// from the constant bank as instruction operands.
+template <int M>
+__global__ void __launch_bounds__(128)
+hbf_dec_single_t(TapsParam tp, float *st, const float *x, float *y, size_t n_out, size_t lanes,
+                 size_t sstride, int layout, size_t J, int vec) {
+    size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (lane >= lanes) return;
+    constexpr int LEN = 2 * M - 1, CH = M > 16 ? 4 : 8;
+    float ev[M - 1 + CH], od[LEN + CH];
+#pragma unroll
+    for (int i = 0; i < M - 1; i++) ev[i] = st[(size_t)i * sstride + lane];
+#pragma unroll
+    for (int i = 0; i < LEN; i++) od[i] = st[(size_t)(M - 1 + i) * sstride + lane];
+    size_t o = 0;
+    for (; o + CH <= n_out; o += CH) {
+#pragma unroll
+        for (int i = 0; i < CH; i++) {
+            const float *p = x + 2 * fidx2(layout, o + i, lane, n_out, lanes, J);
+            float2 v = vec ? *reinterpret_cast<const float2 *>(p) : make_float2(p[0], p[1]);
+            ev[M - 1 + i] = v.x;
+            od[LEN + i] = v.y;
+        }
+#pragma unroll
+        for (int i = 0; i < CH; i++) {
+            float acc = (od[i + LEN] + od[i]) * tp.c[0];
+#pragma unroll
+            for (int k = 1; k < M; k++) acc = acc + (od[i + LEN - k] + od[i + k]) * tp.c[k];
+            y[fidx2(layout, o + i, lane, n_out, lanes, J)] = acc + ev[i];
+        }
+#pragma unroll
+        for (int i = 0; i < M - 1; i++) ev[i] = ev[i + CH];
+#pragma unroll
+        for (int i = 0; i < LEN; i++) od[i] = od[i + CH];
+    }
+    for (; o < n_out; o++) {
+        const float *p = x + 2 * fidx2(layout, o, lane, n_out, lanes, J);
+        ev[M - 1] = p[0];
+        od[LEN] = p[1];
+        float acc = (od[LEN] + od[0]) * tp.c[0];
+#pragma unroll
+        for (int k = 1; k < M; k++) acc = acc + (od[LEN - k] + od[k]) * tp.c[k];
+        y[fidx2(layout, o, lane, n_out, lanes, J)] = acc + ev[0];
+#pragma unroll
+        for (int i = 0; i < M - 1; i++) ev[i] = ev[i + 1];
+#pragma unroll
+        for (int i = 0; i < LEN; i++) od[i] = od[i + 1];
+    }
+#pragma unroll
+    for (int i = 0; i < M - 1; i++) st[(size_t)i * sstride + lane] = ev[i];
+#pragma unroll
+    for (int i = 0; i < LEN; i++) st[(size_t)(M - 1 + i) * sstride + lane] = od[i];
+}
+template <int M>
+__global__ void __launch_bounds__(128)
+hbf_int_single_t(TapsParam tp, float *st, const float *x, float *y, size_t n_in, size_t lanes,
+                 size_t sstride, int layout, size_t J, int vec) {
+    size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (lane >= lanes) return;
+    constexpr int LEN = 2 * M - 1, CH = M > 16 ? 4 : 8;
+    float xs[LEN + CH];
+#pragma unroll
+    for (int i = 0; i < LEN; i++) xs[i] = st[(size_t)i * sstride + lane];
+    size_t o = 0;
+    for (; o + CH <= n_in; o += CH) {
+#pragma unroll
+        for (int i = 0; i < CH; i++) xs[LEN + i] = x[fidx2(layout, o + i, lane, n_in, lanes, J)];
+#pragma unroll
+        for (int i = 0; i < CH; i++) {
+            float acc = (xs[i + LEN] + xs[i]) * tp.c[0];
+#pragma unroll
+            for (int k = 1; k < M; k++) acc = acc + (xs[i + LEN - k] + xs[i + k]) * tp.c[k];
+            float *q = y + 2 * fidx2(layout, o + i, lane, n_in, lanes, J);
+            if (vec) *reinterpret_cast<float2 *>(q) = make_float2(acc, xs[M + i]);
+            else { q[0] = acc; q[1] = xs[M + i]; }
+        }
+#pragma unroll
+        for (int i = 0; i < LEN; i++) xs[i] = xs[i + CH];
+    }
+    for (; o < n_in; o++) {
+        xs[LEN] = x[fidx2(layout, o, lane, n_in, lanes, J)];
+        float acc = (xs[LEN] + xs[0]) * tp.c[0];
+#pragma unroll
+        for (int k = 1; k < M; k++) acc = acc + (xs[LEN - k] + xs[k]) * tp.c[k];
+        float *q = y + 2 * fidx2(layout, o, lane, n_in, lanes, J);
+        q[0] = acc;
+        q[1] = xs[M];
+#pragma unroll
+        for (int i = 0; i < LEN; i++) xs[i] = xs[i + 1];
+    }
+#pragma unroll
     for (int i = 0; i < LEN; i++) st[(size_t)i * sstride + lane] = xs[i];
 }
 __global__ void __launch_bounds__(128)
@@ -306,16 +419,37 @@ static int taps_param(const float *taps, int M, TapsParam *tp) {
     return IDSP_OK;
 }
 
+// one /2 or x2 stage on the ctx stream; J = frames of the stage per ABI frame and lane (frame-major cascades)
+static int hbf_single_dev(idsp_ctx *ctx, bool dec, const TapsParam &tp, float *state, const float *x, float *y,
+                          size_t n, size_t lanes, size_t sstride, int layout, size_t J) {
+    const unsigned grid = (unsigned)((lanes + 127) / 128);
+    const int vec = (((uintptr_t)(dec ? (const void *)x : (const void *)y)) & 7) == 0 ? 1 : 0;  // the pair side
+#define GO(MM)                                                                                                   \
+    case MM:                                                                                                     \
+        if (dec) hbf_dec_single_t<MM><<<grid, 128, 0, ctx->stream>>>(tp, state, x, y, n, lanes, sstride, layout, J, vec); \
+        else hbf_int_single_t<MM><<<grid, 128, 0, ctx->stream>>>(tp, state, x, y, n, lanes, sstride, layout, J, vec);     \
+        IDSP_KERNEL_FAMILY(ctx, "hbf single stage, registers");                                                  \
+        break;
+    switch (ctx->policy == 1 ? 0 : tp.M) {
+        GO(2) GO(3) GO(4) GO(5) GO(6) GO(10) GO(15) GO(23)
+        default:
+            if (dec) hbf_dec_single<<<grid, 128, 0, ctx->stream>>>(tp, state, x, y, n, lanes, sstride, layout, J);
+            else hbf_int_single<<<grid, 128, 0, ctx->stream>>>(tp, state, x, y, n, lanes, sstride, layout, J);
+            IDSP_KERNEL_FAMILY(ctx, "hbf single stage, run-time taps");
+            break;
+    }
+#undef GO
+    IDSP_LAUNCHED(ctx);
+    return IDSP_OK;
+}
+
 extern "C" int idsp_hbf_dec_f32(idsp_ctx *ctx, const float *taps, int M, float *state,
                                 const float *x, float *y, size_t n_out, size_t lanes, int layout) {
     HBF_COMMON_CHECK(n_out);
     TapsParam tp;
     int r = taps_param(taps, M, &tp);
     if (r) return r;
-    hbf_dec_single<<<(unsigned)((lanes + 127) / 128), 128, 0, ctx->stream>>>(tp, state, x, y, n_out,
-                                                                           lanes, lanes, layout);
-    IDSP_LAUNCHED(ctx);
-    return IDSP_OK;
+    return hbf_single_dev(ctx, true, tp, state, x, y, n_out, lanes, lanes, layout, 1);
 }
 extern "C" int idsp_hbf_int_f32(idsp_ctx *ctx, const float *taps, int M, float *state,
                                 const float *x, float *y, size_t n_in, size_t lanes, int layout) {
@@ -323,10 +457,7 @@ extern "C" int idsp_hbf_int_f32(idsp_ctx *ctx, const float *taps, int M, float *
     TapsParam tp;
     int r = taps_param(taps, M, &tp);
     if (r) return r;
-    hbf_int_single<<<(unsigned)((lanes + 127) / 128), 128, 0, ctx->stream>>>(tp, state, x, y, n_in,
-                                                                           lanes, lanes, layout);
-    IDSP_LAUNCHED(ctx);
-    return IDSP_OK;
+    return hbf_single_dev(ctx, false, tp, state, x, y, n_in, lanes, lanes, layout, 1);
 }
 extern "C" int idsp_fir_f32(idsp_ctx *ctx, const float *taps, int M, int odd, int sym,
                             float *state, const float *x, float *y, size_t frames, size_t lanes,
@@ -337,40 +468,36 @@ extern "C" int idsp_fir_f32(idsp_ctx *ctx, const float *taps, int M, int odd, in
     if (r) return r;
     fir_single<<<(unsigned)((lanes + 127) / 128), 128, 0, ctx->stream>>>(
         tp, odd ? 1 : 0, sym ? 1 : 0, state, x, y, frames, lanes, lanes, layout);
+    IDSP_KERNEL_FAMILY(ctx, "fir single stage, run-time taps");
     IDSP_LAUNCHED(ctx);
     return IDSP_OK;
 }
+
+// frames of 2^k floats can be moved with 16-byte (k >= 2) / 8-byte (k == 1) accesses
+static int frame_vec_ok(const void *p, int k) { return (((uintptr_t)p) & (k >= 2 ? 15 : 7)) == 0 ? 1 : 0; }
 
 int hbf_dec_cascade_dev(idsp_ctx *ctx, int k, float *state, const float *x, float *y,
                         size_t n_out, size_t lanes, size_t sstride, int layout) {
     // large aligned lane-major streams: tiled TMA kernel over whole tiles, generic kernel
     // (state carried through `state`) for the remaining frames of every lane
     size_t done = 0;
-    // two bit-identical tiled variants: scalar FP32 (more resident warps) and packed f32x2
-    // (fewer FP issue slots); IDSP_HBF_VARIANT=packed|scalar overrides the default
-    static int variant = -1;
-    if (variant < 0) {
-        const char *e = getenv("IDSP_HBF_VARIANT");
-        variant = (e && e[0] == 'p') ? 1 : 0;
-    }
-    int fr = IDSP_HBF_FAST_NOT_APPLICABLE;
-    if (variant == 1 || ctx->policy == 3) fr = hbf_dec_fast_try(ctx, k, state, x, y, n_out, lanes, sstride, layout, &done);
-    if (fr == IDSP_HBF_FAST_NOT_APPLICABLE)  // the packed variant is lane-major only
-        fr = hbf_dec_fast_try_scalar(ctx, k, state, x, y, n_out, lanes, sstride, layout, &done);
+    int fr = hbf_dec_fast_try_scalar(ctx, k, state, x, y, n_out, lanes, sstride, layout, &done);
     if (fr != IDSP_HBF_FAST_NOT_APPLICABLE && fr != IDSP_OK) return fr;
     if (fr == IDSP_HBF_FAST_NOT_APPLICABLE && ctx->policy == 2 && layout == IDSP_LANE_MAJOR) {
         idsp_set_error("tiled HBF kernel forced but shape/alignment does not qualify");
         return IDSP_EINVAL;
     }
     if (done == n_out) return IDSP_OK;
+    const int vec = frame_vec_ok(x, k);  // the wide side: frames of 2^k floats
     unsigned grid = (unsigned)((lanes + 63) / 64);
     switch (k) {
-        case 1: hbf_dec_cascade_generic<1><<<grid, 64, 0, ctx->stream>>>(state, x, y, done, n_out, lanes, sstride, layout); break;
-        case 2: hbf_dec_cascade_generic<2><<<grid, 64, 0, ctx->stream>>>(state, x, y, done, n_out, lanes, sstride, layout); break;
-        case 3: hbf_dec_cascade_generic<3><<<grid, 64, 0, ctx->stream>>>(state, x, y, done, n_out, lanes, sstride, layout); break;
-        case 4: hbf_dec_cascade_generic<4><<<grid, 64, 0, ctx->stream>>>(state, x, y, done, n_out, lanes, sstride, layout); break;
-        default: hbf_dec_cascade_generic<5><<<grid, 64, 0, ctx->stream>>>(state, x, y, done, n_out, lanes, sstride, layout); break;
+        case 1: hbf_dec_cascade_generic<1><<<grid, 64, 0, ctx->stream>>>(state, x, y, done, n_out, lanes, sstride, layout, vec); break;
+        case 2: hbf_dec_cascade_generic<2><<<grid, 64, 0, ctx->stream>>>(state, x, y, done, n_out, lanes, sstride, layout, vec); break;
+        case 3: hbf_dec_cascade_generic<3><<<grid, 64, 0, ctx->stream>>>(state, x, y, done, n_out, lanes, sstride, layout, vec); break;
+        case 4: hbf_dec_cascade_generic<4><<<grid, 64, 0, ctx->stream>>>(state, x, y, done, n_out, lanes, sstride, layout, vec); break;
+        default: hbf_dec_cascade_generic<5><<<grid, 64, 0, ctx->stream>>>(state, x, y, done, n_out, lanes, sstride, layout, vec); break;
     }
+    IDSP_KERNEL_FAMILY(ctx, done ? "hbf tiled + generic tail" : "hbf generic thread-per-lane");
     IDSP_LAUNCHED(ctx);
     return IDSP_OK;
 }
@@ -404,34 +531,185 @@ extern "C" int idsp_hbf_dec_cascade_f32_host(idsp_ctx *ctx, int log2_rate, float
                                                            (float *)dy, n_out, an, lanes, layout);
                             });
 }
-extern "C" int idsp_hbf_int_cascade_f32(idsp_ctx *ctx, int log2_rate, float *state, const float *x,
-                                        float *y, size_t n_in, size_t lanes, int layout) {
-    HBF_COMMON_CHECK(n_in);
-    IDSP_CHECK_ARG(log2_rate >= 1 && log2_rate <= 5, "log2_rate must be 1..5");
+int hbf_int_cascade_dev(idsp_ctx *ctx, int log2_rate, float *state, const float *x, float *y, size_t n_in,
+                        size_t lanes, size_t sstride, int layout) {
     size_t done = 0;
-    int fr = hbf_int_fast_try(ctx, log2_rate, state, x, y, n_in, lanes, lanes, layout, &done);
+    int fr = hbf_int_fast_try(ctx, log2_rate, state, x, y, n_in, lanes, sstride, layout, &done);
     if (fr != IDSP_HBF_FAST_NOT_APPLICABLE && fr != IDSP_OK) return fr;
     if (fr == IDSP_HBF_FAST_NOT_APPLICABLE && ctx->policy == 2 && layout == IDSP_LANE_MAJOR) {
         idsp_set_error("tiled HBF kernel forced but shape/alignment does not qualify");
         return IDSP_EINVAL;
     }
     if (done == n_in) return IDSP_OK;
+    const int vec = frame_vec_ok(y, log2_rate);
     unsigned grid = (unsigned)((lanes + 63) / 64);
     switch (log2_rate) {
-        case 1: hbf_int_cascade_generic<1><<<grid, 64, 0, ctx->stream>>>(state, x, y, done, n_in, lanes, lanes, layout); break;
-        case 2: hbf_int_cascade_generic<2><<<grid, 64, 0, ctx->stream>>>(state, x, y, done, n_in, lanes, lanes, layout); break;
-        case 3: hbf_int_cascade_generic<3><<<grid, 64, 0, ctx->stream>>>(state, x, y, done, n_in, lanes, lanes, layout); break;
-        case 4: hbf_int_cascade_generic<4><<<grid, 64, 0, ctx->stream>>>(state, x, y, done, n_in, lanes, lanes, layout); break;
-        default: hbf_int_cascade_generic<5><<<grid, 64, 0, ctx->stream>>>(state, x, y, done, n_in, lanes, lanes, layout); break;
+        case 1: hbf_int_cascade_generic<1><<<grid, 64, 0, ctx->stream>>>(state, x, y, done, n_in, lanes, sstride, layout, vec); break;
+        case 2: hbf_int_cascade_generic<2><<<grid, 64, 0, ctx->stream>>>(state, x, y, done, n_in, lanes, sstride, layout, vec); break;
+        case 3: hbf_int_cascade_generic<3><<<grid, 64, 0, ctx->stream>>>(state, x, y, done, n_in, lanes, sstride, layout, vec); break;
+        case 4: hbf_int_cascade_generic<4><<<grid, 64, 0, ctx->stream>>>(state, x, y, done, n_in, lanes, sstride, layout, vec); break;
+        default: hbf_int_cascade_generic<5><<<grid, 64, 0, ctx->stream>>>(state, x, y, done, n_in, lanes, sstride, layout, vec); break;
     }
+    IDSP_KERNEL_FAMILY(ctx, done ? "hbf tiled + generic tail" : "hbf generic thread-per-lane");
     IDSP_LAUNCHED(ctx);
     return IDSP_OK;
 }
+extern "C" int idsp_hbf_int_cascade_f32(idsp_ctx *ctx, int log2_rate, float *state, const float *x,
+                                        float *y, size_t n_in, size_t lanes, int layout) {
+    HBF_COMMON_CHECK(n_in);
+    IDSP_CHECK_ARG(log2_rate >= 1 && log2_rate <= 5, "log2_rate must be 1..5");
+    return hbf_int_cascade_dev(ctx, log2_rate, state, x, y, n_in, lanes, lanes, layout);
+}
+// ---------------------------------------------------------------- caller-supplied tap sets
+static const float H98_TAPS0[15] = {7.02144012e-05f, -2.43279582e-04f, 6.35026936e-04f, -1.39782541e-03f, 2.74613582e-03f,
+                                    -4.96403839e-03f, 8.41806912e-03f, -1.35827601e-02f, 2.11004053e-02f, -3.19267647e-02f,
+                                    4.77024289e-02f, -7.18014345e-02f, 1.12942004e-01f, -2.03279594e-01f, 6.33592923e-01f};
+static const float H98_TAPS1[6] = {-0.00086943f, 0.00577837f, -0.02201674f, 0.06357869f, -0.16627679f, 0.61979312f};
+static const float H98_TAPS2[3] = {0.01414651f, -0.10439639f, 0.59026742f};
+static const float H98_TAPS3[3] = {0.01227974f, -0.09930782f, 0.58702834f};
+static const float H98_TAPS4[2] = {-0.06291796f, 0.5629161f};
+extern "C" const float *idsp_hbf_taps_98(int index, int *M) {  // src/hbf.rs:258-292
+    static const float *t[5] = {H98_TAPS0, H98_TAPS1, H98_TAPS2, H98_TAPS3, H98_TAPS4};
+    static const int m[5] = {15, 6, 3, 3, 2};
+    if (index < 0 || index > 4) return nullptr;
+    if (M) *M = m[index];
+    return t[index];
+}
+extern "C" size_t idsp_hbf_cascade_state_words(int decimate, int nstages, const int *M) {
+    if (!M || nstages < 1 || nstages > 5) return 0;
+    size_t w = 0;
+    for (int i = 0; i < nstages; i++) {
+        if (M[i] < 1 || M[i] > IDSP_HBF_MAX_M) return 0;
+        w += decimate ? (size_t)(3 * M[i] - 2) : (size_t)(2 * M[i] - 1);
+    }
+    return w;
+}
+static bool is_builtin_taps(int nstages, const float *const *taps, const int *M) {
+    for (int i = 0; i < nstages; i++) {
+        int m = 0;
+        const float *t = idsp_hbf_taps(i, &m);
+        if (M[i] != m || memcmp(taps[i], t, sizeof(float) * (size_t)m) != 0) return false;
+    }
+    return true;
+}
+static int cascade_taps_check(int nstages, const float *const *taps, const int *M) {
+    if (nstages < 1 || nstages > 5 || !taps || !M) {
+        idsp_set_error("nstages must be 1..5 and taps / M non-null");
+        return IDSP_EINVAL;
+    }
+    for (int i = 0; i < nstages; i++)
+        if (!taps[i] || M[i] < 1 || M[i] > IDSP_HBF_MAX_M) {
+            idsp_set_error("stage %d: taps must be non-null and 1 <= M <= %d", i, IDSP_HBF_MAX_M);
+            return IDSP_EINVAL;
+        }
+    return IDSP_OK;
+}
+// Decimator: stages nstages-1 -> 0 (src/hbf.rs:385-421).  Other tap sets than HBF_TAPS run stage by stage:
+// stage s reads 2^(n-s) samples per output frame and lane and leaves 2^(n-s-1); the intermediate streams
+// ping-pong through ctx scratch memory in the layout of x (frame-major: [t][lane][samples of the frame]).
+extern "C" int idsp_hbf_dec_cascade_taps_f32(idsp_ctx *ctx, int nstages, const float *const *taps, const int *M,
+                                             float *state, const float *x, float *y, size_t n_out, size_t lanes,
+                                             int layout) {
+    HBF_COMMON_CHECK(n_out);
+    int r = cascade_taps_check(nstages, taps, M);
+    if (r) return r;
+    if (is_builtin_taps(nstages, taps, M)) return hbf_dec_cascade_dev(ctx, nstages, state, x, y, n_out, lanes, lanes, layout);
+    const int n = nstages;
+    void *scr = nullptr;
+    const size_t half = n_out * lanes << (n - 1);  // floats after the first stage
+    if (n > 1) {
+        r = idsp_scratch(ctx, (half + half / 2) * sizeof(float), &scr);
+        if (r) return r;
+    }
+    float *buf[2] = {(float *)scr, (float *)scr + half};
+    const float *src = x;
+    size_t word = 0;
+    for (int s = 0; s < n; s++) {
+        const int ti = n - 1 - s;
+        TapsParam tp;
+        r = taps_param(taps[ti], M[ti], &tp);
+        if (r) return r;
+        const size_t J = (size_t)1 << (n - 1 - s);  // stage outputs per ABI frame and lane
+        float *dst = s == n - 1 ? y : buf[s & 1];
+        r = hbf_single_dev(ctx, true, tp, state + word * lanes, src, dst, n_out * J, lanes, lanes, layout, J);
+        if (r) return r;
+        word += (size_t)(3 * M[ti] - 2);
+        src = dst;
+    }
+    return IDSP_OK;
+}
+// Interpolator: stages 0 -> nstages-1 (src/hbf.rs:476-512)
+extern "C" int idsp_hbf_int_cascade_taps_f32(idsp_ctx *ctx, int nstages, const float *const *taps, const int *M,
+                                             float *state, const float *x, float *y, size_t n_in, size_t lanes,
+                                             int layout) {
+    HBF_COMMON_CHECK(n_in);
+    int r = cascade_taps_check(nstages, taps, M);
+    if (r) return r;
+    if (is_builtin_taps(nstages, taps, M)) return idsp_hbf_int_cascade_f32(ctx, nstages, state, x, y, n_in, lanes, layout);
+    const int n = nstages;
+    void *scr = nullptr;
+    const size_t half = n_in * lanes << (n - 1);  // floats before the last stage
+    if (n > 1) {
+        r = idsp_scratch(ctx, (half + half / 2) * sizeof(float), &scr);
+        if (r) return r;
+    }
+    // the largest intermediate (input of the last stage) sits in buf[(n-2) & 1]
+    float *buf[2];
+    buf[(n - 2) & 1] = (float *)scr;
+    buf[((n - 2) & 1) ^ 1] = (float *)scr + half;
+    const float *src = x;
+    size_t word = 0;
+    for (int s = 0; s < n; s++) {
+        TapsParam tp;
+        r = taps_param(taps[s], M[s], &tp);
+        if (r) return r;
+        const size_t J = (size_t)1 << s;  // stage inputs per ABI frame and lane
+        float *dst = s == n - 1 ? y : buf[s & 1];
+        r = hbf_single_dev(ctx, false, tp, state + word * lanes, src, dst, n_in * J, lanes, lanes, layout, J);
+        if (r) return r;
+        word += (size_t)(2 * M[s] - 1);
+        src = dst;
+    }
+    return IDSP_OK;
+}
+
+// host buffers: the three operators in one PCIe round trip (lanes are independent: lane-major data is cut
+// along lanes, frame-major along frames with the state carried from chunk to chunk)
+extern "C" int idsp_chain_f32(idsp_ctx *ctx, int log2_rate, const float ba[5], float *state,
+                              const float *x, float *y, size_t n_low, size_t lanes, int layout);
+static int chain_dev_strided(idsp_ctx *ctx, int log2_rate, const float ba[5], float *state, const float *x, float *y,
+                             size_t n_low, size_t lanes, size_t sstride, int layout);
+extern "C" int idsp_chain_f32_host(idsp_ctx *ctx, int log2_rate, const float ba[5], float *state,
+                                   const float *x, float *y, size_t n_low, size_t lanes, int layout) {
+    HBF_COMMON_CHECK(n_low);
+    IDSP_CHECK_ARG(ba != nullptr, "ba is null");
+    IDSP_CHECK_ARG(log2_rate >= 1 && log2_rate <= 5, "log2_rate must be 1..5");
+    HostStreamSpec s;
+    s.frames = n_low;
+    s.lanes = lanes;
+    s.in_bytes_per_frame_lane = sizeof(float) << log2_rate;
+    s.out_bytes_per_frame_lane = sizeof(float) << log2_rate;
+    s.layout = layout;
+    s.nblobs = 1;
+    s.blobs[0] = {state, idsp_chain_state_words(log2_rate) * lanes * sizeof(float), true};
+    return idsp_host_stream(ctx, s, x, y, [&](void **blobs, const void *dx, void *dy, size_t a0, size_t an) {
+        float *st = (float *)blobs[0];
+        if (layout == IDSP_FRAME_MAJOR)
+            return chain_dev_strided(ctx, log2_rate, ba, st, (const float *)dx, (float *)dy, an, lanes, lanes, layout);
+        return chain_dev_strided(ctx, log2_rate, ba, st + a0, (const float *)dx, (float *)dy, n_low, an, lanes, layout);
+    });
+}
+
 extern "C" int idsp_chain_f32(idsp_ctx *ctx, int log2_rate, const float ba[5], float *state,
                               const float *x, float *y, size_t n_low, size_t lanes, int layout) {
     HBF_COMMON_CHECK(n_low);
     IDSP_CHECK_ARG(ba != nullptr, "ba is null");
     IDSP_CHECK_ARG(log2_rate >= 1 && log2_rate <= 5, "log2_rate must be 1..5");
+    return chain_dev_strided(ctx, log2_rate, ba, state, x, y, n_low, lanes, lanes, layout);
+}
+// state words of lane l at state[w * sstride + l] (sstride >= lanes: a lane block of a larger SoA state)
+static int chain_dev_strided(idsp_ctx *ctx, int log2_rate, const float ba[5], float *state, const float *x, float *y,
+                             size_t n_low, size_t lanes, size_t sstride, int layout) {
     // Few lanes, lane-major: the fused thread-per-lane kernel would leave most SMs idle (one thread
     // per lane, ~200 registers of delay lines).  Run the three bit-identical pieces instead: the two
     // FIR cascades are time-parallel (tiled kernels, 8 lanes per CTA), only the biquad recurrence is
@@ -451,46 +729,46 @@ extern "C" int idsp_chain_f32(idsp_ctx *ctx, int log2_rate, const float ba[5], f
         int r = idsp_scratch(ctx, n_low * lanes * sizeof(float), &low);
         if (r) return r;
         const size_t wd = (size_t)hbf_dec_words(log2_rate), wi = (size_t)hbf_int_words(log2_rate);
-        r = hbf_dec_cascade_dev(ctx, log2_rate, state, x, (float *)low, n_low, lanes, lanes, layout);
+        r = hbf_dec_cascade_dev(ctx, log2_rate, state, x, (float *)low, n_low, lanes, sstride, layout);
         if (r) return r;
         Df1Op<float, false>::Params bq;
         for (int i = 0; i < 5; i++) bq.ba[i] = ba[i];
         bq.F = 0;
         bq.u = bq.mn = bq.mx = 0.f;
-        bq.st = state + (wd + wi) * lanes;
-        r = hbf_int_bq_fast_try(ctx, log2_rate, state + wd * lanes, (const float *)low, y, n_low, lanes, lanes, bq, wide);
+        bq.st = state + (wd + wi) * sstride;
+        r = hbf_int_bq_fast_try(ctx, log2_rate, state + wd * sstride, (const float *)low, y, n_low, lanes, sstride, bq, wide);
         if (r != IDSP_HBF_FAST_NOT_APPLICABLE) return r;
         // (not reached: the scratch buffer is aligned) the three-kernel composition
-        r = idsp_hbf_int_cascade_f32(ctx, log2_rate, state + wd * lanes, (const float *)low, y, n_low, lanes, layout);
+        r = hbf_int_cascade_dev(ctx, log2_rate, state + wd * sstride, (const float *)low, y, n_low, lanes, sstride, layout);
         if (r) return r;
-        return idsp_biquad_df1_f32(ctx, ba, 0, nullptr, state + (wd + wi) * lanes, y, y, n_low << log2_rate, lanes,
-                                   layout);
+        return idsp_df1_f32_strided(ctx, ba, state + (wd + wi) * sstride, y, y, n_low << log2_rate, lanes, sstride, layout);
     }
     if (layout == IDSP_LANE_MAJOR && ctx->policy != 1 && lanes <= 16384) {
         void *low = nullptr;
         int r = idsp_scratch(ctx, n_low * lanes * sizeof(float), &low);
         if (r) return r;
         const size_t wd = (size_t)hbf_dec_words(log2_rate), wi = (size_t)hbf_int_words(log2_rate);
-        r = hbf_dec_cascade_dev(ctx, log2_rate, state, x, (float *)low, n_low, lanes, lanes, layout);
+        r = hbf_dec_cascade_dev(ctx, log2_rate, state, x, (float *)low, n_low, lanes, sstride, layout);
         if (r) return r;
-        r = idsp_hbf_int_cascade_f32(ctx, log2_rate, state + wd * lanes, (const float *)low, y, n_low, lanes, layout);
+        r = hbf_int_cascade_dev(ctx, log2_rate, state + wd * sstride, (const float *)low, y, n_low, lanes, sstride, layout);
         if (r) return r;
-        return idsp_biquad_df1_f32(ctx, ba, 0, nullptr, state + (wd + wi) * lanes, y, y, n_low << log2_rate, lanes,
-                                   layout);
+        return idsp_df1_f32_strided(ctx, ba, state + (wd + wi) * sstride, y, y, n_low << log2_rate, lanes, sstride, layout);
     }
     Df1Op<float, false>::Params bp;
     for (int i = 0; i < 5; i++) bp.ba[i] = ba[i];
     bp.F = 0;
     bp.u = bp.mn = bp.mx = 0.f;
     bp.st = nullptr;
+    const int vec = frame_vec_ok(x, log2_rate) && frame_vec_ok(y, log2_rate);
     unsigned grid = (unsigned)((lanes + 63) / 64);
     switch (log2_rate) {
-        case 1: chain_generic<1><<<grid, 64, 0, ctx->stream>>>(state, bp, x, y, n_low, lanes, lanes, layout); break;
-        case 2: chain_generic<2><<<grid, 64, 0, ctx->stream>>>(state, bp, x, y, n_low, lanes, lanes, layout); break;
-        case 3: chain_generic<3><<<grid, 64, 0, ctx->stream>>>(state, bp, x, y, n_low, lanes, lanes, layout); break;
-        case 4: chain_generic<4><<<grid, 64, 0, ctx->stream>>>(state, bp, x, y, n_low, lanes, lanes, layout); break;
-        default: chain_generic<5><<<grid, 64, 0, ctx->stream>>>(state, bp, x, y, n_low, lanes, lanes, layout); break;
+        case 1: chain_generic<1><<<grid, 64, 0, ctx->stream>>>(state, bp, x, y, n_low, lanes, sstride, layout, vec); break;
+        case 2: chain_generic<2><<<grid, 64, 0, ctx->stream>>>(state, bp, x, y, n_low, lanes, sstride, layout, vec); break;
+        case 3: chain_generic<3><<<grid, 64, 0, ctx->stream>>>(state, bp, x, y, n_low, lanes, sstride, layout, vec); break;
+        case 4: chain_generic<4><<<grid, 64, 0, ctx->stream>>>(state, bp, x, y, n_low, lanes, sstride, layout, vec); break;
+        default: chain_generic<5><<<grid, 64, 0, ctx->stream>>>(state, bp, x, y, n_low, lanes, sstride, layout, vec); break;
     }
+    IDSP_KERNEL_FAMILY(ctx, "chain single pass thread-per-lane");
     IDSP_LAUNCHED(ctx);
     return IDSP_OK;
 }

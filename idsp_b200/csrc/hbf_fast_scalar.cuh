@@ -568,6 +568,7 @@ static int launch(idsp_ctx *ctx, float *st, const float *x, float *y, size_t n_o
     IDSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(K)));
     unsigned grid = (unsigned)((lanes + NL - 1) / NL);
     kern<<<grid, NT, smem_bytes(K), ctx->stream>>>(st, x, y, n_out, ntiles, lanes, sstride);
+    IDSP_KERNEL_FAMILY(ctx, FM ? "hbf tiled frame-major" : "hbf tiled lane-major");
     IDSP_LAUNCHED(ctx);
     return IDSP_OK;
 }

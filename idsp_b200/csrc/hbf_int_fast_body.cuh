@@ -294,6 +294,7 @@ static int launch(idsp_ctx *ctx, float *st, const float *x, float *y, size_t n_i
     IDSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(K)));
     unsigned grid = (unsigned)((lanes + NL - 1) / NL);
     kern<<<grid, NT + (BQ ? 32 : 0), smem_bytes(K), ctx->stream>>>(st, x, y, n_in, ntiles, lanes, sstride, bq);
+    IDSP_KERNEL_FAMILY(ctx, BQ ? "hbf tiled interpolator + fused biquad warp" : (FM ? "hbf tiled frame-major" : "hbf tiled lane-major"));
     IDSP_LAUNCHED(ctx);
     return IDSP_OK;
 }

@@ -242,6 +242,7 @@ static int launch_lanes(idsp_ctx *ctx, const typename Op::Params &p, const typen
         constexpr int U = sizeof(typename Op::In) >= 8 ? 8 : 16;
         unsigned grid = (unsigned)((lanes + 63) / 64);
         lanes_fm_kernel<Op, U><<<grid, 64, 0, ctx->stream>>>(p, x, y, frames, lanes, sstride);
+        IDSP_KERNEL_FAMILY(ctx, "generic frame-major");
     } else if constexpr (sizeof(typename Op::In) == sizeof(typename Op::Out) && sizeof(typename Op::In) != 4 &&
                          (std::is_integral<typename Op::In>::value || std::is_same<typename Op::In, double>::value)) {
         constexpr int WARPS = 4;
@@ -250,15 +251,18 @@ static int launch_lanes(idsp_ctx *ctx, const typename Op::Params &p, const typen
         if (wide) {
             unsigned grid = (unsigned)((lanes + WARPS * 32 - 1) / (WARPS * 32));
             lanes_lm_wide_kernel<Op, WARPS><<<grid, WARPS * 32, 0, ctx->stream>>>(p, x, y, frames, lanes, sstride);
+            IDSP_KERNEL_FAMILY(ctx, "generic lane-major wide tiles");
         } else {
             unsigned grid = (unsigned)((lanes + 2 * 32 - 1) / (2 * 32));
             lanes_lm_kernel<Op, 2><<<grid, 2 * 32, 0, ctx->stream>>>(p, x, y, frames, lanes, sstride);
+            IDSP_KERNEL_FAMILY(ctx, "generic lane-major");
         }
     } else {
         constexpr int WARPS = 2;
         unsigned grid = (unsigned)((lanes + WARPS * 32 - 1) / (WARPS * 32));
         lanes_lm_kernel<Op, WARPS><<<grid, WARPS * 32, 0, ctx->stream>>>(p, x, y, frames, lanes,
                                                                         sstride);
+        IDSP_KERNEL_FAMILY(ctx, "generic lane-major");
     }
     IDSP_LAUNCHED(ctx);
     return IDSP_OK;

@@ -556,6 +556,87 @@ template <int ORDER, bool SMEM_LUT = false> struct LockinOp {
     }
 };
 
+// Lockin<Lowpass<N>> on (sample, phase) tuples (src/lockin.rs:30-39): the phase comes with every sample
+// instead of a per-lane Accu.  In = (x, phase).
+template <int ORDER, bool SMEM_LUT = false> struct LockinPhaseOp {
+    using In = int2;
+    using Out = int2;
+    static constexpr bool TUNABLE = false;
+    static constexpr bool HEAVY = true;
+    static constexpr bool LM_SMALL = false;
+    static constexpr int SMEM_EXTRA_WORDS = SMEM_LUT ? 256 : 0;
+    struct Params {
+        int32_t k[2];
+        int64_t *st;  // [2*ORDER][stride]
+        const uint32_t *lut;
+    };
+    int64_t i0, i1, q0, q1;
+    const uint32_t *lutp;
+    __device__ __forceinline__ static void init_smem(const Params &p, uint32_t *extra, int tid, int nthreads) {
+        if constexpr (SMEM_LUT) cossin_expand_lut(p.lut, extra, tid, nthreads);
+    }
+    __device__ __forceinline__ void bind(const Params &p, const uint32_t *extra) { lutp = SMEM_LUT ? extra : p.lut; }
+    __device__ __forceinline__ void load(const Params &p, size_t lane, size_t stride) {
+        if constexpr (!SMEM_LUT) lutp = p.lut;
+        i0 = p.st[lane];
+        i1 = ORDER == 2 ? p.st[stride + lane] : 0;
+        q0 = p.st[(size_t)ORDER * stride + lane];
+        q1 = ORDER == 2 ? p.st[(size_t)(ORDER + 1) * stride + lane] : 0;
+    }
+    __device__ __forceinline__ void store(const Params &p, size_t lane, size_t stride) const {
+        p.st[lane] = i0;
+        if (ORDER == 2) p.st[stride + lane] = i1;
+        p.st[(size_t)ORDER * stride + lane] = q0;
+        if (ORDER == 2) p.st[(size_t)(ORDER + 1) * stride + lane] = q1;
+    }
+    __device__ __forceinline__ int2 step(const Params &p, int2 xp) {
+        int32_t c, s;
+        if constexpr (SMEM_LUT) cossin_dev_x(lutp, xp.y, c, s);
+        else cossin_dev<false>(lutp, xp.y, c, s);
+        const int32_t mi = (int32_t)(((int64_t)c * (int64_t)xp.x) >> 32);
+        const int32_t mq = (int32_t)(((int64_t)s * (int64_t)xp.x) >> 32);
+        int2 r;
+        r.x = lowpass_step<ORDER>(p.k[0], p.k[1], i0, i1, mi);
+        r.y = lowpass_step<ORDER>(p.k[0], p.k[1], q0, q1, mq);
+        return r;
+    }
+};
+
+// Lockin<Lowpass<N>> on (sample, LO) tuples (src/lockin.rs:17-28), X = i32, U = Q32<32>.  In = (x, lo.re, lo.im).
+struct XLo {
+    int32_t x, re, im;
+};
+template <int ORDER> struct LockinLoOp : OpHooks {
+    using In = XLo;
+    using Out = int2;
+    static constexpr bool HEAVY = true;
+    struct Params {
+        int32_t k[2];
+        int64_t *st;
+    };
+    int64_t i0, i1, q0, q1;
+    __device__ __forceinline__ void load(const Params &p, size_t lane, size_t stride) {
+        i0 = p.st[lane];
+        i1 = ORDER == 2 ? p.st[stride + lane] : 0;
+        q0 = p.st[(size_t)ORDER * stride + lane];
+        q1 = ORDER == 2 ? p.st[(size_t)(ORDER + 1) * stride + lane] : 0;
+    }
+    __device__ __forceinline__ void store(const Params &p, size_t lane, size_t stride) const {
+        p.st[lane] = i0;
+        if (ORDER == 2) p.st[stride + lane] = i1;
+        p.st[(size_t)ORDER * stride + lane] = q0;
+        if (ORDER == 2) p.st[(size_t)(ORDER + 1) * stride + lane] = q1;
+    }
+    __device__ __forceinline__ int2 step(const Params &p, XLo v) {
+        const int32_t mi = (int32_t)(((int64_t)v.re * (int64_t)v.x) >> 32);
+        const int32_t mq = (int32_t)(((int64_t)v.im * (int64_t)v.x) >> 32);
+        int2 r;
+        r.x = lowpass_step<ORDER>(p.k[0], p.k[1], i0, i1, mi);
+        r.y = lowpass_step<ORDER>(p.k[0], p.k[1], q0, q1, mq);
+        return r;
+    }
+};
+
 // --------------------------------------------------------------------------
 // PLL (src/pll.rs:88-108): type-2 sampled-phase PLL, wrapping 32/64-bit integer math, with the
 // ClampWrap phase-error clamp (src/unwrap.rs:166-194, overflowing_sub :73-81).  SURVEY 8(f) rank 4.

@@ -89,6 +89,25 @@ template <> struct Bits32<float> {
     __device__ __forceinline__ static uint32_t to(float v) { return __float_as_uint(v); }
 };
 
+// 4- or 8-byte sample <-> 32-bit words of a shared-memory tile (8-byte: low word first)
+template <class T, int W = (int)sizeof(T) / 4> struct WordsOf;
+template <class T> struct WordsOf<T, 1> {
+    __device__ __forceinline__ static T from(const uint32_t *w) { return Bits32<T>::from(w[0]); }
+    __device__ __forceinline__ static void to(T v, uint32_t *w) { w[0] = Bits32<T>::to(v); }
+};
+template <> struct WordsOf<int2, 2> {
+    __device__ __forceinline__ static int2 from(const uint32_t *w) { return make_int2((int)w[0], (int)w[1]); }
+    __device__ __forceinline__ static void to(int2 v, uint32_t *w) { w[0] = (uint32_t)v.x; w[1] = (uint32_t)v.y; }
+};
+template <> struct WordsOf<int64_t, 2> {
+    __device__ __forceinline__ static int64_t from(const uint32_t *w) { return (int64_t)((uint64_t)w[0] | ((uint64_t)w[1] << 32)); }
+    __device__ __forceinline__ static void to(int64_t v, uint32_t *w) { w[0] = (uint32_t)(uint64_t)v; w[1] = (uint32_t)((uint64_t)v >> 32); }
+};
+template <> struct WordsOf<double, 2> {
+    __device__ __forceinline__ static double from(const uint32_t *w) { return __hiloint2double((int)w[1], (int)w[0]); }
+    __device__ __forceinline__ static void to(double v, uint32_t *w) { w[0] = (uint32_t)__double2loint(v); w[1] = (uint32_t)__double2hiint(v); }
+};
+
 // ---------------------------------------------------------------- kernel
 // LM = false: frame-major, tile [TF rows][32 words];  LM = true: lane-major,
 // tile [32 rows (lanes)][16 words] with 64-byte swizzle (TF must be 16).
@@ -103,26 +122,27 @@ tma_lanes_kernel(typename Op::Params p, const __grid_constant__ CUtensorMap mx,
                  size_t sstride) {
     using In = typename Op::In;
     using Out = typename Op::Out;
-    static_assert(sizeof(In) == 4 && (sizeof(Out) == 4 || sizeof(Out) == 8), "4-byte in, 4/8-byte out");
+    static_assert((sizeof(In) == 4 || sizeof(In) == 8) && (sizeof(Out) == 4 || sizeof(Out) == 8), "4/8-byte in, 4/8-byte out");
     static_assert(!LM || TF == 16, "lane-major tiles are 16 frames (64B swizzle)");
     static_assert(!(WIDE && LM), "wide boxes are frame-major only");
-    constexpr int OW = sizeof(Out) / 4;             // output words per sample (Complex<i32> = 2)
-    // lane-major 8-byte outputs: the output tile is [32 lanes][16 frames x 2 words] = 128-byte rows
+    constexpr int IW = sizeof(In) / 4;              // input words per sample (Complex<i32>, i64, f64 = 2)
+    constexpr int OW = sizeof(Out) / 4;             // output words per sample
+    // lane-major 8-byte samples: the tile is [32 lanes][16 frames x 2 words] = 128-byte rows
     // written with the 128-byte TMA swizzle (chunk index XOR (l & 7))
     constexpr int BW = WIDE ? 32 * WPC : 32;        // box width in lanes
-    constexpr int TILE_WORDS = TF * BW;
-    constexpr uint32_t TILE_BYTES = TILE_WORDS * 4;
+    constexpr int TILE_WORDS = TF * BW;             // samples per tile
+    constexpr uint32_t TILE_IN_BYTES = TILE_WORDS * IW * 4;
     constexpr int NPIPE = WIDE ? 1 : WPC;            // independent pipelines per CTA
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
     const int pipe = WIDE ? 0 : w;
     const int col = WIDE ? w * 32 + l : l;          // my column inside the box
     // per pipeline: S input stages, O output stages, S mbarriers
-    uint32_t *wbase = reinterpret_cast<uint32_t *>(smem_raw) + (size_t)pipe * (S + O * OW) * TILE_WORDS;
+    uint32_t *wbase = reinterpret_cast<uint32_t *>(smem_raw) + (size_t)pipe * (S * IW + O * OW) * TILE_WORDS;
     uint32_t *sin = wbase;
-    uint32_t *sout = wbase + S * TILE_WORDS;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)NPIPE * (S + O * OW) * TILE_BYTES) + pipe * S;
-    uint32_t *extra = reinterpret_cast<uint32_t *>(smem_raw + (size_t)NPIPE * (S + O * OW) * TILE_BYTES + (size_t)NPIPE * S * 8);
+    uint32_t *sout = wbase + S * IW * TILE_WORDS;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)NPIPE * (S * IW + O * OW) * TILE_WORDS * 4) + pipe * S;
+    uint32_t *extra = reinterpret_cast<uint32_t *>(smem_raw + (size_t)NPIPE * (S * IW + O * OW) * TILE_WORDS * 4 + (size_t)NPIPE * S * 8);
     if constexpr (Op::SMEM_EXTRA_WORDS > 0) {
         Op::init_smem(p, extra, threadIdx.x, WPC * 32);
         __syncthreads();
@@ -149,11 +169,11 @@ tma_lanes_kernel(typename Op::Params p, const __grid_constant__ CUtensorMap mx,
     auto issue_load = [&](size_t tile) {
         const int s = (int)(tile % S);
         const uint32_t bar = smem_u32(&bars[s]);
-        mbar_expect_tx(bar, TILE_BYTES);
+        mbar_expect_tx(bar, TILE_IN_BYTES);
         if (LM)
-            tma_load_2d(smem_u32(sin + s * TILE_WORDS), &mx, (int)(tile * TF), (int)box0, bar);
+            tma_load_2d(smem_u32(sin + s * TILE_WORDS * IW), &mx, (int)(tile * TF * IW), (int)box0, bar);
         else
-            tma_load_2d(smem_u32(sin + s * TILE_WORDS), &mx, (int)box0, (int)(tile * TF), bar);
+            tma_load_2d(smem_u32(sin + s * TILE_WORDS * IW), &mx, (int)(box0 * IW), (int)(tile * TF), bar);
     };
     if (leader) {
 #pragma unroll
@@ -174,76 +194,55 @@ tma_lanes_kernel(typename Op::Params p, const __grid_constant__ CUtensorMap mx,
         }
         sync_pipe();
         mbar_wait(smem_u32(&bars[s]), (uint32_t)((i / S) & 1));
-        const uint32_t *tin = sin + s * TILE_WORDS;
+        const uint32_t *tin = sin + s * TILE_WORDS * IW;
         uint32_t *tout = sout + ob * TILE_WORDS * OW;
         // frames beyond `frames` in the last tile are zero-filled by the TMA load and
         // clipped by the TMA store; they must not advance the filter state.
         const int nvalid = (int)((frames - i * TF) < (size_t)TF ? (frames - i * TF) : (size_t)TF);
         if constexpr (LM) {
-            // row l = my lane, 4 chunks of 16 B, physical chunk = c ^ ((l>>1)&3)
-            const int sw = (l >> 1) & 3;
-            const uint4 *rin = reinterpret_cast<const uint4 *>(tin + l * 16);
-            uint4 *rout = reinterpret_cast<uint4 *>(tout + l * 16);
-            if constexpr (OW == 2) {
-                uint4 *rout8 = reinterpret_cast<uint4 *>(tout + l * 32);
-                const int sw8 = l & 7;
+            // row l = my lane: 4 * W chunks of 16 B (W words per sample); 64-byte rows: physical chunk =
+            // c ^ ((l>>1)&3), 128-byte rows: c ^ (l & 7).  Four samples = IW input chunks -> OW output chunks.
+            const uint4 *rin = reinterpret_cast<const uint4 *>(tin + l * 16 * IW);
+            uint4 *rout = reinterpret_cast<uint4 *>(tout + l * 16 * OW);
+            const int swi = IW == 2 ? (l & 7) : ((l >> 1) & 3);
+            const int swo = OW == 2 ? (l & 7) : ((l >> 1) & 3);
+            auto group = [&](int g) {
+                uint32_t wi[4 * IW], wo[4 * OW];
 #pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    if (c * 4 < nvalid) {  // frames % 4 == 0: whole chunks are valid or not
-                        const uint4 v = rin[c ^ sw];
-                        const Out r0 = op.step(p, Bits32<In>::from(v.x));
-                        const Out r1 = op.step(p, Bits32<In>::from(v.y));
-                        const Out r2 = op.step(p, Bits32<In>::from(v.z));
-                        const Out r3 = op.step(p, Bits32<In>::from(v.w));
-                        rout8[(2 * c) ^ sw8] = make_uint4((uint32_t)r0.x, (uint32_t)r0.y, (uint32_t)r1.x, (uint32_t)r1.y);
-                        rout8[(2 * c + 1) ^ sw8] = make_uint4((uint32_t)r2.x, (uint32_t)r2.y, (uint32_t)r3.x, (uint32_t)r3.y);
-                    }
+                for (int j = 0; j < IW; j++) {
+                    const uint4 v = rin[(g * IW + j) ^ swi];
+                    wi[4 * j] = v.x; wi[4 * j + 1] = v.y; wi[4 * j + 2] = v.z; wi[4 * j + 3] = v.w;
                 }
-            } else if (nvalid == TF) {
 #pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    uint4 v = rin[c ^ sw];
-                    uint4 r;
-                    r.x = Bits32<Out>::to(op.step(p, Bits32<In>::from(v.x)));
-                    r.y = Bits32<Out>::to(op.step(p, Bits32<In>::from(v.y)));
-                    r.z = Bits32<Out>::to(op.step(p, Bits32<In>::from(v.z)));
-                    r.w = Bits32<Out>::to(op.step(p, Bits32<In>::from(v.w)));
-                    rout[c ^ sw] = r;
-                }
-            } else {  // frames % 4 == 0, so whole chunks are valid or not
-                for (int c = 0; c * 4 < nvalid; c++) {
-                    uint4 v = rin[c ^ sw];
-                    uint4 r;
-                    r.x = Bits32<Out>::to(op.step(p, Bits32<In>::from(v.x)));
-                    r.y = Bits32<Out>::to(op.step(p, Bits32<In>::from(v.y)));
-                    r.z = Bits32<Out>::to(op.step(p, Bits32<In>::from(v.z)));
-                    r.w = Bits32<Out>::to(op.step(p, Bits32<In>::from(v.w)));
-                    rout[c ^ sw] = r;
-                }
+                for (int q = 0; q < 4; q++) WordsOf<Out>::to(op.step(p, WordsOf<In>::from(wi + q * IW)), wo + q * OW);
+#pragma unroll
+                for (int j = 0; j < OW; j++)
+                    rout[(g * OW + j) ^ swo] = make_uint4(wo[4 * j], wo[4 * j + 1], wo[4 * j + 2], wo[4 * j + 3]);
+            };
+            if (nvalid == TF) {
+#pragma unroll
+                for (int g = 0; g < 4; g++) group(g);
+            } else {  // frames % 4 == 0, so whole groups are valid or not
+                for (int g = 0; g * 4 < nvalid; g++) group(g);
             }
         } else {
-            if constexpr (OW == 1) {
-                if (nvalid == TF) {
-#pragma unroll
-                    for (int f = 0; f < TF; f++)
-                        tout[f * BW + col] = Bits32<Out>::to(op.step(p, Bits32<In>::from(tin[f * BW + col])));
+            auto one = [&](int f) {
+                uint32_t wi[IW], wo[OW];
+                if constexpr (IW == 2) {
+                    const uint2 v = reinterpret_cast<const uint2 *>(tin)[f * BW + col];
+                    wi[0] = v.x; wi[1] = v.y;
                 } else {
-                    for (int f = 0; f < nvalid; f++)
-                        tout[f * BW + col] = Bits32<Out>::to(op.step(p, Bits32<In>::from(tin[f * BW + col])));
+                    wi[0] = tin[f * BW + col];
                 }
-            } else {  // Out = int2 (Complex<i32>): 8-byte store per sample, box row = 2*BW words
-                if (nvalid == TF) {
+                WordsOf<Out>::to(op.step(p, WordsOf<In>::from(wi)), wo);
+                if constexpr (OW == 2) reinterpret_cast<uint2 *>(tout)[f * BW + col] = make_uint2(wo[0], wo[1]);
+                else tout[f * BW + col] = wo[0];
+            };
+            if (nvalid == TF) {
 #pragma unroll
-                    for (int f = 0; f < TF; f++) {
-                        Out r = op.step(p, Bits32<In>::from(tin[f * BW + col]));
-                        reinterpret_cast<uint2 *>(tout)[f * BW + col] = make_uint2((uint32_t)r.x, (uint32_t)r.y);
-                    }
-                } else {
-                    for (int f = 0; f < nvalid; f++) {
-                        Out r = op.step(p, Bits32<In>::from(tin[f * BW + col]));
-                        reinterpret_cast<uint2 *>(tout)[f * BW + col] = make_uint2((uint32_t)r.x, (uint32_t)r.y);
-                    }
-                }
+                for (int f = 0; f < TF; f++) one(f);
+            } else {
+                for (int f = 0; f < nvalid; f++) one(f);
             }
         }
         fence_async_smem();
@@ -390,25 +389,28 @@ static int tma_launch_cfg(idsp_ctx *ctx, const typename Op::Params &p, const voi
     CUtensorMap mx, my;
     bool ok;
     constexpr int BW = WIDE ? 32 * WPC : 32;
+    constexpr int IW = sizeof(typename Op::In) / 4;
     constexpr int OW = sizeof(typename Op::Out) / 4;
-    static_assert(BW * OW <= 256, "TMA box dimension limit");
+    static_assert(BW * OW <= 256 && BW * IW <= 256, "TMA box dimension limit");
     if (LM) {
-        ok = make_map_2d(&mx, x, frames, lanes, TF, 32, CU_TENSOR_MAP_SWIZZLE_64B) &&
+        ok = make_map_2d(&mx, x, frames * IW, lanes, TF * IW, 32,
+                         IW == 2 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B) &&
              make_map_2d(&my, y, frames * OW, lanes, TF * OW, 32,
                          OW == 2 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
     } else {
-        ok = make_map_2d(&mx, x, lanes, frames, BW, TF, CU_TENSOR_MAP_SWIZZLE_NONE) &&
+        ok = make_map_2d(&mx, x, lanes * IW, frames, BW * IW, TF, CU_TENSOR_MAP_SWIZZLE_NONE) &&
              make_map_2d(&my, y, lanes * OW, frames, BW * OW, TF, CU_TENSOR_MAP_SWIZZLE_NONE);
     }
     if (!ok) return IDSP_TMA_NOT_APPLICABLE;
     constexpr int NPIPE = WIDE ? 1 : WPC;
-    constexpr size_t smem = (size_t)NPIPE * (S + O * OW) * TF * BW * 4 + (size_t)NPIPE * S * 8 +
+    constexpr size_t smem = (size_t)NPIPE * (S * IW + O * OW) * TF * BW * 4 + (size_t)NPIPE * S * 8 +
                             (size_t)Op::SMEM_EXTRA_WORDS * 4;
     auto kern = tma_lanes_kernel<Op, LM, TF, S, O, WPC, WIDE>;
     IDSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const size_t warps = (lanes + 31) / 32;
     unsigned grid = (unsigned)((warps + WPC - 1) / WPC);
     kern<<<grid, WPC * 32, smem, ctx->stream>>>(p, mx, my, frames, lanes, sstride);
+    IDSP_KERNEL_FAMILY(ctx, LM ? "tma lane-major" : (WIDE ? "tma frame-major wide" : "tma frame-major"));
     IDSP_LAUNCHED(ctx);
     return IDSP_OK;
 }
@@ -422,9 +424,10 @@ static int tma_cfg_occupancy() {
     static int occ = -1;
     if (occ < 0) {
         constexpr int BW = WIDE ? 32 * WPC : 32;
+        constexpr int IW = sizeof(typename Op::In) / 4;
         constexpr int OW = sizeof(typename Op::Out) / 4;
         constexpr int NPIPE = WIDE ? 1 : WPC;
-        constexpr size_t smem = (size_t)NPIPE * (S + O * OW) * TF * BW * 4 + (size_t)NPIPE * S * 8 +
+        constexpr size_t smem = (size_t)NPIPE * (S * IW + O * OW) * TF * BW * 4 + (size_t)NPIPE * S * 8 +
                                 (size_t)Op::SMEM_EXTRA_WORDS * 4;
         auto kern = tma_lanes_kernel<Op, LM, TF, S, O, WPC, WIDE>;
         int n = 0;
@@ -453,6 +456,7 @@ static int tma_launch_lm(idsp_ctx *ctx, const typename Op::Params &p, const void
     IDSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     unsigned grid = (unsigned)((lanes + 31) / 32);
     kern<<<grid, 32, smem, ctx->stream>>>(p, mx, my, frames, lanes, sstride);
+    IDSP_KERNEL_FAMILY(ctx, "tma lane-major long rows");
     IDSP_LAUNCHED(ctx);
     return IDSP_OK;
 }
@@ -501,8 +505,9 @@ template <class Op>
 static int tma_try_launch(idsp_ctx *ctx, const typename Op::Params &p, const typename Op::In *x,
                           typename Op::Out *y, size_t frames, size_t lanes, size_t sstride,
                           int layout) {
-    static_assert(sizeof(typename Op::In) == 4 && (sizeof(typename Op::Out) == 4 || sizeof(typename Op::Out) == 8), "");
-    constexpr bool OUT8 = sizeof(typename Op::Out) == 8;
+    static_assert((sizeof(typename Op::In) == 4 || sizeof(typename Op::In) == 8) &&
+                  (sizeof(typename Op::Out) == 4 || sizeof(typename Op::Out) == 8), "");
+    constexpr bool OUT8 = sizeof(typename Op::Out) == 8 || sizeof(typename Op::In) == 8;  // any 8-byte side
     if (ctx->policy == 1) return IDSP_TMA_NOT_APPLICABLE;
     const bool lm = layout == IDSP_LANE_MAJOR;
     bool ok = (((uintptr_t)x | (uintptr_t)y) & 15) == 0 && frames >= 16 &&
@@ -604,7 +609,8 @@ static int tma_try_launch(idsp_ctx *ctx, const typename Op::Params &p, const typ
 template <class Op>
 static int launch_lanes_best(idsp_ctx *ctx, const typename Op::Params &p, const typename Op::In *x,
                              typename Op::Out *y, size_t frames, size_t lanes, size_t sstride, int layout) {
-    if constexpr (sizeof(typename Op::In) == 4 && (sizeof(typename Op::Out) == 4 || sizeof(typename Op::Out) == 8)) {
+    if constexpr ((sizeof(typename Op::In) == 4 || sizeof(typename Op::In) == 8) &&
+                  (sizeof(typename Op::Out) == 4 || sizeof(typename Op::Out) == 8)) {
         int tr = tma_try_launch<Op>(ctx, p, x, y, frames, lanes, sstride, layout);
         if (tr != IDSP_TMA_NOT_APPLICABLE) return tr;
     }

@@ -117,6 +117,7 @@ extern "C" int idsp_cossin_i32(idsp_ctx *ctx, const int32_t *phase, int32_t *cs,
     if (n == 0) return IDSP_OK;
     IDSP_CHECK_ARG(phase && cs, "phase/cs must not be null");
     cossin_kernel<<<map_grid(ctx, (n + 1) / 2), 256, 0, ctx->stream>>>(phase, cs, n);
+    IDSP_KERNEL_FAMILY(ctx, "map cossin");
     IDSP_LAUNCHED(ctx);
     return IDSP_OK;
 }
@@ -126,6 +127,7 @@ extern "C" int idsp_atan2_i32(idsp_ctx *ctx, const int32_t *xy, int32_t *p, size
     if (n == 0) return IDSP_OK;
     IDSP_CHECK_ARG(xy && p, "xy/p must not be null");
     atan2_kernel<<<map_grid(ctx, (n + 1) / 2), 256, 0, ctx->stream>>>(xy, p, n);
+    IDSP_KERNEL_FAMILY(ctx, "map atan2");
     IDSP_LAUNCHED(ctx);
     return IDSP_OK;
 }
@@ -263,6 +265,55 @@ extern "C" int idsp_lockin_i32_host(idsp_ctx *ctx, int order, const int32_t *k,
         });
 }
 
+// (sample, phase) tuples: src/lockin.rs:30-39
+extern "C" int idsp_lockin_phase_i32(idsp_ctx *ctx, int order, const int32_t *k, int64_t *lp_state,
+                                     const int32_t *xp, int32_t *iq, size_t frames, size_t lanes, int layout) {
+    LL_CHECK();
+    IDSP_CHECK_ARG(lp_state && xp && iq, "null pointer argument");
+    IDSP_CHECK_ARG(((((uintptr_t)xp) | ((uintptr_t)iq)) & 7) == 0, "xp and iq must be 8-byte aligned");
+    const uint32_t *lut;
+    IDSP_CUDA(cudaGetSymbolAddress((void **)&lut, g_cossin_lut));
+#define GO(ORDER)                                                                    \
+    do {                                                                             \
+        LockinPhaseOp<ORDER, true>::Params pt;                                       \
+        pt.k[0] = k[0];                                                              \
+        pt.k[1] = ORDER == 2 ? k[1] : 0;                                             \
+        pt.st = lp_state;                                                            \
+        pt.lut = lut;                                                                \
+        int tr = tma_try_launch<LockinPhaseOp<ORDER, true>>(ctx, pt, (const int2 *)xp, (int2 *)iq, frames, lanes, lanes, layout); \
+        if (tr != IDSP_TMA_NOT_APPLICABLE) return tr;                                \
+        LockinPhaseOp<ORDER, false>::Params pg;                                      \
+        pg.k[0] = pt.k[0];                                                           \
+        pg.k[1] = pt.k[1];                                                           \
+        pg.st = lp_state;                                                            \
+        pg.lut = lut;                                                                \
+        return launch_lanes<LockinPhaseOp<ORDER, false>>(ctx, pg, (const int2 *)xp, (int2 *)iq, frames, lanes, lanes, layout); \
+    } while (0)
+    if (order == 1) GO(1);
+    GO(2);
+#undef GO
+}
+
+// (sample, LO) tuples: src/lockin.rs:17-28
+extern "C" int idsp_lockin_lo_i32(idsp_ctx *ctx, int order, const int32_t *k, int64_t *lp_state,
+                                  const int32_t *xlo, int32_t *iq, size_t frames, size_t lanes, int layout) {
+    LL_CHECK();
+    IDSP_CHECK_ARG(lp_state && xlo && iq, "null pointer argument");
+    IDSP_CHECK_ARG((((uintptr_t)iq) & 7) == 0, "iq must be 8-byte aligned");
+    if (order == 1) {
+        LockinLoOp<1>::Params p;
+        p.k[0] = k[0];
+        p.k[1] = 0;
+        p.st = lp_state;
+        return launch_lanes<LockinLoOp<1>>(ctx, p, (const XLo *)xlo, (int2 *)iq, frames, lanes, lanes, layout);
+    }
+    LockinLoOp<2>::Params p;
+    p.k[0] = k[0];
+    p.k[1] = k[1];
+    p.st = lp_state;
+    return launch_lanes<LockinLoOp<2>>(ctx, p, (const XLo *)xlo, (int2 *)iq, frames, lanes, lanes, layout);
+}
+
 // ---------------------------------------------------------------- PLL
 extern "C" int idsp_pll_i32(idsp_ctx *ctx, const int32_t *ba, int32_t *state, const int32_t *x, int32_t *y,
                             size_t frames, size_t lanes, int layout) {
@@ -299,12 +350,12 @@ extern "C" int idsp_fm_disc_i32(idsp_ctx *ctx, int32_t carrier, const int32_t *b
         for (int i = 0; i < 5; i++) p.ba[i] = ba[i];
         p.F = F;
         p.st = state;
-        return launch_lanes<FmDiscOp<1>>(ctx, p, (const int2 *)x, y, frames, lanes, lanes, layout);
+        return launch_lanes_best<FmDiscOp<1>>(ctx, p, (const int2 *)x, y, frames, lanes, lanes, layout);
     }
     FmDiscOp<0>::Params p;
     p.carrier = carrier;
     for (int i = 0; i < 5; i++) p.ba[i] = ba[i];
     p.F = F;
     p.st = state;
-    return launch_lanes<FmDiscOp<0>>(ctx, p, (const int2 *)x, y, frames, lanes, lanes, layout);
+    return launch_lanes_best<FmDiscOp<0>>(ctx, p, (const int2 *)x, y, frames, lanes, lanes, layout);
 }

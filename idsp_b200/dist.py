@@ -113,6 +113,69 @@ def gather_lanes(part: torch.Tensor, frames: int, lanes: int, layout: int, width
     return full
 
 
+class Comm:
+    """The C ABI's communicator (``idsp_b200_comm_*``, raw NCCL over NVLink / NVSwitch on the ctx stream):
+    what a non-Python caller uses to shard lanes.  Here the 128-byte id travels through
+    ``torch.distributed`` (any out-of-band channel works); the data plane itself does not touch torch.
+
+    ``scatter_lanes(full, frames, lanes, layout, width)`` -> this rank's lane block (root passes the full
+    buffer, the others ``None``); ``gather_lanes(part, full, ...)`` is the inverse.  Lane-major blocks are
+    sent / received in place, frame-major blocks are packed with one strided device copy per peer."""
+
+    def __init__(self, device: int, group=None):
+        self.device = int(device)
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self._ctx = default_context(self.device)
+        self._L = _lib.lib()
+        ident = [None]
+        if self.rank == 0 and self.world > 1:
+            buf = (C.c_ubyte * 128)()
+            _lib.check(self._L.idsp_b200_comm_unique_id(buf))
+            ident = [bytes(buf)]
+        if self.world > 1:
+            dist.broadcast_object_list(ident, src=0, group=group)
+        h = C.c_void_p()
+        idbuf = (C.c_ubyte * 128).from_buffer_copy(ident[0]) if ident[0] is not None else None
+        _lib.check(self._L.idsp_b200_comm_init(self._ctx._h, self.world, self.rank, idbuf, C.byref(h)))
+        self._h = h
+
+    def lane_block(self, lanes: int) -> Tuple[int, int]:
+        lo, hi = C.c_size_t(), C.c_size_t()
+        _lib.check(self._L.idsp_b200_lane_block(lanes, self.world, self.rank, 32, C.byref(lo), C.byref(hi)))
+        return int(lo.value), int(hi.value)
+
+    def scatter_lanes(self, full: Optional[torch.Tensor], frames: int, lanes: int, layout: int, width: int = 1,
+                      root: int = 0, dtype=torch.int32, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        lo, hi = self.lane_block(lanes)
+        if full is not None:
+            dtype = full.dtype
+        if out is None:
+            out = torch.empty(frames * (hi - lo) * width, dtype=dtype, device=f"cuda:{self.device}")
+        eb = out.element_size() * width
+        _lib.check(self._L.idsp_scatter_lanes(self._h, None if full is None else C.c_void_p(full.data_ptr()),
+                                              C.c_void_p(out.data_ptr()), frames, lanes, eb, layout, root))
+        return out
+
+    def gather_lanes(self, part: torch.Tensor, full: Optional[torch.Tensor], frames: int, lanes: int, layout: int,
+                     width: int = 1, root: int = 0) -> Optional[torch.Tensor]:
+        if self.rank == root and full is None:
+            full = torch.empty(frames * lanes * width, dtype=part.dtype, device=part.device)
+        eb = part.element_size() * width
+        _lib.check(self._L.idsp_gather_lanes(self._h, C.c_void_p(part.data_ptr()),
+                                             None if full is None else C.c_void_p(full.data_ptr()),
+                                             frames, lanes, eb, layout, root))
+        return full
+
+    def broadcast(self, buf: torch.Tensor, root: int = 0) -> torch.Tensor:
+        _lib.check(self._L.idsp_broadcast(self._h, C.c_void_p(buf.data_ptr()), buf.numel() * buf.element_size(), root))
+        return buf
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.idsp_b200_comm_free(self._h)
+            self._h = None
+
+
 class PeerBuffer:
     """A device buffer owned by rank `owner` and mapped into every process of the group.
 
@@ -163,6 +226,7 @@ class PeerBuffer:
         """collective: importers unmap first, then the owner frees"""
         if self.ptr is None:
             return
+        torch.cuda.synchronize(self.device)  # kernels that still write into the mapping must have finished
         if self.rank != self.owner:
             _lib.check(self._L.idsp_b200_ipc_close(self._ctx._h, C.c_void_p(self.ptr)))
         dist.barrier(group=self.group)

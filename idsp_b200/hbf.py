@@ -28,6 +28,16 @@ def hbf_taps():
     return tuple(_taps(i) for i in range(5))
 
 
+def hbf_taps_98():
+    """``HBF_TAPS_98``: the 98 dB tap set, index 0 = lowest rate (hbf.rs:258-292)."""
+    out = []
+    for i in range(5):
+        m = C.c_int(0)
+        p = _lib.lib().idsp_hbf_taps_98(i, C.byref(m))
+        out.append(np.ctypeslib.as_array(p, shape=(m.value,)).copy())
+    return tuple(out)
+
+
 HBF_PASSBAND = 0.4  # hbf.rs:352
 HBF_CASCADE_BLOCK = 1 << 5  # hbf.rs:357 (CPU heuristic; the GPU tiles differently)
 
@@ -108,11 +118,20 @@ class _Fir(_Proc):
         return 1, 1
 
     def _block(self, ctx, state, x, y, layout):
+        # the kernels size the delay lines from the taps (3M-2 / 2M-1 / 2M-1+odd words): a state built for
+        # another M would be read and written past its end on the device
+        if isinstance(state, (HbfDec, HbfInt)):
+            if state.M != self.M:
+                raise TypeError(f"state was built for M = {state.M} taps, the filter has M = {self.M}")
+            if not (self.SYM and not self.ODD):
+                raise TypeError("HbfDec / HbfInt states belong to EvenSymmetric (hbf.rs:155-236)")
         if isinstance(state, HbfDec):
             ctx.hbf_dec(self.taps, state.words, x, y, lanes=state.lanes, layout=layout)
         elif isinstance(state, HbfInt):
             ctx.hbf_int(self.taps, state.words, x, y, lanes=state.lanes, layout=layout)
         else:
+            if state.words.shape[0] != self.len():
+                raise TypeError(f"FIR state has {state.words.shape[0]} words, the filter needs LEN = {self.len()}")
             ctx.fir(self.taps, self.ODD, self.SYM, state.words, x, y, lanes=state.lanes, layout=layout)
 
     def block(self, state, x, y, layout=0):
@@ -121,6 +140,8 @@ class _Fir(_Proc):
         wi, wo = (2, 1) if isinstance(state, HbfDec) else (1, 2) if isinstance(state, HbfInt) else (1, 1)
         if _numel(x) * wo != _numel(y) * wi:
             raise ValueError("block: x and y lengths do not match")
+        if _numel(x) % (state.lanes * wi):
+            raise ValueError("block: length is not a whole number of frames")
         self._block(self._ctx(state), state, x, y, layout)
 
 
@@ -167,36 +188,65 @@ HbfDec2, HbfDec4, HbfDec8, HbfDec16, HbfDec32 = (_dec_state(k) for k in range(1,
 HbfInt2, HbfInt4, HbfInt8, HbfInt16, HbfInt32 = (_int_state(k) for k in range(1, 6))
 
 
+def _cascade_words(decimate: bool, taps) -> int:
+    return sum((3 * len(t) - 2) if decimate else (2 * len(t) - 1) for t in taps)
+
+
 class HbfDecCascade(_Proc):
     """``HBF_DEC_CASCADE`` truncated to depth k (``.inner().1`` ... in the reference,
-    hbf.rs:385-421): X = [f32; 2^k] -> Y = f32, stages TAPS[k-1] -> TAPS[0]."""
+    hbf.rs:385-421): X = [f32; 2^k] -> Y = f32, stages TAPS[k-1] -> TAPS[0].
+    ``taps``: another tuple of half-band tap sets in the reference's order (index 0 = lowest rate),
+    e.g. ``hbf_taps_98()[:k]``; the default is ``HBF_TAPS``."""
 
-    def __init__(self, log2_rate: int):
+    def __init__(self, log2_rate: int, taps=None):
         if not 1 <= log2_rate <= 5:
             raise ValueError("log2_rate must be 1..5")
         self.k = log2_rate
+        self.taps = None if taps is None else [np.asarray(t, np.float32).reshape(-1) for t in taps]
+        if self.taps is not None and len(self.taps) != self.k:
+            raise ValueError("one tap set per stage")
 
     def widths(self):
         return 1 << self.k, 1
 
+    def state(self, lanes: int = 1, device=None):
+        """default (zero) state for this cascade"""
+        if self.taps is None:
+            return _dec_state(self.k)(lanes, device)
+        return HbfCascadeState(LaneState._alloc(_cascade_words(True, self.taps), lanes, np.float32, device), self.k)
+
     def _block(self, ctx, state, x, y, layout):
         if state.log2_rate != self.k:
             raise TypeError("state depth does not match cascade depth")
-        ctx.hbf_dec_cascade(self.k, state.words, x, y, lanes=state.lanes, layout=layout)
+        if self.taps is None:
+            ctx.hbf_dec_cascade(self.k, state.words, x, y, lanes=state.lanes, layout=layout)
+        else:
+            ctx.hbf_cascade_taps(True, self.taps, state.words, x, y, lanes=state.lanes, layout=layout)
 
 
 class HbfIntCascade(_Proc):
     """``HBF_INT_CASCADE`` truncated to depth k (hbf.rs:476-512): X = f32 -> Y = [f32; 2^k]."""
 
-    def __init__(self, log2_rate: int):
+    def __init__(self, log2_rate: int, taps=None):
         if not 1 <= log2_rate <= 5:
             raise ValueError("log2_rate must be 1..5")
         self.k = log2_rate
+        self.taps = None if taps is None else [np.asarray(t, np.float32).reshape(-1) for t in taps]
+        if self.taps is not None and len(self.taps) != self.k:
+            raise ValueError("one tap set per stage")
 
     def widths(self):
         return 1, 1 << self.k
 
+    def state(self, lanes: int = 1, device=None):
+        if self.taps is None:
+            return _int_state(self.k)(lanes, device)
+        return HbfCascadeState(LaneState._alloc(_cascade_words(False, self.taps), lanes, np.float32, device), self.k)
+
     def _block(self, ctx, state, x, y, layout):
         if state.log2_rate != self.k:
             raise TypeError("state depth does not match cascade depth")
-        ctx.hbf_int_cascade(self.k, state.words, x, y, lanes=state.lanes, layout=layout)
+        if self.taps is None:
+            ctx.hbf_int_cascade(self.k, state.words, x, y, lanes=state.lanes, layout=layout)
+        else:
+            ctx.hbf_cascade_taps(False, self.taps, state.words, x, y, lanes=state.lanes, layout=layout)

@@ -77,10 +77,27 @@ class Biquad(_Proc):
 
     # ---- constructors (biquad.rs:545-576)
     @classmethod
-    def from_ba6(cls, ba, fmt) -> "Biquad":
-        """``From<[[f;3];2]>``: literature-sign ``[[b0,b1,b2],[a0,a1,a2]]``."""
+    def from_ba6(cls, ba, fmt, src: str = "f64") -> "Biquad":
+        """``From<[[f;3];2]>``: literature-sign ``[[b0,b1,b2],[a0,a1,a2]]``.  ``src`` selects the
+        reference impl: ``impl_from_float!(f64)`` (default) or ``impl_from_float!(f32)``
+        (biquad.rs:545-566), which normalises and quantises in f32 -- e.g. ``Filter<f32>`` ->
+        ``Biquad<Q32<30>>`` in examples/fm_disc.rs; it runs through the C ABI builder
+        (``idsp_biquad_from_ba6_f32``)."""
         b, a = ba
         kind = _fmt_kind(fmt)
+        if src == "f32":
+            import ctypes as C
+
+            from . import _lib
+
+            flat = (C.c_float * 6)(*[float(np.float32(v)) for v in (*b, *a)])
+            dt = _INT_INFO[kind][0] if kind in _INT_INFO else _FLT[kind]
+            out = np.zeros(5, dt)
+            _lib.check(_lib.lib().idsp_biquad_from_ba6_f32(flat, _lib.KIND_CODE[kind], fmt.F if isinstance(fmt, Q) else 0,
+                                                           out.ctypes.data_as(C.c_void_p)))
+            return cls(out, fmt)
+        if src != "f64":
+            raise ValueError("src must be 'f64' or 'f32'")
         if kind == "f32":  # the f32 impl does the normalisation in f32 (impl_from_float!(f32))
             f = np.float32
             a0 = f(1.0) / f(a[0])
@@ -144,9 +161,8 @@ class BiquadClamp(Biquad):
         if kind in _INT_INFO:
             info = np.iinfo(_INT_INFO[kind][0])
             lo, hi = info.min, info.max
-        else:  # Clamp::MIN/MAX for floats (src/num.rs:5-31)
-            info = np.finfo(_FLT[kind])
-            lo, hi = info.min, info.max
+        else:  # Clamp::MIN/MAX for floats are NEG_INFINITY / INFINITY (src/num.rs:5-31)
+            lo, hi = -np.inf, np.inf
         self.u = 0 if u is None else u
         self.min = lo if min is None else min
         self.max = hi if max is None else max

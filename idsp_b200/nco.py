@@ -121,6 +121,18 @@ class Lockin:
         ctx = default_context(_dev_of(x))
         ctx.lockin(self.lowpass.k, accu.state, accu.step, state.words, x, iq, lanes=state.lanes, layout=layout)
 
+    def block_phase(self, state: LockinState, xp, iq, layout: int = FRAME_MAJOR):
+        """``SplitProcess<(i32, Wrapping<i32>), Complex<i32>, [S; 2]>`` (src/lockin.rs:30-39): ``xp`` holds
+        (sample, phase) pairs, the phase supplied by the caller (e.g. the PLL output, src/pll.rs:89-108)."""
+        ctx = default_context(_dev_of(xp))
+        ctx.lockin_phase(self.lowpass.k, state.words, xp, iq, lanes=state.lanes, layout=layout)
+
+    def block_lo(self, state: LockinState, xlo, iq, layout: int = FRAME_MAJOR):
+        """``SplitProcess<(X, Complex<U>), Complex<X>, [S; 2]>`` (src/lockin.rs:17-28) with X = i32,
+        U = Q32<32>: ``xlo`` holds (sample, lo.re, lo.im) triples."""
+        ctx = default_context(_dev_of(xlo))
+        ctx.lockin_lo(self.lowpass.k, state.words, xlo, iq, lanes=state.lanes, layout=layout)
+
 
 class PLLState(LaneState):
     """``PLLState`` (src/pll.rs:60-86) per lane as i32 words

@@ -55,7 +55,8 @@ typedef enum {
     IDSP_EINVAL = -1,   /* bad argument (null pointer, F out of range, size mismatch) */
     IDSP_ECUDA = -2,    /* CUDA runtime/driver error, see idsp_b200_last_error() */
     IDSP_ENOMEM = -3,   /* allocation failed */
-    IDSP_ENODEV = -4    /* no usable sm_100 device */
+    IDSP_ENODEV = -4,   /* no usable sm_100 device */
+    IDSP_ENCCL = -5     /* NCCL could not be loaded or returned an error (multi-GPU edges only) */
 } idsp_status_t;
 
 typedef enum { IDSP_FRAME_MAJOR = 0, IDSP_LANE_MAJOR = 1 } idsp_layout_t;
@@ -72,6 +73,10 @@ const char *idsp_b200_last_error(void);
 int idsp_b200_version(void);
 /* Number of kernels this ctx has launched so far (bench `gpu_launches`). */
 uint64_t idsp_b200_launch_count(const idsp_ctx *ctx);
+/* Kernel family of the most recent launch of this ctx, e.g. "tma frame-major wide", "tma lane-major",
+ * "generic frame-major", "hbf tiled lane-major", "hbf generic": the fast paths need aligned pointers and
+ * whole tiles and fall back silently otherwise, this makes the fallback observable.  Static string. */
+const char *idsp_b200_last_kernel(const idsp_ctx *ctx);
 /* Page-locked host memory for the `_host` entry points: buffers obtained here (or pinned by
  * the caller with cudaHostRegister / torch pin_memory) are DMA'd directly; pageable memory
  * works too but is staged by the driver. */
@@ -173,6 +178,22 @@ int idsp_hbf_dec_cascade_f32_host(idsp_ctx *ctx, int log2_rate, float *state, co
  * state = stage states concatenated, lowest-rate stage first. */
 int idsp_hbf_int_cascade_f32(idsp_ctx *ctx, int log2_rate, float *state, const float *x,
                              float *y, size_t n_in, size_t lanes, int layout);
+/* The same cascades over CALLER-SUPPLIED half-band tap sets (e.g. HBF_TAPS_98, src/hbf.rs:258-292, or a
+ * remez design of the caller): `taps[i]` / `M[i]` = stage i in the order of the reference's tap tuples
+ * (index 0 = lowest rate), nstages = log2 of the rate change, 1 <= nstages <= 5, 1 <= M[i] <= IDSP_HBF_MAX_M.
+ * Decimator: stages nstages-1 -> 0 (src/hbf.rs:385-421); interpolator: stages 0 -> nstages-1 (:476-512).
+ * state = stage states concatenated in processing order, as for the built-in cascades:
+ * idsp_hbf_cascade_state_words(decimate, nstages, M) words per lane.  The built-in HBF_TAPS set (compared by
+ * value) takes the tiled kernels; any other set runs stage by stage through ctx scratch memory. */
+size_t idsp_hbf_cascade_state_words(int decimate, int nstages, const int *M);
+int idsp_hbf_dec_cascade_taps_f32(idsp_ctx *ctx, int nstages, const float *const *taps, const int *M,
+                                  float *state, const float *x, float *y, size_t n_out, size_t lanes,
+                                  int layout);
+int idsp_hbf_int_cascade_taps_f32(idsp_ctx *ctx, int nstages, const float *const *taps, const int *M,
+                                  float *state, const float *x, float *y, size_t n_in, size_t lanes,
+                                  int layout);
+/* HBF_TAPS_98 (src/hbf.rs:258-292), index 0 = lowest rate; M = 15, 6, 3, 3, 2. */
+const float *idsp_hbf_taps_98(int index, int *M);
 /* Single-rate linear-phase FIRs `type_fir!` src/hbf.rs:70-138:
  * odd/sym = (1,1) OddSymmetric, (0,1) EvenSymmetric, (1,0) OddAntiSymmetric,
  * (0,0) EvenAntiSymmetric.  state words: [history (2M-1+odd)]. */
@@ -205,6 +226,17 @@ int idsp_lockin_i32(idsp_ctx *ctx, int order, const int32_t *k, int32_t *accu_st
 int idsp_lockin_i32_host(idsp_ctx *ctx, int order, const int32_t *k, int32_t *accu_state,
                          const int32_t *accu_step, int64_t *lp_state, const int32_t *x,
                          int32_t *iq, size_t frames, size_t lanes, int layout);
+/* `Lockin<Lowpass<N>>` on (sample, phase) tuples, `SplitProcess<(i32, Wrapping<i32>), Complex<i32>, [S; 2]>`
+ * src/lockin.rs:30-39: the phase comes from the caller (e.g. the PLL output, src/pll.rs:89-108) instead
+ * of a per-lane `Accu`.  xp = frames * lanes (x, phase) i32 pairs in the layout of x (pair innermost),
+ * 8-byte aligned; lp_state as above. */
+int idsp_lockin_phase_i32(idsp_ctx *ctx, int order, const int32_t *k, int64_t *lp_state, const int32_t *xp,
+                          int32_t *iq, size_t frames, size_t lanes, int layout);
+/* `Lockin<Lowpass<N>>` on (sample, LO) tuples, `SplitProcess<(X, Complex<U>), Complex<X>, [S; 2]>`
+ * src/lockin.rs:17-28 with X = i32, U = Q32<32> (`i32 * Q32<32>` = (x * lo) >> 32,
+ * dsp-fixedpoint/src/lib.rs:449-456): xlo = frames * lanes (x, lo.re, lo.im) i32 triples. */
+int idsp_lockin_lo_i32(idsp_ctx *ctx, int order, const int32_t *k, int64_t *lp_state, const int32_t *xlo,
+                       int32_t *iq, size_t frames, size_t lanes, int layout);
 
 /* ------------------------------------------------------------------ fused chain
  * HbfDec(/2^k) -> HbfInt(x2^k) -> Biquad<f32> DF1 in one pass (BASELINE config 5;
@@ -214,6 +246,9 @@ int idsp_lockin_i32_host(idsp_ctx *ctx, int order, const int32_t *k, int32_t *ac
 size_t idsp_chain_state_words(int log2_rate);
 int idsp_chain_f32(idsp_ctx *ctx, int log2_rate, const float ba[5], float *state,
                    const float *x, float *y, size_t n_low, size_t lanes, int layout);
+/* host buffers: one PCIe round trip carries the three operators */
+int idsp_chain_f32_host(idsp_ctx *ctx, int log2_rate, const float ba[5], float *state,
+                        const float *x, float *y, size_t n_low, size_t lanes, int layout);
 
 /* ------------------------------------------------------------------ cic::Cic
  * `Cic<T, N, M>` src/cic.rs:13-200 (order N = 1..6, comb delay M = 1..3, rate = fast/slow - 1) under
@@ -252,6 +287,87 @@ int idsp_pll_i32(idsp_ctx *ctx, const int32_t *ba, int32_t *state, const int32_t
  * all zero = `Split::new(FmDiscriminator{..}, None)` * `DirectForm1::default()`. */
 int idsp_fm_disc_i32(idsp_ctx *ctx, int32_t carrier, const int32_t *ba, int F, int32_t *state,
                      const int32_t *x, int32_t *y, size_t frames, size_t lanes, int layout);
+
+/* ------------------------------------------------------------------ multi-GPU edges
+ * One process per GPU.  Lanes shard as contiguous blocks (rank r owns idsp_b200_lane_block(...)) with no
+ * collective inside the computation (dsp-process/src/compose.rs:472-475: lanes never interact); the two
+ * edges -- handing lane blocks of a root-resident buffer to the ranks, collecting the results -- are grouped
+ * NCCL point-to-point transfers over NVLink / NVSwitch on the ctx stream (asynchronous like every other
+ * call).  They sit under `Split<Lanes<C>, [S; N]>` (dsp-process/src/split.rs:272-277): scatter x, run any
+ * entry point above on the local block, gather y.  NCCL is loaded at run time (libnccl.so.2); a single
+ * rank communicator (nranks == 1) never touches it.  The fused alternative to the gather is the peer
+ * memory above (kernels store their results straight into the root's buffer).
+ *  - idsp_b200_comm_unique_id: rank 0 creates the 128-byte id and hands it to the other processes by any
+ *    out-of-band means (file, socket, MPI, torch.distributed object broadcast);
+ *  - `elem_bytes` = bytes per frame and lane (4 for i32 / f32 samples, 8 for Complex<i32>, 64 for [f32; 16]);
+ *  - `full` is only read / written on `root` (may be NULL elsewhere), `part` holds this rank's block in the
+ *    same layout with its own lane count (hi - lo). */
+#define IDSP_COMM_ID_BYTES 128
+typedef struct idsp_comm idsp_comm;
+int idsp_b200_comm_unique_id(unsigned char id[IDSP_COMM_ID_BYTES]);
+int idsp_b200_comm_init(idsp_ctx *ctx, int nranks, int rank, const unsigned char id[IDSP_COMM_ID_BYTES],
+                        idsp_comm **out);
+int idsp_b200_comm_free(idsp_comm *comm);
+int idsp_b200_comm_rank(const idsp_comm *comm);
+int idsp_b200_comm_size(const idsp_comm *comm);
+int idsp_b200_nccl_version(void); /* 0 if NCCL cannot be loaded */
+/* lanes [lo, hi) of `rank`: whole units of `align` lanes (0 = 32, a warp), covering [0, lanes) exactly */
+int idsp_b200_lane_block(size_t lanes, int nranks, int rank, size_t align, size_t *lo, size_t *hi);
+int idsp_scatter_lanes(idsp_comm *comm, const void *full, void *part, size_t frames, size_t lanes,
+                       size_t elem_bytes, int layout, int root);
+int idsp_gather_lanes(idsp_comm *comm, const void *part, void *full, size_t frames, size_t lanes,
+                      size_t elem_bytes, int layout, int root);
+/* replicated small data (coefficients): root's bytes to every rank, in place, device memory */
+int idsp_broadcast(idsp_comm *comm, void *buf, size_t bytes, int root);
+
+/* ------------------------------------------------------------------ coefficient builders
+ * Host-side, no device work: the reference's `iir::coefficients::Filter` (src/iir/coefficients.rs:111-527),
+ * `Biquad::from([[T; 3]; 2])` / `from([T; 5])` / `from_zpk` (src/iir/biquad.rs:545-619) and
+ * `pid::Builder::build` (src/iir/pid.rs:236-317), each in the reference's two float widths (the f32 impl
+ * rounds every intermediate to f32, like `Filter<f32>` -> `Biquad<Q32<30>>` in examples/fm_disc.rs).
+ * Quantisation to Q<T, A, F>: (v * 2^F).round() (half away from zero) then Rust `as` (saturating, NaN -> 0),
+ * dsp-fixedpoint/src/num_traits_impl.rs:32-45.  Validation errors (IDSP_EINVAL) carry the reference's
+ * `iir::Error` variant and field in idsp_b200_last_error(), e.g. "OutOfRange(frequency)". */
+typedef enum { IDSP_I8 = 0, IDSP_I16 = 1, IDSP_I32 = 2, IDSP_I64 = 3, IDSP_F32 = 4, IDSP_F64 = 5 } idsp_kind_t;
+typedef enum { /* coefficients::Type, src/iir/coefficients.rs:44-66 */
+    IDSP_LOWPASS = 0, IDSP_HIGHPASS = 1, IDSP_BANDPASS = 2, IDSP_ALLPASS = 3, IDSP_NOTCH = 4,
+    IDSP_PEAKING = 5, IDSP_LOWSHELF = 6, IDSP_HIGHSHELF = 7, IDSP_IHO = 8
+} idsp_filter_type_t;
+typedef enum { IDSP_SHAPE_Q = 0, IDSP_SHAPE_BANDWIDTH = 1, IDSP_SHAPE_SLOPE = 2 } idsp_shape_t;
+/* `Filter<T>` (coefficients.rs:28-41); Default = {0, 1, 1, Q(1/sqrt 2)} */
+typedef struct { double frequency, gain, shelf; int shape_kind; double shape; } idsp_filter_f64;
+typedef struct { float frequency, gain, shelf; int shape_kind; float shape; } idsp_filter_f32;
+void idsp_filter_default_f64(idsp_filter_f64 *f);
+void idsp_filter_default_f32(idsp_filter_f32 *f);
+int idsp_filter_validate_f64(const idsp_filter_f64 *f); /* coefficients.rs:241-265 */
+int idsp_filter_validate_f32(const idsp_filter_f32 *f);
+/* `Filter::build(typ)` (coefficients.rs:466-479): ba6 = [b0, b1, b2, a0, a1, a2], literature sign of a1 / a2 */
+int idsp_filter_build_f64(const idsp_filter_f64 *f, int type, double ba6[6]);
+int idsp_filter_build_f32(const idsp_filter_f32 *f, int type, float ba6[6]);
+/* `Biquad<C>::from([[T; 3]; 2])` (biquad.rs:545-566): normalise by a0, flip the sign of a1 / a2, convert to
+ * the coefficient type `kind` (Q format with F fractional bits, or f32 / f64): out = 5 values of that type. */
+int idsp_biquad_from_ba6_f64(const double ba6[6], int kind, int F, void *ba5_out);
+int idsp_biquad_from_ba6_f32(const float ba6[6], int kind, int F, void *ba5_out);
+/* `Biquad<C>::from([T; 5])` (biquad.rs:568-576): conversion only */
+int idsp_biquad_from_ba5_f64(const double ba5[5], int kind, int F, void *ba5_out);
+int idsp_biquad_from_ba5_f32(const float ba5[5], int kind, int F, void *ba5_out);
+/* `Biquad::from_zpk` (biquad.rs:594-619): pairs are (x, y); complex != 0 means the conjugate pair x +- jy */
+int idsp_biquad_from_zpk_f64(const double zeros[2], int zeros_complex, const double poles[2], int poles_complex,
+                             double gain, int kind, int F, void *ba5_out);
+/* `Filter::build_biquad` / `try_build_biquad` (coefficients.rs:481-497) in one call */
+int idsp_filter_build_biquad_f64(const idsp_filter_f64 *f, int type, int kind, int F, void *ba5_out);
+int idsp_filter_build_biquad_f32(const idsp_filter_f32 *f, int type, int kind, int F, void *ba5_out);
+/* `pid::Builder<T>` (src/iir/pid.rs:38-47): order = pid::Order (P = 2, I = 1, I2 = 0), gain / limit indexed
+ * by pid::Action (I2, I, P, D, D2); Default = {I, 0.., +inf..}.  build(period): pid.rs:236-303, the GAINS are
+ * converted to the coefficient type and accumulated there (wrapping for Q formats). */
+typedef struct { int order; double gain[5], limit[5]; } idsp_pid_f64;
+typedef struct { int order; float gain[5], limit[5]; } idsp_pid_f32;
+void idsp_pid_default_f64(idsp_pid_f64 *b);
+void idsp_pid_default_f32(idsp_pid_f32 *b);
+int idsp_pid_validate_f64(const idsp_pid_f64 *b, double period); /* pid.rs:193-222 */
+int idsp_pid_validate_f32(const idsp_pid_f32 *b, float period);
+int idsp_pid_build_f64(const idsp_pid_f64 *b, double period, int kind, int F, void *ba5_out);
+int idsp_pid_build_f32(const idsp_pid_f32 *b, float period, int kind, int F, void *ba5_out);
 
 #ifdef __cplusplus
 }

@@ -378,6 +378,30 @@ def lockin_lanes(k, accu_state, accu_step, lp_st, x, lanes, layout=FRAME_MAJOR, 
     return iq
 
 
+def lockin_phase_lanes(k, lp_st, xp, lanes, layout=FRAME_MAJOR, nthreads=1):
+    """(sample, phase) tuples, src/lockin.rs:30-39; xp = (x, phase) pairs"""
+    k = _arr(k, np.int32, copy=True)
+    xp = _arr(xp, np.int32).ravel()
+    frames = xp.size // (2 * lanes)
+    order = k.size
+    assert lp_st.dtype == np.int64 and lp_st.shape == (2 * order, lanes)
+    iq = np.empty(frames * lanes * 2, np.int32)
+    lib().orc_lockin_phase_i32_lanes(C.c_int(order), _p(k), _p(lp_st), _p(xp), _p(iq), C.c_size_t(frames), C.c_size_t(lanes), C.c_int(layout), C.c_int(nthreads))
+    return iq
+
+
+def lockin_lo_lanes(k, lp_st, xlo, lanes, layout=FRAME_MAJOR, nthreads=1):
+    """(sample, LO) tuples, src/lockin.rs:17-28; xlo = (x, lo.re, lo.im) triples"""
+    k = _arr(k, np.int32, copy=True)
+    xlo = _arr(xlo, np.int32).ravel()
+    frames = xlo.size // (3 * lanes)
+    order = k.size
+    assert lp_st.dtype == np.int64 and lp_st.shape == (2 * order, lanes)
+    iq = np.empty(frames * lanes * 2, np.int32)
+    lib().orc_lockin_lo_i32_lanes(C.c_int(order), _p(k), _p(lp_st), _p(xlo), _p(iq), C.c_size_t(frames), C.c_size_t(lanes), C.c_int(layout), C.c_int(nthreads))
+    return iq
+
+
 def chain_lanes(k, ba, st, x, lanes, layout=FRAME_MAJOR, nthreads=1):
     ba = _arr(ba, np.float32, copy=True)
     x = _arr(x, np.float32).ravel()

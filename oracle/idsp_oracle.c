@@ -805,6 +805,62 @@ void orc_lockin_i32_lanes(int order, const int32_t *k, int32_t *accu_state,
     });
 }
 
+/* Lockin on (sample, phase) tuples: src/lockin.rs:30-39 (phase -> Complex::from_angle -> Q32<32> LO, then
+ * the (X, Complex<U>) impl).  xp = (x, phase) pairs, pair innermost. */
+void orc_lockin_phase_i32_lanes(int order, const int32_t *k, int64_t *lp_st, const int32_t *xp, int32_t *iq,
+                                size_t frames, size_t lanes, int layout, int nthreads) {
+    make_tables();
+    LANE_BLOCKS(lanes, nthreads, lo, hi, {
+        for (size_t l = lo; l < hi; l++) {
+            int64_t si[2] = {0, 0}, sq[2] = {0, 0};
+            for (int w = 0; w < order; w++) {
+                si[w] = lp_st[(size_t)w * lanes + l];
+                sq[w] = lp_st[(size_t)(order + w) * lanes + l];
+            }
+            for (size_t t = 0; t < frames; t++) {
+                size_t i = layout == ORC_FRAME_MAJOR ? t * lanes + l : l * frames + t;
+                int32_t c, s;
+                cossin_tab(g_cossin, xp[2 * i + 1], &c, &s);
+                int32_t mi = (int32_t)(((int64_t)c * (int64_t)xp[2 * i]) >> 32);
+                int32_t mq = (int32_t)(((int64_t)s * (int64_t)xp[2 * i]) >> 32);
+                iq[2 * i] = lowpass_step(order, k, si, mi);
+                iq[2 * i + 1] = lowpass_step(order, k, sq, mq);
+            }
+            for (int w = 0; w < order; w++) {
+                lp_st[(size_t)w * lanes + l] = si[w];
+                lp_st[(size_t)(order + w) * lanes + l] = sq[w];
+            }
+        }
+    });
+}
+
+/* Lockin on (sample, LO) tuples: src/lockin.rs:17-28 with X = i32, U = Q32<32>; `x * lo.re()` is
+ * i32 * Q32<32> = ((x as i64 * lo as i64) >> 32) as i32 (dsp-fixedpoint/src/lib.rs:449-456).
+ * xlo = (x, lo.re, lo.im) triples. */
+void orc_lockin_lo_i32_lanes(int order, const int32_t *k, int64_t *lp_st, const int32_t *xlo, int32_t *iq,
+                             size_t frames, size_t lanes, int layout, int nthreads) {
+    LANE_BLOCKS(lanes, nthreads, lo, hi, {
+        for (size_t l = lo; l < hi; l++) {
+            int64_t si[2] = {0, 0}, sq[2] = {0, 0};
+            for (int w = 0; w < order; w++) {
+                si[w] = lp_st[(size_t)w * lanes + l];
+                sq[w] = lp_st[(size_t)(order + w) * lanes + l];
+            }
+            for (size_t t = 0; t < frames; t++) {
+                size_t i = layout == ORC_FRAME_MAJOR ? t * lanes + l : l * frames + t;
+                int32_t mi = (int32_t)(((int64_t)xlo[3 * i + 1] * (int64_t)xlo[3 * i]) >> 32);
+                int32_t mq = (int32_t)(((int64_t)xlo[3 * i + 2] * (int64_t)xlo[3 * i]) >> 32);
+                iq[2 * i] = lowpass_step(order, k, si, mi);
+                iq[2 * i + 1] = lowpass_step(order, k, sq, mq);
+            }
+            for (int w = 0; w < order; w++) {
+                lp_st[(size_t)w * lanes + l] = si[w];
+                lp_st[(size_t)(order + w) * lanes + l] = sq[w];
+            }
+        }
+    });
+}
+
 /* config 5 chain: HbfDec(/2^k) -> HbfInt(x2^k) -> Biquad<f32> DF1 */
 void orc_chain_f32_lanes(int k, const float ba[5], float *st, const float *x, float *y,
                          size_t n_low, size_t lanes, int layout, int nthreads) {

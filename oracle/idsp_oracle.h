@@ -152,6 +152,11 @@ void orc_lockin_i32_lanes(int order, const int32_t *k, int32_t *accu_state,
                           const int32_t *accu_step, int64_t *lp_st /*[2*order][lanes]*/,
                           const int32_t *x, int32_t *iq, size_t frames, size_t lanes,
                           int layout, int nthreads);
+/* Lockin on (sample, phase) tuples (lockin.rs:30-39) and on (sample, LO) tuples (lockin.rs:17-28) */
+void orc_lockin_phase_i32_lanes(int order, const int32_t *k, int64_t *lp_st, const int32_t *xp, int32_t *iq,
+                                size_t frames, size_t lanes, int layout, int nthreads);
+void orc_lockin_lo_i32_lanes(int order, const int32_t *k, int64_t *lp_st, const int32_t *xlo, int32_t *iq,
+                             size_t frames, size_t lanes, int layout, int nthreads);
 
 /* f32 chain of config 5: HbfDec(/2^k) -> HbfInt(x2^k) -> Biquad DF1 f32.
  * st = [dec state | int state | df1 state(4)] words per lane (SoA over lanes). */

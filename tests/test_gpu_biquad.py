@@ -303,3 +303,45 @@ def test_df1_wide_tma_boxes(oracle, kind, lanes):
     Lanes(bq).block(st, to_dev(x), y, 0)
     assert_bits_equal(to_np(y), want)
     assert_bits_equal(st.numpy(), so)
+
+
+# ------------------------------------------------------------------ 8-byte samples on the TMA kernels (round 2)
+@pytest.mark.parametrize("kind", ["i64", "f64"])
+@pytest.mark.parametrize("layout", [0, 1])
+def test_df1_8byte_tma_and_generic(oracle, kind, layout):
+    """i64 / f64 DF1 through the generic kernels (policy 1) and the TMA kernels (policy 2: 8-byte boxes,
+    128-byte swizzled lane-major rows), incl. ragged boxes and partial last tiles"""
+    rng = np.random.default_rng(layout + 11)
+    bq = _coeffs(kind, rng)
+    ctx = ib.default_context(0)
+    for policy in (1, 2):
+        ctx.set_kernel_policy(policy)
+        try:
+            for frames, lanes in [(16, 32), (64, 128), (100, 36), (52, 260), (1000, 64), (36, 4), (24, 1024)]:
+                x = rand_samples(rng, kind, frames * lanes).reshape(frames, lanes)
+                flat = layout_flat(x, layout)
+                st0 = rand_samples(rng, kind, 4 * lanes, amp_bits=(BITS[kind] - 4) if kind in BITS else None).reshape(4, lanes)
+                so = st0.copy()
+                want = oracle.biquad_lanes("df1", kind, bq.ba, bq.F, None, so, flat, lanes, layout)
+                st = DirectForm1(to_dev(st0), kind)
+                y = torch.empty_like(to_dev(flat))
+                Lanes(bq).block(st, to_dev(flat), y, layout)
+                assert_bits_equal(to_np(y), want, f"policy={policy} {kind} layout={layout} {frames}x{lanes} [{ctx.last_kernel}]")
+                assert_bits_equal(st.numpy(), so, "state")
+                if policy == 2:
+                    assert ctx.last_kernel.startswith("tma"), ctx.last_kernel
+        finally:
+            ctx.set_kernel_policy(0)
+
+
+def test_last_kernel_reports_the_fallback():
+    """the silent fall-back from the TMA kernels (misaligned view) is observable through the ABI"""
+    ctx = ib.default_context(0)
+    bq = _coeffs("i32", None)
+    lanes, frames = 64, 64
+    x = torch.zeros(frames * lanes + 1, dtype=torch.int32, device=DEV)
+    y = torch.zeros(frames * lanes + 1, dtype=torch.int32, device=DEV)
+    Lanes(bq).block(DirectForm1.default("i32", lanes, DEV), x[:-1], y[:-1], 0)
+    assert ctx.last_kernel.startswith("tma frame-major"), ctx.last_kernel
+    Lanes(bq).block(DirectForm1.default("i32", lanes, DEV), x[1:], y[1:], 0)
+    assert ctx.last_kernel == "generic frame-major", ctx.last_kernel

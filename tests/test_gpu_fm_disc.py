@@ -31,8 +31,19 @@ def test_tracks_known_modulation_on_gpu(oracle):
 
 
 @pytest.mark.parametrize("layout", [0, 1])
-@pytest.mark.parametrize("lanes,frames", [(1, 257), (33, 100), (300, 64)])
-def test_fm_disc_vs_oracle(oracle, layout, lanes, frames):
+@pytest.mark.parametrize("lanes,frames", [(1, 257), (33, 100), (300, 64), (256, 96), (1028, 72)])
+@pytest.mark.parametrize("policy", [0, 1])
+def test_fm_disc_vs_oracle(oracle, layout, lanes, frames, policy):
+    """policy 0: TMA kernels where the chunk qualifies (8-byte in, 4-byte out), policy 1: generic kernels"""
+    import idsp_b200 as ib
+    ib.default_context(0).set_kernel_policy(policy)
+    try:
+        _fm_disc_vs_oracle(oracle, layout, lanes, frames)
+    finally:
+        ib.default_context(0).set_kernel_policy(0)
+
+
+def _fm_disc_vs_oracle(oracle, layout, lanes, frames):
     rng = np.random.default_rng(lanes * 7 + frames)
     ph = rng.integers(-(1 << 31), 1 << 31, (frames, lanes)).astype(np.int32)
     x = oracle.cossin(ph.reshape(-1)).reshape(frames, lanes, 2)

@@ -295,3 +295,186 @@ def test_int_cascade_tiled_kernel_streaming(oracle, k, layout):
             assert_bits_equal(st.numpy(), so, "state")
         finally:
             ctx.set_kernel_policy(0)
+
+
+# ------------------------------------------------------------------ caller-supplied tap sets (HBF_TAPS_98, arbitrary)
+def _oracle_dec_cascade_taps(oracle, taps, so, x_lane):
+    """sequential composition of the reference's single stages, highest rate first (hbf.rs:385-421);
+    so = this lane's state words in processing order, updated in place"""
+    k = len(taps)
+    off, v = 0, x_lane
+    for s in range(k):
+        t = taps[k - 1 - s]
+        w = 3 * len(t) - 2
+        st = so[off:off + w].copy()
+        v = oracle.hbf_dec(t, st, v)
+        so[off:off + w] = st
+        off += w
+    return v
+
+
+def _oracle_int_cascade_taps(oracle, taps, so, x_lane):
+    off, v = 0, x_lane
+    for s in range(len(taps)):
+        t = taps[s]
+        w = 2 * len(t) - 1
+        st = so[off:off + w].copy()
+        v = oracle.hbf_int(t, st, v)
+        so[off:off + w] = st
+        off += w
+    return v
+
+
+def test_hbf_taps_98_values():
+    """HBF_TAPS_98 transcribed from src/hbf.rs:258-292"""
+    t = ib.hbf_taps_98()
+    assert [len(v) for v in t] == [15, 6, 3, 3, 2]
+    assert t[0][0] == np.float32(7.02144012e-05) and t[0][-1] == np.float32(6.33592923e-01)
+    assert t[1].tolist() == [np.float32(v) for v in (-0.00086943, 0.00577837, -0.02201674, 0.06357869, -0.16627679, 0.61979312)]
+    assert t[4].tolist() == [np.float32(-0.06291796), np.float32(0.5629161)]
+    for v in t:  # half-band: DC gain of the /2 stage is 2 (no 0.5 scaling, SURVEY a11)
+        assert abs(2 * float(np.sum(v.astype(np.float64))) + 1 - 2) < 2e-4
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 5])
+@pytest.mark.parametrize("layout", [0, 1])
+@pytest.mark.parametrize("tapset", ["taps98", "random", "builtin"])
+def test_cascade_with_caller_taps(oracle, k, layout, tapset):
+    rng = np.random.default_rng(k * 7 + layout)
+    if tapset == "taps98":
+        taps = list(ib.hbf_taps_98()[:k])
+    elif tapset == "builtin":  # HBF_TAPS passed explicitly must take the built-in (tiled) path and agree with it
+        taps = list(hbf_taps()[:k])
+    else:
+        taps = [(rng.standard_normal(m) * 0.3).astype(np.float32) for m in (7, 1, 12, 32, 9)[:k]]
+    R = 1 << k
+    lanes, n_out = 20, (1024 >> k) + 3
+    xl = rng.uniform(-1, 1, (lanes, n_out * R)).astype(np.float32)
+    xf = np.ascontiguousarray(xl.reshape(lanes, n_out, R).swapaxes(0, 1)).reshape(-1) if layout == 0 else xl.reshape(-1)
+    cfg = HbfDecCascade(k, taps)
+    st = cfg.state(lanes, DEV)
+    so = np.zeros(tuple(st.words.shape), np.float32)
+    want = np.stack([_oracle_dec_cascade_taps(oracle, taps, so[:, l], xl[l]) for l in range(lanes)])  # [lanes][n_out]
+    y = torch.empty(n_out * lanes, dtype=torch.float32, device=DEV)
+    # streamed in two calls: the state carries over like repeated block() calls
+    cut = (n_out // 2)
+    if layout == 0:
+        Lanes(cfg).block(st, to_dev(xf[: cut * lanes * R]), y[: cut * lanes], layout)
+        Lanes(cfg).block(st, to_dev(xf[cut * lanes * R:]), y[cut * lanes:], layout)
+        assert_bits_equal(to_np(y), np.ascontiguousarray(want.T).reshape(-1), f"dec {tapset} k={k}")
+    else:
+        Lanes(cfg).block(st, to_dev(xf), y, layout)
+        assert_bits_equal(to_np(y), want.reshape(-1), f"dec {tapset} k={k}")
+    assert_bits_equal(st.numpy(), so, "dec state")
+    # interpolator
+    cfi = HbfIntCascade(k, taps)
+    sti = cfi.state(lanes, DEV)
+    si = np.zeros(tuple(sti.words.shape), np.float32)
+    want_i = np.stack([_oracle_int_cascade_taps(oracle, taps, si[:, l], want[l]) for l in range(lanes)])  # [lanes][n_out*R]
+    xin = np.ascontiguousarray(want.T).reshape(-1) if layout == 0 else want.reshape(-1)
+    yi = torch.empty(n_out * lanes * R, dtype=torch.float32, device=DEV)
+    Lanes(cfi).block(sti, to_dev(xin), yi, layout)
+    wf = np.ascontiguousarray(want_i.reshape(lanes, n_out, R).swapaxes(0, 1)).reshape(-1) if layout == 0 else want_i.reshape(-1)
+    assert_bits_equal(to_np(yi), wf, f"int {tapset} k={k}")
+    assert_bits_equal(sti.numpy(), si, "int state")
+
+
+def test_builtin_taps_passed_explicitly_use_tiled_kernels():
+    ctx = ib.default_context(0)
+    k, lanes, n_out = 4, 16, 256
+    x = torch.empty(lanes * n_out * 16, dtype=torch.float32, device=DEV).uniform_(-1, 1)
+    y = torch.empty(lanes * n_out, dtype=torch.float32, device=DEV)
+    cfg = HbfDecCascade(k, hbf_taps()[:k])
+    Lanes(cfg).block(cfg.state(lanes, DEV), x, y, 1)
+    assert ctx.last_kernel.startswith("hbf tiled"), ctx.last_kernel
+    cfg = HbfDecCascade(k, ib.hbf_taps_98()[:k])
+    Lanes(cfg).block(cfg.state(lanes, DEV), x, y, 1)
+    assert ctx.last_kernel.startswith("hbf single stage"), ctx.last_kernel
+
+
+# ------------------------------------------------------------------ misaligned caller pointers (ADVICE r1)
+@pytest.mark.parametrize("layout", [0, 1])
+def test_hbf_misaligned_pointers(oracle, layout):
+    """views that are only 4-byte aligned (x[1:], y[1:]) must take the scalar branches, never fault"""
+    rng = np.random.default_rng(3)
+    lanes = 24
+    for k in (1, 2, 4):
+        R = 1 << k
+        n_out = (1024 >> k) + 1
+        xl = rng.uniform(-1, 1, (lanes, n_out * R)).astype(np.float32)
+        xf = np.ascontiguousarray(xl.reshape(lanes, n_out, R).swapaxes(0, 1)).reshape(-1) if layout == 0 else xl.reshape(-1)
+        so = np.zeros((oracle.hbf_dec_state_words(k), lanes), np.float32)
+        want = oracle.hbf_dec_cascade_lanes(k, so, xf, lanes, layout)
+        xb = torch.zeros(xf.size + 1, dtype=torch.float32, device=DEV)
+        xb[1:] = to_dev(xf)
+        yb = torch.zeros(want.size + 1, dtype=torch.float32, device=DEV)
+        st = _dec_state(k)(lanes, DEV)
+        Lanes(HbfDecCascade(k)).block(st, xb[1:], yb[1:], layout)
+        assert_bits_equal(to_np(yb[1:]), want, f"dec /{R} misaligned")
+        si = np.zeros((oracle.hbf_int_state_words(k), lanes), np.float32)
+        want_i = oracle.hbf_int_cascade_lanes(k, si, want, lanes, layout)
+        yi = torch.zeros(want_i.size + 1, dtype=torch.float32, device=DEV)
+        Lanes(HbfIntCascade(k)).block(_int_state(k)(lanes, DEV), yb[1:], yi[1:], layout)
+        assert_bits_equal(to_np(yi[1:]), want_i, f"int x{R} misaligned")
+    # single stages and the chain
+    taps = hbf_taps()[2]
+    M = len(taps)
+    x = rng.uniform(-1, 1, (lanes, 64)).astype(np.float32)
+    xf = np.ascontiguousarray(x.reshape(lanes, 32, 2).swapaxes(0, 1)).reshape(-1) if layout == 0 else x.reshape(-1)
+    want_l = [oracle.hbf_dec(taps, np.zeros(3 * M - 2, np.float32), x[l]) for l in range(lanes)]
+    want = np.stack(want_l, 1).reshape(-1) if layout == 0 else np.concatenate(want_l)
+    xb = torch.zeros(xf.size + 1, dtype=torch.float32, device=DEV)
+    xb[1:] = to_dev(xf)
+    yb = torch.zeros(want.size + 1, dtype=torch.float32, device=DEV)
+    EvenSymmetric(taps).block(HbfDec.default(M, lanes, DEV), xb[1:], yb[1:], layout)
+    assert_bits_equal(to_np(yb[1:]), want, "single stage misaligned")
+    from idsp_b200 import Biquad, Filter, _lib
+    W = int(_lib.lib().idsp_chain_state_words(2))
+    ba = np.asarray(Biquad.from_ba6(Filter().critical_frequency(0.05).lowpass(), "f32").ba)
+    xl = rng.uniform(-1, 1, (lanes, 40 * 4)).astype(np.float32)
+    xf = np.ascontiguousarray(xl.reshape(lanes, 40, 4).swapaxes(0, 1)).reshape(-1) if layout == 0 else xl.reshape(-1)
+    so = np.zeros((W, lanes), np.float32)
+    want = oracle.chain_lanes(2, ba, so, xf, lanes, layout)
+    xb = torch.zeros(xf.size + 1, dtype=torch.float32, device=DEV)
+    xb[1:] = to_dev(xf)
+    yb = torch.zeros(xf.size + 1, dtype=torch.float32, device=DEV)
+    ib.default_context(0).chain(2, ba, torch.zeros((W, lanes), dtype=torch.float32, device=DEV), xb[1:], yb[1:], lanes=lanes, layout=layout)
+    assert_bits_equal(to_np(yb[1:]), want, "chain misaligned")
+
+
+def test_state_validation_errors():
+    """a state built for other taps / another operator is rejected on the host instead of being read out of bounds"""
+    x = torch.zeros(64, dtype=torch.float32, device=DEV)
+    y = torch.zeros(32, dtype=torch.float32, device=DEV)
+    with pytest.raises(TypeError):
+        EvenSymmetric(hbf_taps()[0]).block(HbfDec.default(3, 1, DEV), x, y)          # M = 3 state, 23 taps
+    with pytest.raises(TypeError):
+        OddSymmetric([0.1, 0.2]).block(FirState.default(3, 1, DEV), y, torch.zeros_like(y))  # LEN = 4 needed
+    ctx = ib.default_context(0)
+    with pytest.raises(ValueError):
+        ctx.hbf_dec_cascade(4, torch.zeros((10, 1), dtype=torch.float32, device=DEV), x, torch.zeros(4, dtype=torch.float32, device=DEV), lanes=1)
+    with pytest.raises(ValueError):
+        ctx.biquad("df1", [1, 0, 0, 0, 0], 0, None, torch.zeros((4, 3), dtype=torch.float32, device=DEV), x, None, lanes=3)  # 64 % 3
+    with pytest.raises(TypeError):
+        ctx.biquad("df1", [1, 0, 0, 0, 0], 0, None, torch.zeros((4, 2), dtype=torch.int32, device=DEV), x, None, lanes=2)  # i32 state, f32 samples
+    with pytest.raises(ValueError):
+        ctx.biquad("df1", [1, 0, 0, 0, 0], 0, None, torch.zeros((4, 2), dtype=torch.float32, device=DEV), x, y, lanes=2)   # short output
+
+
+def test_chain_host_buffers(oracle):
+    """idsp_chain_f32_host: numpy in / out, one PCIe round trip for dec -> int -> biquad"""
+    from idsp_b200 import Biquad, Filter, _lib
+    rng = np.random.default_rng(9)
+    k = 4
+    W = int(_lib.lib().idsp_chain_state_words(k))
+    ba = np.asarray(Biquad.from_ba6(Filter().critical_frequency(0.05).lowpass(), "f32").ba)
+    ctx = ib.default_context(0)
+    for layout, lanes, n_low in ((1, 300, 64), (0, 40, 70), (1, 4096, 256)):
+        x = rng.uniform(-1, 1, lanes * n_low * 16).astype(np.float32)
+        so = np.zeros((W, lanes), np.float32)
+        want = oracle.chain_lanes(k, ba, so, x, lanes, layout, nthreads=4)
+        st = np.zeros((W, lanes), np.float32)
+        y = np.empty_like(x)
+        ctx.chain(k, ba, st, x, y, lanes=lanes, layout=layout)
+        assert_bits_equal(y, want, f"chain host layout={layout}")
+        assert_bits_equal(st, so, "chain host state")

@@ -126,3 +126,82 @@ def test_lockin_tma_kernels(oracle, lanes):
             assert_bits_equal(st.numpy(), so)
         finally:
             ctx.set_kernel_policy(0)
+
+
+# ------------------------------------------------------------------ Lockin on caller-supplied phase / LO streams
+@pytest.mark.parametrize("order", [1, 2])
+@pytest.mark.parametrize("layout", [0, 1])
+def test_lockin_phase_stream_vs_oracle(oracle, order, layout):
+    """`SplitProcess<(i32, Wrapping<i32>), Complex<i32>, [S; 2]>` src/lockin.rs:30-39: the phase of every sample
+    comes from the caller.  Shapes cover the generic kernels and both TMA layouts (8-byte in, 8-byte out)."""
+    rng = np.random.default_rng(40 + order)
+    k = [67465188] if order == 1 else [1048576, -94906265]
+    ctx = ib.default_context(0)
+    for frames, lanes in [(50, 70), (128, 128), (3, 1), (52, 37), (16, 64), (43, 260), (64, 1024)]:
+        xp = rng.integers(-(1 << 31), 1 << 31, 2 * frames * lanes).astype(np.int32)
+        xp[0::2] >>= 1  # samples within +-2^30, phases over the full circle
+        so = np.zeros((2 * order, lanes), np.int64)
+        want = oracle.lockin_phase_lanes(k, so, xp, lanes, layout)
+        for policy in (0, 1):
+            ctx.set_kernel_policy(policy)
+            try:
+                st = LockinState.default(order, lanes, DEV)
+                iq = torch.empty(xp.size, dtype=torch.int32, device=DEV)
+                Lockin(Lowpass(k)).block_phase(st, to_dev(xp), iq, layout)
+                assert_bits_equal(to_np(iq), want, f"policy={policy} {frames}x{lanes} ({ctx.last_kernel})")
+                assert_bits_equal(st.numpy(), so)
+            finally:
+                ctx.set_kernel_policy(0)
+
+
+def test_lockin_phase_equals_accu_form(oracle):
+    """feeding the phases an Accu would produce must reproduce idsp_lockin_i32 (src/accu.rs:34-37 + lockin.rs:30-39)"""
+    rng = np.random.default_rng(77)
+    frames, lanes, k = 64, 96, [1048576, -94906265]
+    x = rng.integers(-(1 << 30), 1 << 30, (frames, lanes)).astype(np.int32)
+    a0 = rng.integers(-(1 << 31), 1 << 31, lanes).astype(np.int32)
+    step = rng.integers(-(1 << 31), 1 << 31, lanes).astype(np.int32)
+    ph = (a0.astype(np.int64)[None, :] + (np.arange(1, frames + 1, dtype=np.int64)[:, None] * step.astype(np.int64)[None, :]))
+    ph = (ph & 0xFFFFFFFF).astype(np.uint32).view(np.int32)
+    xp = np.stack([x, ph], -1).reshape(-1)
+    st1, st2 = LockinState.default(2, lanes, DEV), LockinState.default(2, lanes, DEV)
+    iq1 = torch.empty(2 * x.size, dtype=torch.int32, device=DEV)
+    iq2 = torch.empty_like(iq1)
+    Lockin(Lowpass(k)).block(st1, Accu(to_dev(a0), to_dev(step)), to_dev(x.reshape(-1)), iq1, 0)
+    Lockin(Lowpass(k)).block_phase(st2, to_dev(xp), iq2, 0)
+    assert_bits_equal(to_np(iq1), to_np(iq2))
+    assert_bits_equal(st1.numpy(), st2.numpy())
+
+
+@pytest.mark.parametrize("order", [1, 2])
+@pytest.mark.parametrize("layout", [0, 1])
+def test_lockin_lo_stream_vs_oracle(oracle, order, layout):
+    """`SplitProcess<(X, Complex<U>), Complex<X>, [S; 2]>` src/lockin.rs:17-28 with X = i32, U = Q32<32>"""
+    rng = np.random.default_rng(50 + order)
+    k = [67465188] if order == 1 else [1048576, -94906265]
+    for frames, lanes in [(50, 70), (3, 1), (128, 96), (40, 33)]:
+        xlo = rng.integers(-(1 << 31), 1 << 31, 3 * frames * lanes).astype(np.int32)
+        xlo[:9] = [np.iinfo(np.int32).min, np.iinfo(np.int32).min, np.iinfo(np.int32).max, -1, -1, 1, 0, 5, -5]
+        so = np.zeros((2 * order, lanes), np.int64)
+        want = oracle.lockin_lo_lanes(k, so, xlo, lanes, layout)
+        st = LockinState.default(order, lanes, DEV)
+        iq = torch.empty(2 * frames * lanes, dtype=torch.int32, device=DEV)
+        Lockin(Lowpass(k)).block_lo(st, to_dev(xlo), iq, layout)
+        assert_bits_equal(to_np(iq), want, f"{frames}x{lanes}")
+        assert_bits_equal(st.numpy(), so)
+
+
+def test_lockin_lo_equals_phase_form():
+    """the phase impl is defined as cossin(phase) fed to the LO impl (lockin.rs:34-38)"""
+    rng = np.random.default_rng(5)
+    n, k = 4096, [1048576, -94906265]
+    x = rng.integers(-(1 << 30), 1 << 30, n).astype(np.int32)
+    ph = rng.integers(-(1 << 31), 1 << 31, n).astype(np.int32)
+    cs = to_np(ib.cossin(to_dev(ph))).reshape(n, 2)
+    xlo = np.stack([x, cs[:, 0], cs[:, 1]], -1).reshape(-1)
+    xp = np.stack([x, ph], -1).reshape(-1)
+    s1, s2 = LockinState.default(2, 1, DEV), LockinState.default(2, 1, DEV)
+    a, b = torch.empty(2 * n, dtype=torch.int32, device=DEV), torch.empty(2 * n, dtype=torch.int32, device=DEV)
+    Lockin(Lowpass(k)).block_lo(s1, to_dev(xlo), a, 0)
+    Lockin(Lowpass(k)).block_phase(s2, to_dev(xp), b, 0)
+    assert_bits_equal(to_np(a), to_np(b))
