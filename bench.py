@@ -19,11 +19,14 @@ Workloads (BASELINE.json `configs`):
 `roofline`: algorithmic bytes per launch / average launch duration vs MEASURED_PEAKS.json.
 `cpu_baseline`: the CPU oracle (a C port of the reference; the Rust crate cannot be built in
            this image) timed on the host cores on a bounded sample of the same workload.
-`extra`  : the default N = 1 run also measures configs[2] (hbf), configs[3] (lock-in) and configs[4] (chain sweep)
-           in the same process and attaches their lines (a failure there is recorded, never raised).
+`extra`  : the default run (any N) also measures configs[2] (hbf), configs[3] (lock-in, resident per GPU AND as the
+           sharded data plane: root-resident lanes -> NCCL scatter -> lock-in -> NCCL gather / kernels storing
+           into the root's buffer over NVLink) and configs[4] (chain sweep) in the same process and attaches
+           their lines (a failure there is recorded, never raised).
 `--impl reference`: times that CPU path alone and prints the same JSON line with impl=reference.
 N > 1: one process per GPU (torchrun), lanes sharded, no data-path collective ("weak" scaling:
-every rank runs the full 65 536-lane workload on its own lane block).
+every rank runs the full 65 536-lane workload on its own lane block); `extra.lockin_sharded` is the
+one leg with real data movement between GPUs (the edges of the sharded job, BASELINE configs[3]).
 """
 from __future__ import annotations
 
@@ -81,9 +84,18 @@ def traffic_from_profiles(key):
     return None
 
 
-def pcie_peak(dev, mb=256, reps=3):
+def strided_lanes(lanes, n=64):
+    """lane subset of the parity gates: spread over the WHOLE lane range (every CTA / TMA box of the launch is
+    sampled somewhere) plus the first and the last 8 lanes (the last, possibly ragged, box)"""
+    a = np.linspace(0, lanes - 1, max(n - 16, 2)).astype(np.int64)
+    return np.unique(np.concatenate([np.arange(min(8, lanes)), a, np.arange(max(lanes - 8, 0), lanes)]))
+
+
+def pcie_peak(dev, mb=256, reps=3, world=1):
     """pinned-memory copy rates with both directions busy at once (what the e2e leg is bound by):
-    returns (h2d GB/s, d2h GB/s) measured with CUDA events on two streams"""
+    returns (h2d GB/s, d2h GB/s) measured with CUDA events on two streams.  At N > 1 every rank runs it
+    at the same time (barrier before every repetition): the GPUs share the host's memory system and
+    PCIe root, so the yardstick must be measured under the same contention as the e2e leg."""
     import torch
 
     n = mb << 20
@@ -95,7 +107,7 @@ def pcie_peak(dev, mb=256, reps=3):
     best = [0.0, 0.0]
     for _ in range(reps + 1):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-        torch.cuda.synchronize()
+        barrier(world)
         with torch.cuda.stream(s1):
             ev[0].record()
             d_in.copy_(h_in, non_blocking=True)
@@ -107,6 +119,12 @@ def pcie_peak(dev, mb=256, reps=3):
         torch.cuda.synchronize()
         best[0] = max(best[0], n / (ev[0].elapsed_time(ev[1]) * 1e-3) / 1e9)
         best[1] = max(best[1], n / (ev[2].elapsed_time(ev[3]) * 1e-3) / 1e9)
+    if world > 1:  # the slowest rank bounds the job
+        import torch.distributed as dist
+
+        t = torch.tensor(best, dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        best = [float(t[0]), float(t[1])]
     return best[0], best[1]
 
 
@@ -374,6 +392,22 @@ def time_steps(step, steps, warmup, world, local, ctx, dev):
     return max_over_ranks(e0.elapsed_time(e1), world, dev), launches, clocks
 
 
+def sustained_loop(step, ms_per_step, world, dev, seconds=2.0):
+    """the same step repeated for >= `seconds` (the timed K steps are a short burst at boost clocks; a long
+    job runs under the power cap): returns (ms per step, steps)"""
+    import torch
+
+    n = int(max(8, min(20000, seconds * 1e3 / max(ms_per_step, 1e-3))))
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(n):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    return max_over_ranks(e0.elapsed_time(e1), world, dev) / n, n
+
+
 LOCKIN_LANES_TOTAL = 1_048_576
 LOCKIN_FRAMES = 16_384
 LOCKIN_K = [1048576, -94906265]  # Lowpass<2>: [k^2/2^32, -k/q], k = 2^26, q = 1/sqrt(2)
@@ -406,12 +440,13 @@ def run_lockin(args, rank, world, local):
 
     step(0)
     torch.cuda.synchronize()
-    sub = 32
-    xs = xin[0].view(frames, lanes)[:, :sub].contiguous().cpu().numpy().reshape(-1)
+    idx = torch.from_numpy(strided_lanes(lanes, 48)).to(dev)
+    sub = int(idx.numel())
+    xs = xin[0].view(frames, lanes).index_select(1, idx).contiguous().cpu().numpy().reshape(-1)
     a0 = np.zeros(sub, np.int32)
     so = np.zeros((4, sub), np.int64)
-    want = O.lockin_lanes(LOCKIN_K, a0, step_t[:sub].cpu().numpy(), so, xs, sub, 0, nthreads=host_threads())
-    got = iq[0].view(frames, lanes, 2)[:, :sub].contiguous().cpu().numpy().reshape(-1)
+    want = O.lockin_lanes(LOCKIN_K, a0, step_t.index_select(0, idx).cpu().numpy(), so, xs, sub, 0, nthreads=host_threads())
+    got = iq[0].view(frames, lanes, 2).index_select(1, idx).contiguous().cpu().numpy().reshape(-1)
     if not np.array_equal(got, want):
         raise SystemExit("bench: GPU lock-in output differs from the oracle -- refusing to report a number")
     ms, launches, clocks = time_steps(step, args.steps, args.warmup, world, local, ctx, dev)
@@ -430,8 +465,139 @@ def run_lockin(args, rank, world, local):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": per_launch_bytes,
                      "note": "~70 integer instructions per sample: issue-bound and HBM-bound ceilings nearly coincide"},
-        "gpu_launches": int(launches), "clocks": clocks, "parity_check": "first step == oracle on 32 lanes x all frames",
+        "gpu_launches": int(launches), "clocks": clocks,
+        "parity_check": f"first step == oracle on {sub} lanes strided over the whole lane range (+ first / last 8) x all frames",
     }
+
+
+def run_lockin_sharded(args, rank, world, local):
+    """configs[3] as a DATA PLANE: rank 0 holds the samples of all `131072 x world` lanes (1 048 576 at 8 GPUs),
+    contiguous lane blocks go to the ranks (idsp_scatter_lanes: raw NCCL send/recv over NVLink), every rank runs
+    the fused lock-in on its own block (no collective inside the computation, compose.rs:472-475), and the
+    Complex<i32> results return to rank 0 either (a) through idsp_gather_lanes or (b) straight from the kernels'
+    epilogues into rank 0's buffer mapped over NVLink (CUDA IPC peer memory).  Lane-major, so that a lane block
+    of the root's buffers is one contiguous range.  Each phase is timed with CUDA events on every rank (max over
+    ranks); the gathered result is compared with the CPU oracle on lanes strided over every rank's block."""
+    import torch
+
+    import oracle as O
+    from idsp_b200 import Accu, Lockin, LockinState, Lowpass
+    from idsp_b200.dist import Comm, PeerBuffer
+    from idsp_b200.engine import default_context
+
+    dev = f"cuda:{local}"
+    ctx = default_context(local)
+    lpg = LOCKIN_LANES_TOTAL // 8
+    lanes, frames = lpg * world, args.sharded_frames
+    comm = Comm(local)
+    lo, hi = comm.lane_block(lanes)
+    nl = hi - lo
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(44)
+    x_full = step_full = None
+    if rank == 0:
+        x_full = torch.randint(-(1 << 30), 1 << 30, (lanes * frames,), dtype=torch.int32, device=dev, generator=gen)
+        step_full = torch.randint(-(1 << 31), (1 << 31) - 1, (lanes,), dtype=torch.int64, device=dev, generator=gen).to(torch.int32)
+    # the root's result buffer: a plain device allocation exported to every rank (also the gather target)
+    pb = PeerBuffer(lanes * frames * 2, torch.int32, local, owner=0) if world > 1 else None
+    if rank == 0:
+        iq_full = pb.tensor() if pb is not None else torch.empty(lanes * frames * 2, dtype=torch.int32, device=dev)
+    else:
+        iq_full = None
+    xs = torch.empty(nl * frames, dtype=torch.int32, device=dev)
+    iq = torch.empty(nl * frames * 2, dtype=torch.int32, device=dev)
+    steps_l = comm.scatter_lanes(step_full, 1, lanes, 1, dtype=torch.int32)
+    cfg = Lockin(Lowpass(LOCKIN_K))
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+
+    def one_pass(fused):
+        """scatter -> lock-in -> gather (or lock-in storing into the root's buffer); returns per-phase ms"""
+        st = LockinState.default(2, nl, dev)
+        acc = Accu(torch.zeros(nl, dtype=torch.int32, device=dev), steps_l)
+        e = [ev() for _ in range(4)]
+        barrier(world)
+        e[0].record()
+        comm.scatter_lanes(x_full, frames, lanes, 1, out=xs)
+        e[1].record()
+        if fused and world > 1:
+            cfg.block(st, acc, xs, pb.view(lo * frames * 2, nl * frames * 2), 1)
+            e[2].record()
+            e[3].record()
+        else:
+            cfg.block(st, acc, xs, iq, 1)
+            e[2].record()
+            comm.gather_lanes(iq, iq_full, frames, lanes, 1, width=2)
+            e[3].record()
+        torch.cuda.synchronize()
+        barrier(world)
+        t = [e[i].elapsed_time(e[i + 1]) for i in range(3)] + [e[0].elapsed_time(e[3])]
+        return [max_over_ranks(v, world, dev) for v in t]
+
+    def check(tag):
+        if rank != 0:
+            return True
+        # lanes strided over the block of every rank (first, last and a few inside)
+        sel = []
+        for r in range(world):
+            a, b = r * lpg, (r + 1) * lpg
+            sel += [a, a + 1, a + lpg // 3, a + lpg // 2 + 17, b - 2, b - 1]
+        idx = torch.tensor(sel, dtype=torch.int64, device=dev)
+        xsub = x_full.view(lanes, frames).index_select(0, idx).contiguous().cpu().numpy().reshape(-1)
+        want = O.lockin_lanes(LOCKIN_K, np.zeros(len(sel), np.int32), step_full.index_select(0, idx).cpu().numpy(),
+                              np.zeros((4, len(sel)), np.int64), xsub, len(sel), 1, nthreads=host_threads())
+        got = iq_full.view(lanes, frames * 2).index_select(0, idx).contiguous().cpu().numpy().reshape(-1)
+        return bool(np.array_equal(got, want))
+
+    res = {}
+    for fused in ((False, True) if world > 1 else (False,)):
+        if rank == 0:
+            iq_full.zero_()
+        one_pass(fused)  # warm-up (NCCL channels, peer mappings) -- and the pass the oracle checks
+        ok = check("fused" if fused else "nccl")
+        okt = torch.tensor([1 if ok else 0], device=dev)
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.broadcast(okt, 0)
+        if not int(okt.item()):
+            raise SystemExit("bench: sharded lock-in output differs from the oracle -- refusing to report a number")
+        reps = max(2, min(args.steps, 5))
+        tt = np.array([one_pass(fused) for _ in range(reps)])
+        res["fused" if fused else "nccl"] = tt.mean(0)
+    comm.close()
+    if pb is not None:
+        del iq_full
+        pb.close()
+    if rank != 0:
+        return None
+    n = lanes * frames
+    t = res["nccl"]
+    out_bytes_remote = 8.0 * n * (world - 1) / world
+    in_bytes_remote = 4.0 * n * (world - 1) / world
+    line = {
+        "metric": "GSa/s, i32 DDC lock-in, lanes sharded from / to rank 0 (scatter -> lock-in -> gather over NVLink)",
+        "unit": "GSa/s", "n_gpus": world, "higher_is_better": True, "scaling": "weak", "dtype": "i32", "data": "synthetic",
+        "config": {"workload": f"configs[3]: DDC lock-in i32, {lanes} lanes sharded over {world} GPU(s) ({lpg} per GPU), "
+                               f"{frames} of the 16384 frames resident on the root per pass, lane-major",
+                   "lanes_total": lanes, "lanes_per_gpu": lpg, "frames_per_pass": frames,
+                   "edges": "idsp_scatter_lanes / idsp_gather_lanes (C ABI, raw NCCL send/recv, in place for lane-major blocks)"},
+        "value": n / (t[3] * 1e-3) / 1e9,  # end to end over NVLink: scatter + compute + gather
+        "resident_GSa/s": n / (t[1] * 1e-3) / 1e9,  # the lock-in kernels alone (all ranks, max over ranks)
+        "ms": {"scatter": t[0], "lockin": t[1], "gather": t[2], "total": t[3]},
+        "nvlink_GBs": {"scatter_egress_of_root": (in_bytes_remote / (t[0] * 1e-3) / 1e9) if world > 1 else None,
+                       "gather_ingress_of_root": (out_bytes_remote / (t[2] * 1e-3) / 1e9) if world > 1 else None,
+                       "nominal_per_direction": 900.0},
+        "parity_check": f"gathered Complex<i32> of 6 lanes per rank block ({6 * world} lanes, first / last / inside) x all frames == oracle, both variants",
+        "passes_timed": int(max(2, min(args.steps, 5))),
+    }
+    if "fused" in res:
+        f = res["fused"]
+        line["fused_peer_store"] = {
+            "what": "kernels store their result tiles into rank 0's buffer over NVLink from their own epilogue (no separate gather)",
+            "value": n / (f[3] * 1e-3) / 1e9, "ms": {"scatter": f[0], "lockin_with_stores_to_root": f[1], "total": f[3]},
+            "ingress_of_root_GBs": out_bytes_remote / (f[1] * 1e-3) / 1e9,
+        }
+    return line
 
 
 def run_chain(args, rank, world, local):
@@ -460,20 +626,21 @@ def run_chain(args, rank, world, local):
         def step(i):
             ctx.chain(k, ba, st, x, y, lanes=lanes, layout=1)
 
-        if lg == 10:
+        if lg in (10, 16, 20):  # one point per kernel path: fused two-pass (8- and 16-lane tiles), single pass
             step(0)
             torch.cuda.synchronize()
-            sub = 8
-            xs = x.view(lanes, n_low * 16)[:sub, :512 * 16].contiguous().cpu().numpy()
+            idx = torch.from_numpy(strided_lanes(lanes, 24)).to(dev)
+            sub, ns = int(idx.numel()), min(n_low, 512) * 16
+            xs = x.view(lanes, n_low * 16).index_select(0, idx)[:, :ns].contiguous().cpu().numpy()
             so = np.zeros((W, sub), np.float32)
-            want = O.chain_lanes(k, ba, so, xs.reshape(-1), sub, 1)
-            got = y.view(lanes, n_low * 16)[:sub, :512 * 16].contiguous().cpu().numpy().reshape(-1)
+            want = O.chain_lanes(k, ba, so, xs.reshape(-1), sub, 1, nthreads=host_threads())
+            got = y.view(lanes, n_low * 16).index_select(0, idx)[:, :ns].contiguous().cpu().numpy().reshape(-1)
             if not np.array_equal(got.view(np.uint32), want.view(np.uint32)):
-                raise SystemExit("bench: GPU chain output differs from the oracle")
+                raise SystemExit(f"bench: GPU chain output differs from the oracle at 2^{lg} lanes")
             st.zero_()
         ms, launches, clocks = time_steps(step, 3, 2, world, local, ctx, dev)
         points.append({"lanes_per_gpu": lanes, "samples_per_lane": n_low * 16, "GSa/s": world * n * 3 / (ms * 1e-3) / 1e9,
-                       "GB/s": 8.0 * n * 3 / (ms * 1e-3) / 1e9})
+                       "GB/s": 8.0 * n * 3 / (ms * 1e-3) / 1e9, "kernel": ctx.last_kernel})
         del x, y, st
         torch.cuda.empty_cache()
     if rank != 0:
@@ -488,7 +655,7 @@ def run_chain(args, rank, world, local):
         "sweep": points,
         "roofline": {"bound": "hbm", "achieved": best["GB/s"], "peak": peak, "unit": "GB/s", "frac": best["GB/s"] / peak,
                      "traffic": None, "peak_source": peak_src},
-        "parity_check": "2^10-lane point == oracle on 8 lanes x 8192 samples",
+        "parity_check": "2^10-, 2^16- and 2^20-lane points == oracle on 24+ lanes strided over the lane range x up to 8192 samples",
     }
 
 
@@ -571,20 +738,24 @@ def run_biquad(args, rank, world, local):
     def step(i):
         cfg.block(st, xin[i % nring], yout[i % 2], layout)
 
-    # parity gate: first step against the oracle on a lane subset (all frames of 64 lanes)
+    # parity gate: first step against the oracle on lanes strided over the whole launch (every CTA's box is
+    # sampled somewhere, plus the first and last 8 lanes), all frames, and the filter state after the step
     step(0)
     torch.cuda.synchronize()
-    sub = 64
+    idx_np = strided_lanes(lanes, 80)
+    idx = torch.from_numpy(idx_np).to(dev)
+    sub = int(idx.numel())
     if layout == 0:
-        xs = xin[0].view(frames, lanes)[:, :sub].contiguous().cpu().numpy()
-        got = yout[0].view(frames, lanes)[:, :sub].contiguous().cpu().numpy().reshape(-1)
+        xs = xin[0].view(frames, lanes).index_select(1, idx).contiguous().cpu().numpy()
+        got = yout[0].view(frames, lanes).index_select(1, idx).contiguous().cpu().numpy().reshape(-1)
     else:
-        xs = xin[0].view(lanes, frames)[:sub].contiguous().cpu().numpy()
-        got = yout[0].view(lanes, frames)[:sub].contiguous().cpu().numpy().reshape(-1)
+        xs = xin[0].view(lanes, frames).index_select(0, idx).contiguous().cpu().numpy()
+        got = yout[0].view(lanes, frames).index_select(0, idx).contiguous().cpu().numpy().reshape(-1)
     so = np.zeros((4, sub), np.int32)
     want = O.biquad_lanes("df1", "i32", bq.ba, F_BITS, None, so, xs.reshape(-1), sub, layout, nthreads=host_threads())
-    if not np.array_equal(got, want) or not np.array_equal(st.numpy()[:, :sub], so):
+    if not np.array_equal(got, want) or not np.array_equal(st.numpy()[:, idx_np], so):
         raise SystemExit("bench: GPU output differs from the oracle -- refusing to report a number")
+    kernel_family = ctx.last_kernel
 
     for i in range(args.warmup):
         step(i + 1)
@@ -599,11 +770,17 @@ def run_biquad(args, rank, world, local):
     e1.record()
     torch.cuda.synchronize()
     launches = ctx.launches - l0
-    keep_busy_until_sampled(sampler, step)
-    clocks = sampler.stop()
-    barrier(world)
     ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
     value = world * n * steps / (ms * 1e-3) / 1e9
+    if args.profile or args.full:
+        keep_busy_until_sampled(sampler, step)
+        sus_ms, sus_n = None, 0
+    else:
+        # the K timed steps are a ~25 ms burst at boost clocks: the same step for >= 2 s shows the rate a long
+        # job sustains under the power cap (the clock sampler keeps running through it)
+        sus_ms, sus_n = sustained_loop(step, ms / steps, world, dev, args.sustained_seconds)
+    clocks = sampler.stop()
+    barrier(world)
 
     if args.profile:
         if rank == 0:
@@ -625,7 +802,7 @@ def run_biquad(args, rank, world, local):
     torch.cuda.synchronize()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, world, dev)
     e2e = world * ef * lanes * esteps / (e2e_ms * 1e-3) / 1e9
-    h2d_gbs, d2h_gbs = pcie_peak(dev)
+    h2d_gbs, d2h_gbs = pcie_peak(dev, world=world)
 
     del xin, yout, xh, yh
     torch.cuda.empty_cache()
@@ -635,6 +812,7 @@ def run_biquad(args, rank, world, local):
     per_launch_bytes = 8.0 * n  # 4 B read + 4 B written per sample; state/coeff traffic ~0
     achieved = per_launch_bytes * launches / (ms * 1e-3) / 1e9 if launches else 0.0
     cpu_v, cpu_dt, cpu_sample = cpu_calibrated("biquad", host_threads(), args.cpu_seconds) if world == 1 else (None, None, "measured at N=1 only")
+    cpu1_v = cpu_calibrated("biquad", 1, max(2.0, args.cpu_seconds / 4))[0] if world == 1 else None
     line = {
         "metric": metric_name("biquad"), "value": value, "unit": "GSa/s", "n_gpus": world, "steps": steps,
         "warmup": args.warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
@@ -642,14 +820,22 @@ def run_biquad(args, rank, world, local):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic_from_profiles("biquad_df1_i32_fm_bytes_per_launch"),
                      "peak_source": peak_src, "kernel": "tma_lanes_kernel<Df1Op<int,false,1>> (frame-major: 256-lane x 8-frame TMA boxes)" if layout == 0 else "tma_lanes_kernel<Df1Op<int,false,1>> (lane-major: swizzled 16-frame x 32-lane TMA boxes)",
-                     "algorithmic_bytes_per_launch": per_launch_bytes},
+                     "kernel_family": kernel_family,
+                     "algorithmic_bytes_per_launch": per_launch_bytes,
+                     "sustained": None if sus_ms is None else {
+                         "what": f"the same step repeated {sus_n} times (>= {args.sustained_seconds} s), power-capped clocks",
+                         "value_GSa/s": world * n / (sus_ms * 1e-3) / 1e9, "achieved": per_launch_bytes / (sus_ms * 1e-3) / 1e9,
+                         "frac": per_launch_bytes / (sus_ms * 1e-3) / 1e9 / peak, "steps": sus_n}},
         "cpu_baseline": {"value": cpu_v, "unit": "GSa/s", "cores": host_threads(), "kind": "port",
-                         "sample": cpu_sample, "seconds": cpu_dt},
+                         "sample": cpu_sample, "seconds": cpu_dt, "one_core": {"value": cpu1_v, "unit": "GSa/s", "cores": 1},
+                         "build": O.build_flags() + " -ffp-contract=off -fopenmp (built on this host)"},
         "e2e": {"value": e2e, "unit": "GSa/s", "h2d_bytes_per_step": 4 * ef * lanes, "d2h_bytes_per_step": 4 * ef * lanes,
                 "frames_per_step": ef, "steps": esteps, "api": "idsp_biquad_df1_i32_host (pinned host buffers)",
-                "pcie_gbs": {"h2d": h2d_gbs, "d2h": d2h_gbs, "how": "256 MiB pinned copies, both directions at once"},
+                "pcie_gbs": {"h2d": h2d_gbs, "d2h": d2h_gbs,
+                             "how": "256 MiB pinned copies, both directions at once, all ranks at the same time (barrier), slowest rank"},
                 "bound": "PCIe: 4 B in + 4 B out per sample", "frac_of_pcie": (e2e / world) * 4.0 / min(h2d_gbs, d2h_gbs)},
-        "gpu_launches": int(launches), "clocks": clocks, "parity_check": "first step == oracle on 64 lanes x all frames",
+        "gpu_launches": int(launches), "clocks": clocks,
+        "parity_check": f"first step == oracle on {sub} lanes strided over all {lanes} lanes (every TMA box family, first / last 8) x all frames + state",
     }
     if layout == 1:
         line["config"]["workload"] = line["config"]["workload"].replace("frame-major", "lane-major")
@@ -727,13 +913,14 @@ def run_hbf(args, rank, world, local):
 
     step(0)
     torch.cuda.synchronize()
-    sub = 32
+    idx = torch.from_numpy(strided_lanes(lanes_s, 40)).to(dev)
+    sub = int(idx.numel())
     if hl == 1:
-        xs = xin[0].view(lanes_s, HBF_INPUTS)[:sub].contiguous().cpu().numpy().reshape(-1)
-        got = yout[0].view(lanes_s, n_out)[:sub].contiguous().cpu().numpy().reshape(-1)
+        xs = xin[0].view(lanes_s, HBF_INPUTS).index_select(0, idx).contiguous().cpu().numpy().reshape(-1)
+        got = yout[0].view(lanes_s, n_out).index_select(0, idx).contiguous().cpu().numpy().reshape(-1)
     else:
-        xs = xin[0].view(n_out, lanes_s, 16)[:, :sub].contiguous().cpu().numpy().reshape(-1)
-        got = yout[0].view(n_out, lanes_s)[:, :sub].contiguous().cpu().numpy().reshape(-1)
+        xs = xin[0].view(n_out, lanes_s, 16).index_select(1, idx).contiguous().cpu().numpy().reshape(-1)
+        got = yout[0].view(n_out, lanes_s).index_select(1, idx).contiguous().cpu().numpy().reshape(-1)
     so = np.zeros((O.hbf_dec_state_words(4), sub), np.float32)
     want = O.hbf_dec_cascade_lanes(4, so, xs, sub, hl, nthreads=host_threads())
     if not np.array_equal(got.view(np.uint32), want.view(np.uint32)):
@@ -775,7 +962,7 @@ def run_hbf(args, rank, world, local):
     torch.cuda.synchronize()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, world, dev)
     e2e = world * el * HBF_INPUTS * esteps / (e2e_ms * 1e-3) / 1e9
-    h2d_gbs, d2h_gbs = pcie_peak(dev)
+    h2d_gbs, d2h_gbs = pcie_peak(dev, world=world)
     del xin, yout, xh, yh
     torch.cuda.empty_cache()
     if rank != 0:
@@ -798,9 +985,11 @@ def run_hbf(args, rank, world, local):
                          "sample": cpu_sample, "seconds": cpu_dt},
         "e2e": {"value": e2e, "unit": "GSa/s", "h2d_bytes_per_step": 4 * el * HBF_INPUTS, "d2h_bytes_per_step": 4 * el * n_out,
                 "steps": esteps, "api": "idsp_hbf_dec_cascade_f32_host (pinned host buffers)",
-                "pcie_gbs": {"h2d": h2d_gbs, "d2h": d2h_gbs, "how": "256 MiB pinned copies, both directions at once"},
+                "pcie_gbs": {"h2d": h2d_gbs, "d2h": d2h_gbs,
+                             "how": "256 MiB pinned copies, both directions at once, all ranks at the same time (barrier), slowest rank"},
                 "bound": "PCIe: 4 B in + 0.25 B out per sample", "frac_of_pcie": (e2e / world) * 4.0 / h2d_gbs},
-        "gpu_launches": int(launches), "clocks": clocks, "parity_check": "first step == oracle on 32 lanes",
+        "gpu_launches": int(launches), "clocks": clocks,
+        "parity_check": f"first step == oracle on {sub} lanes strided over the slice (first / last 8 included) x all samples",
     }
     return line
 
@@ -811,7 +1000,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="biquad", choices=["biquad", "hbf", "lockin", "chain", "plumbing"])
+    ap.add_argument("--workload", default="biquad", choices=["biquad", "hbf", "lockin", "lockin_sharded", "chain", "plumbing"])
     ap.add_argument("--frames", type=int, default=16384, help="frames per step (biquad)")
     ap.add_argument("--ring", type=int, default=3, help="distinct resident input blocks")
     ap.add_argument("--full", action="store_true", help="run the whole 1e7-frame job (biquad)")
@@ -819,6 +1008,8 @@ def main():
     ap.add_argument("--e2e-frames", type=int, default=2048)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--sustained-seconds", type=float, default=2.0, help="length of the sustained-rate loop after the timed steps")
+    ap.add_argument("--sharded-frames", type=int, default=4096, help="frames per pass of the sharded lock-in leg (root-resident)")
     ap.add_argument("--layout", type=int, default=None, choices=[0, 1],
                     help="0 frame-major, 1 lane-major (default: biquad 0, hbf 1)")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary (hbf) measurement of the default run")
@@ -848,26 +1039,34 @@ def main():
             extra = run_hbf(a2, rank, world, local)
             if line is not None and extra is not None:
                 line["extra"] = {"hbf_dec16_f32": {k: extra[k] for k in ("metric", "value", "unit", "steps", "ms_per_step", "dtype", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "parity_check")}}
-            # BASELINE configs[3] and configs[4] in the same run (N = 1 only, short; a failure here must not
-            # cost the headline line, so it is recorded instead of raised)
-            if world == 1 and line is not None:
-                import torch
+            # BASELINE configs[3] (resident per GPU, and as the sharded data plane over NVLink) and configs[4] in
+            # the same run at every N; a failure here must not cost the headline line, so it is recorded
+            # instead of raised (every rank takes the same path: the legs contain collectives)
+            import torch
 
+            if line is not None:
                 line.setdefault("extra", {})
-                for name, fn, keys in (("lockin_i32", run_lockin, ("metric", "value", "unit", "steps", "ms_per_step", "dtype", "config", "roofline", "gpu_launches", "parity_check")),
-                                       ("chain_f32", run_chain, ("metric", "value", "unit", "dtype", "config", "sweep", "roofline", "parity_check"))):
-                    try:
-                        torch.cuda.empty_cache()
-                        a3 = copy.copy(args)
-                        a3.steps = min(args.steps, 24)
-                        res = fn(a3, rank, world, local)
-                        line["extra"][name] = {k: res[k] for k in keys}
-                    except (Exception, SystemExit) as e:  # noqa: BLE001
+            for name, fn, keys in (("lockin_i32", run_lockin, ("metric", "value", "unit", "n_gpus", "steps", "ms_per_step", "dtype", "config", "roofline", "gpu_launches", "parity_check")),
+                                   ("lockin_sharded", run_lockin_sharded, None),
+                                   ("chain_f32", run_chain, ("metric", "value", "unit", "n_gpus", "dtype", "config", "sweep", "roofline", "e2e", "parity_check"))):
+                try:
+                    torch.cuda.empty_cache()
+                    a3 = copy.copy(args)
+                    a3.steps = min(args.steps, 24)
+                    res = fn(a3, rank, world, local)
+                    if line is not None and res is not None:
+                        line["extra"][name] = res if keys is None else {k: res[k] for k in keys if k in res}
+                except (Exception, SystemExit) as e:  # noqa: BLE001
+                    if world > 1:
+                        raise  # a rank that left a collective leg cannot rejoin: fail loudly instead of hanging
+                    if line is not None:
                         line["extra"][name] = {"error": f"{type(e).__name__}: {e}"[:300]}
     elif args.workload == "hbf":
         line = run_hbf(args, rank, world, local)
     elif args.workload == "lockin":
         line = run_lockin(args, rank, world, local)
+    elif args.workload == "lockin_sharded":
+        line = run_lockin_sharded(args, rank, world, local)
     elif args.workload == "plumbing":
         line = run_plumbing(args, rank, world, local)
     else:

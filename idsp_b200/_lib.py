@@ -37,6 +37,8 @@ def _signatures():
         "idsp_b200_ipc_export": ([_c_p, _c_p, _c_p], _i),
         "idsp_b200_ipc_open": ([_c_p, _c_p, C.POINTER(_c_p)], _i),
         "idsp_b200_ipc_close": ([_c_p, _c_p], _i),
+        "idsp_b200_memcpy": ([_c_p, _c_p, _c_p, _sz, _i], _i),
+        "idsp_b200_memset": ([_c_p, _c_p, _i, _sz], _i),
         "idsp_hbf_taps": ([_i, C.POINTER(_i)], C.POINTER(C.c_float)),
         "idsp_hbf_dec_state_words": ([_i], _sz),
         "idsp_hbf_int_state_words": ([_i], _sz),

@@ -195,6 +195,25 @@ extern "C" int idsp_b200_ipc_close(idsp_ctx *ctx, void *ptr) {
     return IDSP_OK;
 }
 
+extern "C" int idsp_b200_memcpy(idsp_ctx *ctx, void *dst, const void *src, size_t bytes, int kind) {
+    int r = idsp_use_device(ctx);
+    if (r) return r;
+    if (bytes == 0) return IDSP_OK;
+    IDSP_CHECK_ARG(dst != nullptr && src != nullptr, "dst/src is null");
+    IDSP_CHECK_ARG(kind >= 0 && kind <= 2, "kind must be 0 (h2d), 1 (d2h) or 2 (d2d)");
+    const cudaMemcpyKind k = kind == 0 ? cudaMemcpyHostToDevice : kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    IDSP_CUDA(cudaMemcpyAsync(dst, src, bytes, k, ctx->stream));
+    return IDSP_OK;
+}
+extern "C" int idsp_b200_memset(idsp_ctx *ctx, void *ptr, int value, size_t bytes) {
+    int r = idsp_use_device(ctx);
+    if (r) return r;
+    if (bytes == 0) return IDSP_OK;
+    IDSP_CHECK_ARG(ptr != nullptr, "ptr is null");
+    IDSP_CUDA(cudaMemsetAsync(ptr, value, bytes, ctx->stream));
+    return IDSP_OK;
+}
+
 extern "C" int idsp_b200_set_kernel_policy(idsp_ctx *ctx, int policy) {
     if (!ctx || policy < 0 || policy > 3) {
         idsp_set_error("idsp_b200_set_kernel_policy: bad argument");
@@ -282,11 +301,8 @@ int idsp_host_stream(idsp_ctx *ctx, const HostStreamSpec &spec, const void *x, v
     const size_t bigger = in_unit > out_unit ? in_unit : out_unit;
     // chunk size per direction: small enough that the un-overlapped first H2D / last D2H are a
     // few per cent of a call, large enough to keep PCIe efficient (IDSP_HOST_CHUNK_MB overrides)
-    static size_t chunk_mb = 0;
-    if (!chunk_mb) {
-        const char *e = getenv("IDSP_HOST_CHUNK_MB");
-        chunk_mb = e && atoi(e) > 0 ? (size_t)atoi(e) : 32;
-    }
+    const char *cm = getenv("IDSP_HOST_CHUNK_MB");  // read per call: no shared mutable state between ctxs
+    const size_t chunk_mb = cm && atoi(cm) > 0 ? (size_t)atoi(cm) : 32;
     const size_t target = chunk_mb << 20;
     size_t chunk = bigger ? target / bigger : n_axis;
     if (fm) {
@@ -318,7 +334,14 @@ int idsp_host_stream(idsp_ctx *ctx, const HostStreamSpec &spec, const void *x, v
         IDSP_CUDA(cudaEventRecord(ctx->ev_h2d[b], ctx->s_h2d));
         IDSP_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[b], 0));
         r = launch(dblobs, ctx->dev_in[b], ctx->dev_out[b], a0, an);
-        if (r) return r;
+        if (r) {
+            // copies into the caller's buffers may still be in flight: drain all three streams before
+            // handing the error back (the caller may free x / y right away)
+            cudaStreamSynchronize(ctx->s_h2d);
+            cudaStreamSynchronize(ctx->stream);
+            cudaStreamSynchronize(ctx->s_d2h);
+            return r;
+        }
         IDSP_CUDA(cudaEventRecord(ctx->ev_k[b], ctx->stream));
         IDSP_CUDA(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_k[b], 0));
         IDSP_CUDA(cudaMemcpyAsync((char *)y + a0 * out_unit, ctx->dev_out[b], an * out_unit,

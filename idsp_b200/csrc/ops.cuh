@@ -459,9 +459,21 @@ __device__ __forceinline__ int32_t sat_sub(int32_t a, int32_t b) {
     asm("sub.sat.s32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
     return r;
 }
+// IDSP_LP_DUPK (experiment, off): read the gains of the second `s1 += d` from a second copy in the kernel
+// parameters so that ptxas cannot merge the two updates.  Measured effect: ptxas then emits 4 more
+// IMAD.WIDE but keeps the 3-input carry-chain adds, so nothing is saved on the ALU pipe.
+#ifdef IDSP_LP_DUPK
+#define IDSP_KB(p, i) (p).kk[i]
+#else
+#define IDSP_KB(p, i) (p).k[i]
+#endif
+// k0b / k1b: the same gains read from a second copy in the kernel parameters.  ptxas cannot prove the two
+// copies equal, so the second `s1 += d` stays two IMAD.WIDE (multiplier pipe, a quarter busy in the
+// lock-in kernel) instead of being merged with the first into 64-bit carry-chain adds on the ALU pipe,
+// which bounds that kernel: 4 IMAD.WIDE instead of 2 IMAD.WIDE + 4 IADD3 per step.
 template <int ORDER>
-__device__ __forceinline__ int32_t lowpass_step(int32_t k0, int32_t k1, int64_t &s0, int64_t &s1,
-                                                int32_t x) {
+__device__ __forceinline__ int32_t lowpass_step(int32_t k0, int32_t k1, int32_t k0b, int32_t k1b, int64_t &s0,
+                                                int64_t &s1, int32_t x) {
     // d = dx*k0 (+ (s1>>32)*k1); every `+= d` below is folded into multiply-adds, which is
     // exact because i64 addition wraps (src/lowpass.rs:59-72 in release arithmetic)
     const int32_t dx = sat_sub(x, (int32_t)(s0 >> 32));
@@ -469,14 +481,14 @@ __device__ __forceinline__ int32_t lowpass_step(int32_t k0, int32_t k1, int64_t 
     if constexpr (ORDER == 1) {
         s0 = mad_wide(dx, k0, s0);
         y = (int32_t)(s0 >> 32);
-        s0 = mad_wide(dx, k0, s0);
+        s0 = mad_wide(dx, k0b, s0);
     } else {
         const int32_t s1h = (int32_t)(s1 >> 32);
         s1 = mad_wide(dx, k0, mad_wide(s1h, k1, s1));
         s0 = (int64_t)((uint64_t)s0 + (uint64_t)s1);
         y = (int32_t)(s0 >> 32);
         s0 = (int64_t)((uint64_t)s0 + (uint64_t)s1);
-        s1 = mad_wide(dx, k0, mad_wide(s1h, k1, s1));
+        s1 = mad_wide(dx, k0b, mad_wide(s1h, k1b, s1));
     }
     return y;
 }
@@ -486,6 +498,7 @@ template <int ORDER> struct LowpassOp : OpHooks {
     static constexpr bool LM_SMALL = true;
     struct Params {
         int32_t k[2];
+        int32_t kk[2];  // = k (see lowpass_step)
         int64_t *st;
     };
     int64_t s0, s1;
@@ -498,7 +511,7 @@ template <int ORDER> struct LowpassOp : OpHooks {
         if (ORDER == 2) p.st[stride + lane] = s1;
     }
     __device__ __forceinline__ int32_t step(const Params &p, int32_t x) {
-        return lowpass_step<ORDER>(p.k[0], p.k[1], s0, s1, x);
+        return lowpass_step<ORDER>(p.k[0], p.k[1], IDSP_KB(p, 0), IDSP_KB(p, 1), s0, s1, x);
     }
 };
 
@@ -514,6 +527,7 @@ template <int ORDER, bool SMEM_LUT = false> struct LockinOp {
     static constexpr int SMEM_EXTRA_WORDS = SMEM_LUT ? 256 : 0;  // expanded cossin table staged per CTA
     struct Params {
         int32_t k[2];
+        int32_t kk[2];  // = k (see lowpass_step)
         int32_t *accu_state;
         const int32_t *accu_step;
         int64_t *st;  // [2*ORDER][stride]
@@ -550,8 +564,8 @@ template <int ORDER, bool SMEM_LUT = false> struct LockinOp {
         int32_t mi = (int32_t)(((int64_t)c * (int64_t)x) >> 32);
         int32_t mq = (int32_t)(((int64_t)s * (int64_t)x) >> 32);
         int2 r;
-        r.x = lowpass_step<ORDER>(p.k[0], p.k[1], i0, i1, mi);
-        r.y = lowpass_step<ORDER>(p.k[0], p.k[1], q0, q1, mq);
+        r.x = lowpass_step<ORDER>(p.k[0], p.k[1], IDSP_KB(p, 0), IDSP_KB(p, 1), i0, i1, mi);
+        r.y = lowpass_step<ORDER>(p.k[0], p.k[1], IDSP_KB(p, 0), IDSP_KB(p, 1), q0, q1, mq);
         return r;
     }
 };
@@ -567,6 +581,7 @@ template <int ORDER, bool SMEM_LUT = false> struct LockinPhaseOp {
     static constexpr int SMEM_EXTRA_WORDS = SMEM_LUT ? 256 : 0;
     struct Params {
         int32_t k[2];
+        int32_t kk[2];  // = k (see lowpass_step)
         int64_t *st;  // [2*ORDER][stride]
         const uint32_t *lut;
     };
@@ -596,8 +611,8 @@ template <int ORDER, bool SMEM_LUT = false> struct LockinPhaseOp {
         const int32_t mi = (int32_t)(((int64_t)c * (int64_t)xp.x) >> 32);
         const int32_t mq = (int32_t)(((int64_t)s * (int64_t)xp.x) >> 32);
         int2 r;
-        r.x = lowpass_step<ORDER>(p.k[0], p.k[1], i0, i1, mi);
-        r.y = lowpass_step<ORDER>(p.k[0], p.k[1], q0, q1, mq);
+        r.x = lowpass_step<ORDER>(p.k[0], p.k[1], IDSP_KB(p, 0), IDSP_KB(p, 1), i0, i1, mi);
+        r.y = lowpass_step<ORDER>(p.k[0], p.k[1], IDSP_KB(p, 0), IDSP_KB(p, 1), q0, q1, mq);
         return r;
     }
 };
@@ -612,6 +627,7 @@ template <int ORDER> struct LockinLoOp : OpHooks {
     static constexpr bool HEAVY = true;
     struct Params {
         int32_t k[2];
+        int32_t kk[2];  // = k (see lowpass_step)
         int64_t *st;
     };
     int64_t i0, i1, q0, q1;
@@ -631,8 +647,8 @@ template <int ORDER> struct LockinLoOp : OpHooks {
         const int32_t mi = (int32_t)(((int64_t)v.re * (int64_t)v.x) >> 32);
         const int32_t mq = (int32_t)(((int64_t)v.im * (int64_t)v.x) >> 32);
         int2 r;
-        r.x = lowpass_step<ORDER>(p.k[0], p.k[1], i0, i1, mi);
-        r.y = lowpass_step<ORDER>(p.k[0], p.k[1], q0, q1, mq);
+        r.x = lowpass_step<ORDER>(p.k[0], p.k[1], IDSP_KB(p, 0), IDSP_KB(p, 1), i0, i1, mi);
+        r.y = lowpass_step<ORDER>(p.k[0], p.k[1], IDSP_KB(p, 0), IDSP_KB(p, 1), q0, q1, mq);
         return r;
     }
 };

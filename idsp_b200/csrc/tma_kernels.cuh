@@ -528,6 +528,24 @@ static int tma_try_launch(idsp_ctx *ctx, const typename Op::Params &p, const typ
             // one warp per CTA, 64-byte input rows / 128-byte output rows, 10 KB per warp: the op
             // is ALU-bound, so resident warps count for more than long DRAM bursts
             r = tma_launch_cfg<Op, true, 16, 3, 1, 1>(ctx, p, x, y, frames, lanes, sstride);
+#ifdef IDSP_TUNE
+        } else if (getenv("IDSP_OUT8_CFG") && Op::HEAVY) {
+            // tuning builds: tile shape / residency sweep of the compute-bound 8-byte ops (lock-in)
+            switch (atoi(getenv("IDSP_OUT8_CFG"))) {
+                case 1: r = tma_launch_cfg<Op, false, 4, 4, 2, 4, true>(ctx, p, x, y, frames, lanes, sstride); break;
+                case 2: r = tma_launch_cfg<Op, false, 4, 3, 2, 4, true>(ctx, p, x, y, frames, lanes, sstride); break;
+                case 3: r = tma_launch_cfg<Op, false, 8, 3, 1, 1>(ctx, p, x, y, frames, lanes, sstride); break;
+                case 4: r = tma_launch_cfg<Op, false, 8, 3, 1, 2>(ctx, p, x, y, frames, lanes, sstride); break;
+                case 5: r = tma_launch_cfg<Op, false, 4, 4, 2, 2>(ctx, p, x, y, frames, lanes, sstride); break;
+                case 6: r = tma_launch_cfg<Op, false, 8, 2, 1, 4, true>(ctx, p, x, y, frames, lanes, sstride); break;
+                case 7: r = tma_launch_cfg<Op, false, 4, 3, 1, 4, true>(ctx, p, x, y, frames, lanes, sstride); break;
+                case 8: r = tma_launch_cfg<Op, false, 16, 2, 1, 1>(ctx, p, x, y, frames, lanes, sstride); break;
+                case 9: r = tma_launch_cfg<Op, false, 4, 4, 2, 1>(ctx, p, x, y, frames, lanes, sstride); break;
+                case 10: r = tma_launch_cfg<Op, false, 8, 3, 2, 2, true>(ctx, p, x, y, frames, lanes, sstride); break;
+                case 11: r = tma_launch_cfg<Op, false, 4, 4, 2, 2, true>(ctx, p, x, y, frames, lanes, sstride); break;
+                default: r = tma_launch_cfg<Op, false, 8, 3, 2, 4, true>(ctx, p, x, y, frames, lanes, sstride); break;
+            }
+#endif
         } else if ((lanes + 127) / 128 >= sms) {
             // compute-bound: avoid a nearly empty last wave (131 072 lanes: 1024 CTAs fit in one
             // wave with 3 load stages, 7 CTAs per SM, but need 1.15 waves with 4 stages, 6 per SM)

@@ -185,14 +185,14 @@ extern "C" int idsp_lowpass_i32(idsp_ctx *ctx, int order, const int32_t *k, int6
     IDSP_CHECK_ARG(state && x && y, "state/x/y must not be null");
     if (order == 1) {
         LowpassOp<1>::Params p;
-        p.k[0] = k[0];
-        p.k[1] = 0;
+        p.k[0] = p.kk[0] = k[0];
+        p.k[1] = p.kk[1] = 0;
         p.st = state;
         return launch_lanes_best<LowpassOp<1>>(ctx, p, x, y, frames, lanes, lanes, layout);
     }
     LowpassOp<2>::Params p;
-    p.k[0] = k[0];
-    p.k[1] = k[1];
+    p.k[0] = p.kk[0] = k[0];
+    p.k[1] = p.kk[1] = k[1];
     p.st = state;
     return launch_lanes_best<LowpassOp<2>>(ctx, p, x, y, frames, lanes, lanes, layout);
 }
@@ -205,8 +205,8 @@ int lockin_dev(idsp_ctx *ctx, int order, const int32_t *k, int32_t *accu_state,
 #define GO(ORDER)                                                                    \
     do {                                                                             \
         LockinOp<ORDER, true>::Params pt;                                            \
-        pt.k[0] = k[0];                                                              \
-        pt.k[1] = ORDER == 2 ? k[1] : 0;                                             \
+        pt.k[0] = pt.kk[0] = k[0];                                                   \
+        pt.k[1] = pt.kk[1] = ORDER == 2 ? k[1] : 0;                                  \
         pt.accu_state = accu_state;                                                  \
         pt.accu_step = accu_step;                                                    \
         pt.st = lp_state;                                                            \
@@ -214,8 +214,8 @@ int lockin_dev(idsp_ctx *ctx, int order, const int32_t *k, int32_t *accu_state,
         int tr = tma_try_launch<LockinOp<ORDER, true>>(ctx, pt, x, (int2 *)iq, frames, lanes, sstride, layout); \
         if (tr != IDSP_TMA_NOT_APPLICABLE) return tr;                                \
         LockinOp<ORDER, false>::Params pg;                                           \
-        pg.k[0] = pt.k[0];                                                           \
-        pg.k[1] = pt.k[1];                                                           \
+        pg.k[0] = pg.kk[0] = pt.k[0];                                                \
+        pg.k[1] = pg.kk[1] = pt.k[1];                                                \
         pg.accu_state = accu_state;                                                  \
         pg.accu_step = accu_step;                                                    \
         pg.st = lp_state;                                                            \
@@ -276,15 +276,15 @@ extern "C" int idsp_lockin_phase_i32(idsp_ctx *ctx, int order, const int32_t *k,
 #define GO(ORDER)                                                                    \
     do {                                                                             \
         LockinPhaseOp<ORDER, true>::Params pt;                                       \
-        pt.k[0] = k[0];                                                              \
-        pt.k[1] = ORDER == 2 ? k[1] : 0;                                             \
+        pt.k[0] = pt.kk[0] = k[0];                                                   \
+        pt.k[1] = pt.kk[1] = ORDER == 2 ? k[1] : 0;                                  \
         pt.st = lp_state;                                                            \
         pt.lut = lut;                                                                \
         int tr = tma_try_launch<LockinPhaseOp<ORDER, true>>(ctx, pt, (const int2 *)xp, (int2 *)iq, frames, lanes, lanes, layout); \
         if (tr != IDSP_TMA_NOT_APPLICABLE) return tr;                                \
         LockinPhaseOp<ORDER, false>::Params pg;                                      \
-        pg.k[0] = pt.k[0];                                                           \
-        pg.k[1] = pt.k[1];                                                           \
+        pg.k[0] = pg.kk[0] = pt.k[0];                                                \
+        pg.k[1] = pg.kk[1] = pt.k[1];                                                \
         pg.st = lp_state;                                                            \
         pg.lut = lut;                                                                \
         return launch_lanes<LockinPhaseOp<ORDER, false>>(ctx, pg, (const int2 *)xp, (int2 *)iq, frames, lanes, lanes, layout); \
@@ -302,14 +302,14 @@ extern "C" int idsp_lockin_lo_i32(idsp_ctx *ctx, int order, const int32_t *k, in
     IDSP_CHECK_ARG((((uintptr_t)iq) & 7) == 0, "iq must be 8-byte aligned");
     if (order == 1) {
         LockinLoOp<1>::Params p;
-        p.k[0] = k[0];
-        p.k[1] = 0;
+        p.k[0] = p.kk[0] = k[0];
+        p.k[1] = p.kk[1] = 0;
         p.st = lp_state;
         return launch_lanes<LockinLoOp<1>>(ctx, p, (const XLo *)xlo, (int2 *)iq, frames, lanes, lanes, layout);
     }
     LockinLoOp<2>::Params p;
-    p.k[0] = k[0];
-    p.k[1] = k[1];
+    p.k[0] = p.kk[0] = k[0];
+    p.k[1] = p.kk[1] = k[1];
     p.st = lp_state;
     return launch_lanes<LockinLoOp<2>>(ctx, p, (const XLo *)xlo, (int2 *)iq, frames, lanes, lanes, layout);
 }

@@ -124,7 +124,10 @@ class Comm:
 
     def __init__(self, device: int, group=None):
         self.device = int(device)
-        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if dist.is_available() and dist.is_initialized():
+            self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        else:  # single process: a one-rank communicator (never touches NCCL)
+            self.rank, self.world = 0, 1
         self._ctx = default_context(self.device)
         self._L = _lib.lib()
         ident = [None]

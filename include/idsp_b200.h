@@ -96,6 +96,13 @@ int idsp_b200_mfree(idsp_ctx *ctx, void *ptr);
 int idsp_b200_ipc_export(idsp_ctx *ctx, const void *ptr, unsigned char handle[IDSP_IPC_HANDLE_BYTES]);
 int idsp_b200_ipc_open(idsp_ctx *ctx, const unsigned char handle[IDSP_IPC_HANDLE_BYTES], void **ptr);
 int idsp_b200_ipc_close(idsp_ctx *ctx, void *ptr);
+/* Copies on the ctx stream for callers that keep samples and state resident on the device between calls
+ * (a chained graph, dsp-process/src/compose.rs:13-113, then crosses PCIe once at each end instead of once
+ * per stage): kind 0 = host -> device, 1 = device -> host, 2 = device -> device.  Asynchronous like every
+ * other call (pinned host memory: idsp_b200_host_alloc); idsp_b200_sync() before reading a download.
+ * idsp_b200_memset zero-fills device memory (zero state = the reference's `Default`). */
+int idsp_b200_memcpy(idsp_ctx *ctx, void *dst, const void *src, size_t bytes, int kind);
+int idsp_b200_memset(idsp_ctx *ctx, void *ptr, int value, size_t bytes);
 /* Kernel selection: 0 = automatic (default), 1 = force the generic LDG kernels,
  * 2 = force the TMA kernels (IDSP_EINVAL if the shape does not qualify),
  * 3 = automatic, with the packed f32x2 variant of the tiled half-band decimator (bit-identical

@@ -87,7 +87,10 @@ template <int F> Biquad<Q32<F>> biquad_from_ba6(const double (&b)[3], const doub
 // BiquadClamp<C, T> (src/iir/biquad.rs:121-171)
 template <class C, class T> struct BiquadClamp {
     Biquad<C> coeff;
-    T u = 0, min = std::numeric_limits<T>::lowest(), max = std::numeric_limits<T>::max();
+    // Clamp::MIN / MAX (src/num.rs:33-54): -inf / +inf for floats, the integer limits otherwise
+    T u = 0;
+    T min = std::numeric_limits<T>::has_infinity ? -std::numeric_limits<T>::infinity() : std::numeric_limits<T>::lowest();
+    T max = std::numeric_limits<T>::has_infinity ? std::numeric_limits<T>::infinity() : std::numeric_limits<T>::max();
 };
 
 // [DirectForm1<T>; N] as the ABI's SoA words [x0 | x1 | y0 | y1] x lanes (biquad.rs:260-269)
@@ -154,6 +157,183 @@ void block(Engine &e, const Lanes<HbfDecCascade<K>> &, HbfDecState<K> &state, co
     check(idsp_hbf_dec_cascade_f32_host(e.ctx(), K, state.words.data(), x, y, y_len / state.lanes, state.lanes,
                                         Layout::value));
 }
+
+// ---------------------------------------------------------------------------------------------
+// Device-resident buffers and states: a chained graph (the reference's tuple chaining,
+// dsp-process/src/compose.rs:13-113, and `Major` scratch-buffered chaining :569-613) keeps its samples
+// and filter states in HBM between stages and crosses PCIe once at each end -- this is what makes the
+// resident-data throughput of the kernels reachable from a reference-side caller.
+// ---------------------------------------------------------------------------------------------
+template <class T> class GpuBuffer {
+   public:
+    GpuBuffer(Engine &e, size_t n, bool zero = false) : e_(&e), n_(n) {
+        void *p = nullptr;
+        check(idsp_b200_malloc(e.ctx(), n * sizeof(T), &p));
+        p_ = static_cast<T *>(p);
+        if (zero) check(idsp_b200_memset(e.ctx(), p_, 0, n * sizeof(T)));
+    }
+    ~GpuBuffer() {
+        if (p_) idsp_b200_mfree(e_->ctx(), p_);
+    }
+    GpuBuffer(const GpuBuffer &) = delete;
+    GpuBuffer &operator=(const GpuBuffer &) = delete;
+    GpuBuffer(GpuBuffer &&o) noexcept : e_(o.e_), p_(o.p_), n_(o.n_) { o.p_ = nullptr; }
+    T *data() { return p_; }
+    const T *data() const { return p_; }
+    size_t size() const { return n_; }
+    void upload(const T *host, size_t n) {
+        if (n > n_) throw Error("GpuBuffer::upload: too long");
+        check(idsp_b200_memcpy(e_->ctx(), p_, host, n * sizeof(T), 0));
+    }
+    void download(T *host, size_t n) const {  // synchronises: the data is in `host` on return
+        if (n > n_) throw Error("GpuBuffer::download: too long");
+        check(idsp_b200_memcpy(e_->ctx(), host, p_, n * sizeof(T), 1));
+        check(idsp_b200_sync(e_->ctx()));
+    }
+
+   private:
+    Engine *e_;
+    T *p_ = nullptr;
+    size_t n_;
+};
+// `[S; N]` on the device: zeroed SoA words (= `Default`), word count from the ABI
+template <class T> struct GpuState {
+    size_t lanes;
+    GpuBuffer<T> words;
+    GpuState(Engine &e, size_t words_per_lane, size_t n) : lanes(n), words(e, words_per_lane * n, true) {}
+};
+
+// Lanes<Biquad<Q32<F>>> on [DirectForm1<i32>; N], device buffers (src/iir/biquad.rs:366-383)
+template <int F, class Layout = FrameMajor>
+void block(Engine &e, const Lanes<Biquad<Q32<F>>> &c, GpuState<int32_t> &state, const GpuBuffer<int32_t> &x,
+           GpuBuffer<int32_t> &y, size_t len, Layout = Layout{}) {
+    if (len % state.lanes || len > x.size() || len > y.size()) throw Error("block: bad length");
+    int32_t ba[5];
+    for (int i = 0; i < 5; i++) ba[i] = c.inner.ba[i].bits;
+    check(idsp_biquad_df1_i32(e.ctx(), ba, F, nullptr, state.words.data(), x.data(), y.data(), len / state.lanes,
+                              state.lanes, Layout::value));
+}
+// Lanes<Biquad<f32>> on [DirectForm1<f32>; N]
+template <class Layout = FrameMajor>
+void block(Engine &e, const Lanes<Biquad<float>> &c, GpuState<float> &state, const GpuBuffer<float> &x,
+           GpuBuffer<float> &y, size_t len, Layout = Layout{}) {
+    if (len % state.lanes || len > x.size() || len > y.size()) throw Error("block: bad length");
+    check(idsp_biquad_df1_f32(e.ctx(), c.inner.ba.data(), 0, nullptr, state.words.data(), x.data(), y.data(),
+                              len / state.lanes, state.lanes, Layout::value));
+}
+inline GpuState<int32_t> df1_state_i32(Engine &e, size_t lanes) { return GpuState<int32_t>(e, 4, lanes); }
+inline GpuState<float> df1_state_f32(Engine &e, size_t lanes) { return GpuState<float>(e, 4, lanes); }
+
+// HBF_DEC_CASCADE / HBF_INT_CASCADE truncated to depth K on device buffers (src/hbf.rs:385-421, 476-512):
+// SplitProcess<[f32; 2^K], f32, HbfDec..> and SplitProcess<f32, [f32; 2^K], HbfInt..>
+template <int K> struct HbfIntCascade {};
+template <int K> GpuState<float> hbf_dec_state(Engine &e, size_t lanes) { return GpuState<float>(e, idsp_hbf_dec_state_words(K), lanes); }
+template <int K> GpuState<float> hbf_int_state(Engine &e, size_t lanes) { return GpuState<float>(e, idsp_hbf_int_state_words(K), lanes); }
+template <int K, class Layout = FrameMajor>
+void block(Engine &e, const Lanes<HbfDecCascade<K>> &, GpuState<float> &state, const GpuBuffer<float> &x, size_t x_len,
+           GpuBuffer<float> &y, size_t y_len, Layout = Layout{}) {
+    if (x_len != (y_len << K) || y_len % state.lanes || x_len > x.size() || y_len > y.size())
+        throw Error("block: x and y lengths do not match");
+    check(idsp_hbf_dec_cascade_f32(e.ctx(), K, state.words.data(), x.data(), y.data(), y_len / state.lanes, state.lanes,
+                                   Layout::value));
+}
+template <int K, class Layout = FrameMajor>
+void block(Engine &e, const Lanes<HbfIntCascade<K>> &, GpuState<float> &state, const GpuBuffer<float> &x, size_t x_len,
+           GpuBuffer<float> &y, size_t y_len, Layout = Layout{}) {
+    if (y_len != (x_len << K) || x_len % state.lanes || x_len > x.size() || y_len > y.size())
+        throw Error("block: x and y lengths do not match");
+    check(idsp_hbf_int_cascade_f32(e.ctx(), K, state.words.data(), x.data(), y.data(), x_len / state.lanes, state.lanes,
+                                   Layout::value));
+}
+
+// Tuple chaining that stays on the device: (HbfDecCascade<K>, HbfIntCascade<K>, Biquad<f32>) as one
+// processor, like `(a, b, c)` / `a * b * c` in the reference (compose.rs:13-113).  `fused` runs the
+// library's single entry point (idsp_chain_f32: one or two passes over HBM), otherwise the three stages
+// run one after the other through device-resident intermediates; both give identical bits.
+template <int K> struct DecIntBiquad {
+    Biquad<float> iir;
+};
+template <int K> struct DecIntBiquadState {
+    size_t lanes;
+    GpuBuffer<float> words;  // [dec cascade | int cascade | DirectForm1] per lane, SoA
+    DecIntBiquadState(Engine &e, size_t n) : lanes(n), words(e, idsp_chain_state_words(K) * n, true) {}
+};
+template <int K, class Layout = FrameMajor>
+void block(Engine &e, const Lanes<DecIntBiquad<K>> &c, DecIntBiquadState<K> &state, const GpuBuffer<float> &x,
+           GpuBuffer<float> &y, size_t len, bool fused = true, Layout = Layout{}) {
+    const size_t lanes = state.lanes;
+    if (len % (lanes << K) || len > x.size() || len > y.size()) throw Error("block: bad length");
+    const size_t n_low = len / (lanes << K);
+    if (fused) {
+        check(idsp_chain_f32(e.ctx(), K, c.inner.iir.ba.data(), state.words.data(), x.data(), y.data(), n_low, lanes,
+                             Layout::value));
+        return;
+    }
+    GpuBuffer<float> low(e, n_low * lanes);
+    float *st = state.words.data();
+    const size_t wd = idsp_hbf_dec_state_words(K), wi = idsp_hbf_int_state_words(K);
+    check(idsp_hbf_dec_cascade_f32(e.ctx(), K, st, x.data(), low.data(), n_low, lanes, Layout::value));
+    check(idsp_hbf_int_cascade_f32(e.ctx(), K, st + wd * lanes, low.data(), y.data(), n_low, lanes, Layout::value));
+    check(idsp_biquad_df1_f32(e.ctx(), c.inner.iir.ba.data(), 0, nullptr, st + (wd + wi) * lanes, y.data(), y.data(),
+                              n_low << K, lanes, Layout::value));
+    e.sync();  // `low` is released on return
+}
+// one PCIe round trip for the three operators on host slices
+template <int K, class Layout = FrameMajor>
+void block(Engine &e, const Lanes<DecIntBiquad<K>> &c, std::vector<float> &state_words, size_t lanes, const float *x,
+           float *y, size_t len, Layout = Layout{}) {
+    if (len % (lanes << K) || state_words.size() != idsp_chain_state_words(K) * lanes) throw Error("block: bad length");
+    check(idsp_chain_f32_host(e.ctx(), K, c.inner.iir.ba.data(), state_words.data(), x, y, len / (lanes << K), lanes,
+                              Layout::value));
+}
+
+// Lowpass<N> / Lockin<Lowpass<N>> with the phase from a per-lane Accu (src/lowpass.rs:13, src/lockin.rs:30-39,
+// src/accu.rs:29-38), device buffers; iq = Complex<i32> per sample
+template <int N> struct Lowpass {
+    std::array<int32_t, N> k;
+};
+template <class C> struct Lockin {
+    C lowpass;
+};
+template <int N> struct LockinState {
+    size_t lanes;
+    GpuBuffer<int32_t> accu_state, accu_step;
+    GpuBuffer<int64_t> lp;
+    LockinState(Engine &e, size_t n) : lanes(n), accu_state(e, n, true), accu_step(e, n, true), lp(e, 2 * N * n, true) {}
+};
+template <int N, class Layout = FrameMajor>
+void block(Engine &e, const Lanes<Lockin<Lowpass<N>>> &c, LockinState<N> &state, const GpuBuffer<int32_t> &x,
+           GpuBuffer<int32_t> &iq, size_t len, Layout = Layout{}) {
+    if (len % state.lanes || len > x.size() || 2 * len > iq.size()) throw Error("block: bad length");
+    check(idsp_lockin_i32(e.ctx(), N, c.inner.lowpass.k.data(), state.accu_state.data(), state.accu_step.data(),
+                          state.lp.data(), x.data(), iq.data(), len / state.lanes, state.lanes, Layout::value));
+}
+
+// coefficient builders across the ABI (src/iir/coefficients.rs, src/iir/pid.rs): design parameters in,
+// a Biquad<Q32<F>> / Biquad<f32> out
+struct Filter {
+    idsp_filter_f64 f;
+    Filter() { idsp_filter_default_f64(&f); }
+    Filter &critical_frequency(double f0) { f.frequency = 6.283185307179586476925286766559 * f0; return *this; }
+    Filter &gain(double k) { f.gain = k; return *this; }
+    Filter &shelf(double a) { f.shelf = a; return *this; }
+    Filter &q(double v) { f.shape_kind = IDSP_SHAPE_Q; f.shape = v; return *this; }
+    Filter &bandwidth(double v) { f.shape_kind = IDSP_SHAPE_BANDWIDTH; f.shape = v; return *this; }
+    Filter &shelf_slope(double v) { f.shape_kind = IDSP_SHAPE_SLOPE; f.shape = v; return *this; }
+    void validate() const { check(idsp_filter_validate_f64(&f)); }
+    template <int F> Biquad<Q32<F>> build_biquad(idsp_filter_type_t typ) const {
+        int32_t raw[5];
+        check(idsp_filter_build_biquad_f64(&f, typ, IDSP_I32, F, raw));
+        Biquad<Q32<F>> b;
+        for (int i = 0; i < 5; i++) b.ba[i] = Q32<F>::from_bits(raw[i]);
+        return b;
+    }
+    Biquad<float> build_biquad_f32(idsp_filter_type_t typ) const {
+        Biquad<float> b;
+        check(idsp_filter_build_biquad_f64(&f, typ, IDSP_F32, 0, b.ba.data()));
+        return b;
+    }
+};
 
 // cossin(phase) -> (cos, sin), atan2(y, x) (src/cossin.rs:14-67, src/atan2.rs:66-82), slice forms
 inline void cossin(Engine &e, const int32_t *phase, int32_t *cs, size_t n) {

@@ -39,6 +39,29 @@ _CT = {
 }
 
 
+def build_native() -> str:
+    """Rebuild the oracle for the host it runs on (`-march=native`, SURVEY 8(d) "CPU side-by-side") into
+    oracle/_native/ and make it the library this process uses; used by bench.py's CPU legs on the box they
+    are timed on.  Falls back to the portable build (x86-64-v3) if the compiler is missing."""
+    global _SO, _lib
+    out_dir = os.path.join(_HERE, "_native")
+    so = os.path.join(out_dir, "libidsp_oracle.so")
+    try:
+        os.makedirs(out_dir, exist_ok=True)
+        subprocess.check_call(["gcc", "-O3", "-march=native", "-ffp-contract=off", "-fno-fast-math", "-fopenmp", "-fPIC",
+                               "-std=gnu11", "-shared", "-o", so, os.path.join(_HERE, "idsp_oracle.c"), "-lm"],
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    except Exception:
+        return build()
+    if _lib is None:
+        _SO = so
+    return so
+
+
+def build_flags() -> str:
+    return "-O3 -march=native" if _SO.endswith(os.path.join("_native", "libidsp_oracle.so")) else "-O3 -march=x86-64-v3"
+
+
 def build(force: bool = False) -> str:
     """Compile the oracle with the committed Makefile (gcc, -ffp-contract=off)."""
     src = [os.path.join(_HERE, f) for f in ("idsp_oracle.c", "idsp_oracle.h", "Makefile")]

@@ -26,7 +26,26 @@ def test_cpp_mirror_compiles(tmp_path):
 
 
 @pytest.mark.gpu
-def test_cpp_mirror_kats(tmp_path):
+def test_cpp_mirror_kats(tmp_path, oracle):
+    import numpy as np
+
     exe = _build(tmp_path)
-    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    out = str(tmp_path)
+    r = subprocess.run([exe, out], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "cpp mirror ok" in r.stdout, r.stdout + r.stderr
+    # the device-resident graphs the program ran, against the CPU oracle (bit patterns)
+    x = np.fromfile(os.path.join(out, "chain_x.bin"), np.float32)
+    y = np.fromfile(os.path.join(out, "chain_y.bin"), np.float32)
+    ba = np.fromfile(os.path.join(out, "chain_ba.bin"), np.float32)
+    stw = np.fromfile(os.path.join(out, "chain_state.bin"), np.float32)
+    lanes, k = 48, 4
+    so = np.zeros((stw.size // lanes, lanes), np.float32)
+    want = oracle.chain_lanes(k, ba, so, x, lanes, 1)
+    assert np.array_equal(y.view(np.uint32), want.view(np.uint32))
+    assert np.array_equal(stw.view(np.uint32), so.reshape(-1).view(np.uint32))
+    xl = np.fromfile(os.path.join(out, "lockin_x.bin"), np.int32)
+    step = np.fromfile(os.path.join(out, "lockin_step.bin"), np.int32)
+    iq = np.fromfile(os.path.join(out, "lockin_iq.bin"), np.int32)
+    lanes = step.size
+    want = oracle.lockin_lanes([1048576, -94906265], np.zeros(lanes, np.int32), step, np.zeros((4, lanes), np.int64), xl, lanes, 0)
+    assert np.array_equal(iq, want)

@@ -52,6 +52,8 @@ def main():
     ap.add_argument("--only", default=None, help="regex: time only the rows whose name matches (e.g. under ncu)")
     ap.add_argument("--reps", type=int, default=None)
     ap.add_argument("--hbf-in", type=int, default=8192, help="high-rate samples per lane and call of the HBF rows")
+    ap.add_argument("--policy", type=int, default=0, help="kernel policy (1 = generic kernels only)")
+    ap.add_argument("--out", default="gpurun_out/rows.json")
     args = ap.parse_args()
     peak, src = peak_hbm()
     lanes = 65536
@@ -66,11 +68,12 @@ def main():
         ms = timeit(fn, reps)
         gbs = samples * bytes_per_sample / ms / 1e6
         rows.append({"row": name, "reference": ref, "GSa/s": samples / ms / 1e6, "GB/s": gbs, "frac_of_peak": gbs / peak,
-                     "bytes_per_sample": bytes_per_sample, "ms": ms})
-        print(f"{name:46s} {samples / ms / 1e6:9.1f} GSa/s {gbs:8.1f} GB/s {100 * gbs / peak:5.1f}%", flush=True)
+                     "bytes_per_sample": bytes_per_sample, "ms": ms, "kernel": ctx0.last_kernel})
+        print(f"{name:46s} {samples / ms / 1e6:9.1f} GSa/s {gbs:8.1f} GB/s {100 * gbs / peak:5.1f}%  [{ctx0.last_kernel}]", flush=True)
 
     lp = Filter().critical_frequency(0.01).lowpass()
     ctx0 = ib.default_context(0)
+    ctx0.set_kernel_policy(args.policy)
     for layout, lname in ((0, "frame-major"), (1, "lane-major")):
         for kind in ("i8", "i16", "i32", "i64", "f32", "f64"):
             fmt = Q(kind, BITS[kind] - 2) if kind in BITS else kind
@@ -106,7 +109,30 @@ def main():
         sk = LockinState.default(2, lanes, DEV)
         add(f"a18-a20 Accu+Lockin<Lowpass<2>> i32 {lname}", "lockin.rs:17-39", n, 12,
             lambda: Lockin(Lowpass([1048576, -94906265])).block(sk, acc, x, iq, layout))
-        del x, y, iq
+        # caller-supplied phase: (x, phase) pairs in, Complex<i32> out (lockin.rs:30-39)
+        xp = rnd("i32", 2 * n)
+        add(f"a20 Lockin<Lowpass<2>> on (x, phase) i32 {lname}", "lockin.rs:30-39", n, 16,
+            lambda: Lockin(Lowpass([1048576, -94906265])).block_phase(sk, xp, iq, layout))
+        del x, y, iq, xp
+        # single /2 and x2 stages with run-time taps (a11 / a12) and the 98 dB tap set as a /16 cascade
+        from idsp_b200 import EvenSymmetric, HbfDec, HbfInt, hbf_taps, hbf_taps_98
+        for ti in (0, 3):
+            tp = hbf_taps()[ti]
+            sl, sn = 65536, 2048
+            xs, ys = rnd("f32", sl * sn * 2), torch.empty(sl * sn, dtype=torch.float32, device=DEV)
+            sd_, si_ = HbfDec.default(len(tp), sl, DEV), HbfInt.default(len(tp), sl, DEV)
+            add(f"a11 HbfDec /2 single stage M={len(tp)} f32 {lname}", "hbf.rs:155-192", sl * sn * 2, 6,
+                lambda: EvenSymmetric(tp).block(sd_, xs, ys, layout))
+            add(f"a12 HbfInt x2 single stage M={len(tp)} f32 {lname}", "hbf.rs:207-236", sl * sn * 2, 6,
+                lambda: EvenSymmetric(tp).block(si_, ys, xs, layout))
+            del xs, ys
+        c98 = HbfDecCascade(4, hbf_taps_98()[:4])
+        sl, sn = 65536, 256
+        xs, ys = rnd("f32", sl * sn * 16), torch.empty(sl * sn, dtype=torch.float32, device=DEV)
+        s98 = c98.state(sl, DEV)
+        add(f"a13 HbfDec /16 cascade, HBF_TAPS_98 (stage by stage) f32 {lname}", "hbf.rs:258-292, 385-421", sl * sn * 16, 4.25,
+            lambda: Lanes(c98).block(s98, xs, ys, layout))
+        del xs, ys
         # hbf cascades: 262144 lanes (config 3 shape, fewer frames)
         hl = 65536 if args.quick else 262144
         for k in (1, 2, 3, 4, 5):
@@ -166,8 +192,8 @@ def main():
     add("a16 cossin i32", "cossin.rs:14-67", n, 12, lambda: ctx.cossin(ph, cs))
     pp = torch.empty(n, dtype=torch.int32, device=DEV)
     add("a17 atan2 i32", "atan2.rs:66-82", n, 12, lambda: ctx.atan2(cs, pp))
-    os.makedirs("gpurun_out", exist_ok=True)
-    json.dump({"peak_GBs": peak, "peak_source": src, "rows": rows}, open("gpurun_out/rows.json", "w"), indent=1)
+    os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
+    json.dump({"peak_GBs": peak, "peak_source": src, "policy": args.policy, "rows": rows}, open(args.out, "w"), indent=1)
     print("\n| §8 row | reference | GSa/s | algorithmic GB/s | of measured HBM peak |\n|---|---|---|---|---|")
     for r in rows:
         print(f"| {r['row']} | `{r['reference']}` | {r['GSa/s']:.1f} | {r['GB/s']:.0f} | {100 * r['frac_of_peak']:.1f} % |")
