@@ -546,6 +546,13 @@ static int tma_try_launch(idsp_ctx *ctx, const typename Op::Params &p, const typ
                 default: r = tma_launch_cfg<Op, false, 8, 3, 2, 4, true>(ctx, p, x, y, frames, lanes, sstride); break;
             }
 #endif
+        } else if (Op::HEAVY && sizeof(typename Op::In) == 4) {
+            // lock-in (4-byte in, 8-byte out, ALU-pipe bound): independent per-warp pipelines of 16-frame
+            // tiles, 2 load stages + 1 store stage (8 KB per warp): no CTA-wide barrier per tile.  Sweep of
+            // 12 tile shapes / residencies on 131 072 lanes (profiles/r2_sweep_lockin_tile_shapes.log):
+            // 336 GSa/s against 326 for the 128-lane shared boxes; more resident warps do not help (the
+            // kernel is bound by the ALU pipe, not by latency).
+            r = tma_launch_cfg<Op, false, 16, 2, 1, 1>(ctx, p, x, y, frames, lanes, sstride);
         } else if ((lanes + 127) / 128 >= sms) {
             // compute-bound: avoid a nearly empty last wave (131 072 lanes: 1024 CTAs fit in one
             // wave with 3 load stages, 7 CTAs per SM, but need 1.15 waves with 4 stages, 6 per SM)

@@ -205,3 +205,113 @@ def test_lockin_stores_into_root_buffer_over_nvlink():
         p.join(300)
         assert p.exitcode == 0
     assert list(ok) == [1] * world
+
+
+# ------------------------------------------------------------------ the C ABI's own communicator (raw NCCL, round 2)
+def _worker_cabi(rank, world, port, ok, out_path):
+    """idsp_b200_comm_init / idsp_scatter_lanes / idsp_gather_lanes / idsp_broadcast: every dtype width, both
+    layouts, ragged lane counts (blocks of different sizes, an empty block), then the sharded lock-in through it.
+    torch.distributed only carries the 128-byte NCCL id (gloo: the data plane must not depend on torch's NCCL)."""
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = f"cuda:{rank}"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from idsp_b200 import Accu, Lockin, LockinState, Lowpass, _lib
+        from idsp_b200.dist import Comm, all_blocks
+
+        assert _lib.lib().idsp_b200_nccl_version() >= 20700
+        comm = Comm(rank)
+        rng = np.random.default_rng(11)  # same stream on every rank: everyone can compute the expected block
+        for dtype, width in ((torch.int32, 1), (torch.int32, 2), (torch.float32, 16), (torch.int64, 1), (torch.int8, 1)):
+            for layout in (0, 1):
+                for frames, lanes in ((7, 40 * world + 5), (64, 32), (33, 1000), (1, 32 * world)):
+                    n = frames * lanes * width
+                    src = torch.from_numpy(rng.integers(-100, 100, n).astype(np.int64)).to(dtype)
+                    lo, hi = all_blocks(world, lanes)[rank]
+                    assert (lo, hi) == comm.lane_block(lanes)
+                    full = src.to(dev) if rank == 0 else None
+                    part = comm.scatter_lanes(full, frames, lanes, layout, width=width, dtype=dtype)
+                    v = src.view(frames, lanes, width) if layout == 0 else src.view(lanes, frames, width).permute(1, 0, 2)
+                    want = v[:, lo:hi] if layout == 0 else v[:, lo:hi].permute(1, 0, 2)
+                    torch.cuda.synchronize()
+                    assert torch.equal(part.cpu(), want.contiguous().view(-1)), (dtype, width, layout, frames, lanes)
+                    back = comm.gather_lanes(part + 1 if dtype != torch.float32 else part + 1.0, None, frames, lanes, layout, width=width)
+                    torch.cuda.synchronize()
+                    if rank == 0:
+                        assert torch.equal(back.cpu(), src + 1), (dtype, width, layout, frames, lanes)
+        b = torch.arange(5, dtype=torch.int32, device=dev) * (1 if rank == 0 else 0)
+        comm.broadcast(b)
+        torch.cuda.synchronize()
+        assert b.cpu().tolist() == [0, 1, 2, 3, 4]
+        # sharded lock-in through the C ABI edges, frame-major (packed blocks) and lane-major (in place)
+        for layout in (0, 1):
+            frames, lanes = 256, 4096 * world + 96
+            xn = np.random.default_rng(4).integers(-(1 << 30), 1 << 30, frames * lanes).astype(np.int32)
+            stn = np.random.default_rng(5).integers(-(1 << 31), 1 << 31, lanes).astype(np.int32)
+            lo, hi = comm.lane_block(lanes)
+            x = torch.from_numpy(xn).to(dev) if rank == 0 else None
+            step = torch.from_numpy(stn).to(dev) if rank == 0 else None
+            xs = comm.scatter_lanes(x, frames, lanes, layout)
+            sts = comm.scatter_lanes(step, 1, lanes, 0)
+            iq = torch.empty(2 * xs.numel(), dtype=torch.int32, device=dev)
+            Lockin(Lowpass(K)).block(LockinState.default(2, hi - lo, dev), Accu(torch.zeros(hi - lo, dtype=torch.int32, device=dev), sts), xs, iq, layout)
+            t0 = time.perf_counter()
+            full = comm.gather_lanes(iq, None, frames, lanes, layout, width=2)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            if rank == 0:
+                import oracle as O
+
+                O.build()
+                want = O.lockin_lanes(K, np.zeros(lanes, np.int32), stn, np.zeros((4, lanes), np.int64), xn, lanes, layout, nthreads=8)
+                assert np.array_equal(full.cpu().numpy(), want), "C-ABI gathered lock-in output differs from the oracle"
+                line = f"world={world} C-ABI comm (NCCL {_lib.lib().idsp_b200_nccl_version()}): layout={layout} lanes={lanes} frames={frames} scatter -> lock-in -> gather bit-exact ({8 * frames * lanes / (t1 - t0) / 1e9:.1f} GB/s gather incl. launch)"
+                print(line, flush=True)
+                if out_path:
+                    with open(out_path, "a") as f:
+                        f.write(line + "\n")
+        comm.close()
+        ok[rank] = 1
+    finally:
+        dist.destroy_process_group()
+
+
+def test_c_abi_comm_scatter_gather_broadcast():
+    """SURVEY 8(b) `idsp_b200_comm_init / idsp_scatter_lanes / idsp_gather_lanes` under dsp-process/src/split.rs:272-277"""
+    world = min(torch.cuda.device_count(), 8)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs")
+    ctx = mp.get_context("spawn")
+    ok = ctx.Array("i", [0] * world)
+    port = _free_port()
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    out_path = os.path.join(out, "dist_nccl.log") if os.path.isdir(out) else None
+    procs = [ctx.Process(target=_worker_cabi, args=(r, world, port, ok, out_path)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    assert list(ok) == [1] * world
+
+
+def test_c_abi_comm_single_rank():
+    """nranks == 1 never touches NCCL: scatter / gather are the (strided) local copies"""
+    from idsp_b200.dist import Comm
+
+    comm = Comm(0)
+    assert (comm.rank, comm.world) == (0, 1)
+    for layout in (0, 1):
+        src = torch.arange(6 * 50 * 2, dtype=torch.int32, device="cuda:0")
+        part = comm.scatter_lanes(src, 6, 50, layout, width=2)
+        torch.cuda.synchronize()
+        assert torch.equal(part, src)
+        full = comm.gather_lanes(part, None, 6, 50, layout, width=2)
+        torch.cuda.synchronize()
+        assert torch.equal(full, src)
+    comm.close()

@@ -77,3 +77,68 @@ def test_peer_view_is_a_device_output():
 
     v = PeerView(0x7F0000001000, 64, torch.int32)
     assert _is_dev(v) and v.numel() == 64 and _ptr(v).value == 0x7F0000001000
+
+
+def test_c_abi_lane_block_matches_the_python_partition():
+    """idsp_b200_lane_block (C ABI, used by idsp_scatter_lanes / idsp_gather_lanes) == dist.lane_block"""
+    import ctypes as C
+
+    from idsp_b200 import _lib
+    from idsp_b200.dist import all_blocks
+
+    L = _lib.lib()
+    for lanes in (0, 1, 31, 32, 33, 1000, 65536, 1048576, 1048576 + 5):
+        for world in (1, 2, 3, 4, 8):
+            got = []
+            for r in range(world):
+                lo, hi = C.c_size_t(), C.c_size_t()
+                assert L.idsp_b200_lane_block(lanes, world, r, 0, C.byref(lo), C.byref(hi)) == 0
+                got.append((lo.value, hi.value))
+            assert got == all_blocks(world, lanes), (lanes, world)
+    lo, hi = C.c_size_t(), C.c_size_t()
+    assert L.idsp_b200_lane_block(100, 2, 2, 0, C.byref(lo), C.byref(hi)) == -1  # rank out of range
+
+
+def test_engine_argument_validation_is_host_side():
+    """state shape / word type / whole frames / output length are checked before anything reaches the device
+    (a short or mistyped state would be read and written out of bounds by the kernels)"""
+    import numpy as np
+    import pytest
+
+    from idsp_b200.engine import Context
+
+    x, y = np.zeros(64, np.float32), np.zeros(64, np.float32)
+    Context._check_state("t", np.zeros((4, 2), np.float32), 4, 2, "f32")
+    with pytest.raises(ValueError):
+        Context._check_state("t", np.zeros((3, 2), np.float32), 4, 2, "f32")      # too few words
+    with pytest.raises(ValueError):
+        Context._check_state("t", np.zeros((4, 3), np.float32), 4, 2, "f32")      # wrong lane count
+    with pytest.raises(TypeError):
+        Context._check_state("t", np.zeros((4, 2), np.int32), 4, 2, "f32")        # i32 words for f32 samples
+    with pytest.raises(ValueError):
+        Context._check_state("t", np.zeros(8, np.float32), 4, 2, "f32")           # not [words, lanes]
+    c = Context.__new__(Context)
+    assert c._check_io("t", x, y, 2, 1, 1) == 32
+    with pytest.raises(ValueError):
+        c._check_io("t", x, y, 3, 1, 1)                                            # 64 % 3: partial frame
+    with pytest.raises(ValueError):
+        c._check_io("t", x, y[:32], 2, 1, 1)                                       # short output
+    with pytest.raises(TypeError):
+        c._check_io("t", x, y.astype(np.int32), 2, 1, 1)
+    assert c._check_io("t", x, y[:4], 1, 16, 1) == 4                               # /16 decimator shapes
+
+
+def test_state_must_match_the_taps():
+    import numpy as np
+    import pytest
+
+    from idsp_b200 import EvenSymmetric, HbfDec, OddSymmetric, hbf_taps
+    from idsp_b200.hbf import FirState
+
+    x, y = np.zeros(64, np.float32), np.zeros(32, np.float32)
+    with pytest.raises(TypeError):
+        EvenSymmetric(hbf_taps()[0])._block(None, HbfDec.default(3, 1, None), x, y, 0)       # M = 3 state, 23 taps
+    with pytest.raises(TypeError):
+        OddSymmetric([0.1, 0.2])._block(None, FirState.default(3, 1, None), y, y.copy(), 0)  # LEN = 4 needed
+    with pytest.raises(TypeError):
+        OddSymmetric([0.1, 0.2])._block(None, HbfDec.default(2, 1, None), x, y, 0)           # HbfDec needs EvenSymmetric
