@@ -565,9 +565,15 @@ template <int K, bool FM>
 static int launch(idsp_ctx *ctx, float *st, const float *x, float *y, size_t n_out, size_t ntiles,
                   size_t lanes, size_t sstride) {
     auto kern = hbf_dec_fast_kernel<K, FM>;
-    IDSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(K)));
+    size_t smem = smem_bytes(K);
+#ifdef IDSP_TUNE
+    // occupancy experiment: pad the dynamic shared memory so that fewer CTAs fit on an SM (is the kernel
+    // bound by issue slots or by latency?)
+    if (getenv("IDSP_HBF_EXTRA_SMEM")) smem += (size_t)atoi(getenv("IDSP_HBF_EXTRA_SMEM"));
+#endif
+    IDSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     unsigned grid = (unsigned)((lanes + NL - 1) / NL);
-    kern<<<grid, NT, smem_bytes(K), ctx->stream>>>(st, x, y, n_out, ntiles, lanes, sstride);
+    kern<<<grid, NT, smem, ctx->stream>>>(st, x, y, n_out, ntiles, lanes, sstride);
     IDSP_KERNEL_FAMILY(ctx, FM ? "hbf tiled frame-major" : "hbf tiled lane-major");
     IDSP_LAUNCHED(ctx);
     return IDSP_OK;

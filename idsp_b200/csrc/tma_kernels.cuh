@@ -529,7 +529,7 @@ static int tma_try_launch(idsp_ctx *ctx, const typename Op::Params &p, const typ
             // is ALU-bound, so resident warps count for more than long DRAM bursts
             r = tma_launch_cfg<Op, true, 16, 3, 1, 1>(ctx, p, x, y, frames, lanes, sstride);
 #ifdef IDSP_TUNE
-        } else if (getenv("IDSP_OUT8_CFG") && Op::HEAVY) {
+        } else if (getenv("IDSP_OUT8_CFG") && (Op::HEAVY || sizeof(typename Op::In) == 8)) {
             // tuning builds: tile shape / residency sweep of the compute-bound 8-byte ops (lock-in)
             switch (atoi(getenv("IDSP_OUT8_CFG"))) {
                 case 1: r = tma_launch_cfg<Op, false, 4, 4, 2, 4, true>(ctx, p, x, y, frames, lanes, sstride); break;
