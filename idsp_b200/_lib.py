@@ -95,6 +95,11 @@ def _signatures():
     for n in ("idsp_scatter_lanes", "idsp_gather_lanes"):
         sig[n] = ([_c_p, _c_p, _c_p, _sz, _sz, _sz, _i, _i], _i)
     sig["idsp_broadcast"] = ([_c_p, _c_p, _sz, _i], _i)
+    sig["idsp_comm_group_begin"] = ([_c_p], _i)
+    sig["idsp_comm_group_end"] = ([_c_p], _i)
+    sig["idsp_comm_send"] = ([_c_p, _c_p, _sz, _i], _i)
+    sig["idsp_comm_recv"] = ([_c_p, _c_p, _sz, _i], _i)
+    sig["idsp_b200_stream_wait"] = ([_c_p, _c_p], _i)
     # coefficient builders (host side)
     for s_, ft in (("f64", C.c_double), ("f32", C.c_float)):
         sig[f"idsp_filter_default_{s_}"] = ([_c_p], None)

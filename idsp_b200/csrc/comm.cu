@@ -356,3 +356,45 @@ extern "C" int idsp_broadcast(idsp_comm *c, void *buf, size_t bytes, int root) {
     IDSP_NCCL(N->Broadcast(buf, buf, bytes, 0, root, c->comm, c->ctx->stream));
     return IDSP_OK;
 }
+
+// ---------------------------------------------------------------- point-to-point building blocks
+extern "C" int idsp_comm_group_begin(idsp_comm *c) {
+    IDSP_CHECK_ARG(c != nullptr, "comm is null");
+    if (c->nranks == 1) return IDSP_OK;
+    Nccl *N = need_nccl(__func__);
+    if (!N) return IDSP_ENCCL;
+    IDSP_NCCL(N->GroupStart());
+    return IDSP_OK;
+}
+extern "C" int idsp_comm_group_end(idsp_comm *c) {
+    IDSP_CHECK_ARG(c != nullptr, "comm is null");
+    if (c->nranks == 1) return IDSP_OK;
+    Nccl *N = need_nccl(__func__);
+    if (!N) return IDSP_ENCCL;
+    IDSP_NCCL(N->GroupEnd());
+    return IDSP_OK;
+}
+extern "C" int idsp_comm_send(idsp_comm *c, const void *buf, size_t bytes, int peer) {
+    IDSP_CHECK_ARG(c != nullptr, "comm is null");
+    int r = idsp_use_device(c->ctx);
+    if (r) return r;
+    IDSP_CHECK_ARG(peer >= 0 && peer < c->nranks && peer != c->rank, "peer out of range");
+    if (bytes == 0) return IDSP_OK;
+    IDSP_CHECK_ARG(buf != nullptr, "buf is null");
+    Nccl *N = need_nccl(__func__);
+    if (!N) return IDSP_ENCCL;
+    IDSP_NCCL(N->Send(buf, bytes, 0, peer, c->comm, c->ctx->stream));
+    return IDSP_OK;
+}
+extern "C" int idsp_comm_recv(idsp_comm *c, void *buf, size_t bytes, int peer) {
+    IDSP_CHECK_ARG(c != nullptr, "comm is null");
+    int r = idsp_use_device(c->ctx);
+    if (r) return r;
+    IDSP_CHECK_ARG(peer >= 0 && peer < c->nranks && peer != c->rank, "peer out of range");
+    if (bytes == 0) return IDSP_OK;
+    IDSP_CHECK_ARG(buf != nullptr, "buf is null");
+    Nccl *N = need_nccl(__func__);
+    if (!N) return IDSP_ENCCL;
+    IDSP_NCCL(N->Recv(buf, bytes, 0, peer, c->comm, c->ctx->stream));
+    return IDSP_OK;
+}

@@ -26,6 +26,7 @@ struct idsp_ctx {
     void *dev_scratch;
     size_t dev_scratch_bytes;
     cudaEvent_t ev_h2d[IDSP_HOST_RING], ev_k[IDSP_HOST_RING], ev_d2h[IDSP_HOST_RING];
+    cudaEvent_t ev_order;  // idsp_b200_stream_wait
 };
 
 void idsp_set_error(const char *fmt, ...);

@@ -83,6 +83,8 @@ static void free_staging(idsp_ctx *c) {
     c->dev_state = nullptr;
     if (c->dev_scratch) cudaFree(c->dev_scratch);
     c->dev_scratch = nullptr;
+    if (c->ev_order) cudaEventDestroy(c->ev_order);
+    c->ev_order = nullptr;
     c->dev_in_bytes = c->dev_out_bytes = c->dev_state_bytes = c->dev_scratch_bytes = 0;
     if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
     if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
@@ -211,6 +213,17 @@ extern "C" int idsp_b200_memset(idsp_ctx *ctx, void *ptr, int value, size_t byte
     if (bytes == 0) return IDSP_OK;
     IDSP_CHECK_ARG(ptr != nullptr, "ptr is null");
     IDSP_CUDA(cudaMemsetAsync(ptr, value, bytes, ctx->stream));
+    return IDSP_OK;
+}
+
+extern "C" int idsp_b200_stream_wait(idsp_ctx *waiter, idsp_ctx *signal) {
+    int r = idsp_use_device(signal);
+    if (r) return r;
+    IDSP_CHECK_ARG(waiter != nullptr, "waiter is null");
+    IDSP_CHECK_ARG(waiter->device == signal->device, "both contexts must be on the same device");
+    if (!signal->ev_order) IDSP_CUDA(cudaEventCreateWithFlags(&signal->ev_order, cudaEventDisableTiming));
+    IDSP_CUDA(cudaEventRecord(signal->ev_order, signal->stream));
+    IDSP_CUDA(cudaStreamWaitEvent(waiter->stream, signal->ev_order, 0));
     return IDSP_OK;
 }
 

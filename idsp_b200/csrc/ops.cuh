@@ -725,6 +725,7 @@ template <int MODE = 0>  // MODE 1: 0 <= F < 32 (funnel-shift quantiser, no test
 struct FmDiscOp : OpHooks {
     using In = int2;   // Complex<Q32<32>> as raw (re, im)
     using Out = int32_t;
+    static constexpr bool HEAVY = true;  // ~90 instructions per sample (atan2): per-warp pipelines
     struct Params {
         int32_t carrier;
         int32_t ba[5];

@@ -24,6 +24,8 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "lane_kernels.cuh"
 
@@ -546,23 +548,20 @@ static int tma_try_launch(idsp_ctx *ctx, const typename Op::Params &p, const typ
                 default: r = tma_launch_cfg<Op, false, 8, 3, 2, 4, true>(ctx, p, x, y, frames, lanes, sstride); break;
             }
 #endif
-        } else if (Op::HEAVY && sizeof(typename Op::In) == 4) {
-            // lock-in (4-byte in, 8-byte out, ALU-pipe bound): independent per-warp pipelines of 16-frame
-            // tiles, 2 load stages + 1 store stage (8 KB per warp): no CTA-wide barrier per tile.  Sweep of
-            // 12 tile shapes / residencies on 131 072 lanes (profiles/r2_sweep_lockin_tile_shapes.log):
-            // 336 GSa/s against 326 for the 128-lane shared boxes; more resident warps do not help (the
-            // kernel is bound by the ALU pipe, not by latency).
+        } else if (Op::HEAVY || std::is_integral<typename Op::In>::value) {
+            // compute-bound ops with an 8-byte side (lock-in: ALU pipe; FM discriminator: atan2; i64 biquad:
+            // 64 x 64 -> 128 multiplies): independent per-warp pipelines of 16-frame tiles, 2 load stages +
+            // 1 store stage, no CTA-wide barrier per tile.  Sweeps of 12 tile shapes / residencies on 131 072
+            // and 65 536 lanes (profiles/r2_sweep_lockin_tile_shapes.log, r2_sweep_8byte_tile_shapes.log):
+            // lock-in 336 GSa/s against 326 for the 128-lane shared boxes, (x, phase) lock-in 269 / 254,
+            // FM discriminator 188 / 180, i64 DF1 145 / 137; more resident warps do not help (the kernels
+            // are bound by a pipe, not by latency).
             r = tma_launch_cfg<Op, false, 16, 2, 1, 1>(ctx, p, x, y, frames, lanes, sstride);
         } else if ((lanes + 127) / 128 >= sms) {
-            // compute-bound: avoid a nearly empty last wave (131 072 lanes: 1024 CTAs fit in one
-            // wave with 3 load stages, 7 CTAs per SM, but need 1.15 waves with 4 stages, 6 per SM)
-            const size_t n4 = (lanes + 127) / 128;
-            const double c4 = tail_cost(n4, sms, tma_cfg_occupancy<Op, false, 8, 4, 2, 4, true>());
-            const double c3 = tail_cost(n4, sms, tma_cfg_occupancy<Op, false, 8, 3, 2, 4, true>());
-            if (c3 < 0.95 * c4)
-                r = tma_launch_cfg<Op, false, 8, 3, 2, 4, true>(ctx, p, x, y, frames, lanes, sstride);
-            else
-                r = tma_launch_cfg<Op, false, 8, 4, 2, 4, true>(ctx, p, x, y, frames, lanes, sstride);
+            // HBM-bound 8-byte streams (f64 biquads): 128-lane boxes (1 KB rows) with 2 load stages + 1 store
+            // stage -- 24 KB per CTA instead of 48, i.e. twice the CTAs in flight: f64 DF1 347 -> 389 GSa/s
+            // = 95 % of the HBM peak (same sweep)
+            r = tma_launch_cfg<Op, false, 8, 2, 1, 4, true>(ctx, p, x, y, frames, lanes, sstride);
         } else
             r = tma_launch_cfg<Op, false, 8, 4, 2, 1>(ctx, p, x, y, frames, lanes, sstride);
     } else if (lm) {

@@ -122,13 +122,17 @@ class Comm:
     buffer, the others ``None``); ``gather_lanes(part, full, ...)`` is the inverse.  Lane-major blocks are
     sent / received in place, frame-major blocks are packed with one strided device copy per peer."""
 
-    def __init__(self, device: int, group=None):
+    def __init__(self, device: int, group=None, own_stream: bool = False):
+        """own_stream: give the communicator its own ctx / CUDA stream so that transfers overlap kernels running
+        on the default ctx; order the two with ``compute_after()`` / ``after_compute()``"""
         self.device = int(device)
         if dist.is_available() and dist.is_initialized():
             self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         else:  # single process: a one-rank communicator (never touches NCCL)
             self.rank, self.world = 0, 1
-        self._ctx = default_context(self.device)
+        from .engine import Context
+
+        self._ctx = Context(self.device, use_torch_stream=False) if own_stream else default_context(self.device)
         self._L = _lib.lib()
         ident = [None]
         if self.rank == 0 and self.world > 1:
@@ -168,6 +172,38 @@ class Comm:
                                              None if full is None else C.c_void_p(full.data_ptr()),
                                              frames, lanes, eb, layout, root))
         return full
+
+    # ---- pipelined edges: point-to-point pieces on the communicator's stream
+    def group(self):
+        comm = self
+
+        class _G:
+            def __enter__(self_):
+                _lib.check(comm._L.idsp_comm_group_begin(comm._h))
+
+            def __exit__(self_, *a):
+                _lib.check(comm._L.idsp_comm_group_end(comm._h))
+
+        return _G()
+
+    def send(self, t: torch.Tensor, peer: int):
+        _lib.check(self._L.idsp_comm_send(self._h, C.c_void_p(t.data_ptr()), t.numel() * t.element_size(), peer))
+
+    def recv(self, t: torch.Tensor, peer: int):
+        _lib.check(self._L.idsp_comm_recv(self._h, C.c_void_p(t.data_ptr()), t.numel() * t.element_size(), peer))
+
+    def compute_after(self, compute_ctx=None):
+        """kernels queued on the compute ctx from now on start after everything queued on the communicator so far"""
+        cc = compute_ctx or default_context(self.device)
+        _lib.check(self._L.idsp_b200_stream_wait(cc._h, self._ctx._h))
+
+    def after_compute(self, compute_ctx=None):
+        """transfers queued from now on start after the kernels queued on the compute ctx so far"""
+        cc = compute_ctx or default_context(self.device)
+        _lib.check(self._L.idsp_b200_stream_wait(self._ctx._h, cc._h))
+
+    def sync(self):
+        self._ctx.sync()
 
     def broadcast(self, buf: torch.Tensor, root: int = 0) -> torch.Tensor:
         _lib.check(self._L.idsp_broadcast(self._h, C.c_void_p(buf.data_ptr()), buf.numel() * buf.element_size(), root))

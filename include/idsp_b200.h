@@ -103,6 +103,9 @@ int idsp_b200_ipc_close(idsp_ctx *ctx, void *ptr);
  * idsp_b200_memset zero-fills device memory (zero state = the reference's `Default`). */
 int idsp_b200_memcpy(idsp_ctx *ctx, void *dst, const void *src, size_t bytes, int kind);
 int idsp_b200_memset(idsp_ctx *ctx, void *ptr, int value, size_t bytes);
+/* Stream order between two contexts of the same process: everything queued on `signal` so far completes
+ * before anything queued on `waiter` after this call starts (an event, no host synchronisation). */
+int idsp_b200_stream_wait(idsp_ctx *waiter, idsp_ctx *signal);
 /* Kernel selection: 0 = automatic (default), 1 = force the generic LDG kernels,
  * 2 = force the TMA kernels (IDSP_EINVAL if the shape does not qualify),
  * 3 = automatic, with the packed f32x2 variant of the tiled half-band decimator (bit-identical
@@ -326,6 +329,14 @@ int idsp_gather_lanes(idsp_comm *comm, const void *part, void *full, size_t fram
                       size_t elem_bytes, int layout, int root);
 /* replicated small data (coefficients): root's bytes to every rank, in place, device memory */
 int idsp_broadcast(idsp_comm *comm, void *buf, size_t bytes, int root);
+/* Building blocks for pipelined edges (a lane block handed over in sub-blocks while the previous one is being
+ * filtered): plain point-to-point transfers on the communicator's ctx stream, grouped into one NCCL launch
+ * between idsp_comm_group_begin / _end.  Give the communicator its own ctx (its own stream) and order the
+ * compute ctx behind it with idsp_b200_stream_wait(). */
+int idsp_comm_group_begin(idsp_comm *comm);
+int idsp_comm_group_end(idsp_comm *comm);
+int idsp_comm_send(idsp_comm *comm, const void *buf, size_t bytes, int peer);
+int idsp_comm_recv(idsp_comm *comm, void *buf, size_t bytes, int peer);
 
 /* ------------------------------------------------------------------ coefficient builders
  * Host-side, no device work: the reference's `iir::coefficients::Filter` (src/iir/coefficients.rs:111-527),
