@@ -569,6 +569,40 @@ def run_lockin_sharded(args, rank, world, local):
         got = iq_full.view(lanes, frames * 2).index_select(0, idx).contiguous().cpu().numpy().reshape(-1)
         return bool(np.array_equal(got, want))
 
+    NSUB = 4  # sub-blocks of a rank's lane block in the pipelined variant
+    sub_l = nl // NSUB
+    comm_p = Comm(local, own_stream=True) if world > 1 else None  # transfers on their own stream
+    xs_sub = [xs[j * sub_l * frames:(j + 1) * sub_l * frames] for j in range(NSUB)]
+
+    def one_pass_pipelined():
+        """(c) the block travels in NSUB sub-blocks: sub-block j+1 is on the wire (root egress) while sub-block j is
+        filtered and its result tiles are stored into the root's buffer (root ingress) -- both NVLink directions
+        busy at once.  The root filters its own lanes in place.  Returns total ms (max over ranks)."""
+        sts = [LockinState.default(2, sub_l, dev) for _ in range(NSUB)]
+        accs = [Accu(torch.zeros(sub_l, dtype=torch.int32, device=dev), steps_l[j * sub_l:(j + 1) * sub_l].contiguous()) for j in range(NSUB)]
+        e0, e1 = ev(), ev()
+        barrier(world)
+        e0.record()
+        comm_p.after_compute()  # the transfers start after e0
+        for j in range(NSUB):
+            if rank == 0:
+                with comm_p.group():
+                    for p in range(1, world):
+                        a = (p * lpg + j * sub_l) * frames
+                        comm_p.send(x_full[a:a + sub_l * frames], p)
+                xj = x_full[(lo + j * sub_l) * frames:(lo + (j + 1) * sub_l) * frames]
+                out = iq_full[(lo + j * sub_l) * frames * 2:(lo + (j + 1) * sub_l) * frames * 2]
+            else:
+                comm_p.recv(xs_sub[j], 0)
+                comm_p.compute_after()  # the kernel on sub-block j waits for its samples only
+                xj, out = xs_sub[j], pb.view((lo + j * sub_l) * frames * 2, sub_l * frames * 2)
+            cfg.block(sts[j], accs[j], xj, out, 1)
+        e1.record()
+        torch.cuda.synchronize()
+        comm_p.sync()
+        barrier(world)
+        return max_over_ranks(e0.elapsed_time(e1), world, dev)
+
     res = {}
     for fused in ((False, True) if world > 1 else (False,)):
         if rank == 0:
@@ -585,6 +619,19 @@ def run_lockin_sharded(args, rank, world, local):
         reps = max(2, min(args.steps, 5))
         tt = np.array([one_pass(fused) for _ in range(reps)])
         res["fused" if fused else "nccl"] = tt.mean(0)
+    if world > 1 and nl % (NSUB * 32) == 0:
+        if rank == 0:
+            iq_full.zero_()
+        one_pass_pipelined()
+        okt = torch.tensor([1 if check("pipelined") else 0], device=dev)
+        import torch.distributed as dist
+
+        dist.broadcast(okt, 0)
+        if not int(okt.item()):
+            raise SystemExit("bench: pipelined sharded lock-in output differs from the oracle -- refusing to report a number")
+        res["pipelined"] = float(np.mean([one_pass_pipelined() for _ in range(max(2, min(args.steps, 5)))]))
+    if comm_p is not None:
+        comm_p.close()
     comm.close()
     if pb is not None:
         del iq_full
@@ -617,6 +664,15 @@ def run_lockin_sharded(args, rank, world, local):
             "what": "kernels store their result tiles into rank 0's buffer over NVLink from their own epilogue (no separate gather)",
             "value": n / (f[3] * 1e-3) / 1e9, "ms": {"scatter": f[0], "lockin_with_stores_to_root": f[1], "total": f[3]},
             "ingress_of_root_GBs": out_bytes_remote / (f[1] * 1e-3) / 1e9,
+        }
+    if "pipelined" in res:
+        pm = res["pipelined"]
+        line["pipelined_scatter_compute_store"] = {
+            "what": f"the lane block travels in {NSUB} sub-blocks (idsp_comm_send / _recv on the communicator's own stream): "
+                    "sub-block j+1 is on the wire while sub-block j is filtered and its tiles are stored into rank 0's buffer, "
+                    "so root egress and root ingress overlap",
+            "value": n / (pm * 1e-3) / 1e9, "ms_total": pm, "sub_blocks": NSUB,
+            "root_link_GBs": {"egress": in_bytes_remote / (pm * 1e-3) / 1e9, "ingress": out_bytes_remote / (pm * 1e-3) / 1e9},
         }
     return line
 
