@@ -584,13 +584,18 @@ extern "C" size_t idsp_hbf_cascade_state_words(int decimate, int nstages, const 
     }
     return w;
 }
-static bool is_builtin_taps(int nstages, const float *const *taps, const int *M) {
-    for (int i = 0; i < nstages; i++) {
-        int m = 0;
-        const float *t = idsp_hbf_taps(i, &m);
-        if (M[i] != m || memcmp(taps[i], t, sizeof(float) * (size_t)m) != 0) return false;
+// 1 = HBF_TAPS, 2 = HBF_TAPS_98 (compared by value: both sets are compiled into the tiled kernels), 0 = other
+static int builtin_tap_set(int nstages, const float *const *taps, const int *M) {
+    for (int set = 1; set <= 2; set++) {
+        bool same = true;
+        for (int i = 0; i < nstages && same; i++) {
+            int m = 0;
+            const float *t = set == 1 ? idsp_hbf_taps(i, &m) : idsp_hbf_taps_98(i, &m);
+            same = M[i] == m && memcmp(taps[i], t, sizeof(float) * (size_t)m) == 0;
+        }
+        if (same) return set;
     }
-    return true;
+    return 0;
 }
 static int cascade_taps_check(int nstages, const float *const *taps, const int *M) {
     if (nstages < 1 || nstages > 5 || !taps || !M) {
@@ -613,7 +618,22 @@ extern "C" int idsp_hbf_dec_cascade_taps_f32(idsp_ctx *ctx, int nstages, const f
     HBF_COMMON_CHECK(n_out);
     int r = cascade_taps_check(nstages, taps, M);
     if (r) return r;
-    if (is_builtin_taps(nstages, taps, M)) return hbf_dec_cascade_dev(ctx, nstages, state, x, y, n_out, lanes, lanes, layout);
+    const int set = builtin_tap_set(nstages, taps, M);
+    if (set == 1) return hbf_dec_cascade_dev(ctx, nstages, state, x, y, n_out, lanes, lanes, layout);
+    // HBF_TAPS_98: the tiled kernels take the whole tiles of the call; a frame-major tail is contiguous and is
+    // finished stage by stage below (the state is in the ABI layout in between), a lane-major call that is
+    // not a whole number of tiles runs stage by stage as a whole
+    if (set == 2 && (layout == IDSP_FRAME_MAJOR || n_out % ((size_t)hfs98::TT >> nstages) == 0)) {
+        size_t done = 0;
+        int fr = hbf98_dec_fast_try(ctx, nstages, state, x, y, n_out, lanes, lanes, layout, &done);
+        if (fr != IDSP_HBF_FAST_NOT_APPLICABLE && fr != IDSP_OK) return fr;
+        if (fr == IDSP_OK && done == n_out) return IDSP_OK;
+        if (fr == IDSP_OK) {
+            x += done * lanes << nstages;
+            y += done * lanes;
+            n_out -= done;
+        }
+    }
     const int n = nstages;
     void *scr = nullptr;
     const size_t half = n_out * lanes << (n - 1);  // floats after the first stage
@@ -645,7 +665,19 @@ extern "C" int idsp_hbf_int_cascade_taps_f32(idsp_ctx *ctx, int nstages, const f
     HBF_COMMON_CHECK(n_in);
     int r = cascade_taps_check(nstages, taps, M);
     if (r) return r;
-    if (is_builtin_taps(nstages, taps, M)) return idsp_hbf_int_cascade_f32(ctx, nstages, state, x, y, n_in, lanes, layout);
+    const int set = builtin_tap_set(nstages, taps, M);
+    if (set == 1) return idsp_hbf_int_cascade_f32(ctx, nstages, state, x, y, n_in, lanes, layout);
+    if (set == 2 && (layout == IDSP_FRAME_MAJOR || n_in % ((size_t)hfi98::TOUT >> nstages) == 0)) {
+        size_t done = 0;
+        int fr = hbf98_int_fast_try(ctx, nstages, state, x, y, n_in, lanes, lanes, layout, &done);
+        if (fr != IDSP_HBF_FAST_NOT_APPLICABLE && fr != IDSP_OK) return fr;
+        if (fr == IDSP_OK && done == n_in) return IDSP_OK;
+        if (fr == IDSP_OK) {
+            x += done * lanes;
+            y += done * lanes << nstages;
+            n_in -= done;
+        }
+    }
     const int n = nstages;
     void *scr = nullptr;
     const size_t half = n_in * lanes << (n - 1);  // floats before the last stage

@@ -47,6 +47,8 @@ __device__ __forceinline__ void bulk_store_1d(void *dst, uint32_t src, uint32_t 
 }
 }  // namespace idsp
 
+#define HFI_TAPS HbfTaps
+#define HFI_M hbf_m
 // default shape: 8 lanes x 512 outputs per tile
 #define HFI_NS hfi
 #define HFI_NL 8
@@ -64,41 +66,59 @@ __device__ __forceinline__ void bulk_store_1d(void *dst, uint32_t src, uint32_t 
 #undef HFI_NS
 #undef HFI_NL
 #undef HFI_TOUT
+#undef HFI_TAPS
+#undef HFI_M
+// HBF_TAPS_98 (src/hbf.rs:258-292) on the default shape
+#define HFI_TAPS HbfTaps98
+#define HFI_M hbf98_m
+#define HFI_NS hfi98
+#define HFI_NL 8
+#define HFI_TOUT 512
+#include "hbf_int_fast_body.cuh"
+#undef HFI_NS
+#undef HFI_NL
+#undef HFI_TOUT
+#undef HFI_TAPS
+#undef HFI_M
 
 namespace idsp {
 // Runs the tiled kernel over the first (n_in / TI) * TI input frames of every lane; *done =
 // frames covered (the generic kernel finishes the tail), or IDSP_HBF_FAST_NOT_APPLICABLE.
-static int hbf_int_fast_try(idsp_ctx *ctx, int k, float *state, const float *x, float *y, size_t n_in,
-                            size_t lanes, size_t sstride, int layout, size_t *done) {
-    *done = 0;
-    const bool fm = layout == IDSP_FRAME_MAJOR;
-    // frame-major x32 measured faster on the generic thread-per-lane kernel (714 vs 560 GSa/s)
-    if (ctx->policy == 1 || (fm && k > 4 && ctx->policy != 2)) return IDSP_HBF_FAST_NOT_APPLICABLE;
-    const size_t TI = (size_t)hfi::TOUT >> k;
-    const size_t ntiles = n_in / TI;
-    const bool ok = ntiles >= 1 && ((((uintptr_t)x) | ((uintptr_t)y)) & 15) == 0 && (fm || (n_in % 4) == 0);
-    if (!ok) return IDSP_HBF_FAST_NOT_APPLICABLE;
-    int r;
-    if (fm) {
-        switch (k) {
-            case 1: r = hfi::launch<1, true>(ctx, state, x, y, n_in, ntiles, lanes, sstride); break;
-            case 2: r = hfi::launch<2, true>(ctx, state, x, y, n_in, ntiles, lanes, sstride); break;
-            case 3: r = hfi::launch<3, true>(ctx, state, x, y, n_in, ntiles, lanes, sstride); break;
-            case 4: r = hfi::launch<4, true>(ctx, state, x, y, n_in, ntiles, lanes, sstride); break;
-            default: r = hfi::launch<5, true>(ctx, state, x, y, n_in, ntiles, lanes, sstride); break;
-        }
-    } else {
-        switch (k) {
-            case 1: r = hfi::launch<1, false>(ctx, state, x, y, n_in, ntiles, lanes, sstride); break;
-            case 2: r = hfi::launch<2, false>(ctx, state, x, y, n_in, ntiles, lanes, sstride); break;
-            case 3: r = hfi::launch<3, false>(ctx, state, x, y, n_in, ntiles, lanes, sstride); break;
-            case 4: r = hfi::launch<4, false>(ctx, state, x, y, n_in, ntiles, lanes, sstride); break;
-            default: r = hfi::launch<5, false>(ctx, state, x, y, n_in, ntiles, lanes, sstride); break;
-        }
+// (frame-major x32 measured faster on the generic thread-per-lane kernel: 714 vs 560 GSa/s)
+#define IDSP_DEF_INT_FAST_TRY(NAME, NS) \
+    static int NAME(idsp_ctx *ctx, int k, float *state, const float *x, float *y, size_t n_in, \
+                                size_t lanes, size_t sstride, int layout, size_t *done) { \
+        *done = 0; \
+        const bool fm = layout == IDSP_FRAME_MAJOR; \
+        if (ctx->policy == 1 || (fm && k > 4 && ctx->policy != 2)) return IDSP_HBF_FAST_NOT_APPLICABLE; \
+        const size_t TI = (size_t)NS::TOUT >> k; \
+        const size_t ntiles = n_in / TI; \
+        const bool ok = ntiles >= 1 && ((((uintptr_t)x) | ((uintptr_t)y)) & 15) == 0 && (fm || (n_in % 4) == 0); \
+        if (!ok) return IDSP_HBF_FAST_NOT_APPLICABLE; \
+        int r; \
+        if (fm) { \
+            switch (k) { \
+                case 1: r = NS::launch<1, true>(ctx, state, x, y, n_in, ntiles, lanes, sstride); break; \
+                case 2: r = NS::launch<2, true>(ctx, state, x, y, n_in, ntiles, lanes, sstride); break; \
+                case 3: r = NS::launch<3, true>(ctx, state, x, y, n_in, ntiles, lanes, sstride); break; \
+                case 4: r = NS::launch<4, true>(ctx, state, x, y, n_in, ntiles, lanes, sstride); break; \
+                default: r = NS::launch<5, true>(ctx, state, x, y, n_in, ntiles, lanes, sstride); break; \
+            } \
+        } else { \
+            switch (k) { \
+                case 1: r = NS::launch<1, false>(ctx, state, x, y, n_in, ntiles, lanes, sstride); break; \
+                case 2: r = NS::launch<2, false>(ctx, state, x, y, n_in, ntiles, lanes, sstride); break; \
+                case 3: r = NS::launch<3, false>(ctx, state, x, y, n_in, ntiles, lanes, sstride); break; \
+                case 4: r = NS::launch<4, false>(ctx, state, x, y, n_in, ntiles, lanes, sstride); break; \
+                default: r = NS::launch<5, false>(ctx, state, x, y, n_in, ntiles, lanes, sstride); break; \
+            } \
+        } \
+        if (r == IDSP_OK) *done = ntiles * TI; \
+        return r; \
     }
-    if (r == IDSP_OK) *done = ntiles * TI;
-    return r;
-}
+IDSP_DEF_INT_FAST_TRY(hbf_int_fast_try, hfi)
+IDSP_DEF_INT_FAST_TRY(hbf98_int_fast_try, hfi98)
+#undef IDSP_DEF_INT_FAST_TRY
 
 // HbfInt x2^k -> Biquad DF1 f32 in one pass (lane-major, whole tiles only); `bq.st` = the biquad's SoA
 // state [x1, x2, y1, y2][sstride].  wide = false: 8 lanes x 512 outputs per CTA tile (most CTAs: few

@@ -1,5 +1,6 @@
 // hbf_int_fast_body.cuh -- body of the tiled interpolator, included by hbf_int_fast.cuh once per tile shape
-// (HFI_NS = namespace, HFI_NL = lanes per CTA, HFI_TOUT = output samples per lane and tile).  No include guard.
+// (HFI_NS = namespace, HFI_NL = lanes per CTA, HFI_TOUT = output samples per lane and tile) and tap set
+// (HFI_TAPS = tap struct template, HFI_M = tap count function).  No include guard.
 namespace idsp {
 namespace HFI_NS {
 
@@ -10,7 +11,7 @@ constexpr int TOUT = HFI_TOUT;  // output samples per lane per tile
 __host__ __device__ constexpr int up4(int v) { return (v + 3) & ~3; }
 __host__ __device__ constexpr int oddpitch(int v) { return (up4(v) / 4) % 2 ? up4(v) : up4(v) + 4; }
 // stage s of a x2^K cascade uses TAPS[s] (lowest rate first, src/hbf.rs:503-512)
-__host__ __device__ constexpr int st_m(int s) { return hbf_m(s); }
+__host__ __device__ constexpr int st_m(int s) { return HFI_M(s); }
 __host__ __device__ constexpr int ti(int K) { return TOUT >> K; }                 // inputs per tile
 __host__ __device__ constexpr int st_nin(int K, int s) { return ti(K) << s; }      // inputs of stage s per tile
 __host__ __device__ constexpr int st_r(int K, int s) {                             // inputs per item
@@ -36,7 +37,7 @@ __host__ __device__ constexpr int st_word(int s) {  // ABI state word offset of 
 
 // One item: inputs n0 .. n0+R-1 of row `row` = [H hist | n new]; writes 2R outputs to dst
 template <int TI_, int R> struct IntItem {
-    static constexpr int M = HbfTaps<TI_>::M;
+    static constexpr int M = HFI_TAPS<TI_>::M;
     static constexpr int LEN = 2 * M - 1;
     static constexpr int H = up4(LEN);
     static constexpr int RO = H - LEN;
@@ -52,10 +53,10 @@ template <int TI_, int R> struct IntItem {
 #pragma unroll
         for (int q = 0; q < R; q++) {
             // window of input n0+q: w[RO+q .. RO+q+2M-1]
-            float acc = (w[RO + q + 2 * M - 1] + w[RO + q]) * HbfTaps<TI_>::c(0);
+            float acc = (w[RO + q + 2 * M - 1] + w[RO + q]) * HFI_TAPS<TI_>::c(0);
 #pragma unroll
             for (int i = 1; i < M; i++)
-                acc = acc + (w[RO + q + 2 * M - 1 - i] + w[RO + q + i]) * HbfTaps<TI_>::c(i);
+                acc = acc + (w[RO + q + 2 * M - 1 - i] + w[RO + q + i]) * HFI_TAPS<TI_>::c(i);
             o[2 * q] = acc;
             o[2 * q + 1] = w[RO + q + M];
         }
@@ -256,15 +257,19 @@ hbf_int_fast_kernel(float *st, const float *x, float *y, size_t n_in, size_t nti
             constexpr int R = 1 << K;
             constexpr int PF_ = R >= 4 ? 4 : 2;  // floats per piece: 16 bytes, or the 8-byte frame of x2
             const float *stg = sm + off_out(K) + ob * NL * OUT_PITCH;
-            for (int c = tid; c < NL * TOUT / PF_; c += NT) {
-                const int l = c % NL, q = c / NL;  // piece q = output samples PF_*q .. of lane l's tile
-                if (l < nl) {
-                    float *dst = y + ((i * TI + (PF_ * q) / R) * lanes + lane0 + l) * R + (PF_ * q) % R;
-                    if constexpr (PF_ == 4) {
-                        *reinterpret_cast<float4 *>(dst) = lds128v(stg + l * OUT_PITCH + PF_ * q);
-                    } else {
-                        *reinterpret_cast<float2 *>(dst) = *reinterpret_cast<const float2 *>(stg + l * OUT_PITCH + PF_ * q);
-                    }
+            // thread -> (lane l = tid % NL, pieces q0, q0 + NT/NL, ...): piece q = output samples PF_*q .. of
+            // lane l's tile; a pass advances by ADV samples = whole frames, so both pointers move by constants
+            constexpr int QPT = NT / NL, ADV = PF_ * QPT;
+            static_assert(NT % NL == 0 && ADV % R == 0, "a pass must advance every lane by whole frames");
+            const int l = tid % NL, q0 = tid / NL;
+            if (l < nl) {
+                float *dst = y + ((i * TI + (PF_ * q0) / R) * lanes + lane0 + l) * R + (PF_ * q0) % R;
+                const float *src = stg + l * OUT_PITCH + PF_ * q0;
+                const size_t dstep = (size_t)ADV * lanes;
+#pragma unroll 4
+                for (int q = q0; q < TOUT / PF_; q += QPT, dst += dstep, src += ADV) {
+                    if constexpr (PF_ == 4) *reinterpret_cast<float4 *>(dst) = lds128v(src);
+                    else *reinterpret_cast<float2 *>(dst) = *reinterpret_cast<const float2 *>(src);
                 }
             }
         } else if (tid < nl) {

@@ -29,6 +29,24 @@ template <> struct HbfTaps<2> { static constexpr int M = 5; __device__ __forcein
 template <> struct HbfTaps<3> { static constexpr int M = 4; __device__ __forceinline__ static float c(int i) { constexpr float t[4] = IDSP_HBF_TAPS3; return t[i]; } };
 template <> struct HbfTaps<4> { static constexpr int M = 3; __device__ __forceinline__ static float c(int i) { constexpr float t[3] = IDSP_HBF_TAPS4; return t[i]; } };
 
+// HBF_TAPS_98 (src/hbf.rs:258-292): filter design data of the reference, index 0 = lowest rate.
+#define IDSP_HBF98_TAPS0 {7.02144012e-05f, -2.43279582e-04f, 6.35026936e-04f, -1.39782541e-03f, 2.74613582e-03f, \
+    -4.96403839e-03f, 8.41806912e-03f, -1.35827601e-02f, 2.11004053e-02f, -3.19267647e-02f, 4.77024289e-02f,   \
+    -7.18014345e-02f, 1.12942004e-01f, -2.03279594e-01f, 6.33592923e-01f}
+#define IDSP_HBF98_TAPS1 {-0.00086943f, 0.00577837f, -0.02201674f, 0.06357869f, -0.16627679f, 0.61979312f}
+#define IDSP_HBF98_TAPS2 {0.01414651f, -0.10439639f, 0.59026742f}
+#define IDSP_HBF98_TAPS3 {0.01227974f, -0.09930782f, 0.58702834f}
+#define IDSP_HBF98_TAPS4 {-0.06291796f, 0.5629161f}
+template <int IDX> struct HbfTaps98;
+template <> struct HbfTaps98<0> { static constexpr int M = 15; __device__ __forceinline__ static float c(int i) { constexpr float t[15] = IDSP_HBF98_TAPS0; return t[i]; } };
+template <> struct HbfTaps98<1> { static constexpr int M = 6; __device__ __forceinline__ static float c(int i) { constexpr float t[6] = IDSP_HBF98_TAPS1; return t[i]; } };
+template <> struct HbfTaps98<2> { static constexpr int M = 3; __device__ __forceinline__ static float c(int i) { constexpr float t[3] = IDSP_HBF98_TAPS2; return t[i]; } };
+template <> struct HbfTaps98<3> { static constexpr int M = 3; __device__ __forceinline__ static float c(int i) { constexpr float t[3] = IDSP_HBF98_TAPS3; return t[i]; } };
+template <> struct HbfTaps98<4> { static constexpr int M = 2; __device__ __forceinline__ static float c(int i) { constexpr float t[2] = IDSP_HBF98_TAPS4; return t[i]; } };
+__host__ __device__ constexpr int hbf98_m(int idx) {
+    return idx == 0 ? 15 : idx == 1 ? 6 : idx == 2 ? 3 : idx == 3 ? 3 : 2;
+}
+
 __host__ __device__ constexpr int hbf_m(int idx) {
     return idx == 0 ? 23 : idx == 1 ? 10 : idx == 2 ? 5 : idx == 3 ? 4 : 3;
 }

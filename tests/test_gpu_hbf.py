@@ -336,11 +336,16 @@ def test_hbf_taps_98_values():
         assert abs(2 * float(np.sum(v.astype(np.float64))) + 1 - 2) < 2e-4
 
 
-@pytest.mark.parametrize("k", [1, 2, 3, 5])
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5])
 @pytest.mark.parametrize("layout", [0, 1])
-@pytest.mark.parametrize("tapset", ["taps98", "random", "builtin"])
+@pytest.mark.parametrize("tapset", ["taps98", "taps98_whole_tiles", "random", "builtin"])
 def test_cascade_with_caller_taps(oracle, k, layout, tapset):
+    """taps98: ragged length (frame-major: tiled kernels + stage-by-stage tail, lane-major: stage by stage);
+    taps98_whole_tiles: the tiled kernels compiled for HBF_TAPS_98 in both layouts; random: arbitrary run-time taps"""
     rng = np.random.default_rng(k * 7 + layout)
+    whole = tapset == "taps98_whole_tiles"
+    if whole:
+        tapset = "taps98"
     if tapset == "taps98":
         taps = list(ib.hbf_taps_98()[:k])
     elif tapset == "builtin":  # HBF_TAPS passed explicitly must take the built-in (tiled) path and agree with it
@@ -348,7 +353,7 @@ def test_cascade_with_caller_taps(oracle, k, layout, tapset):
     else:
         taps = [(rng.standard_normal(m) * 0.3).astype(np.float32) for m in (7, 1, 12, 32, 9)[:k]]
     R = 1 << k
-    lanes, n_out = 20, (1024 >> k) + 3
+    lanes, n_out = 20, (1024 >> k) * (2 if whole else 1) + (0 if whole else 3)
     xl = rng.uniform(-1, 1, (lanes, n_out * R)).astype(np.float32)
     xf = np.ascontiguousarray(xl.reshape(lanes, n_out, R).swapaxes(0, 1)).reshape(-1) if layout == 0 else xl.reshape(-1)
     cfg = HbfDecCascade(k, taps)
@@ -389,7 +394,13 @@ def test_builtin_taps_passed_explicitly_use_tiled_kernels():
     assert ctx.last_kernel.startswith("hbf tiled"), ctx.last_kernel
     cfg = HbfDecCascade(k, ib.hbf_taps_98()[:k])
     Lanes(cfg).block(cfg.state(lanes, DEV), x, y, 1)
-    assert ctx.last_kernel.startswith("hbf single stage"), ctx.last_kernel
+    assert ctx.last_kernel.startswith("hbf tiled"), ctx.last_kernel          # HBF_TAPS_98 is compiled in too
+    Lanes(cfg).block(cfg.state(lanes, DEV), x[: lanes * 250 * 16], y[: lanes * 250], 1)
+    assert ctx.last_kernel.startswith("hbf single stage"), ctx.last_kernel   # ragged lane-major: stage by stage
+    other = [t * np.float32(0.5) for t in ib.hbf_taps_98()[:k]]
+    cfg = HbfDecCascade(k, other)
+    Lanes(cfg).block(cfg.state(lanes, DEV), x, y, 1)
+    assert ctx.last_kernel.startswith("hbf single stage"), ctx.last_kernel   # any other tap set: run-time taps
 
 
 # ------------------------------------------------------------------ misaligned caller pointers

@@ -130,8 +130,12 @@ def main():
         sl, sn = 65536, 256
         xs, ys = rnd("f32", sl * sn * 16), torch.empty(sl * sn, dtype=torch.float32, device=DEV)
         s98 = c98.state(sl, DEV)
-        add(f"a13 HbfDec /16 cascade, HBF_TAPS_98 (stage by stage) f32 {lname}", "hbf.rs:258-292, 385-421", sl * sn * 16, 4.25,
+        add(f"a13 HbfDec /16 cascade, HBF_TAPS_98 f32 {lname}", "hbf.rs:258-292, 385-421", sl * sn * 16, 4.25,
             lambda: Lanes(c98).block(s98, xs, ys, layout))
+        other = HbfDecCascade(4, [t * np.float32(0.5) for t in hbf_taps_98()[:4]])
+        so_ = other.state(sl, DEV)
+        add(f"a13 HbfDec /16 cascade, run-time taps (stage by stage) f32 {lname}", "hbf.rs:155-192, 385-421", sl * sn * 16, 4.25,
+            lambda: Lanes(other).block(so_, xs, ys, layout))
         del xs, ys
         # hbf cascades: 262144 lanes (config 3 shape, fewer frames)
         hl = 65536 if args.quick else 262144
