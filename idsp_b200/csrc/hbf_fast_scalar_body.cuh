@@ -173,15 +173,22 @@ __device__ __forceinline__ void put_split(float *erow_new, float *orow_new, int 
 template <int K, int s>
 __device__ __forceinline__ void carry_rows(float *sm, int wsel, int nw, int lid) {
     constexpr int CE = he(K, s) / 4, CO = ho(K, s) / 4, C = CE + CO;
-    constexpr int LP = 32 / C;  // lanes per warp pass
     static_assert(C <= 32, "row history too long for one warp");
-    const int sub = lid / C, j = lid % C;
+    // a lane's C pieces sit in a group of CP = 2^k >= C consecutive threads (shift / mask; threads j >= C of a
+    // group idle): LP lanes per warp pass.  (The earlier `lid / C`, `lid % C` form with LP = 32 / C was evaluated
+    // with `act` false for every thread in ONE instantiation -- HBF_TAPS_98, /32, rows 2, C = 3, LP = 10 > NL --
+    // although the same constants work one stage earlier: device printf showed sub = 0, lane = 0, act = 0.  No
+    // race, no memory error (compute-sanitizer clean); this form does not trigger it and is cheaper.)
+    constexpr int CP = C <= 1 ? 1 : C <= 2 ? 2 : C <= 4 ? 4 : C <= 8 ? 8 : C <= 16 ? 16 : 32;
+    constexpr int LP = 32 / CP;
+    const int sub = lid / CP, j = lid % CP;
     const bool odd = j >= CE;
     const int pitch = odd ? po(K, s) : pe(K, s);
-    int lane = wsel * LP + sub;
-    float *row = sm + (odd ? off_o(K, s) + 4 * (j - CE) : off_e(K, s) + 4 * j) + lane * pitch;
-    for (; lane - sub < NL; lane += nw * LP, row += nw * LP * pitch) {  // lane - sub is warp-uniform
-        const bool act = sub < LP && lane < NL;
+    const int joff = odd ? off_o(K, s) + 4 * (j - CE) : off_e(K, s) + 4 * j;
+    for (int l0 = wsel * LP; l0 < NL; l0 += nw * LP) {  // l0 is warp-uniform
+        const int lane = l0 + sub;
+        const bool act = j < C && lane < NL;
+        float *row = sm + joff + lane * pitch;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (act) v = lds128(row + st_n(s));
         __syncwarp();

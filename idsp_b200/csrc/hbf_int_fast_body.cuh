@@ -72,13 +72,15 @@ template <int TI_, int R> struct IntItem {
 template <int K, int s>
 __device__ __forceinline__ void carry_rows(float *sm, int warp, int lid) {
     constexpr int C = hist(s) / 4;
-    constexpr int LP = 32 / C;  // lanes per warp pass
     static_assert(C <= 32, "row history too long for one warp");
-    const int sub = lid / C, j = lid % C;
-    int lane = warp * LP + sub;
-    float *row = sm + off_u(K, s) + lane * pitch(K, s) + 4 * j;
-    for (; lane - sub < NL; lane += (NT / 32) * LP, row += (NT / 32) * LP * pitch(K, s)) {  // warp-uniform trip count
-        const bool act = sub < LP && lane < NL;
+    // a lane's C pieces sit in a group of CP = 2^k >= C consecutive threads (see hbf_fast_scalar_body.cuh)
+    constexpr int CP = C <= 1 ? 1 : C <= 2 ? 2 : C <= 4 ? 4 : C <= 8 ? 8 : C <= 16 ? 16 : 32;
+    constexpr int LP = 32 / CP;  // lanes per warp pass
+    const int sub = lid / CP, j = lid % CP;
+    for (int l0 = warp * LP; l0 < NL; l0 += (NT / 32) * LP) {  // l0 is warp-uniform
+        const int lane = l0 + sub;
+        const bool act = j < C && lane < NL;
+        float *row = sm + off_u(K, s) + lane * pitch(K, s) + 4 * j;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (act) v = lds128v(row + st_nin(K, s));
         __syncwarp();
