@@ -91,7 +91,7 @@ def strided_lanes(lanes, n=64):
     return np.unique(np.concatenate([np.arange(min(8, lanes)), a, np.arange(max(lanes - 8, 0), lanes)]))
 
 
-def pcie_peak(dev, mb=256, reps=3, world=1):
+def pcie_peak(dev, mb=512, reps=4, world=1):
     """pinned-memory copy rates with both directions busy at once (what the e2e leg is bound by):
     returns (h2d GB/s, d2h GB/s) measured with CUDA events on two streams.  At N > 1 every rank runs it
     at the same time (barrier before every repetition): the GPUs share the host's memory system and

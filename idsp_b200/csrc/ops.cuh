@@ -33,6 +33,7 @@ template <> struct is_float<double> { static constexpr bool value = true; };
 
 // Defaults of the optional Op hooks used by the TMA kernels (tma_kernels.cuh)
 struct OpHooks {
+    static constexpr bool SHARE_CTA = false;  // per-CTA shared-memory extras worth sharing between per-warp pipelines
     static constexpr bool TUNABLE = false;
     static constexpr bool HEAVY = false;  // compute-bound: lane-major TMA kernels trade tile size for resident warps
     static constexpr bool LM_SMALL = false;  // in between: fewer lane-major stages of the same tile
@@ -359,35 +360,58 @@ __device__ __forceinline__ void cossin_dev(const uint32_t *lut, int32_t phase, i
     so = s;
 }
 
-// Same function on a pre-expanded table: entry i of the staged shared-memory table holds
-// c14 = ((lut & 0xffff) + 65536) << 14 and s15 = (lut >> 16) << 15, i.e. the two values the
-// reference forms before the interpolation (src/cossin.rs:44-60).  With d10 = dphi << 10,
+// Expanded table values used below: c14 = ((lut & 0xffff) + 65536) << 14 and s15 = (lut >> 16) << 15, i.e. the
+// two values the reference forms before the interpolation (src/cossin.rs:44-60).  With d10 = dphi << 10,
 //   (s * dphi) >> 7 == (s15 * d10) >> 32   and   (c * dphi) >> 8 == (c14 * d10) >> 32
-// exactly (floor of the same rational; |d10| < 2^24, c14 < 2^31), so each correction is one
-// IMAD.HI and the unpack / shift instructions disappear.  Bit-exact with cossin_dev
-// (tests/test_gpu_nco.py sweeps it against the oracle).
-__device__ __forceinline__ void cossin_expand_lut(const uint32_t *lut, uint32_t *table, int tid, int nthreads) {
-    for (int i = tid; i < 128; i += nthreads) {
-        const uint32_t w = lut[i];
-        table[2 * i] = ((w & 0xffffu) + 65536u) << 14;
-        table[2 * i + 1] = (w >> 16) << 15;
+// exactly (floor of the same rational; |d10| < 2^24, c14 < 2^31), so each first-order correction is one IMAD.HI
+// and the unpack / shift instructions disappear; d10 = ((frac * 51471) >> 6) & ~0x3ff.
+// Full-circle form of the same function for the lock-in kernels (round 2).  The reference folds the phase into
+// the first octant (conditional NOT), looks the octant's (cos, sin) pair up, interpolates and then unmaps with a
+// swap and two negations (src/cossin.rs:17-21, 56-65): ~17 ALU-pipe instructions per call.  Here the table is
+// indexed by the top TEN phase bits (3 octant bits + 7 index bits: 1024 entries of 8 bytes), each entry already
+// reversed, swapped and signed for its octant, and the remaining per-octant signs are small multipliers:
+//   entry = {Cb, Sb}:  no swap: Cb = sc*c14, Sb = ss*s15;   swap: Cb = sc*s15, Sb = ss*c14   (sc, ss = +-1)
+//   cos = Cb + kc * hi(Sb * (ss * d10)),   sin = Sb + ks * hi(Cb * (sc * d10)),   kc = swap ? sc : -sc, ks = swap ? -ss : ss
+// (ss*Sb and sc*Cb are the unsigned table values the reference multiplies by d10, whichever way the octant swaps)
+// and d10 = ((frac*51471) >> 6) & ~0x3ff with frac*51471 = fr*m1 + m0: for the odd (reversed) octants the folded
+// fraction is ~f = -f - 1 (f = fr - 2^14), so (m1, m0) = (-51471, 2^14*51471 - 51471), else (51471, -2^14*51471).
+// hi() is the signed high word; a sign is only ever moved between the two FACTORS of a product (the 64-bit
+// product is the same integer) or applied to the rounded high word exactly where the reference applies it, so
+// every intermediate equals the reference's: bit-exact, checked over all 2^25 distinct inputs against the oracle
+// (tests/test_gpu_nco.py).  Per call: 6 ALU-pipe + 8 multiplier-pipe instructions, LDS.64 + LDS.128 + LDS.64.
+constexpr int COSSIN_FULL_WORDS = 1024 * 2 + 8 * 4 + 8 * 2;
+__device__ __forceinline__ void cossin_expand_full(const uint32_t *lut, uint32_t *table, int tid, int nthreads) {
+    for (int e = tid; e < 1024 + 8; e += nthreads) {
+        const int o3 = e < 1024 ? e >> 7 : e - 1024;
+        const int p31 = (o3 >> 2) & 1, p30 = (o3 >> 1) & 1, p29 = o3 & 1;
+        const bool swap = (p29 ^ p30) != 0;
+        const int32_t sc = (p30 ^ p31) ? -1 : 1, ss = p31 ? -1 : 1;
+        int32_t *t = reinterpret_cast<int32_t *>(table);
+        if (e < 1024) {
+            const int ir = e & 127;
+            const uint32_t w = lut[p29 ? 127 - ir : ir];
+            const int32_t c14 = (int32_t)(((w & 0xffffu) + 65536u) << 14), s15 = (int32_t)((w >> 16) << 15);
+            t[2 * e] = swap ? sc * s15 : sc * c14;
+            t[2 * e + 1] = swap ? ss * c14 : ss * s15;
+        } else {
+            t[2048 + 4 * o3] = p29 ? -51471 : 51471;
+            t[2048 + 4 * o3 + 1] = p29 ? 16384 * 51471 - 51471 : -16384 * 51471;
+            t[2048 + 4 * o3 + 2] = swap ? sc : -sc;
+            t[2048 + 4 * o3 + 3] = swap ? -ss : ss;
+            t[2080 + 2 * o3] = ss;
+            t[2080 + 2 * o3 + 1] = sc;
+        }
     }
 }
-__device__ __forceinline__ void cossin_dev_x(const uint32_t *table, int32_t phase, int32_t &co, int32_t &so) {
-    uint32_t octant = (uint32_t)phase;
-    if (octant & (1u << 29)) phase = ~phase;
-    const uint32_t ph = (((uint32_t)phase) << 3) >> 10;
-    const uint2 e = *reinterpret_cast<const uint2 *>(table + 2 * (ph >> 15));
-    const int32_t frac = (int32_t)(ph & 0x7fffu) - (1 << 14);
-    const int32_t d10 = ((frac * 51471) >> 6) & ~0x3ff;
-    int32_t c = (int32_t)e.x - __mulhi((int32_t)e.y, d10);
-    int32_t s = (int32_t)e.y + __mulhi((int32_t)e.x, d10);
-    octant ^= octant >> 1;
-    if (octant & (1u << 29)) { int32_t t = c; c = s; s = t; }
-    if (octant & (1u << 30)) c = -c;
-    if (octant & (1u << 31)) s = -s;
-    co = c;
-    so = s;
+__device__ __forceinline__ void cossin_dev_full(const uint32_t *table, int32_t phase, int32_t &co, int32_t &so) {
+    const uint32_t p = (uint32_t)phase;
+    const int2 e = *reinterpret_cast<const int2 *>(table + ((p >> 22) << 1));
+    const int4 u = *reinterpret_cast<const int4 *>(table + 2048 + ((p >> 29) << 2));
+    const int2 v = *reinterpret_cast<const int2 *>(table + 2080 + ((p >> 29) << 1));
+    const int32_t fr = (int32_t)((p >> 7) & 0x7fffu);
+    const int32_t d10 = ((fr * u.x + u.y) >> 6) & ~0x3ff;  // folded fraction * 51471, as the reference's dphi << 10
+    co = e.x + u.z * __mulhi(e.y, v.x * d10);
+    so = e.y + u.w * __mulhi(e.x, v.y * d10);
 }
 
 // --------------------------------------------------------------------------
@@ -524,7 +548,8 @@ template <int ORDER, bool SMEM_LUT = false> struct LockinOp {
     static constexpr bool TUNABLE = false;
     static constexpr bool HEAVY = true;
     static constexpr bool LM_SMALL = false;
-    static constexpr int SMEM_EXTRA_WORDS = SMEM_LUT ? 256 : 0;  // expanded cossin table staged per CTA
+    static constexpr int SMEM_EXTRA_WORDS = SMEM_LUT ? COSSIN_FULL_WORDS : 0;  // full-circle cossin table per CTA
+    static constexpr bool SHARE_CTA = SMEM_LUT;  // several per-warp pipelines per CTA share the 16 KB table
     struct Params {
         int32_t k[2];
         int32_t kk[2];  // = k (see lowpass_step)
@@ -537,7 +562,7 @@ template <int ORDER, bool SMEM_LUT = false> struct LockinOp {
     int64_t i0, i1, q0, q1;
     const uint32_t *lutp;
     __device__ __forceinline__ static void init_smem(const Params &p, uint32_t *extra, int tid, int nthreads) {
-        if constexpr (SMEM_LUT) cossin_expand_lut(p.lut, extra, tid, nthreads);
+        if constexpr (SMEM_LUT) cossin_expand_full(p.lut, extra, tid, nthreads);
     }
     __device__ __forceinline__ void bind(const Params &p, const uint32_t *extra) { lutp = SMEM_LUT ? extra : p.lut; }
     __device__ __forceinline__ void load(const Params &p, size_t lane, size_t stride) {
@@ -559,7 +584,7 @@ template <int ORDER, bool SMEM_LUT = false> struct LockinOp {
     __device__ __forceinline__ int2 step(const Params &p, int32_t x) {
         ph += dph;
         int32_t c, s;
-        if constexpr (SMEM_LUT) cossin_dev_x(lutp, (int32_t)ph, c, s);
+        if constexpr (SMEM_LUT) cossin_dev_full(lutp, (int32_t)ph, c, s);
         else cossin_dev<false>(lutp, (int32_t)ph, c, s);
         int32_t mi = (int32_t)(((int64_t)c * (int64_t)x) >> 32);
         int32_t mq = (int32_t)(((int64_t)s * (int64_t)x) >> 32);
@@ -578,7 +603,8 @@ template <int ORDER, bool SMEM_LUT = false> struct LockinPhaseOp {
     static constexpr bool TUNABLE = false;
     static constexpr bool HEAVY = true;
     static constexpr bool LM_SMALL = false;
-    static constexpr int SMEM_EXTRA_WORDS = SMEM_LUT ? 256 : 0;
+    static constexpr int SMEM_EXTRA_WORDS = SMEM_LUT ? COSSIN_FULL_WORDS : 0;
+    static constexpr bool SHARE_CTA = SMEM_LUT;
     struct Params {
         int32_t k[2];
         int32_t kk[2];  // = k (see lowpass_step)
@@ -588,7 +614,7 @@ template <int ORDER, bool SMEM_LUT = false> struct LockinPhaseOp {
     int64_t i0, i1, q0, q1;
     const uint32_t *lutp;
     __device__ __forceinline__ static void init_smem(const Params &p, uint32_t *extra, int tid, int nthreads) {
-        if constexpr (SMEM_LUT) cossin_expand_lut(p.lut, extra, tid, nthreads);
+        if constexpr (SMEM_LUT) cossin_expand_full(p.lut, extra, tid, nthreads);
     }
     __device__ __forceinline__ void bind(const Params &p, const uint32_t *extra) { lutp = SMEM_LUT ? extra : p.lut; }
     __device__ __forceinline__ void load(const Params &p, size_t lane, size_t stride) {
@@ -606,7 +632,7 @@ template <int ORDER, bool SMEM_LUT = false> struct LockinPhaseOp {
     }
     __device__ __forceinline__ int2 step(const Params &p, int2 xp) {
         int32_t c, s;
-        if constexpr (SMEM_LUT) cossin_dev_x(lutp, xp.y, c, s);
+        if constexpr (SMEM_LUT) cossin_dev_full(lutp, xp.y, c, s);
         else cossin_dev<false>(lutp, xp.y, c, s);
         const int32_t mi = (int32_t)(((int64_t)c * (int64_t)xp.x) >> 32);
         const int32_t mq = (int32_t)(((int64_t)s * (int64_t)xp.x) >> 32);

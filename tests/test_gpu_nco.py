@@ -205,3 +205,16 @@ def test_lockin_lo_equals_phase_form():
     Lockin(Lowpass(k)).block_lo(s1, to_dev(xlo), a, 0)
     Lockin(Lowpass(k)).block_phase(s2, to_dev(xp), b, 0)
     assert_bits_equal(to_np(a), to_np(b))
+
+
+def test_cossin_exhaustive_over_every_distinct_phase(oracle):
+    """cossin() ignores the low 7 phase bits ((phase << 3) >> 10, src/cossin.rs:22-25): 2^25 distinct inputs.  All of
+    them (random low bits) through the full-circle table kernel against the oracle -- the table folds the octant
+    reversal, swap and negations of cossin.rs:17-21, 56-65 into 1024 pre-mapped entries, so every octant boundary
+    and every table edge is covered here."""
+    rng = np.random.default_rng(25)
+    for part in range(4):
+        hi = np.arange(part << 23, (part + 1) << 23, dtype=np.int64)
+        ph = ((hi << 7) | rng.integers(0, 128, hi.size)).astype(np.uint32).view(np.int32)
+        got = to_np(ib.cossin(to_dev(ph)))
+        assert_bits_equal(got, oracle.cossin(ph), f"part {part}")
