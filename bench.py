@@ -91,7 +91,7 @@ def strided_lanes(lanes, n=64):
     return np.unique(np.concatenate([np.arange(min(8, lanes)), a, np.arange(max(lanes - 8, 0), lanes)]))
 
 
-def pcie_peak(dev, mb=512, reps=4, world=1):
+def pcie_peak(dev, mb=512, reps=4, world=1, bidir=True):
     """pinned-memory copy rates with both directions busy at once (what the e2e leg is bound by):
     returns (h2d GB/s, d2h GB/s) measured with CUDA events on two streams.  At N > 1 every rank runs it
     at the same time (barrier before every repetition): the GPUs share the host's memory system and
@@ -114,7 +114,10 @@ def pcie_peak(dev, mb=512, reps=4, world=1):
             ev[1].record()
         with torch.cuda.stream(s2):
             ev[2].record()
-            h_out.copy_(d_out, non_blocking=True)
+            if bidir:  # bidir=False: host -> device alone (a decimator returns 1/16 of what it reads)
+                h_out.copy_(d_out, non_blocking=True)
+            else:
+                h_out[: n // 16].copy_(d_out[: n // 16], non_blocking=True)
             ev[3].record()
         torch.cuda.synchronize()
         best[0] = max(best[0], n / (ev[0].elapsed_time(ev[1]) * 1e-3) / 1e9)
@@ -926,7 +929,7 @@ def run_biquad(args, rank, world, local):
         "e2e": {"value": e2e, "unit": "GSa/s", "h2d_bytes_per_step": 4 * ef * lanes, "d2h_bytes_per_step": 4 * ef * lanes,
                 "frames_per_step": ef, "steps": esteps, "api": "idsp_biquad_df1_i32_host (pinned host buffers)",
                 "pcie_gbs": {"h2d": h2d_gbs, "d2h": d2h_gbs,
-                             "how": "256 MiB pinned copies, both directions at once, all ranks at the same time (barrier), slowest rank"},
+                             "how": "512 MiB pinned copies, both directions at once, all ranks at the same time (barrier), slowest rank"},
                 "bound": "PCIe: 4 B in + 4 B out per sample", "frac_of_pcie": (e2e / world) * 4.0 / min(h2d_gbs, d2h_gbs)},
         "gpu_launches": int(launches), "clocks": clocks,
         "parity_check": f"first step == oracle on {sub} lanes strided over all {lanes} lanes (every TMA box family, first / last 8) x all frames + state",
@@ -1056,7 +1059,7 @@ def run_hbf(args, rank, world, local):
     torch.cuda.synchronize()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, world, dev)
     e2e = world * el * HBF_INPUTS * esteps / (e2e_ms * 1e-3) / 1e9
-    h2d_gbs, d2h_gbs = pcie_peak(dev, world=world)
+    h2d_gbs, d2h_gbs = pcie_peak(dev, world=world, bidir=False)
     del xin, yout, xh, yh
     torch.cuda.empty_cache()
     if rank != 0:
@@ -1079,8 +1082,8 @@ def run_hbf(args, rank, world, local):
                          "sample": cpu_sample, "seconds": cpu_dt},
         "e2e": {"value": e2e, "unit": "GSa/s", "h2d_bytes_per_step": 4 * el * HBF_INPUTS, "d2h_bytes_per_step": 4 * el * n_out,
                 "steps": esteps, "api": "idsp_hbf_dec_cascade_f32_host (pinned host buffers)",
-                "pcie_gbs": {"h2d": h2d_gbs, "d2h": d2h_gbs,
-                             "how": "256 MiB pinned copies, both directions at once, all ranks at the same time (barrier), slowest rank"},
+                "pcie_gbs": {"h2d": h2d_gbs, "d2h": None,
+                             "how": "512 MiB pinned host -> device copies with 1/16 of that going back at the same time, all ranks at the same time (barrier), slowest rank"},
                 "bound": "PCIe: 4 B in + 0.25 B out per sample", "frac_of_pcie": (e2e / world) * 4.0 / h2d_gbs},
         "gpu_launches": int(launches), "clocks": clocks,
         "parity_check": f"first step == oracle on {sub} lanes strided over the slice (first / last 8 included) x all samples",

@@ -33,7 +33,6 @@ template <> struct is_float<double> { static constexpr bool value = true; };
 
 // Defaults of the optional Op hooks used by the TMA kernels (tma_kernels.cuh)
 struct OpHooks {
-    static constexpr bool SHARE_CTA = false;  // per-CTA shared-memory extras worth sharing between per-warp pipelines
     static constexpr bool TUNABLE = false;
     static constexpr bool HEAVY = false;  // compute-bound: lane-major TMA kernels trade tile size for resident warps
     static constexpr bool LM_SMALL = false;  // in between: fewer lane-major stages of the same tile
@@ -59,15 +58,35 @@ template <class T> __device__ __forceinline__ T clamp_nt(T v, T lo, T hi) {
 // Q*T -> wide accu: dsp-fixedpoint/src/ops.rs:91-97, lib.rs:310-312
 // accu.as_() = (acc >> F) as T: num_traits_impl.rs:74-104, lib.rs:297-299
 // --------------------------------------------------------------------------
+// 32-bit multiply-accumulate whose ORDER the compiler keeps (plain C++ integer sums are re-associated).
+__device__ __forceinline__ int32_t madlo(int32_t a, int32_t b, int32_t c) {
+    int32_t d;
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
 template <class T, bool ISF = is_float<T>::value> struct Sos;
 
 template <class T> struct Sos<T, false> {
     using A = typename Wide<T>::A;
     using UA = typename Wide<T>::UA;
     using UT = typename Wide<T>::UT;
+    // The five products are summed in wrapping arithmetic (wrapA), which is associative: the
+    // order is free.  8- / 16-bit samples: one 32-bit multiply-add chain, the operands that exist earliest
+    // first and a1*y1 (the recurrence) last; the accumulator wraps at 16 / 32 bits = the low bits of the
+    // 32-bit sum (i8 lane-major 1 411 -> 1 814 GSa/s, i16 frame-major 870 -> 934).  i32: the compiler's
+    // single IMAD.WIDE accumulate chain is kept -- forcing an order makes ptxas split every multiply-add into
+    // IMAD.WIDE + two carry adds (DF1 i32 805 -> 763 GSa/s, Cascade<4> unchanged: that kernel is bound by
+    // the issue rate of IMAD.WIDE, not by the length of the chain).
     __device__ __forceinline__ static T eval(const T *ba, int F, T x0, T x1, T x2, T y1, T y2) {
-        UA acc = (UA)((A)ba[0] * (A)x0) + (UA)((A)ba[1] * (A)x1) + (UA)((A)ba[2] * (A)x2) +
-                 (UA)((A)ba[3] * (A)y1) + (UA)((A)ba[4] * (A)y2);
+        UA acc;
+        if constexpr (sizeof(T) < 4) {
+            const int32_t a32 = madlo(ba[3], y1, madlo(ba[0], x0, madlo(ba[1], x1, madlo(ba[4], y2, madlo(ba[2], x2, 0)))));
+            acc = (UA)(uint32_t)a32;
+        } else {
+            acc = (UA)((A)ba[0] * (A)x0) + (UA)((A)ba[1] * (A)x1) + (UA)((A)ba[2] * (A)x2) +
+                  (UA)((A)ba[3] * (A)y1) + (UA)((A)ba[4] * (A)y2);
+        }
         A q = F >= 0 ? (A)((A)acc >> F) : (A)(UA)(acc << (-F));
         return (T)(UT)(UA)q;
     }
@@ -192,18 +211,19 @@ template <class T, int N, int MODE = 0> struct CascadeOp : OpHooks {
 #pragma unroll
         for (int w = 0; w < 2 + 2 * N; w++) p.st[(size_t)w * stride + lane] = d[w];
     }
+    template <int S> __device__ __forceinline__ T section(const Params &p, T x0) {
+        T y0;
+        if constexpr (MODE == 1)
+            y0 = SosI32Fast::eval(p.ba[S], p.F, x0, d[2 * S], d[2 * S + 1], d[2 * S + 2], d[2 * S + 3]);
+        else
+            y0 = Sos<T>::eval(p.ba[S], p.F, x0, d[2 * S], d[2 * S + 1], d[2 * S + 2], d[2 * S + 3]);
+        d[2 * S + 1] = d[2 * S];
+        d[2 * S] = x0;
+        if constexpr (S + 1 < N) return section<S + 1>(p, y0);
+        else return y0;
+    }
     __device__ __forceinline__ T step(const Params &p, T x0) {
-#pragma unroll
-        for (int s = 0; s < N; s++) {
-            T y0;
-            if constexpr (MODE == 1)
-                y0 = SosI32Fast::eval(p.ba[s], p.F, x0, d[2 * s], d[2 * s + 1], d[2 * s + 2], d[2 * s + 3]);
-            else
-                y0 = Sos<T>::eval(p.ba[s], p.F, x0, d[2 * s], d[2 * s + 1], d[2 * s + 2], d[2 * s + 3]);
-            d[2 * s + 1] = d[2 * s];
-            d[2 * s] = x0;
-            x0 = y0;
-        }
+        x0 = section<0>(p, x0);
         d[2 * N + 1] = d[2 * N];
         d[2 * N] = x0;
         return x0;
@@ -360,58 +380,35 @@ __device__ __forceinline__ void cossin_dev(const uint32_t *lut, int32_t phase, i
     so = s;
 }
 
-// Expanded table values used below: c14 = ((lut & 0xffff) + 65536) << 14 and s15 = (lut >> 16) << 15, i.e. the
-// two values the reference forms before the interpolation (src/cossin.rs:44-60).  With d10 = dphi << 10,
+// Same function on a pre-expanded table: entry i of the staged shared-memory table holds
+// c14 = ((lut & 0xffff) + 65536) << 14 and s15 = (lut >> 16) << 15, i.e. the two values the
+// reference forms before the interpolation (src/cossin.rs:44-60).  With d10 = dphi << 10,
 //   (s * dphi) >> 7 == (s15 * d10) >> 32   and   (c * dphi) >> 8 == (c14 * d10) >> 32
-// exactly (floor of the same rational; |d10| < 2^24, c14 < 2^31), so each first-order correction is one IMAD.HI
-// and the unpack / shift instructions disappear; d10 = ((frac * 51471) >> 6) & ~0x3ff.
-// Full-circle form of the same function for the lock-in kernels (round 2).  The reference folds the phase into
-// the first octant (conditional NOT), looks the octant's (cos, sin) pair up, interpolates and then unmaps with a
-// swap and two negations (src/cossin.rs:17-21, 56-65): ~17 ALU-pipe instructions per call.  Here the table is
-// indexed by the top TEN phase bits (3 octant bits + 7 index bits: 1024 entries of 8 bytes), each entry already
-// reversed, swapped and signed for its octant, and the remaining per-octant signs are small multipliers:
-//   entry = {Cb, Sb}:  no swap: Cb = sc*c14, Sb = ss*s15;   swap: Cb = sc*s15, Sb = ss*c14   (sc, ss = +-1)
-//   cos = Cb + kc * hi(Sb * (ss * d10)),   sin = Sb + ks * hi(Cb * (sc * d10)),   kc = swap ? sc : -sc, ks = swap ? -ss : ss
-// (ss*Sb and sc*Cb are the unsigned table values the reference multiplies by d10, whichever way the octant swaps)
-// and d10 = ((frac*51471) >> 6) & ~0x3ff with frac*51471 = fr*m1 + m0: for the odd (reversed) octants the folded
-// fraction is ~f = -f - 1 (f = fr - 2^14), so (m1, m0) = (-51471, 2^14*51471 - 51471), else (51471, -2^14*51471).
-// hi() is the signed high word; a sign is only ever moved between the two FACTORS of a product (the 64-bit
-// product is the same integer) or applied to the rounded high word exactly where the reference applies it, so
-// every intermediate equals the reference's: bit-exact, checked over all 2^25 distinct inputs against the oracle
-// (tests/test_gpu_nco.py).  Per call: 6 ALU-pipe + 8 multiplier-pipe instructions, LDS.64 + LDS.128 + LDS.64.
-constexpr int COSSIN_FULL_WORDS = 1024 * 2 + 8 * 4 + 8 * 2;
-__device__ __forceinline__ void cossin_expand_full(const uint32_t *lut, uint32_t *table, int tid, int nthreads) {
-    for (int e = tid; e < 1024 + 8; e += nthreads) {
-        const int o3 = e < 1024 ? e >> 7 : e - 1024;
-        const int p31 = (o3 >> 2) & 1, p30 = (o3 >> 1) & 1, p29 = o3 & 1;
-        const bool swap = (p29 ^ p30) != 0;
-        const int32_t sc = (p30 ^ p31) ? -1 : 1, ss = p31 ? -1 : 1;
-        int32_t *t = reinterpret_cast<int32_t *>(table);
-        if (e < 1024) {
-            const int ir = e & 127;
-            const uint32_t w = lut[p29 ? 127 - ir : ir];
-            const int32_t c14 = (int32_t)(((w & 0xffffu) + 65536u) << 14), s15 = (int32_t)((w >> 16) << 15);
-            t[2 * e] = swap ? sc * s15 : sc * c14;
-            t[2 * e + 1] = swap ? ss * c14 : ss * s15;
-        } else {
-            t[2048 + 4 * o3] = p29 ? -51471 : 51471;
-            t[2048 + 4 * o3 + 1] = p29 ? 16384 * 51471 - 51471 : -16384 * 51471;
-            t[2048 + 4 * o3 + 2] = swap ? sc : -sc;
-            t[2048 + 4 * o3 + 3] = swap ? -ss : ss;
-            t[2080 + 2 * o3] = ss;
-            t[2080 + 2 * o3 + 1] = sc;
-        }
+// exactly (floor of the same rational; |d10| < 2^24, c14 < 2^31), so each correction is one
+// IMAD.HI and the unpack / shift instructions disappear.  Bit-exact with cossin_dev
+// (tests/test_gpu_nco.py sweeps it against the oracle).
+__device__ __forceinline__ void cossin_expand_lut(const uint32_t *lut, uint32_t *table, int tid, int nthreads) {
+    for (int i = tid; i < 128; i += nthreads) {
+        const uint32_t w = lut[i];
+        table[2 * i] = ((w & 0xffffu) + 65536u) << 14;
+        table[2 * i + 1] = (w >> 16) << 15;
     }
 }
-__device__ __forceinline__ void cossin_dev_full(const uint32_t *table, int32_t phase, int32_t &co, int32_t &so) {
-    const uint32_t p = (uint32_t)phase;
-    const int2 e = *reinterpret_cast<const int2 *>(table + ((p >> 22) << 1));
-    const int4 u = *reinterpret_cast<const int4 *>(table + 2048 + ((p >> 29) << 2));
-    const int2 v = *reinterpret_cast<const int2 *>(table + 2080 + ((p >> 29) << 1));
-    const int32_t fr = (int32_t)((p >> 7) & 0x7fffu);
-    const int32_t d10 = ((fr * u.x + u.y) >> 6) & ~0x3ff;  // folded fraction * 51471, as the reference's dphi << 10
-    co = e.x + u.z * __mulhi(e.y, v.x * d10);
-    so = e.y + u.w * __mulhi(e.x, v.y * d10);
+__device__ __forceinline__ void cossin_dev_x(const uint32_t *table, int32_t phase, int32_t &co, int32_t &so) {
+    uint32_t octant = (uint32_t)phase;
+    if (octant & (1u << 29)) phase = ~phase;
+    const uint32_t ph = (((uint32_t)phase) << 3) >> 10;
+    const uint2 e = *reinterpret_cast<const uint2 *>(table + 2 * (ph >> 15));
+    const int32_t frac = (int32_t)(ph & 0x7fffu) - (1 << 14);
+    const int32_t d10 = ((frac * 51471) >> 6) & ~0x3ff;
+    int32_t c = (int32_t)e.x - __mulhi((int32_t)e.y, d10);
+    int32_t s = (int32_t)e.y + __mulhi((int32_t)e.x, d10);
+    octant ^= octant >> 1;
+    if (octant & (1u << 29)) { int32_t t = c; c = s; s = t; }
+    if (octant & (1u << 30)) c = -c;
+    if (octant & (1u << 31)) s = -s;
+    co = c;
+    so = s;
 }
 
 // --------------------------------------------------------------------------
@@ -548,8 +545,7 @@ template <int ORDER, bool SMEM_LUT = false> struct LockinOp {
     static constexpr bool TUNABLE = false;
     static constexpr bool HEAVY = true;
     static constexpr bool LM_SMALL = false;
-    static constexpr int SMEM_EXTRA_WORDS = SMEM_LUT ? COSSIN_FULL_WORDS : 0;  // full-circle cossin table per CTA
-    static constexpr bool SHARE_CTA = SMEM_LUT;  // several per-warp pipelines per CTA share the 16 KB table
+    static constexpr int SMEM_EXTRA_WORDS = SMEM_LUT ? 256 : 0;  // expanded cossin table staged per CTA
     struct Params {
         int32_t k[2];
         int32_t kk[2];  // = k (see lowpass_step)
@@ -562,7 +558,7 @@ template <int ORDER, bool SMEM_LUT = false> struct LockinOp {
     int64_t i0, i1, q0, q1;
     const uint32_t *lutp;
     __device__ __forceinline__ static void init_smem(const Params &p, uint32_t *extra, int tid, int nthreads) {
-        if constexpr (SMEM_LUT) cossin_expand_full(p.lut, extra, tid, nthreads);
+        if constexpr (SMEM_LUT) cossin_expand_lut(p.lut, extra, tid, nthreads);
     }
     __device__ __forceinline__ void bind(const Params &p, const uint32_t *extra) { lutp = SMEM_LUT ? extra : p.lut; }
     __device__ __forceinline__ void load(const Params &p, size_t lane, size_t stride) {
@@ -584,7 +580,7 @@ template <int ORDER, bool SMEM_LUT = false> struct LockinOp {
     __device__ __forceinline__ int2 step(const Params &p, int32_t x) {
         ph += dph;
         int32_t c, s;
-        if constexpr (SMEM_LUT) cossin_dev_full(lutp, (int32_t)ph, c, s);
+        if constexpr (SMEM_LUT) cossin_dev_x(lutp, (int32_t)ph, c, s);
         else cossin_dev<false>(lutp, (int32_t)ph, c, s);
         int32_t mi = (int32_t)(((int64_t)c * (int64_t)x) >> 32);
         int32_t mq = (int32_t)(((int64_t)s * (int64_t)x) >> 32);
@@ -603,8 +599,7 @@ template <int ORDER, bool SMEM_LUT = false> struct LockinPhaseOp {
     static constexpr bool TUNABLE = false;
     static constexpr bool HEAVY = true;
     static constexpr bool LM_SMALL = false;
-    static constexpr int SMEM_EXTRA_WORDS = SMEM_LUT ? COSSIN_FULL_WORDS : 0;
-    static constexpr bool SHARE_CTA = SMEM_LUT;
+    static constexpr int SMEM_EXTRA_WORDS = SMEM_LUT ? 256 : 0;
     struct Params {
         int32_t k[2];
         int32_t kk[2];  // = k (see lowpass_step)
@@ -614,7 +609,7 @@ template <int ORDER, bool SMEM_LUT = false> struct LockinPhaseOp {
     int64_t i0, i1, q0, q1;
     const uint32_t *lutp;
     __device__ __forceinline__ static void init_smem(const Params &p, uint32_t *extra, int tid, int nthreads) {
-        if constexpr (SMEM_LUT) cossin_expand_full(p.lut, extra, tid, nthreads);
+        if constexpr (SMEM_LUT) cossin_expand_lut(p.lut, extra, tid, nthreads);
     }
     __device__ __forceinline__ void bind(const Params &p, const uint32_t *extra) { lutp = SMEM_LUT ? extra : p.lut; }
     __device__ __forceinline__ void load(const Params &p, size_t lane, size_t stride) {
@@ -632,7 +627,7 @@ template <int ORDER, bool SMEM_LUT = false> struct LockinPhaseOp {
     }
     __device__ __forceinline__ int2 step(const Params &p, int2 xp) {
         int32_t c, s;
-        if constexpr (SMEM_LUT) cossin_dev_full(lutp, xp.y, c, s);
+        if constexpr (SMEM_LUT) cossin_dev_x(lutp, xp.y, c, s);
         else cossin_dev<false>(lutp, xp.y, c, s);
         const int32_t mi = (int32_t)(((int64_t)c * (int64_t)xp.x) >> 32);
         const int32_t mq = (int32_t)(((int64_t)s * (int64_t)xp.x) >> 32);

@@ -144,8 +144,7 @@ tma_lanes_kernel(typename Op::Params p, const __grid_constant__ CUtensorMap mx,
     uint32_t *sin = wbase;
     uint32_t *sout = wbase + S * IW * TILE_WORDS;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)NPIPE * (S * IW + O * OW) * TILE_WORDS * 4) + pipe * S;
-    // Op extras (lookup tables) behind the mbarriers, 16-byte aligned (LDS.128)
-    uint32_t *extra = reinterpret_cast<uint32_t *>(smem_raw + (size_t)NPIPE * (S * IW + O * OW) * TILE_WORDS * 4 + (((size_t)NPIPE * S * 8 + 15) & ~(size_t)15));
+    uint32_t *extra = reinterpret_cast<uint32_t *>(smem_raw + (size_t)NPIPE * (S * IW + O * OW) * TILE_WORDS * 4 + (size_t)NPIPE * S * 8);
     if constexpr (Op::SMEM_EXTRA_WORDS > 0) {
         Op::init_smem(p, extra, threadIdx.x, WPC * 32);
         __syncthreads();
@@ -406,7 +405,7 @@ static int tma_launch_cfg(idsp_ctx *ctx, const typename Op::Params &p, const voi
     }
     if (!ok) return IDSP_TMA_NOT_APPLICABLE;
     constexpr int NPIPE = WIDE ? 1 : WPC;
-    constexpr size_t smem = (size_t)NPIPE * (S * IW + O * OW) * TF * BW * 4 + (((size_t)NPIPE * S * 8 + 15) & ~(size_t)15) +
+    constexpr size_t smem = (size_t)NPIPE * (S * IW + O * OW) * TF * BW * 4 + (size_t)NPIPE * S * 8 +
                             (size_t)Op::SMEM_EXTRA_WORDS * 4;
     auto kern = tma_lanes_kernel<Op, LM, TF, S, O, WPC, WIDE>;
     IDSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -430,7 +429,7 @@ static int tma_cfg_occupancy() {
         constexpr int IW = sizeof(typename Op::In) / 4;
         constexpr int OW = sizeof(typename Op::Out) / 4;
         constexpr int NPIPE = WIDE ? 1 : WPC;
-        constexpr size_t smem = (size_t)NPIPE * (S * IW + O * OW) * TF * BW * 4 + (((size_t)NPIPE * S * 8 + 15) & ~(size_t)15) +
+        constexpr size_t smem = (size_t)NPIPE * (S * IW + O * OW) * TF * BW * 4 + (size_t)NPIPE * S * 8 +
                                 (size_t)Op::SMEM_EXTRA_WORDS * 4;
         auto kern = tma_lanes_kernel<Op, LM, TF, S, O, WPC, WIDE>;
         int n = 0;
@@ -530,12 +529,7 @@ static int tma_try_launch(idsp_ctx *ctx, const typename Op::Params &p, const typ
         if (lm) {
             // one warp per CTA, 64-byte input rows / 128-byte output rows, 10 KB per warp: the op
             // is ALU-bound, so resident warps count for more than long DRAM bursts
-            // (ops that stage a large table per CTA -- the lock-in's 16 KB full-circle cossin table -- put four
-            // per-warp pipelines in a CTA so that the table is shared)
-            if constexpr (Op::SMEM_EXTRA_WORDS >= 1024)
-                r = tma_launch_cfg<Op, true, 16, 3, 1, 4>(ctx, p, x, y, frames, lanes, sstride);
-            else
-                r = tma_launch_cfg<Op, true, 16, 3, 1, 1>(ctx, p, x, y, frames, lanes, sstride);
+            r = tma_launch_cfg<Op, true, 16, 3, 1, 1>(ctx, p, x, y, frames, lanes, sstride);
 #ifdef IDSP_TUNE
         } else if (getenv("IDSP_OUT8_CFG") && (Op::HEAVY || sizeof(typename Op::In) == 8)) {
             // tuning builds: tile shape / residency sweep of the compute-bound 8-byte ops (lock-in)
@@ -562,17 +556,7 @@ static int tma_try_launch(idsp_ctx *ctx, const typename Op::Params &p, const typ
             // lock-in 336 GSa/s against 326 for the 128-lane shared boxes, (x, phase) lock-in 269 / 254,
             // FM discriminator 188 / 180, i64 DF1 145 / 137; more resident warps do not help (the kernels
             // are bound by a pipe, not by latency).
-            if constexpr (Op::SMEM_EXTRA_WORDS >= 1024) {
-#ifdef IDSP_TUNE
-                const int wpc = getenv("IDSP_LOCKIN_WPC") ? atoi(getenv("IDSP_LOCKIN_WPC")) : 4;
-                if (wpc == 2) r = tma_launch_cfg<Op, false, 16, 2, 1, 2>(ctx, p, x, y, frames, lanes, sstride);
-                else if (wpc == 8) r = tma_launch_cfg<Op, false, 16, 2, 1, 8>(ctx, p, x, y, frames, lanes, sstride);
-                else if (wpc == 1) r = tma_launch_cfg<Op, false, 16, 2, 1, 1>(ctx, p, x, y, frames, lanes, sstride);
-                else
-#endif
-                r = tma_launch_cfg<Op, false, 16, 2, 1, 4>(ctx, p, x, y, frames, lanes, sstride);  // 4 pipelines share the table
-            } else
-                r = tma_launch_cfg<Op, false, 16, 2, 1, 1>(ctx, p, x, y, frames, lanes, sstride);
+            r = tma_launch_cfg<Op, false, 16, 2, 1, 1>(ctx, p, x, y, frames, lanes, sstride);
         } else if ((lanes + 127) / 128 >= sms) {
             // HBM-bound 8-byte streams (f64 biquads): 128-lane boxes (1 KB rows) with 2 load stages + 1 store
             // stage -- 24 KB per CTA instead of 48, i.e. twice the CTAs in flight: f64 DF1 347 -> 389 GSa/s
