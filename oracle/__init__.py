@@ -53,8 +53,10 @@ def build_native() -> str:
                               stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     except Exception:
         return build()
-    if _lib is None:
-        _SO = so
+    # switch this process to the native build even if the portable one is already loaded (a second dlopen of a
+    # different file: the C library is stateless, so calls made before and after give the same results)
+    if _SO != so:
+        _SO, _lib = so, None
     return so
 
 
