@@ -305,20 +305,40 @@ template <int K, int s, bool LOAD> struct StateIO {
             constexpr int LEN = 2 * M - 1;
             constexpr int WORDS = 3 * M - 2;
             float *stw = st + (size_t)st_word(K, s) * sstride + lane0;
-            for (int idx = tid; idx < WORDS * NL; idx += NT) {
-                const int lane = idx % NL, w = idx / NL;
-                if (lane >= nl) continue;
-                float *p;
+            // shared-memory slot of state word w of lane `lane`
+            auto slot = [&](int lane, int w) -> float * {
                 if constexpr (s == 0) {
                     constexpr int HR = raw_h(K);
                     float *row = sm + (rawbuf * NL + lane) * raw_pitch(K) + roff;
-                    p = w < M - 1 ? row + (HR - 2 * M + 2 + 2 * w) : row + (HR - 4 * M + 3 + 2 * (w - (M - 1)));
+                    return w < M - 1 ? row + (HR - 2 * M + 2 + 2 * w) : row + (HR - 4 * M + 3 + 2 * (w - (M - 1)));
                 } else {
-                    p = w < M - 1 ? sm + off_e(K, s) + lane * pe(K, s) + (he(K, s) - (M - 1) + w)
-                                  : sm + off_o(K, s) + lane * po(K, s) + (ho(K, s) - LEN + (w - (M - 1)));
+                    return w < M - 1 ? sm + off_e(K, s) + lane * pe(K, s) + (he(K, s) - (M - 1) + w)
+                                     : sm + off_o(K, s) + lane * po(K, s) + (ho(K, s) - LEN + (w - (M - 1)));
                 }
-                if constexpr (LOAD) *p = stw[(size_t)w * sstride + lane];
-                else stw[(size_t)w * sstride + lane] = *p;
+            };
+            if constexpr (LOAD) {
+                // all the loads of a thread are issued before the first store (read-only path: the compiler may
+                // hoist them over the shared-memory stores of the previous stage too), so that entering a call
+                // costs one global-memory round trip, not one per state word: short calls of a streaming
+                // caller are dominated by this prologue otherwise (13 % of a 16-tile call)
+                constexpr int IT = (WORDS * NL + NT - 1) / NT;
+                float v[IT];
+#pragma unroll
+                for (int it = 0; it < IT; it++) {
+                    const int idx = tid + it * NT, lane = idx % NL, w = idx / NL;
+                    v[it] = (idx < WORDS * NL && lane < nl) ? __ldg(stw + (size_t)w * sstride + lane) : 0.f;
+                }
+#pragma unroll
+                for (int it = 0; it < IT; it++) {
+                    const int idx = tid + it * NT, lane = idx % NL, w = idx / NL;
+                    if (idx < WORDS * NL && lane < nl) *slot(lane, w) = v[it];
+                }
+            } else {
+                for (int idx = tid; idx < WORDS * NL; idx += NT) {
+                    const int lane = idx % NL, w = idx / NL;
+                    if (lane >= nl) continue;
+                    stw[(size_t)w * sstride + lane] = *slot(lane, w);
+                }
             }
             StateIO<K, s + 1, LOAD>::run(sm, st, sstride, lane0, nl, tid, rawbuf, roff);
         }

@@ -111,12 +111,25 @@ template <int K, int s, bool LOAD> struct StateIO {
         if constexpr (s < K) {
             constexpr int LEN = 2 * st_m(s) - 1;
             float *stw = st + (size_t)st_word(s) * sstride + lane0;
-            for (int idx = tid; idx < LEN * NL; idx += NT) {
-                const int lane = idx % NL, w = idx / NL;
-                if (lane >= nl) continue;
-                float *p = sm + off_u(K, s) + lane * pitch(K, s) + (hist(s) - LEN + w);
-                if constexpr (LOAD) *p = stw[(size_t)w * sstride + lane];
-                else stw[(size_t)w * sstride + lane] = *p;
+            if constexpr (LOAD) {  // loads first, then stores: one global round trip (see hbf_fast_scalar_body.cuh)
+                constexpr int IT = (LEN * NL + NT - 1) / NT;
+                float v[IT];
+#pragma unroll
+                for (int it = 0; it < IT; it++) {
+                    const int idx = tid + it * NT, lane = idx % NL, w = idx / NL;
+                    v[it] = (idx < LEN * NL && lane < nl) ? __ldg(stw + (size_t)w * sstride + lane) : 0.f;
+                }
+#pragma unroll
+                for (int it = 0; it < IT; it++) {
+                    const int idx = tid + it * NT, lane = idx % NL, w = idx / NL;
+                    if (idx < LEN * NL && lane < nl) sm[off_u(K, s) + lane * pitch(K, s) + (hist(s) - LEN + w)] = v[it];
+                }
+            } else {
+                for (int idx = tid; idx < LEN * NL; idx += NT) {
+                    const int lane = idx % NL, w = idx / NL;
+                    if (lane >= nl) continue;
+                    stw[(size_t)w * sstride + lane] = sm[off_u(K, s) + lane * pitch(K, s) + (hist(s) - LEN + w)];
+                }
             }
             StateIO<K, s + 1, LOAD>::run(sm, st, sstride, lane0, nl, tid);
         }
@@ -191,7 +204,6 @@ hbf_int_fast_kernel(float *st, const float *x, float *y, size_t n_in, size_t nti
             return;
         }
     }
-    StateIO<K, 0, true>::run(sm, st, sstride, lane0, nl, tid);
 
     // input prefetch (the input is 1/2^K of the traffic): float4 v = tid + j*NT of the tile
     float4 nxt[NVT];  // FM uses .x only
@@ -211,6 +223,7 @@ hbf_int_fast_kernel(float *st, const float *x, float *y, size_t n_in, size_t nti
         }
     };
     if (ntiles) fetch(0);
+    StateIO<K, 0, true>::run(sm, st, sstride, lane0, nl, tid);  // after the first fetch: one round trip for both
 
     for (size_t i = 0; i < ntiles; i++) {
         const int ob = (int)(i & 1);
