@@ -387,18 +387,34 @@ __device__ __forceinline__ void cossin_dev(const uint32_t *lut, int32_t phase, i
 // exactly (floor of the same rational; |d10| < 2^24, c14 < 2^31), so each correction is one
 // IMAD.HI and the unpack / shift instructions disappear.  Bit-exact with cossin_dev
 // (tests/test_gpu_nco.py sweeps it against the oracle).
+// REP > 1: the table is replicated REP times, entry-major (entry i, copy r at word 2 * (REP * i + r)); a
+// thread reads copy `threadIdx.x % REP` only.  With REP = 16 an entry spans all 32 banks and the 16 threads
+// of a half-warp (one 8-byte access phase) hit 16 different bank pairs whatever their entries are: the
+// data-dependent lookups are conflict free (plain table: 59 % of the load wavefronts were replays).
+// Measured (profiles/r2_cossin_table_replication.log): the `cossin` map kernel gains 3.5 % (455 -> 471 GSa/s);
+// the lock-in kernels do not (336 -> 326 GSa/s with 16 copies shared by 4 warps, (x, phase) 287 -> 217): their
+// limiter is the ALU pipe, not the shared-memory replays, and the table costs residency.  So: 16 copies in the
+// map kernel, one in the lock-in kernels.
+#ifndef IDSP_COSSIN_REP
+#define IDSP_COSSIN_REP 16
+#endif
+#ifndef IDSP_LOCKIN_LUT_REP
+#define IDSP_LOCKIN_LUT_REP 1
+#endif
+template <int REP = 1>
 __device__ __forceinline__ void cossin_expand_lut(const uint32_t *lut, uint32_t *table, int tid, int nthreads) {
-    for (int i = tid; i < 128; i += nthreads) {
-        const uint32_t w = lut[i];
+    for (int i = tid; i < 128 * REP; i += nthreads) {
+        const uint32_t w = lut[i / REP];
         table[2 * i] = ((w & 0xffffu) + 65536u) << 14;
         table[2 * i + 1] = (w >> 16) << 15;
     }
 }
+template <int REP = 1>
 __device__ __forceinline__ void cossin_dev_x(const uint32_t *table, int32_t phase, int32_t &co, int32_t &so) {
     uint32_t octant = (uint32_t)phase;
     if (octant & (1u << 29)) phase = ~phase;
     const uint32_t ph = (((uint32_t)phase) << 3) >> 10;
-    const uint2 e = *reinterpret_cast<const uint2 *>(table + 2 * (ph >> 15));
+    const uint2 e = *reinterpret_cast<const uint2 *>(table + 2 * REP * (ph >> 15));
     const int32_t frac = (int32_t)(ph & 0x7fffu) - (1 << 14);
     const int32_t d10 = ((frac * 51471) >> 6) & ~0x3ff;
     int32_t c = (int32_t)e.x - __mulhi((int32_t)e.y, d10);
@@ -545,7 +561,7 @@ template <int ORDER, bool SMEM_LUT = false> struct LockinOp {
     static constexpr bool TUNABLE = false;
     static constexpr bool HEAVY = true;
     static constexpr bool LM_SMALL = false;
-    static constexpr int SMEM_EXTRA_WORDS = SMEM_LUT ? 256 : 0;  // expanded cossin table staged per CTA
+    static constexpr int SMEM_EXTRA_WORDS = SMEM_LUT ? 256 * IDSP_LOCKIN_LUT_REP : 0;  // expanded cossin table staged per CTA
     struct Params {
         int32_t k[2];
         int32_t kk[2];  // = k (see lowpass_step)
@@ -558,9 +574,11 @@ template <int ORDER, bool SMEM_LUT = false> struct LockinOp {
     int64_t i0, i1, q0, q1;
     const uint32_t *lutp;
     __device__ __forceinline__ static void init_smem(const Params &p, uint32_t *extra, int tid, int nthreads) {
-        if constexpr (SMEM_LUT) cossin_expand_lut(p.lut, extra, tid, nthreads);
+        if constexpr (SMEM_LUT) cossin_expand_lut<IDSP_LOCKIN_LUT_REP>(p.lut, extra, tid, nthreads);
     }
-    __device__ __forceinline__ void bind(const Params &p, const uint32_t *extra) { lutp = SMEM_LUT ? extra : p.lut; }
+    __device__ __forceinline__ void bind(const Params &p, const uint32_t *extra) {
+        lutp = SMEM_LUT ? extra + 2 * (threadIdx.x % IDSP_LOCKIN_LUT_REP) : p.lut;
+    }
     __device__ __forceinline__ void load(const Params &p, size_t lane, size_t stride) {
         if constexpr (!SMEM_LUT) lutp = p.lut;
         ph = (uint32_t)p.accu_state[lane];
@@ -580,7 +598,7 @@ template <int ORDER, bool SMEM_LUT = false> struct LockinOp {
     __device__ __forceinline__ int2 step(const Params &p, int32_t x) {
         ph += dph;
         int32_t c, s;
-        if constexpr (SMEM_LUT) cossin_dev_x(lutp, (int32_t)ph, c, s);
+        if constexpr (SMEM_LUT) cossin_dev_x<IDSP_LOCKIN_LUT_REP>(lutp, (int32_t)ph, c, s);
         else cossin_dev<false>(lutp, (int32_t)ph, c, s);
         int32_t mi = (int32_t)(((int64_t)c * (int64_t)x) >> 32);
         int32_t mq = (int32_t)(((int64_t)s * (int64_t)x) >> 32);
@@ -599,7 +617,7 @@ template <int ORDER, bool SMEM_LUT = false> struct LockinPhaseOp {
     static constexpr bool TUNABLE = false;
     static constexpr bool HEAVY = true;
     static constexpr bool LM_SMALL = false;
-    static constexpr int SMEM_EXTRA_WORDS = SMEM_LUT ? 256 : 0;
+    static constexpr int SMEM_EXTRA_WORDS = SMEM_LUT ? 256 * IDSP_LOCKIN_LUT_REP : 0;
     struct Params {
         int32_t k[2];
         int32_t kk[2];  // = k (see lowpass_step)
@@ -609,9 +627,11 @@ template <int ORDER, bool SMEM_LUT = false> struct LockinPhaseOp {
     int64_t i0, i1, q0, q1;
     const uint32_t *lutp;
     __device__ __forceinline__ static void init_smem(const Params &p, uint32_t *extra, int tid, int nthreads) {
-        if constexpr (SMEM_LUT) cossin_expand_lut(p.lut, extra, tid, nthreads);
+        if constexpr (SMEM_LUT) cossin_expand_lut<IDSP_LOCKIN_LUT_REP>(p.lut, extra, tid, nthreads);
     }
-    __device__ __forceinline__ void bind(const Params &p, const uint32_t *extra) { lutp = SMEM_LUT ? extra : p.lut; }
+    __device__ __forceinline__ void bind(const Params &p, const uint32_t *extra) {
+        lutp = SMEM_LUT ? extra + 2 * (threadIdx.x % IDSP_LOCKIN_LUT_REP) : p.lut;
+    }
     __device__ __forceinline__ void load(const Params &p, size_t lane, size_t stride) {
         if constexpr (!SMEM_LUT) lutp = p.lut;
         i0 = p.st[lane];
@@ -627,7 +647,7 @@ template <int ORDER, bool SMEM_LUT = false> struct LockinPhaseOp {
     }
     __device__ __forceinline__ int2 step(const Params &p, int2 xp) {
         int32_t c, s;
-        if constexpr (SMEM_LUT) cossin_dev_x(lutp, xp.y, c, s);
+        if constexpr (SMEM_LUT) cossin_dev_x<IDSP_LOCKIN_LUT_REP>(lutp, xp.y, c, s);
         else cossin_dev<false>(lutp, xp.y, c, s);
         const int32_t mi = (int32_t)(((int64_t)c * (int64_t)xp.x) >> 32);
         const int32_t mq = (int32_t)(((int64_t)s * (int64_t)xp.x) >> 32);

@@ -529,7 +529,10 @@ static int tma_try_launch(idsp_ctx *ctx, const typename Op::Params &p, const typ
         if (lm) {
             // one warp per CTA, 64-byte input rows / 128-byte output rows, 10 KB per warp: the op
             // is ALU-bound, so resident warps count for more than long DRAM bursts
-            r = tma_launch_cfg<Op, true, 16, 3, 1, 1>(ctx, p, x, y, frames, lanes, sstride);
+            if constexpr (Op::SMEM_EXTRA_WORDS >= 1024)  // a big per-CTA table is shared between 4 warps
+                r = tma_launch_cfg<Op, true, 16, 3, 1, 4>(ctx, p, x, y, frames, lanes, sstride);
+            else
+                r = tma_launch_cfg<Op, true, 16, 3, 1, 1>(ctx, p, x, y, frames, lanes, sstride);
 #ifdef IDSP_TUNE
         } else if (getenv("IDSP_OUT8_CFG") && (Op::HEAVY || sizeof(typename Op::In) == 8)) {
             // tuning builds: tile shape / residency sweep of the compute-bound 8-byte ops (lock-in)
@@ -556,7 +559,11 @@ static int tma_try_launch(idsp_ctx *ctx, const typename Op::Params &p, const typ
             // lock-in 336 GSa/s against 326 for the 128-lane shared boxes, (x, phase) lock-in 269 / 254,
             // FM discriminator 188 / 180, i64 DF1 145 / 137; more resident warps do not help (the kernels
             // are bound by a pipe, not by latency).
-            r = tma_launch_cfg<Op, false, 16, 2, 1, 1>(ctx, p, x, y, frames, lanes, sstride);
+            // (an Op with a big per-CTA table -- the replicated cossin table -- shares it between 4 warps)
+            if constexpr (Op::SMEM_EXTRA_WORDS >= 1024)
+                r = tma_launch_cfg<Op, false, 16, 2, 1, 4>(ctx, p, x, y, frames, lanes, sstride);
+            else
+                r = tma_launch_cfg<Op, false, 16, 2, 1, 1>(ctx, p, x, y, frames, lanes, sstride);
         } else if ((lanes + 127) / 128 >= sms) {
             // HBM-bound 8-byte streams (f64 biquads): 128-lane boxes (1 KB rows) with 2 load stages + 1 store
             // stage -- 24 KB per CTA instead of 48, i.e. twice the CTAs in flight: f64 DF1 347 -> 389 GSa/s

@@ -11,9 +11,10 @@ using namespace idsp;
 // bytes (with 4 phases per thread the two 16-byte stores of a thread interleave with its neighbours'
 // and every 32-byte sector is written in two halves); two such pairs in flight per thread.
 __global__ void __launch_bounds__(256) cossin_kernel(const int32_t *phase, int32_t *cs, size_t n) {
-    __shared__ __align__(8) uint32_t lut[256];
-    cossin_expand_lut(g_cossin_lut, lut, threadIdx.x, blockDim.x);
+    __shared__ __align__(8) uint32_t lut_all[256 * IDSP_COSSIN_REP];
+    cossin_expand_lut<IDSP_COSSIN_REP>(g_cossin_lut, lut_all, threadIdx.x, blockDim.x);
     __syncthreads();
+    const uint32_t *lut = lut_all + 2 * (threadIdx.x % IDSP_COSSIN_REP);  // this thread's copy (conflict-free lookups)
     const size_t n2 = n / 2;
     const bool vec = ((((uintptr_t)phase) & 7) | (((uintptr_t)cs) & 15)) == 0;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -32,10 +33,10 @@ __global__ void __launch_bounds__(256) cossin_kernel(const int32_t *phase, int32
                 qn = reinterpret_cast<const int2 *>(phase)[i + 3 * stride];
             }
             int4 a, b;
-            cossin_dev_x(lut, p.x, a.x, a.y);
-            cossin_dev_x(lut, p.y, a.z, a.w);
-            cossin_dev_x(lut, q.x, b.x, b.y);
-            cossin_dev_x(lut, q.y, b.z, b.w);
+            cossin_dev_x<IDSP_COSSIN_REP>(lut, p.x, a.x, a.y);
+            cossin_dev_x<IDSP_COSSIN_REP>(lut, p.y, a.z, a.w);
+            cossin_dev_x<IDSP_COSSIN_REP>(lut, q.x, b.x, b.y);
+            cossin_dev_x<IDSP_COSSIN_REP>(lut, q.y, b.z, b.w);
             reinterpret_cast<int4 *>(cs)[i] = a;
             reinterpret_cast<int4 *>(cs)[i + stride] = b;
             p = pn;
@@ -44,15 +45,15 @@ __global__ void __launch_bounds__(256) cossin_kernel(const int32_t *phase, int32
         for (; i < n2; i += stride) {
             const int2 p = reinterpret_cast<const int2 *>(phase)[i];
             int4 a;
-            cossin_dev_x(lut, p.x, a.x, a.y);
-            cossin_dev_x(lut, p.y, a.z, a.w);
+            cossin_dev_x<IDSP_COSSIN_REP>(lut, p.x, a.x, a.y);
+            cossin_dev_x<IDSP_COSSIN_REP>(lut, p.y, a.z, a.w);
             reinterpret_cast<int4 *>(cs)[i] = a;
         }
         i = n2 * 2 + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     }
     for (; i < n; i += stride) {
         int32_t c, s;
-        cossin_dev_x(lut, phase[i], c, s);
+        cossin_dev_x<IDSP_COSSIN_REP>(lut, phase[i], c, s);
         cs[2 * i] = c;
         cs[2 * i + 1] = s;
     }
