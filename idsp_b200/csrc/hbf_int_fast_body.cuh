@@ -175,31 +175,42 @@ hbf_int_fast_kernel(float *st, const float *x, float *y, size_t n_in, size_t nti
             Df1Op<float, false> op;
             op.x1 = op.x2 = op.y1 = op.y2 = 0.f;
             if (act) op.load(bq, lane0 + j, sstride);
+            // The bulk store of tile i is not waited for where it is issued: its shared-memory reads complete
+            // while the first quarter of tile i + 1 is filtered, and only then is buffer i & 1 handed back to
+            // the FIR warps (they need it for tile i + 2, one and a half tiles later) -- the store latency
+            // (11 % of this warp's time, and this warp is the critical path of the CTA) leaves the chain.
+            constexpr int Q1 = TOUT / 16;  // pieces of 4 samples filtered before the previous buffer is released
             for (size_t i = 0; i < ntiles; i++) {
                 const int ob = (int)(i & 1);
                 nbar_sync(2 + ob, NTA);  // tile i is staged
-                if (act) {
-                    float *row = sm + off_out(K) + (ob * NL + j) * OUT_PITCH;
-                    float4 v0 = lds128v(row), v1 = lds128v(row + 4);  // loads run two pieces ahead of the chain
+                float *row = sm + off_out(K) + (ob * NL + (act ? j : 0)) * OUT_PITCH;
+                float4 v0 = lds128v(row), v1 = lds128v(row + 4);  // loads run two pieces ahead of the chain
+                auto piece = [&](int q) {
+                    float4 v = v0;
+                    v0 = v1;
+                    if (q + 2 < TOUT / 4) v1 = lds128v(row + 4 * (q + 2));
+                    v.x = op.step(bq, v.x);
+                    v.y = op.step(bq, v.y);
+                    v.z = op.step(bq, v.z);
+                    v.w = op.step(bq, v.w);
+                    if (act) *reinterpret_cast<float4 *>(row + 4 * q) = v;
+                };
 #pragma unroll 4
-                    for (int q = 0; q < TOUT / 4; q++) {
-                        float4 v = v0;
-                        v0 = v1;
-                        if (q + 2 < TOUT / 4) v1 = lds128v(row + 4 * (q + 2));
-                        v.x = op.step(bq, v.x);
-                        v.y = op.step(bq, v.y);
-                        v.z = op.step(bq, v.z);
-                        v.w = op.step(bq, v.w);
-                        *reinterpret_cast<float4 *>(row + 4 * q) = v;
-                    }
+                for (int q = 0; q < Q1; q++) piece(q);
+                if (i >= 1 && i + 1 < ntiles) {  // tile i - 1 has left its buffer: the FIR warps may stage tile i + 1
+                    if (act) tma_wait_read<0>();
+                    __syncwarp();
+                    nbar_arrive(4 + (ob ^ 1), NTA);
+                }
+#pragma unroll 4
+                for (int q = Q1; q < TOUT / 4; q++) piece(q);
+                if (act) {
                     fence_async_smem();
                     bulk_store_1d(y + (lane0 + j) * n_out + i * TOUT, smem_u32(row), TOUT * 4);
                     tma_commit();
-                    tma_wait_read<0>();  // the FIR warps are one tile ahead: this wait is off their path
                 }
-                __syncwarp();
-                if (i + 2 < ntiles) nbar_arrive(4 + ob, NTA);  // buffer ob may be refilled (tile i + 2)
             }
+            if (act) tma_wait_read<0>();
             if (act) op.store(bq, lane0 + j, sstride);
             return;
         }
