@@ -753,7 +753,10 @@ static int chain_dev_strided(idsp_ctx *ctx, int log2_rate, const float ba[5], fl
     // three kernels 44 / 145 / 276 / - / -, thread-per-lane fused - / - / - / 320 / 353, this path with 8-lane
     // tiles 86 / 243 / 250 / 271 / 245 and with 16-lane tiles 71 / 221 / 313 / 337 / 304.  Short streams
     // (fewer than 8 tiles per call) and more lanes stay on the single-pass thread-per-lane kernel.
-    const bool wide = lanes > 8192;
+    int wide = lanes > 8192 ? 1 : 0;  // 0: 8-lane tiles, 1: 16-lane tiles
+#ifdef IDSP_TUNE
+    if (const char *e = getenv("IDSP_CHAIN_WIDE")) wide = atoi(e);  // 2: 32-lane tiles with 8 FIR warps
+#endif
     const size_t tile_low = hbf_int_bq_tile(log2_rate, wide);
     if (layout == IDSP_LANE_MAJOR && ctx->policy != 1 && n_low % tile_low == 0 && n_low >= 8 * tile_low &&
         (lanes <= 131072 || ctx->policy == 2) && ((((uintptr_t)x) | ((uintptr_t)y)) & 15) == 0) {

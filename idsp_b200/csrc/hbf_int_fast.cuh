@@ -66,6 +66,20 @@ __device__ __forceinline__ void bulk_store_1d(void *dst, uint32_t src, uint32_t 
 #undef HFI_NS
 #undef HFI_NL
 #undef HFI_TOUT
+#ifdef IDSP_TUNE
+// tuning builds: 32 lanes x 256 outputs per tile, 8 FIR warps, two CTAs per SM (IDSP_CHAIN_WIDE=2)
+#define HFI_NS hfi32
+#define HFI_NL 32
+#define HFI_TOUT 256
+#define HFI_NT 256
+#define HFI_MINB 2
+#include "hbf_int_fast_body.cuh"
+#undef HFI_NS
+#undef HFI_NL
+#undef HFI_TOUT
+#undef HFI_NT
+#undef HFI_MINB
+#endif
 #undef HFI_TAPS
 #undef HFI_M
 // HBF_TAPS_98 (src/hbf.rs:258-292) on the default shape
@@ -123,9 +137,9 @@ IDSP_DEF_INT_FAST_TRY(hbf98_int_fast_try, hfi98)
 // HbfInt x2^k -> Biquad DF1 f32 in one pass (lane-major, whole tiles only); `bq.st` = the biquad's SoA
 // state [x1, x2, y1, y2][sstride].  wide = false: 8 lanes x 512 outputs per CTA tile (most CTAs: few
 // lanes), wide = true: 16 x 256 (the biquad warp advances 16 lanes per instruction: many lanes).
-static size_t hbf_int_bq_tile(int k, bool wide) { return (size_t)(wide ? hfi16::TOUT : hfi::TOUT) >> k; }
+static size_t hbf_int_bq_tile(int k, int wide) { return (size_t)(wide ? hfi16::TOUT : hfi::TOUT) >> k; }
 static int hbf_int_bq_fast_try(idsp_ctx *ctx, int k, float *state, const float *x, float *y, size_t n_in, size_t lanes,
-                               size_t sstride, const Df1Op<float, false>::Params &bq, bool wide) {
+                               size_t sstride, const Df1Op<float, false>::Params &bq, int wide) {
     const size_t TI = hbf_int_bq_tile(k, wide);
     if (ctx->policy == 1 || n_in == 0 || n_in % TI != 0 || ((((uintptr_t)x) | ((uintptr_t)y)) & 15) != 0)
         return IDSP_HBF_FAST_NOT_APPLICABLE;
@@ -138,6 +152,9 @@ static int hbf_int_bq_fast_try(idsp_ctx *ctx, int k, float *state, const float *
         case 4: return NS::launch<4, false, true>(ctx, state, x, y, n_in, ntiles, lanes, sstride, bq);    \
         default: return NS::launch<5, false, true>(ctx, state, x, y, n_in, ntiles, lanes, sstride, bq);   \
     }
+#ifdef IDSP_TUNE
+    if (wide == 2) { IDSP_GO(hfi32) }
+#endif
     if (wide) { IDSP_GO(hfi16) }
     IDSP_GO(hfi)
 #undef IDSP_GO

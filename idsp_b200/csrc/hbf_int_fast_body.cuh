@@ -5,7 +5,13 @@ namespace idsp {
 namespace HFI_NS {
 
 constexpr int NL = HFI_NL;      // lanes per CTA
-constexpr int NT = 128;         // threads per CTA (FIR warps)
+#ifdef HFI_NT
+constexpr int NT = HFI_NT;      // threads per CTA (FIR warps)
+constexpr int MINB = HFI_MINB;  // CTAs per SM the kernel is compiled for
+#else
+constexpr int NT = 128;
+constexpr int MINB = 4;
+#endif
 constexpr int TOUT = HFI_TOUT;  // output samples per lane per tile
 
 __host__ __device__ constexpr int up4(int v) { return (v + 3) & ~3; }
@@ -144,7 +150,7 @@ template <int K, int s, bool LOAD> struct StateIO {
 // time -- while the four FIR warps already compute the next tile (HbfInt -> Biquad of the config-5 chain
 // without a second pass over HBM).
 template <int K, bool FM, bool BQ = false>
-__global__ void __launch_bounds__(NT + (BQ ? 32 : 0), BQ ? HFI_BQ_MINB : 4)
+__global__ void __launch_bounds__(NT + (BQ ? 32 : 0), BQ ? (NT > 128 ? MINB : HFI_BQ_MINB) : MINB)
 hbf_int_fast_kernel(float *st, const float *x, float *y, size_t n_in, size_t ntiles, size_t lanes, size_t sstride,
                     Df1Op<float, false>::Params bq) {
     static_assert(!(BQ && FM), "the fused biquad variant is lane-major");
