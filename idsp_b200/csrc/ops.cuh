@@ -508,12 +508,19 @@ __device__ __forceinline__ int32_t sat_sub(int32_t a, int32_t b) {
 // copies equal, so the second `s1 += d` stays two IMAD.WIDE (multiplier pipe, a quarter busy in the
 // lock-in kernel) instead of being merged with the first into 64-bit carry-chain adds on the ALU pipe,
 // which bounds that kernel: 4 IMAD.WIDE instead of 2 IMAD.WIDE + 4 IADD3 per step.
-template <int ORDER>
+template <int ORDER, bool FAST = false>
 __device__ __forceinline__ int32_t lowpass_step(int32_t k0, int32_t k1, int32_t k0b, int32_t k1b, int64_t &s0,
-                                                int64_t &s1, int32_t x) {
+                                                int64_t &s1, int32_t x, uint32_t *flag = nullptr) {
     // d = dx*k0 (+ (s1>>32)*k1); every `+= d` below is folded into multiply-adds, which is
     // exact because i64 addition wraps (src/lowpass.rs:59-72 in release arithmetic)
-    const int32_t dx = sat_sub(x, (int32_t)(s0 >> 32));
+    int32_t dx;
+    if constexpr (FAST) {
+        const int32_t sh = (int32_t)(s0 >> 32);
+        dx = (int32_t)((uint32_t)x - (uint32_t)sh);
+        *flag |= (uint32_t)sh ^ ((uint32_t)sh << 1);
+    } else {
+        dx = sat_sub(x, (int32_t)(s0 >> 32));
+    }
     int32_t y;
     if constexpr (ORDER == 1) {
         s0 = mad_wide(dx, k0, s0);
@@ -551,6 +558,32 @@ template <int ORDER> struct LowpassOp : OpHooks {
         return lowpass_step<ORDER>(p.k[0], p.k[1], IDSP_KB(p, 0), IDSP_KB(p, 1), s0, s1, x);
     }
 };
+
+// Speculative saturation (tile kernels, tma_kernels.cuh).  `x.saturating_sub(s0 >> 32)` (src/lowpass.rs:56) costs
+// five instructions (PTX sub.sat.s32 is emulated: subtract, two sign-logic predicates, two selects), four of them
+// on the ALU pipe that bounds the lock-in kernels.  The mixer output is (lo * x) >> 32 with |lo| < 2^31 - 2^14
+// (cossin's range), so |mix| < 2^30, and the difference cannot saturate while the state's high word lies in
+// [-2^30, 2^30) -- i.e. while its two top bits agree.  step_fast() subtracts with wrap-around and ORs
+// `sh ^ (sh << 1)` of every state word it used into a flag; a tile whose flag has bit 31 set is rolled back
+// (spec_rollback) and redone with the exact step().  Results are bit-identical by construction; a lane whose
+// low-pass state is within 6 dB of full scale pays the tile twice.  (336 -> 362 GSa/s on configs[3].)
+#define IDSP_LOCKIN_SPEC_MEMBERS(RESTORE_EXTRA, SAVE_EXTRA)                                       \
+    static constexpr bool SPECULATIVE = true;                                                      \
+    uint32_t flag;                                                                                 \
+    int64_t b_i0, b_i1, b_q0, b_q1;                                                                \
+    __device__ __forceinline__ void spec_begin() {                                                 \
+        flag = 0; b_i0 = i0; b_i1 = i1; b_q0 = q0; b_q1 = q1; SAVE_EXTRA                           \
+    }                                                                                              \
+    __device__ __forceinline__ bool spec_failed() const { return (int32_t)flag < 0; }              \
+    __device__ __forceinline__ void spec_rollback() {                                              \
+        i0 = b_i0; i1 = b_i1; q0 = b_q0; q1 = b_q1; RESTORE_EXTRA                                  \
+    }
+template <bool FAST, class Op, class P, class X> __device__ __forceinline__ auto op_step(Op &op, const P &p, X x) {
+    if constexpr (FAST) return op.step_fast(p, x);
+    else return op.step(p, x);
+}
+template <class Op, class = void> struct op_speculative { static constexpr bool value = false; };
+template <class Op> struct op_speculative<Op, decltype((void)Op::SPECULATIVE)> { static constexpr bool value = Op::SPECULATIVE; };
 
 // Accu (src/accu.rs:34-37) -> Complex::from_angle (src/complex.rs:237-240) ->
 // Lockin<Lowpass<N>> (src/lockin.rs:17-39); mix = i32 * Q32<32> -> (lo*x)>>32
@@ -607,6 +640,20 @@ template <int ORDER, bool SMEM_LUT = false> struct LockinOp {
         r.y = lowpass_step<ORDER>(p.k[0], p.k[1], IDSP_KB(p, 0), IDSP_KB(p, 1), q0, q1, mq);
         return r;
     }
+    IDSP_LOCKIN_SPEC_MEMBERS(ph = b_ph;, b_ph = ph;)
+    uint32_t b_ph;
+    __device__ __forceinline__ int2 step_fast(const Params &p, int32_t x) {
+        ph += dph;
+        int32_t c, s;
+        if constexpr (SMEM_LUT) cossin_dev_x<IDSP_LOCKIN_LUT_REP>(lutp, (int32_t)ph, c, s);
+        else cossin_dev<false>(lutp, (int32_t)ph, c, s);
+        const int32_t mi = (int32_t)(((int64_t)c * (int64_t)x) >> 32);
+        const int32_t mq = (int32_t)(((int64_t)s * (int64_t)x) >> 32);
+        int2 r;
+        r.x = lowpass_step<ORDER, true>(p.k[0], p.k[1], IDSP_KB(p, 0), IDSP_KB(p, 1), i0, i1, mi, &flag);
+        r.y = lowpass_step<ORDER, true>(p.k[0], p.k[1], IDSP_KB(p, 0), IDSP_KB(p, 1), q0, q1, mq, &flag);
+        return r;
+    }
 };
 
 // Lockin<Lowpass<N>> on (sample, phase) tuples (src/lockin.rs:30-39): the phase comes with every sample
@@ -654,6 +701,18 @@ template <int ORDER, bool SMEM_LUT = false> struct LockinPhaseOp {
         int2 r;
         r.x = lowpass_step<ORDER>(p.k[0], p.k[1], IDSP_KB(p, 0), IDSP_KB(p, 1), i0, i1, mi);
         r.y = lowpass_step<ORDER>(p.k[0], p.k[1], IDSP_KB(p, 0), IDSP_KB(p, 1), q0, q1, mq);
+        return r;
+    }
+    IDSP_LOCKIN_SPEC_MEMBERS(, )
+    __device__ __forceinline__ int2 step_fast(const Params &p, int2 xp) {
+        int32_t c, s;
+        if constexpr (SMEM_LUT) cossin_dev_x<IDSP_LOCKIN_LUT_REP>(lutp, xp.y, c, s);
+        else cossin_dev<false>(lutp, xp.y, c, s);
+        const int32_t mi = (int32_t)(((int64_t)c * (int64_t)xp.x) >> 32);
+        const int32_t mq = (int32_t)(((int64_t)s * (int64_t)xp.x) >> 32);
+        int2 r;
+        r.x = lowpass_step<ORDER, true>(p.k[0], p.k[1], IDSP_KB(p, 0), IDSP_KB(p, 1), i0, i1, mi, &flag);
+        r.y = lowpass_step<ORDER, true>(p.k[0], p.k[1], IDSP_KB(p, 0), IDSP_KB(p, 1), q0, q1, mq, &flag);
         return r;
     }
 };

@@ -208,7 +208,7 @@ tma_lanes_kernel(typename Op::Params p, const __grid_constant__ CUtensorMap mx,
             uint4 *rout = reinterpret_cast<uint4 *>(tout + l * 16 * OW);
             const int swi = IW == 2 ? (l & 7) : ((l >> 1) & 3);
             const int swo = OW == 2 ? (l & 7) : ((l >> 1) & 3);
-            auto group = [&](int g) {
+            auto group = [&](int g, auto fast) {
                 uint32_t wi[4 * IW], wo[4 * OW];
 #pragma unroll
                 for (int j = 0; j < IW; j++) {
@@ -216,19 +216,30 @@ tma_lanes_kernel(typename Op::Params p, const __grid_constant__ CUtensorMap mx,
                     wi[4 * j] = v.x; wi[4 * j + 1] = v.y; wi[4 * j + 2] = v.z; wi[4 * j + 3] = v.w;
                 }
 #pragma unroll
-                for (int q = 0; q < 4; q++) WordsOf<Out>::to(op.step(p, WordsOf<In>::from(wi + q * IW)), wo + q * OW);
+                for (int q = 0; q < 4; q++) {
+                    WordsOf<Out>::to(op_step<decltype(fast)::value>(op, p, WordsOf<In>::from(wi + q * IW)), wo + q * OW);
+                }
 #pragma unroll
                 for (int j = 0; j < OW; j++)
                     rout[(g * OW + j) ^ swo] = make_uint4(wo[4 * j], wo[4 * j + 1], wo[4 * j + 2], wo[4 * j + 3]);
             };
+            constexpr bool SPEC = op_speculative<Op>::value;  // see IDSP_LOCKIN_SPEC_MEMBERS (ops.cuh)
+            if constexpr (SPEC) op.spec_begin();
             if (nvalid == TF) {
 #pragma unroll
-                for (int g = 0; g < 4; g++) group(g);
+                for (int g = 0; g < 4; g++) group(g, std::integral_constant<bool, SPEC>());
             } else {  // frames % 4 == 0, so whole groups are valid or not
-                for (int g = 0; g * 4 < nvalid; g++) group(g);
+                for (int g = 0; g * 4 < nvalid; g++) group(g, std::integral_constant<bool, SPEC>());
+            }
+            if constexpr (SPEC) {
+                if (op.spec_failed()) {  // per thread: redo this lane's tile with the exact step
+                    op.spec_rollback();
+#pragma unroll 1
+                    for (int g = 0; g * 4 < nvalid; g++) group(g, std::false_type());
+                }
             }
         } else {
-            auto one = [&](int f) {
+            auto one = [&](int f, auto fast) {
                 uint32_t wi[IW], wo[OW];
                 if constexpr (IW == 2) {
                     const uint2 v = reinterpret_cast<const uint2 *>(tin)[f * BW + col];
@@ -236,15 +247,24 @@ tma_lanes_kernel(typename Op::Params p, const __grid_constant__ CUtensorMap mx,
                 } else {
                     wi[0] = tin[f * BW + col];
                 }
-                WordsOf<Out>::to(op.step(p, WordsOf<In>::from(wi)), wo);
+                WordsOf<Out>::to(op_step<decltype(fast)::value>(op, p, WordsOf<In>::from(wi)), wo);
                 if constexpr (OW == 2) reinterpret_cast<uint2 *>(tout)[f * BW + col] = make_uint2(wo[0], wo[1]);
                 else tout[f * BW + col] = wo[0];
             };
+            constexpr bool SPEC = op_speculative<Op>::value;  // see IDSP_LOCKIN_SPEC_MEMBERS (ops.cuh)
+            if constexpr (SPEC) op.spec_begin();
             if (nvalid == TF) {
 #pragma unroll
-                for (int f = 0; f < TF; f++) one(f);
+                for (int f = 0; f < TF; f++) one(f, std::integral_constant<bool, SPEC>());
             } else {
-                for (int f = 0; f < nvalid; f++) one(f);
+                for (int f = 0; f < nvalid; f++) one(f, std::integral_constant<bool, SPEC>());
+            }
+            if constexpr (SPEC) {
+                if (op.spec_failed()) {  // per thread: redo this lane's tile with the exact step
+                    op.spec_rollback();
+#pragma unroll 1
+                    for (int f = 0; f < nvalid; f++) one(f, std::false_type());
+                }
             }
         }
         fence_async_smem();

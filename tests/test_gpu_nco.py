@@ -218,3 +218,53 @@ def test_cossin_exhaustive_over_every_distinct_phase(oracle):
         ph = ((hi << 7) | rng.integers(0, 128, hi.size)).astype(np.uint32).view(np.int32)
         got = to_np(ib.cossin(to_dev(ph)))
         assert_bits_equal(got, oracle.cossin(ph), f"part {part}")
+
+
+# ------------------------------------------------------------------ speculative saturation of the tile kernels
+@pytest.mark.parametrize("order", [1, 2])
+@pytest.mark.parametrize("layout", [0, 1])
+def test_lockin_saturating_states_take_the_exact_path(oracle, order, layout):
+    """The TMA lock-in kernels subtract without saturation while the low-pass state's high word is inside
+    [-2^30, 2^30) and redo a tile with `saturating_sub` (src/lowpass.rs:56) otherwise (ops.cuh,
+    IDSP_LOCKIN_SPEC_MEMBERS).  Start a third of the lanes from states at / near full scale -- so that the
+    subtraction really saturates -- drive full-scale samples, and compare every output and the final state
+    with the oracle; the other lanes stay on the speculative path in the same warps."""
+    rng = np.random.default_rng(900 + 2 * order + layout)
+    k = [67465188] if order == 1 else [1048576, -94906265]
+    ctx = ib.default_context(0)
+    for frames, lanes in [(64, 256), (48, 132), (16, 64)]:
+        x = rng.integers(-(1 << 31), 1 << 31, frames * lanes).astype(np.int32)
+        a0 = rng.integers(-(1 << 31), 1 << 31, lanes).astype(np.int32)
+        step = rng.integers(-(1 << 31), 1 << 31, lanes).astype(np.int32)
+        s0 = np.zeros((2 * order, lanes), np.int64)
+        hot = rng.random(lanes) < 0.34
+        big = rng.integers(-(1 << 63), (1 << 63) - 1, (2 * order, lanes), dtype=np.int64)
+        edge = np.array([np.iinfo(np.int64).min, np.iinfo(np.int64).max, (1 << 62), -(1 << 62), (1 << 62) - 1, -(1 << 62) - 1], np.int64)
+        big[:, : min(lanes, edge.size)] = edge[: min(lanes, edge.size)]
+        hot[: min(lanes, edge.size)] = True
+        s0[:, hot] = big[:, hot]
+        # Accu form
+        ao, so = a0.copy(), s0.copy()
+        want = oracle.lockin_lanes(k, ao, step, so, x, lanes, layout)
+        st = LockinState.default(order, lanes, DEV)
+        st.words.copy_(torch.from_numpy(s0).to(DEV))
+        acc = Accu(to_dev(a0), to_dev(step))
+        iq = torch.empty(2 * x.size, dtype=torch.int32, device=DEV)
+        Lockin(Lowpass(k)).block(st, acc, to_dev(x), iq, layout)
+        assert "tma" in ctx.last_kernel, ctx.last_kernel
+        assert_bits_equal(to_np(iq), want, f"accu form {frames}x{lanes}")
+        assert_bits_equal(st.numpy(), so)
+        assert_bits_equal(to_np(acc.state), ao)
+        # (x, phase) form
+        xp = np.empty(2 * x.size, np.int32)
+        xp[0::2] = x
+        xp[1::2] = rng.integers(-(1 << 31), 1 << 31, x.size).astype(np.int32)
+        so = s0.copy()
+        want = oracle.lockin_phase_lanes(k, so, xp, lanes, layout)
+        st = LockinState.default(order, lanes, DEV)
+        st.words.copy_(torch.from_numpy(s0).to(DEV))
+        iq = torch.empty(xp.size, dtype=torch.int32, device=DEV)
+        Lockin(Lowpass(k)).block_phase(st, to_dev(xp), iq, layout)
+        assert "tma" in ctx.last_kernel, ctx.last_kernel
+        assert_bits_equal(to_np(iq), want, f"phase form {frames}x{lanes}")
+        assert_bits_equal(st.numpy(), so)
