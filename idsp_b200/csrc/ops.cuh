@@ -380,6 +380,15 @@ __device__ __forceinline__ void cossin_dev(const uint32_t *lut, int32_t phase, i
     so = s;
 }
 
+// (a * b) >> 32 whose result ptxas cannot fold into a following add / subtract: it turns mul.hi + add into
+// IMAD.HI with a 64-bit addend {0, c}, which costs two register moves per fold to build the pair -- more work
+// on the multiplier pipe than the add it saves (the lock-in kernels ran 12 such moves per sample).
+__device__ __forceinline__ int32_t mulhi_opaque(int32_t a, int32_t b) {
+    int32_t lo, hi;
+    asm volatile("{ .reg .b64 t; mul.wide.s32 t, %2, %3; mov.b64 {%0, %1}, t; }" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
+    (void)lo;
+    return hi;
+}
 // Same function on a pre-expanded table: entry i of the staged shared-memory table holds
 // c14 = ((lut & 0xffff) + 65536) << 14 and s15 = (lut >> 16) << 15, i.e. the two values the
 // reference forms before the interpolation (src/cossin.rs:44-60).  With d10 = dphi << 10,
@@ -409,7 +418,9 @@ __device__ __forceinline__ void cossin_expand_lut(const uint32_t *lut, uint32_t 
         table[2 * i + 1] = (w >> 16) << 15;
     }
 }
-template <int REP = 1>
+// WIDE_HI: the two corrections as unfoldable high-word products (mulhi_opaque): pays in the lock-in kernels
+// (multiplier pipe, 365 -> 370 GSa/s), not in the HBM-bound map kernel (468 -> 450)
+template <int REP = 1, bool WIDE_HI = false>
 __device__ __forceinline__ void cossin_dev_x(const uint32_t *table, int32_t phase, int32_t &co, int32_t &so) {
     uint32_t octant = (uint32_t)phase;
     if (octant & (1u << 29)) phase = ~phase;
@@ -417,8 +428,14 @@ __device__ __forceinline__ void cossin_dev_x(const uint32_t *table, int32_t phas
     const uint2 e = *reinterpret_cast<const uint2 *>(table + 2 * REP * (ph >> 15));
     const int32_t frac = (int32_t)(ph & 0x7fffu) - (1 << 14);
     const int32_t d10 = ((frac * 51471) >> 6) & ~0x3ff;
-    int32_t c = (int32_t)e.x - __mulhi((int32_t)e.y, d10);
-    int32_t s = (int32_t)e.y + __mulhi((int32_t)e.x, d10);
+    int32_t c, s;
+    if constexpr (WIDE_HI) {
+        c = (int32_t)e.x - mulhi_opaque((int32_t)e.y, d10);
+        s = (int32_t)e.y + mulhi_opaque((int32_t)e.x, d10);
+    } else {
+        c = (int32_t)e.x - __mulhi((int32_t)e.y, d10);
+        s = (int32_t)e.y + __mulhi((int32_t)e.x, d10);
+    }
     octant ^= octant >> 1;
     if (octant & (1u << 29)) { int32_t t = c; c = s; s = t; }
     if (octant & (1u << 30)) c = -c;
@@ -645,10 +662,10 @@ template <int ORDER, bool SMEM_LUT = false> struct LockinOp {
     __device__ __forceinline__ int2 step_fast(const Params &p, int32_t x) {
         ph += dph;
         int32_t c, s;
-        if constexpr (SMEM_LUT) cossin_dev_x<IDSP_LOCKIN_LUT_REP>(lutp, (int32_t)ph, c, s);
+        if constexpr (SMEM_LUT) cossin_dev_x<IDSP_LOCKIN_LUT_REP, true>(lutp, (int32_t)ph, c, s);
         else cossin_dev<false>(lutp, (int32_t)ph, c, s);
-        const int32_t mi = (int32_t)(((int64_t)c * (int64_t)x) >> 32);
-        const int32_t mq = (int32_t)(((int64_t)s * (int64_t)x) >> 32);
+        const int32_t mi = mulhi_opaque(c, x);
+        const int32_t mq = mulhi_opaque(s, x);
         int2 r;
         r.x = lowpass_step<ORDER, true>(p.k[0], p.k[1], IDSP_KB(p, 0), IDSP_KB(p, 1), i0, i1, mi, &flag);
         r.y = lowpass_step<ORDER, true>(p.k[0], p.k[1], IDSP_KB(p, 0), IDSP_KB(p, 1), q0, q1, mq, &flag);
@@ -706,10 +723,10 @@ template <int ORDER, bool SMEM_LUT = false> struct LockinPhaseOp {
     IDSP_LOCKIN_SPEC_MEMBERS(, )
     __device__ __forceinline__ int2 step_fast(const Params &p, int2 xp) {
         int32_t c, s;
-        if constexpr (SMEM_LUT) cossin_dev_x<IDSP_LOCKIN_LUT_REP>(lutp, xp.y, c, s);
+        if constexpr (SMEM_LUT) cossin_dev_x<IDSP_LOCKIN_LUT_REP, true>(lutp, xp.y, c, s);
         else cossin_dev<false>(lutp, xp.y, c, s);
-        const int32_t mi = (int32_t)(((int64_t)c * (int64_t)xp.x) >> 32);
-        const int32_t mq = (int32_t)(((int64_t)s * (int64_t)xp.x) >> 32);
+        const int32_t mi = mulhi_opaque(c, xp.x);
+        const int32_t mq = mulhi_opaque(s, xp.x);
         int2 r;
         r.x = lowpass_step<ORDER, true>(p.k[0], p.k[1], IDSP_KB(p, 0), IDSP_KB(p, 1), i0, i1, mi, &flag);
         r.y = lowpass_step<ORDER, true>(p.k[0], p.k[1], IDSP_KB(p, 0), IDSP_KB(p, 1), q0, q1, mq, &flag);
