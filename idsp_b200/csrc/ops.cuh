@@ -48,6 +48,15 @@ __device__ __forceinline__ int64_t mad_wide(int32_t a, int32_t b, int64_t c) {
     asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"(c));
     return r;
 }
+// (a * b) >> 32 whose result ptxas cannot fold into a following add / subtract: it turns mul.hi + add into
+// IMAD.HI with a 64-bit addend {0, c}, which costs two register moves per fold to build the pair -- more work
+// on the multiplier pipe than the add it saves (the lock-in kernels ran 12 such moves per sample).
+__device__ __forceinline__ int32_t mulhi_opaque(int32_t a, int32_t b) {
+    int32_t lo, hi;
+    asm volatile("{ .reg .b64 t; mul.wide.s32 t, %2, %3; mov.b64 {%0, %1}, t; }" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
+    (void)lo;
+    return hi;
+}
 // num_traits::clamp (src/iir/biquad.rs:400): `<`/`>` compares so NaN passes through
 template <class T> __device__ __forceinline__ T clamp_nt(T v, T lo, T hi) {
     return v < lo ? lo : (v > hi ? hi : v);
@@ -380,15 +389,6 @@ __device__ __forceinline__ void cossin_dev(const uint32_t *lut, int32_t phase, i
     so = s;
 }
 
-// (a * b) >> 32 whose result ptxas cannot fold into a following add / subtract: it turns mul.hi + add into
-// IMAD.HI with a 64-bit addend {0, c}, which costs two register moves per fold to build the pair -- more work
-// on the multiplier pipe than the add it saves (the lock-in kernels ran 12 such moves per sample).
-__device__ __forceinline__ int32_t mulhi_opaque(int32_t a, int32_t b) {
-    int32_t lo, hi;
-    asm volatile("{ .reg .b64 t; mul.wide.s32 t, %2, %3; mov.b64 {%0, %1}, t; }" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
-    (void)lo;
-    return hi;
-}
 // Same function on a pre-expanded table: entry i of the staged shared-memory table holds
 // c14 = ((lut & 0xffff) + 65536) << 14 and s15 = (lut >> 16) << 15, i.e. the two values the
 // reference forms before the interpolation (src/cossin.rs:44-60).  With d10 = dphi << 10,
@@ -482,7 +482,10 @@ __device__ __forceinline__ uint32_t atani_dev(uint32_t x) {
     int32_t r = 0;
 #pragma unroll
     for (int i = 5; i >= 0; i--) {
-        r = __mulhi(r, x2);  // Q32<32>*Q32<32> = (i64 product) >> 32, ops.rs:145-153: signed high word
+        // Q32<32>*Q32<32> = (i64 product) >> 32, ops.rs:145-153: signed high word.  (mulhi_opaque: ptxas folds
+        // mul.hi + add into IMAD.HI with a {0, coefficient} addend pair and rebuilds the pair with two moves
+        // per Horner step: 13 moves per call on the multiplier pipe that bounds this function)
+        r = mulhi_opaque(r, x2);
         r = (int32_t)((uint32_t)r + (uint32_t)ATANI[i]);
     }
     return (uint32_t)(((int64_t)r * (int64_t)(uint64_t)x) >> 28);
