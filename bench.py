@@ -719,8 +719,12 @@ def run_chain(args, rank, world, local):
                 raise SystemExit(f"bench: GPU chain output differs from the oracle at 2^{lg} lanes")
             st.zero_()
         ms, launches, clocks = time_steps(step, 3, 2, world, local, ctx, dev)
+        # the biquad recurrence advances one sample per lane per dependent FMUL -> FADD -> FADD chain (3 x 4 cycles on
+        # sm_100a, bit-exactness forbids re-association): with few lanes that chain, not bandwidth, bounds the job
+        sm_ghz = ((clocks or {}).get("sm_mhz") or 1900.0) / 1e3
         points.append({"lanes_per_gpu": lanes, "samples_per_lane": n_low * 16, "GSa/s": world * n * 3 / (ms * 1e-3) / 1e9,
-                       "GB/s": 8.0 * n * 3 / (ms * 1e-3) / 1e9, "kernel": ctx.last_kernel})
+                       "GB/s": 8.0 * n * 3 / (ms * 1e-3) / 1e9, "kernel": ctx.last_kernel,
+                       "recurrence_critical_path_bound_GSa/s": world * lanes * sm_ghz / 12.0})
         del x, y, st
         torch.cuda.empty_cache()
     # end to end through ONE host call (idsp_chain_f32_host): the three operators share one PCIe round trip
