@@ -52,8 +52,14 @@ __host__ __device__ constexpr int ho(int K, int s) { return up4(2 * st_m(K, s) -
 __host__ __device__ constexpr int pe(int K, int s) { return oddpitch(he(K, s) + st_n(s)); }
 __host__ __device__ constexpr int po(int K, int s) { return oddpitch(ho(K, s) + st_n(s)); }
 // float offsets inside dynamic shared memory
+// the raw ring: S buffers of NL padded rows; the frame-major /16 tensor-map layout (FmTma: S x 4 boxes of
+// TT/16 + 1 lines of 32 floats) lives in the same space
+__host__ __device__ constexpr int raw_floats(int K) {
+    const int rows = S * NL * raw_pitch(K), boxes = S * 4 * (TT / 16 + 1) * 32;
+    return (K == 4 && NL == 8 && boxes > rows) ? boxes : rows;
+}
 __host__ __device__ constexpr int off_e(int K, int s) {
-    int o = S * NL * raw_pitch(K);
+    int o = raw_floats(K);
     for (int i = 1; i < s; i++) o += NL * (pe(K, i) + po(K, i));
     return o;
 }
@@ -92,14 +98,7 @@ template <int TI, int R> struct RawItem {
     static constexpr int M = HFS_TAPS<TI>::M;
     static constexpr int HR = up4(4 * M - 2);
     static constexpr int W = HR + 2 * R;
-    __device__ __forceinline__ static void run(const float *row, int p0, float (&y)[R]) {
-        float w[W];
-        const float *src = row + 2 * p0;
-#pragma unroll
-        for (int j = 0; j < W / 4; j++) {
-            float4 v = lds128(src + 4 * j);
-            w[4 * j] = v.x; w[4 * j + 1] = v.y; w[4 * j + 2] = v.z; w[4 * j + 3] = v.w;
-        }
+    __device__ __forceinline__ static void fir(const float (&w)[W], float (&y)[R]) {
 #pragma unroll
         for (int q = 0; q < R; q++) {
             float acc = (w[2 * q + 1 + HR] + w[2 * q - 4 * M + 3 + HR]) * HFS_TAPS<TI>::c(0);
@@ -109,7 +108,70 @@ template <int TI, int R> struct RawItem {
             y[q] = acc + w[2 * q - 2 * M + 2 + HR];
         }
     }
+    __device__ __forceinline__ static void run(const float *row, int p0, float (&y)[R]) {
+        float w[W];
+        const float *src = row + 2 * p0;
+#pragma unroll
+        for (int j = 0; j < W / 4; j++) {
+            float4 v = lds128(src + 4 * j);
+            w[4 * j] = v.x; w[4 * j + 1] = v.y; w[4 * j + 2] = v.z; w[4 * j + 3] = v.w;
+        }
+        fir(w, y);
+    }
+    // The same item on the frame-major tensor-map layout of /16 (see FmTma below): lane `lane`, outputs
+    // 16 * j16 .. (R == 16, i.e. two frames of input behind one frame of history) of raw buffer `buf`.
+    __device__ __forceinline__ static void run_fm(uint32_t sm_base, int buf, int lane, int j16, float (&y)[R]);
 };
+
+// Frame-major input of the /16 cascade through the tensor-map unit.  The stream is x[frame][lane][16]: the two
+// lanes of a pair are 128 contiguous bytes per frame, so a 2-D box of 32 floats x 33 frames (one frame of history
+// in front of the 32 frames of a tile) is one lane pair's tile, and a CTA's 8 lanes are four such boxes per tile --
+// four instructions instead of 1 056 16-byte LDGSTS copies.  The boxes land as [frame][lane pair][16] lines of 128
+// bytes with the 128-byte swizzle, which XORs the 16-byte chunk index with bits 7-9 of the ABSOLUTE shared-memory
+// address (measured, tools/tma_swizzle_probe.cu: destinations need 128-byte alignment only, rows before the start
+// of the tensor are zero-filled).  The four boxes of a buffer are packed back to back (33 lines each), which
+// staggers their swizzle phase: the eight lanes of a quarter-warp that read chunk c of the same frame hit eight
+// different 16-byte slots -- conflict free without padding.  A window chunk is addressed as A ^ (c << 4) with a
+// per-item, per-frame base A.
+struct FmTma {
+    static constexpr int LINES = TT / 16 + 1;      // 128-byte lines per box: history frame + the tile's frames
+    static constexpr int BUF_LINES = 4 * LINES;    // per raw buffer (4 lane pairs)
+    static constexpr uint32_t BOX_BYTES = LINES * 128;
+    // byte address of line `line` (absolute line index from the 1024-aligned base) for a lane with pair bit b
+    __device__ __forceinline__ static uint32_t line_base(uint32_t sm_base, int line, int b) {
+        return sm_base + (uint32_t)line * 128u + (uint32_t)((((b << 2) ^ line) & 7) << 4);
+    }
+    // address of one float: lane, frame row (0 = history frame) and sample 0..15 inside the frame
+    __device__ __forceinline__ static uint32_t word(uint32_t sm_base, int buf, int lane, int row, int smp) {
+        const int line = buf * BUF_LINES + (lane >> 1) * LINES + row;
+        return (line_base(sm_base, line, lane & 1) ^ (uint32_t)((smp >> 2) << 4)) + (uint32_t)(smp & 3) * 4u;
+    }
+};
+__device__ __forceinline__ float4 lds128a(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "r"(addr));
+    return v;
+}
+template <int TI, int R>
+__device__ __forceinline__ void RawItem<TI, R>::run_fm(uint32_t sm_base, int buf, int lane, int j16, float (&y)[R]) {
+    static_assert(R == 16, "an item is two frames of input");
+    static_assert(HR <= 16 && HR % 4 == 0, "the raw history fits the frame in front of the tile");
+    float w[W];
+    const int line0 = buf * FmTma::BUF_LINES + (lane >> 1) * FmTma::LINES + 2 * j16;  // row 2*j16 = frame 2*j16 - 1
+    uint32_t A[3];
+#pragma unroll
+    for (int fr = 0; fr < 3; fr++) A[fr] = FmTma::line_base(sm_base, line0 + fr, lane & 1);
+#pragma unroll
+    for (int j = 0; j < W / 4; j++) {
+        constexpr int H4 = HR / 4;
+        const int rel = j - H4 + 4;  // chunk index counted from the start of row 2*j16 (the history frame of the item)
+        float4 v = lds128a(A[rel / 4] ^ (uint32_t)((rel % 4) << 4));
+        w[4 * j] = v.x; w[4 * j + 1] = v.y; w[4 * j + 2] = v.z; w[4 * j + 3] = v.w;
+    }
+    fir(w, y);
+}
 
 // One item of a de-interleaved stage: erow = [HE hist | n new], orow = [HO hist | n new].
 // The item spans R outputs starting at p0 (p0 % 4 == 0 keeps the LDS.128 aligned); this call
@@ -295,7 +357,9 @@ template <int K, int s> struct StageRun {
 __device__ __forceinline__ void bar_idle(int count) { asm volatile("bar.sync 1, %0;" ::"r"(count) : "memory"); }
 
 // ABI state <-> shared-memory histories (see header comment of include/idsp_b200.h)
-template <int K, int s, bool LOAD> struct StateIO {
+// WHICH: 0 = every stage, 1 = stage 0 only, 2 = every stage but stage 0.  FMT: stage 0's raw history lives in the
+// tensor-map layout (FmTma) of raw buffer `rawbuf`, in row 0 (head) on entry and in the tile's last row on exit.
+template <int K, int s, bool LOAD, bool FMT = false, int WHICH = 0> struct StateIO {
     // raw history lives at row[roff .. roff+HR): roff = 0 (head) on entry, TT (tail of the
     // last tile) on exit
     __device__ __forceinline__ static void run(float *sm, float *st, size_t sstride, size_t lane0, int nl,
@@ -304,19 +368,26 @@ template <int K, int s, bool LOAD> struct StateIO {
             constexpr int M = st_m(K, s);
             constexpr int LEN = 2 * M - 1;
             constexpr int WORDS = 3 * M - 2;
+            constexpr bool SKIP = (WHICH == 1 && s != 0) || (WHICH == 2 && s == 0);
             float *stw = st + (size_t)st_word(K, s) * sstride + lane0;
             // shared-memory slot of state word w of lane `lane`
             auto slot = [&](int lane, int w) -> float * {
                 if constexpr (s == 0) {
                     constexpr int HR = raw_h(K);
-                    float *row = sm + (rawbuf * NL + lane) * raw_pitch(K) + roff;
-                    return w < M - 1 ? row + (HR - 2 * M + 2 + 2 * w) : row + (HR - 4 * M + 3 + 2 * (w - (M - 1)));
+                    const int hs = w < M - 1 ? (HR - 2 * M + 2 + 2 * w) : (HR - 4 * M + 3 + 2 * (w - (M - 1)));
+                    if constexpr (FMT) {
+                        const uint32_t a = FmTma::word(smem_u32(sm), rawbuf, lane, roff ? TT / 16 : 0, 16 - HR + hs);
+                        return sm + (a - smem_u32(sm)) / 4;
+                    } else {
+                        return sm + (rawbuf * NL + lane) * raw_pitch(K) + roff + hs;
+                    }
                 } else {
                     return w < M - 1 ? sm + off_e(K, s) + lane * pe(K, s) + (he(K, s) - (M - 1) + w)
                                      : sm + off_o(K, s) + lane * po(K, s) + (ho(K, s) - LEN + (w - (M - 1)));
                 }
             };
-            if constexpr (LOAD) {
+            if constexpr (SKIP) {
+            } else if constexpr (LOAD) {
                 // all the loads of a thread are issued before the first store (read-only path: the compiler may
                 // hoist them over the shared-memory stores of the previous stage too), so that entering a call
                 // costs one global-memory round trip, not one per state word: short calls of a streaming
@@ -340,7 +411,7 @@ template <int K, int s, bool LOAD> struct StateIO {
                     stw[(size_t)w * sstride + lane] = *slot(lane, w);
                 }
             }
-            StateIO<K, s + 1, LOAD>::run(sm, st, sstride, lane0, nl, tid, rawbuf, roff);
+            StateIO<K, s + 1, LOAD, FMT, WHICH>::run(sm, st, sstride, lane0, nl, tid, rawbuf, roff);
         }
     }
 };
@@ -360,10 +431,13 @@ __device__ __forceinline__ void cp_async_arrive(uint32_t bar) {  // arrives when
 // x[t][lane][2^K], y[t][lane]: the per-lane rows of a tile are gathered with 16-byte (/2: 8-byte) LDGSTS
 // copies (8 lanes x 4 pieces of one frame per warp instruction = 512 contiguous bytes of HBM,
 // 8 different shared-memory rows per quarter-warp), every thread arriving on the tile's mbarrier.
-template <int K, bool FM>
+// FMT (frame-major /16 only): the input tiles arrive as tensor-map boxes (FmTma) instead of LDGSTS pieces.
+template <int K, bool FM, bool FMT = false>
 __global__ void __launch_bounds__(NT, HFS_MINB)
 hbf_dec_fast_kernel(float *st, const float *x, float *y, size_t n_out, size_t ntiles, size_t lanes,
-                    size_t sstride) {
+                    size_t sstride, const __grid_constant__ CUtensorMap xmap) {
+    static_assert(!FMT || (FM && K == 4 && NL == 8 && TT == 512 && S * FmTma::BUF_LINES * 32 <= raw_floats(K)),
+                  "tensor-map input: frame-major /16, 8 lanes x 512 samples, inside the raw ring");
     const size_t ylanes = FM ? lanes : 0;
     constexpr int TI0 = K - 1;
     // /2 runs the 23-tap stage on the raw stream: 16 outputs per item need a 124-float window and spill
@@ -372,7 +446,7 @@ hbf_dec_fast_kernel(float *st, const float *x, float *y, size_t n_out, size_t nt
     constexpr int HR = raw_h(K);
     constexpr int PR = raw_pitch(K);
     constexpr int TO = TT >> K;
-    extern __shared__ __align__(128) float sm[];
+    extern __shared__ __align__(1024) float sm[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(sm + smem_floats(K));
     const int tid = threadIdx.x;
     const size_t lane0 = (size_t)blockIdx.x * NL;
@@ -383,11 +457,12 @@ hbf_dec_fast_kernel(float *st, const float *x, float *y, size_t n_out, size_t nt
     for (int i = tid; i < smem_floats(K); i += NT) sm[i] = 0.f;
     if (tid == 0) {
 #pragma unroll
-        for (int b = 0; b < S; b++) mbar_init(smem_u32(&bars[b]), FM ? NT : 1);
+        for (int b = 0; b < S; b++) mbar_init(smem_u32(&bars[b]), (FM && !FMT) ? NT : 1);
         mbar_fence_init();
     }
     __syncthreads();
-    StateIO<K, 0, true>::run(sm, st, sstride, lane0, nl, tid, 0, 0);
+    // (FMT: the raw history of tile 0 is scattered after the tile has landed -- its box covers the history row)
+    StateIO<K, 0, true, FMT, FMT ? 2 : 0>::run(sm, st, sstride, lane0, nl, tid, 0, 0);
     // generic-proxy writes above (zero fill) precede async-proxy (TMA) writes to the same rows
     fence_async_smem();
     __syncthreads();
@@ -402,7 +477,15 @@ hbf_dec_fast_kernel(float *st, const float *x, float *y, size_t n_out, size_t nt
         const int b = (int)(tile % S);
         const uint32_t bar = smem_u32(&bars[b]);
         const uint32_t hist = tile ? HR : 0;
-        if constexpr (FM) {
+        if constexpr (FMT) {
+            if (tid == 0) {
+                mbar_expect_tx(bar, 4 * FmTma::BOX_BYTES);
+#pragma unroll
+                for (int q = 0; q < 4; q++)  // lane pair q: columns (lane0 + 2q) * 16 .., frames 32 * tile - 1 ..
+                    tma_load_2d(smem_u32(sm) + (uint32_t)(b * FmTma::BUF_LINES + q * FmTma::LINES) * 128u, &xmap,
+                                (int)((lane0 + 2 * q) * 16), (int)(tile * (TT / 16)) - 1, bar);
+            }
+        } else if constexpr (FM) {
             constexpr int R = 1 << K;            // floats per frame and lane
             constexpr int PF_ = R >= 4 ? 4 : 2;  // floats per piece: 16 bytes, or the whole 8-byte frame of /2
             // piece q = PF_ consecutive stream samples of one lane, counted from the start of the history.
@@ -443,6 +526,12 @@ hbf_dec_fast_kernel(float *st, const float *x, float *y, size_t n_out, size_t nt
 #pragma unroll
     for (int b = 0; b < S; b++)
         if ((size_t)b < ntiles) issue(b);
+    if constexpr (FMT) {
+        // tile 0 has landed (its history row zero-filled: frame -1 does not exist): now the state goes there
+        if (ntiles) mbar_wait(smem_u32(&bars[0]), 0);
+        StateIO<K, 0, true, true, 1>::run(sm, st, sstride, lane0, nl, tid, 0, 0);
+        __syncthreads();
+    }
     // steady state (tile >= S >= 1, lane-major): source / destination of this warp's rows are kept in
     // registers, so a refill is one multiply-add per pointer plus the copy itself
     constexpr int LPW_ = (NL + NT / 32 - 1) / (NT / 32);
@@ -477,7 +566,8 @@ hbf_dec_fast_kernel(float *st, const float *x, float *y, size_t n_out, size_t nt
         for (int idx = c0 + gt; idx < c1; idx += G) {
             const int lane = idx % NL, p0 = (idx / NL) * R0;
             float out[R0];
-            RawItem<TI0, R0>::run(raw + lane * PR, p0, out);
+            if constexpr (FMT) RawItem<TI0, R0>::run_fm(smem_u32(sm), b, lane, idx / NL, out);
+            else RawItem<TI0, R0>::run(raw + lane * PR, p0, out);
             if constexpr (K == 1) {
                 if (lane < nl && FM) {
                     float *dst = y + (t * TO + p0) * lanes + lane0 + lane;
@@ -561,22 +651,40 @@ hbf_dec_fast_kernel(float *st, const float *x, float *y, size_t n_out, size_t nt
         __syncthreads();
     }
     // the raw history of the stream is the tail of the last tile's buffer
-    StateIO<K, 0, false>::run(sm, st, sstride, lane0, nl, tid, (int)((ntiles - 1) % S), TT);
+    StateIO<K, 0, false, FMT>::run(sm, st, sstride, lane0, nl, tid, (int)((ntiles - 1) % S), TT);
 }
 
+#ifndef HFS_FM_TMA
+#define HFS_FM_TMA 1
+#endif
 template <int K, bool FM>
 static int launch(idsp_ctx *ctx, float *st, const float *x, float *y, size_t n_out, size_t ntiles,
                   size_t lanes, size_t sstride) {
-    auto kern = hbf_dec_fast_kernel<K, FM>;
     size_t smem = smem_bytes(K);
 #ifdef IDSP_TUNE
     // occupancy experiment: pad the dynamic shared memory so that fewer CTAs fit on an SM (is the kernel
     // bound by issue slots or by latency?)
     if (getenv("IDSP_HBF_EXTRA_SMEM")) smem += (size_t)atoi(getenv("IDSP_HBF_EXTRA_SMEM"));
 #endif
-    IDSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     unsigned grid = (unsigned)((lanes + NL - 1) / NL);
-    kern<<<grid, NT, smem, ctx->stream>>>(st, x, y, n_out, ntiles, lanes, sstride);
+    CUtensorMap xmap;
+    memset(&xmap, 0, sizeof(xmap));
+    if constexpr (FM && K == 4 && NL == 8 && TT == 512 && HFS_FM_TMA) {
+        // x[frame][lane][16] as a 2-D tensor of (lanes * 16) x frames words; box = one lane pair x (1 + 32) frames
+        const bool tune_off = getenv("IDSP_HBF_FM_LDGSTS") != nullptr;  // A/B switch: the LDGSTS gather
+        if (!tune_off && lanes * 16 < (1ull << 32) && n_out < (1ull << 31) &&
+            make_map_2d(&xmap, x, (uint64_t)lanes * 16, (uint64_t)n_out, 32, FmTma::LINES, CU_TENSOR_MAP_SWIZZLE_128B)) {
+            auto kern = hbf_dec_fast_kernel<K, true, true>;
+            IDSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<grid, NT, smem, ctx->stream>>>(st, x, y, n_out, ntiles, lanes, sstride, xmap);
+            IDSP_KERNEL_FAMILY(ctx, "hbf tiled frame-major (tensor-map input)");
+            IDSP_LAUNCHED(ctx);
+            return IDSP_OK;
+        }
+    }
+    auto kern = hbf_dec_fast_kernel<K, FM, false>;
+    IDSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, NT, smem, ctx->stream>>>(st, x, y, n_out, ntiles, lanes, sstride, xmap);
     IDSP_KERNEL_FAMILY(ctx, FM ? "hbf tiled frame-major" : "hbf tiled lane-major");
     IDSP_LAUNCHED(ctx);
     return IDSP_OK;

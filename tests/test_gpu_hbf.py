@@ -489,3 +489,40 @@ def test_chain_host_buffers(oracle):
         ctx.chain(k, ba, st, x, y, lanes=lanes, layout=layout)
         assert_bits_equal(y, want, f"chain host layout={layout}")
         assert_bits_equal(st, so, "chain host state")
+
+
+@pytest.mark.parametrize("taps98", [False, True])
+@pytest.mark.parametrize("lanes", [1, 2, 9, 64, 131])
+def test_dec16_frame_major_tensor_map_input(oracle, lanes, taps98):
+    """frame-major /16 (`[[f32; 16]; lanes]` frames, BASELINE configs[2]): the input tiles of the tiled kernel are
+    tensor-map boxes of one lane pair x 33 frames in the 128-byte swizzled layout (hbf_fast_scalar_body.cuh, FmTma).
+    Odd lane counts (a box half / fully outside the tensor), one lane, several CTAs; whole tiles + a ragged tail;
+    state carried over three calls; both compiled tap sets; == the oracle bit for bit."""
+    rng = np.random.default_rng(4242 + lanes)
+    k, R, TO = 4, 16, 32
+    chunks = [3 * TO, 2 * TO + 5, 4 * TO]
+    n_out = sum(chunks)
+    x = rng.uniform(-1, 1, (n_out, lanes, R)).astype(np.float32)
+    ctx = ib.default_context(0)
+    if taps98:
+        taps = list(ib.hbf_taps_98()[:k])
+        casc = HbfDecCascade(k, taps)
+        st = casc.state(lanes, DEV)
+        so = np.zeros(tuple(st.words.shape), np.float32)
+        xl = np.ascontiguousarray(x.swapaxes(0, 1)).reshape(lanes, n_out * R)  # [lanes][samples]
+        want = np.stack([_oracle_dec_cascade_taps(oracle, taps, so[:, l], xl[l]) for l in range(lanes)]).T
+    else:
+        casc = HbfDecCascade(k)
+        so = np.zeros((oracle.hbf_dec_state_words(k), lanes), np.float32)
+        want = oracle.hbf_dec_cascade_lanes(k, so, layout_flat(x, 1), lanes, 1).reshape(lanes, n_out).T
+        st = _dec_state(k)(lanes, DEV)
+    outs, a = [], 0
+    for c in chunks:
+        y = torch.empty(lanes * c, dtype=torch.float32, device=DEV)
+        Lanes(casc).block(st, to_dev(layout_flat(x[a:a + c], 0)), y, 0)
+        if c % TO == 0:
+            assert ctx.last_kernel == "hbf tiled frame-major (tensor-map input)", ctx.last_kernel
+        outs.append(to_np(y).reshape(c, lanes))
+        a += c
+    assert_bits_equal(np.concatenate(outs, axis=0), want, f"lanes={lanes} taps98={taps98}")
+    assert_bits_equal(st.numpy(), so, "state")
