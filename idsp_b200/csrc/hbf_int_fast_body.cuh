@@ -32,7 +32,24 @@ __host__ __device__ constexpr int off_u(int K, int s) {  // float offset of stag
 }
 constexpr int OUT_PITCH = oddpitch(TOUT);
 __host__ __device__ constexpr int off_out(int K) { return off_u(K, K); }
-__host__ __device__ constexpr int smem_floats(int K) { return off_out(K) + 2 * NL * OUT_PITCH; }
+// Frame-major x16 output through the tensor-map unit (mirror image of FmTma in hbf_fast_scalar_body.cuh): the
+// staged tile of a lane pair is 32 lines of 128 bytes ([frame][pair][16 floats], 128-byte swizzle by absolute
+// shared-memory address) plus one unused line, so that the four pairs' swizzle phases stagger and the eight lanes
+// of a quarter-warp store conflict free; four `cp.async.bulk.tensor` stores move a CTA's tile.
+struct FmOut {
+    static constexpr int LINES = TOUT / 16 + 1;
+    static constexpr int BUF_LINES = 4 * LINES;
+    // address of chunk 0 of (buffer, lane, frame); chunk c of that frame sits at the result ^ (c << 4)
+    __device__ __forceinline__ static uint32_t frame_base(uint32_t stg, int buf, int lane, int frame) {
+        const uint32_t line = stg + (uint32_t)(buf * BUF_LINES + (lane >> 1) * LINES + frame) * 128u;
+        return line + (((((uint32_t)(lane & 1)) << 2) ^ (line >> 7)) & 7u) * 16u;
+    }
+};
+__host__ __device__ constexpr int stage_floats(int K) {
+    const int rows = 2 * NL * OUT_PITCH, boxes = 2 * 4 * (TOUT / 16 + 1) * 32;
+    return (K == 4 && NL == 8 && TOUT == 512 && boxes > rows) ? boxes : rows;
+}
+__host__ __device__ constexpr int smem_floats(int K) { return off_out(K) + stage_floats(K); }
 __host__ __device__ constexpr size_t smem_bytes(int K) { return (size_t)smem_floats(K) * 4; }
 __host__ __device__ constexpr int st_word(int s) {  // ABI state word offset of stage s
     int w = 0;
@@ -42,13 +59,13 @@ __host__ __device__ constexpr int st_word(int s) {  // ABI state word offset of 
 
 
 // One item: inputs n0 .. n0+R-1 of row `row` = [H hist | n new]; writes 2R outputs to dst
-template <int TI_, int R> struct IntItem {
+template <int TI_, int R, bool FMT = false> struct IntItem {
     static constexpr int M = HFI_TAPS<TI_>::M;
     static constexpr int LEN = 2 * M - 1;
     static constexpr int H = up4(LEN);
     static constexpr int RO = H - LEN;
     static constexpr int W = up4(RO + R + LEN);
-    __device__ __forceinline__ static void run(const float *row, int n0, float *dst) {
+    __device__ __forceinline__ static void run(const float *row, int n0, float *dst, uint32_t dst_sw = 0) {
         float w[W];
 #pragma unroll
         for (int j = 0; j < W / 4; j++) {
@@ -67,8 +84,16 @@ template <int TI_, int R> struct IntItem {
             o[2 * q + 1] = w[RO + q + M];
         }
 #pragma unroll
-        for (int j = 0; j < 2 * R / 4; j++)
-            reinterpret_cast<float4 *>(dst)[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+        for (int j = 0; j < 2 * R / 4; j++) {
+            if constexpr (FMT) {  // dst_sw = FmOut::frame_base(...): 2R = 16 outputs = the four chunks of one frame
+                static_assert(!FMT || R == 8, "an item is one output frame");
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst_sw ^ (uint32_t)(j << 4)), "f"(o[4 * j]),
+                             "f"(o[4 * j + 1]), "f"(o[4 * j + 2]), "f"(o[4 * j + 3])
+                             : "memory");
+            } else {
+                reinterpret_cast<float4 *>(dst)[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+            }
+        }
     }
 };
 
@@ -95,7 +120,7 @@ __device__ __forceinline__ void carry_rows(float *sm, int warp, int lid) {
     }
 }
 
-template <int K, int s> struct StageRun {
+template <int K, int s, bool FMT = false> struct StageRun {
     __device__ __forceinline__ static void run(float *sm, int tid, int obuf) {
         constexpr int R = st_r(K, s);
         constexpr int ITEMS = NL * st_nin(K, s) / R;
@@ -105,7 +130,11 @@ template <int K, int s> struct StageRun {
             float *dst;
             if constexpr (s == K - 1) dst = sm + off_out(K) + (obuf * NL + lane) * OUT_PITCH + 2 * n0;
             else dst = sm + off_u(K, s + 1) + lane * pitch(K, s + 1) + hist(s + 1) + 2 * n0;
-            IntItem<s, R>::run(U + lane * pitch(K, s), n0, dst);
+            if constexpr (FMT && s == K - 1)
+                IntItem<s, R, true>::run(U + lane * pitch(K, s), n0, nullptr,
+                                         FmOut::frame_base(smem_u32(sm + off_out(K)), obuf, lane, n0 / R));
+            else
+                IntItem<s, R>::run(U + lane * pitch(K, s), n0, dst);
         }
         // the input rows of the previous stage were consumed one barrier ago
         if constexpr (s >= 1) carry_rows<K, s - 1>(sm, tid >> 5, tid & 31);
@@ -149,10 +178,12 @@ template <int K, int s, bool LOAD> struct StateIO {
 // staged output tile in place before it is stored -- one thread per lane, the recurrence is serial in
 // time -- while the four FIR warps already compute the next tile (HbfInt -> Biquad of the config-5 chain
 // without a second pass over HBM).
-template <int K, bool FM, bool BQ = false>
+template <int K, bool FM, bool BQ = false, bool FMT = false>
 __global__ void __launch_bounds__(NT + (BQ ? 32 : 0), BQ ? (NT > 128 ? MINB : HFI_BQ_MINB) : MINB)
 hbf_int_fast_kernel(float *st, const float *x, float *y, size_t n_in, size_t ntiles, size_t lanes, size_t sstride,
-                    Df1Op<float, false>::Params bq) {
+                    Df1Op<float, false>::Params bq, const __grid_constant__ CUtensorMap ymap) {
+    static_assert(!FMT || (FM && !BQ && K == 4 && NL == 8 && TOUT == 512 && 2 * FmOut::BUF_LINES * 32 <= stage_floats(K)),
+                  "tensor-map output: frame-major x16, 8 lanes x 512 samples");
     static_assert(!(BQ && FM), "the fused biquad variant is lane-major");
     constexpr int NTA = NT + (BQ ? 32 : 0);
     auto fir_sync = [&]() {
@@ -162,7 +193,7 @@ hbf_int_fast_kernel(float *st, const float *x, float *y, size_t n_in, size_t nti
     constexpr int TI = ti(K);
     constexpr int NV = FM ? NL * TI : NL * TI / 4;  // loads per input tile (floats if FM, float4 else)
     constexpr int NVT = (NV + NT - 1) / NT;         // ... per thread
-    extern __shared__ __align__(128) float sm[];
+    extern __shared__ __align__(1024) float sm[];
     const int tid = threadIdx.x;
     const size_t lane0 = (size_t)blockIdx.x * NL;
     const int nl = (int)((lanes - lane0) < (size_t)NL ? (lanes - lane0) : (size_t)NL);
@@ -265,6 +296,9 @@ hbf_int_fast_kernel(float *st, const float *x, float *y, size_t n_in, size_t nti
         if constexpr (!FM && !BQ) {
             if (tid < nl) tma_wait_read<1>();
         }
+        if constexpr (FMT) {
+            if (tid == 0) tma_wait_read<1>();
+        }
         fir_sync();
         if constexpr (K >= 2) { StageRun<K, 0>::run(sm, tid, ob); fir_sync(); }
         if constexpr (K >= 3) { StageRun<K, 1>::run(sm, tid, ob); fir_sync(); }
@@ -273,7 +307,7 @@ hbf_int_fast_kernel(float *st, const float *x, float *y, size_t n_in, size_t nti
         if constexpr (BQ) {
             if (i >= 2) nbar_sync(4 + ob, NTA);  // the biquad warp has stored tile i - 2 out of this buffer
         }
-        StageRun<K, K - 1>::run(sm, tid, ob);  // -> staging (and carries rows K-2)
+        StageRun<K, K - 1, FMT>::run(sm, tid, ob);  // -> staging (and carries rows K-2)
         if constexpr (BQ) {
             nbar_arrive(2 + ob, NTA);  // hand the staged tile to the biquad warp
             fir_sync();
@@ -283,9 +317,17 @@ hbf_int_fast_kernel(float *st, const float *x, float *y, size_t n_in, size_t nti
             }
             continue;
         }
-        if constexpr (!FM) fence_async_smem();  // writers make the staging rows visible to the async proxy
+        if constexpr (!FM || FMT) fence_async_smem();  // writers make the staging rows visible to the async proxy
         __syncthreads();
-        if constexpr (FM) {
+        if constexpr (FMT) {
+            if (tid == 0) {
+#pragma unroll
+                for (int q = 0; q < 4; q++)  // lane pair q: columns (lane0 + 2q) * 16 .., frames 32 * i ..
+                    tma_store_2d(&ymap, smem_u32(sm + off_out(K)) + (uint32_t)(ob * FmOut::BUF_LINES + q * FmOut::LINES) * 128u,
+                                 (int)((lane0 + 2 * q) * 16), (int)(i * (TOUT / 16)));
+                tma_commit();
+            }
+        } else if constexpr (FM) {
             constexpr int R = 1 << K;
             constexpr int PF_ = R >= 4 ? 4 : 2;  // floats per piece: 16 bytes, or the 8-byte frame of x2
             const float *stg = sm + off_out(K) + ob * NL * OUT_PITCH;
@@ -321,16 +363,33 @@ hbf_int_fast_kernel(float *st, const float *x, float *y, size_t n_in, size_t nti
     if constexpr (!FM && !BQ) {
         if (tid < nl) tma_wait_read<0>();
     }
+    if constexpr (FMT) {
+        if (tid == 0) tma_wait_read<0>();
+    }
     StateIO<K, 0, false>::run(sm, st, sstride, lane0, nl, tid);
 }
 
 template <int K, bool FM, bool BQ = false>
 static int launch(idsp_ctx *ctx, float *st, const float *x, float *y, size_t n_in, size_t ntiles, size_t lanes,
                   size_t sstride, const Df1Op<float, false>::Params &bq = Df1Op<float, false>::Params()) {
-    auto kern = hbf_int_fast_kernel<K, FM, BQ>;
-    IDSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(K)));
     unsigned grid = (unsigned)((lanes + NL - 1) / NL);
-    kern<<<grid, NT + (BQ ? 32 : 0), smem_bytes(K), ctx->stream>>>(st, x, y, n_in, ntiles, lanes, sstride, bq);
+    CUtensorMap ymap;
+    memset(&ymap, 0, sizeof(ymap));
+    if constexpr (FM && !BQ && K == 4 && NL == 8 && TOUT == 512) {
+        // y[frame][lane][16] as a 2-D tensor of (lanes * 16) x frames words; box = one lane pair x 32 frames
+        if (!getenv("IDSP_HBF_FM_LDGSTS") && lanes * 16 < (1ull << 32) && n_in < (1ull << 31) &&
+            make_map_2d(&ymap, y, (uint64_t)lanes * 16, (uint64_t)n_in, 32, TOUT / 16, CU_TENSOR_MAP_SWIZZLE_128B)) {
+            auto kern = hbf_int_fast_kernel<K, true, false, true>;
+            IDSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(K)));
+            kern<<<grid, NT, smem_bytes(K), ctx->stream>>>(st, x, y, n_in, ntiles, lanes, sstride, bq, ymap);
+            IDSP_KERNEL_FAMILY(ctx, "hbf tiled frame-major (tensor-map output)");
+            IDSP_LAUNCHED(ctx);
+            return IDSP_OK;
+        }
+    }
+    auto kern = hbf_int_fast_kernel<K, FM, BQ, false>;
+    IDSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(K)));
+    kern<<<grid, NT + (BQ ? 32 : 0), smem_bytes(K), ctx->stream>>>(st, x, y, n_in, ntiles, lanes, sstride, bq, ymap);
     IDSP_KERNEL_FAMILY(ctx, BQ ? "hbf tiled interpolator + fused biquad warp" : (FM ? "hbf tiled frame-major" : "hbf tiled lane-major"));
     IDSP_LAUNCHED(ctx);
     return IDSP_OK;

@@ -526,3 +526,30 @@ def test_dec16_frame_major_tensor_map_input(oracle, lanes, taps98):
         a += c
     assert_bits_equal(np.concatenate(outs, axis=0), want, f"lanes={lanes} taps98={taps98}")
     assert_bits_equal(st.numpy(), so, "state")
+
+
+@pytest.mark.parametrize("lanes", [1, 2, 9, 64, 131])
+def test_int16_frame_major_tensor_map_output(oracle, lanes):
+    """frame-major x16 (`[[f32; 16]; lanes]` output frames): the staged output tile leaves as four tensor-map
+    stores per CTA (one lane pair x 32 frames each, 128-byte swizzled staging lines, hbf_int_fast_body.cuh FmOut).
+    Odd lane counts (half / whole boxes outside the tensor are clipped), one lane, several CTAs, whole tiles +
+    ragged tails, state carried over three calls == the oracle bit for bit."""
+    rng = np.random.default_rng(777 + lanes)
+    k, R, TI = 4, 16, 32
+    chunks = [3 * TI, 2 * TI + 5, 4 * TI]
+    n_in = sum(chunks)
+    x = rng.uniform(-1, 1, (n_in, lanes)).astype(np.float32)
+    so = np.zeros((oracle.hbf_int_state_words(k), lanes), np.float32)
+    want = oracle.hbf_int_cascade_lanes(k, so, layout_flat(x, 1), lanes, 1).reshape(lanes, n_in, R).transpose(1, 0, 2)
+    ctx = ib.default_context(0)
+    st = _int_state(k)(lanes, DEV)
+    outs, a = [], 0
+    for c in chunks:
+        y = torch.full((lanes * c * R,), float("nan"), dtype=torch.float32, device=DEV)
+        Lanes(HbfIntCascade(k)).block(st, to_dev(layout_flat(x[a:a + c], 0)), y, 0)
+        if c % TI == 0:
+            assert ctx.last_kernel == "hbf tiled frame-major (tensor-map output)", ctx.last_kernel
+        outs.append(to_np(y).reshape(c, lanes, R))
+        a += c
+    assert_bits_equal(np.concatenate(outs, axis=0), want, f"lanes={lanes}")
+    assert_bits_equal(st.numpy(), so, "state")
