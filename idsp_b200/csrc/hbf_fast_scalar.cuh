@@ -59,14 +59,14 @@ namespace idsp {
 // Runs the tiled kernel over the first (n_out / TO) * TO frames of every lane.  Returns
 // the number of frames it covered in *done (the caller finishes the tail with the
 // generic kernel), or IDSP_HBF_FAST_NOT_APPLICABLE.
-// (frame-major /32 measured faster on the generic thread-per-lane kernel: 946 vs 823 GSa/s, whose 128-byte frames
-// already coalesce well, so it only takes the tiled kernel when forced with policy 2)
+// (frame-major /32 with the LDGSTS gather measured slower than the generic thread-per-lane kernel, 823 vs 946
+// GSa/s; with tensor-map input tiles the tiled kernel is the default for /32 too)
 #define IDSP_DEF_DEC_FAST_TRY(NAME, NS) \
     static int NAME(idsp_ctx *ctx, int k, float *state, const float *x, float *y, size_t n_out, \
                                 size_t lanes, size_t sstride, int layout, size_t *done) { \
         *done = 0; \
         const bool fm = layout == IDSP_FRAME_MAJOR; \
-        if (ctx->policy == 1 || (fm && k > 4 && ctx->policy != 2)) return IDSP_HBF_FAST_NOT_APPLICABLE; \
+        if (ctx->policy == 1 || (fm && k > 4 && ctx->policy != 2 && getenv("IDSP_HBF_FM_LDGSTS"))) return IDSP_HBF_FAST_NOT_APPLICABLE; \
         const size_t TO = (size_t)NS::TT >> k; \
         const size_t ntiles = n_out / TO; \
         const bool ok = ntiles >= 1 && (((uintptr_t)x) & 15) == 0 && (fm || ((n_out << k) % 4) == 0); \

@@ -54,9 +54,11 @@ __host__ __device__ constexpr int po(int K, int s) { return oddpitch(ho(K, s) + 
 // float offsets inside dynamic shared memory
 // the raw ring: S buffers of NL padded rows; the frame-major /16 tensor-map layout (FmTma: S x 4 boxes of
 // TT/16 + 1 lines of 32 floats) lives in the same space
+__host__ __device__ constexpr bool fm_tma_rate(int K) { return (K == 4 || K == 5) && NL == 8 && TT == 512; }
 __host__ __device__ constexpr int raw_floats(int K) {
-    const int rows = S * NL * raw_pitch(K), boxes = S * 4 * (TT / 16 + 1) * 32;
-    return (K == 4 && NL == 8 && boxes > rows) ? boxes : rows;
+    const int R = 1 << K, lpl = 32 / (R > 32 ? 32 : R), hf = (raw_h(K) + R - 1) / R;
+    const int rows = S * NL * raw_pitch(K), boxes = S * (NL / (lpl ? lpl : 1)) * (TT / R + hf) * 32;
+    return (fm_tma_rate(K) && boxes > rows) ? boxes : rows;
 }
 __host__ __device__ constexpr int off_e(int K, int s) {
     int o = raw_floats(K);
@@ -120,7 +122,7 @@ template <int TI, int R> struct RawItem {
     }
     // The same item on the frame-major tensor-map layout of /16 (see FmTma below): lane `lane`, outputs
     // 16 * j16 .. (R == 16, i.e. two frames of input behind one frame of history) of raw buffer `buf`.
-    __device__ __forceinline__ static void run_fm(uint32_t sm_base, int buf, int lane, int j16, float (&y)[R]);
+    template <int K> __device__ __forceinline__ static void run_fm(uint32_t sm_base, int buf, int lane, int j16, float (&y)[R]);
 };
 
 // Frame-major input of the /16 cascade through the tensor-map unit.  The stream is x[frame][lane][16]: the two
@@ -133,18 +135,28 @@ template <int TI, int R> struct RawItem {
 // staggers their swizzle phase: the eight lanes of a quarter-warp that read chunk c of the same frame hit eight
 // different 16-byte slots -- conflict free without padding.  A window chunk is addressed as A ^ (c << 4) with a
 // per-item, per-frame base A.
-struct FmTma {
-    static constexpr int LINES = TT / 16 + 1;      // 128-byte lines per box: history frame + the tile's frames
-    static constexpr int BUF_LINES = 4 * LINES;    // per raw buffer (4 lane pairs)
+// General form (K = 4, 5): a frame of a lane is R = 2^K floats, LPL = 32 / R lanes share a 128-byte line, a CTA's
+// NL lanes are NB = NL / LPL boxes of LINES = frames per tile + history frames; LINES is odd, so box q's swizzle
+// phase is q lines ahead of box 0's.
+template <int K> struct FmTma {
+    static constexpr int R = 1 << K;               // floats per frame and lane
+    static constexpr int LPL = 32 / R;             // lanes per 128-byte line
+    static constexpr int NB = NL / LPL;            // boxes per raw buffer
+    static constexpr int HF = (raw_h(K) + R - 1) / R;  // history frames in front of a tile
+    static constexpr int LINES = TT / R + HF;      // 128-byte lines per box
+    static constexpr int BUF_LINES = NB * LINES;   // per raw buffer
     static constexpr uint32_t BOX_BYTES = LINES * 128;
-    // byte address of line `line` (absolute line index from the 1024-aligned base) for a lane with pair bit b
-    __device__ __forceinline__ static uint32_t line_base(uint32_t sm_base, int line, int b) {
-        return sm_base + (uint32_t)line * 128u + (uint32_t)((((b << 2) ^ line) & 7) << 4);
+    static_assert(LPL >= 1 && NL % LPL == 0 && (NB == 1 || LINES % 2 == 1), "staggered swizzle phases need an odd box height");
+    // byte address of chunk 0 of `lane`'s frame in line `line` (absolute line index from the 1024-aligned base)
+    __device__ __forceinline__ static uint32_t line_base(uint32_t sm_base, int line, int lane) {
+        return sm_base + (uint32_t)line * 128u + (uint32_t)(((((lane % LPL) * (R / 4)) ^ line) & 7) << 4);
     }
-    // address of one float: lane, frame row (0 = history frame) and sample 0..15 inside the frame
+    __device__ __forceinline__ static int line_of(int buf, int lane, int row) {
+        return buf * BUF_LINES + (lane / LPL) * LINES + row;
+    }
+    // address of one float: lane, box row (0 = first history frame) and sample 0..R-1 inside the frame
     __device__ __forceinline__ static uint32_t word(uint32_t sm_base, int buf, int lane, int row, int smp) {
-        const int line = buf * BUF_LINES + (lane >> 1) * LINES + row;
-        return (line_base(sm_base, line, lane & 1) ^ (uint32_t)((smp >> 2) << 4)) + (uint32_t)(smp & 3) * 4u;
+        return (line_base(sm_base, line_of(buf, lane, row), lane) ^ (uint32_t)((smp >> 2) << 4)) + (uint32_t)(smp & 3) * 4u;
     }
 };
 __device__ __forceinline__ float4 lds128a(uint32_t addr) {
@@ -155,19 +167,21 @@ __device__ __forceinline__ float4 lds128a(uint32_t addr) {
     return v;
 }
 template <int TI, int R>
+template <int K>
 __device__ __forceinline__ void RawItem<TI, R>::run_fm(uint32_t sm_base, int buf, int lane, int j16, float (&y)[R]) {
-    static_assert(R == 16, "an item is two frames of input");
-    static_assert(HR <= 16 && HR % 4 == 0, "the raw history fits the frame in front of the tile");
+    using F = FmTma<K>;
+    static_assert(R == 16 && 32 % F::R == 0, "an item is 32 input samples = a whole number of frames");
+    static_assert(HR % 4 == 0 && HR <= F::HF * F::R, "the raw history fits the frames in front of the tile");
+    constexpr int NR = F::HF + 32 / F::R;  // box rows an item's window touches
     float w[W];
-    const int line0 = buf * FmTma::BUF_LINES + (lane >> 1) * FmTma::LINES + 2 * j16;  // row 2*j16 = frame 2*j16 - 1
-    uint32_t A[3];
+    const int line0 = F::line_of(buf, lane, j16 * (32 / F::R));  // first history row of the item
+    uint32_t A[NR];
 #pragma unroll
-    for (int fr = 0; fr < 3; fr++) A[fr] = FmTma::line_base(sm_base, line0 + fr, lane & 1);
+    for (int r = 0; r < NR; r++) A[r] = F::line_base(sm_base, line0 + r, lane);
 #pragma unroll
     for (int j = 0; j < W / 4; j++) {
-        constexpr int H4 = HR / 4;
-        const int rel = j - H4 + 4;  // chunk index counted from the start of row 2*j16 (the history frame of the item)
-        float4 v = lds128a(A[rel / 4] ^ (uint32_t)((rel % 4) << 4));
+        const int smp = F::HF * F::R - HR + 4 * j;  // sample index counted from the start of row line0
+        float4 v = lds128a(A[smp / F::R] ^ (uint32_t)(((smp % F::R) / 4) << 4));
         w[4 * j] = v.x; w[4 * j + 1] = v.y; w[4 * j + 2] = v.z; w[4 * j + 3] = v.w;
     }
     fir(w, y);
@@ -376,7 +390,9 @@ template <int K, int s, bool LOAD, bool FMT = false, int WHICH = 0> struct State
                     constexpr int HR = raw_h(K);
                     const int hs = w < M - 1 ? (HR - 2 * M + 2 + 2 * w) : (HR - 4 * M + 3 + 2 * (w - (M - 1)));
                     if constexpr (FMT) {
-                        const uint32_t a = FmTma::word(smem_u32(sm), rawbuf, lane, roff ? TT / 16 : 0, 16 - HR + hs);
+                        using F = FmTma<K>;
+                        const int sp = roff + F::HF * F::R - HR + hs;  // sample counted from the first history row
+                        const uint32_t a = F::word(smem_u32(sm), rawbuf, lane, sp / F::R, sp % F::R);
                         return sm + (a - smem_u32(sm)) / 4;
                     } else {
                         return sm + (rawbuf * NL + lane) * raw_pitch(K) + roff + hs;
@@ -436,8 +452,8 @@ template <int K, bool FM, bool FMT = false>
 __global__ void __launch_bounds__(NT, HFS_MINB)
 hbf_dec_fast_kernel(float *st, const float *x, float *y, size_t n_out, size_t ntiles, size_t lanes,
                     size_t sstride, const __grid_constant__ CUtensorMap xmap) {
-    static_assert(!FMT || (FM && K == 4 && NL == 8 && TT == 512 && S * FmTma::BUF_LINES * 32 <= raw_floats(K)),
-                  "tensor-map input: frame-major /16, 8 lanes x 512 samples, inside the raw ring");
+    static_assert(!FMT || (FM && fm_tma_rate(K) && S * FmTma<FMT ? K : 4>::BUF_LINES * 32 <= raw_floats(K)),
+                  "tensor-map input: frame-major /16 or /32, 8 lanes x 512 samples, inside the raw ring");
     const size_t ylanes = FM ? lanes : 0;
     constexpr int TI0 = K - 1;
     // /2 runs the 23-tap stage on the raw stream: 16 outputs per item need a 124-float window and spill
@@ -478,12 +494,13 @@ hbf_dec_fast_kernel(float *st, const float *x, float *y, size_t n_out, size_t nt
         const uint32_t bar = smem_u32(&bars[b]);
         const uint32_t hist = tile ? HR : 0;
         if constexpr (FMT) {
+            using F = FmTma<FMT ? K : 4>;
             if (tid == 0) {
-                mbar_expect_tx(bar, 4 * FmTma::BOX_BYTES);
+                mbar_expect_tx(bar, F::NB * F::BOX_BYTES);
 #pragma unroll
-                for (int q = 0; q < 4; q++)  // lane pair q: columns (lane0 + 2q) * 16 .., frames 32 * tile - 1 ..
-                    tma_load_2d(smem_u32(sm) + (uint32_t)(b * FmTma::BUF_LINES + q * FmTma::LINES) * 128u, &xmap,
-                                (int)((lane0 + 2 * q) * 16), (int)(tile * (TT / 16)) - 1, bar);
+                for (int q = 0; q < F::NB; q++)  // box q: lanes lane0 + q * LPL .., frames tile * (TT / R) - HF ..
+                    tma_load_2d(smem_u32(sm) + (uint32_t)(b * F::BUF_LINES + q * F::LINES) * 128u, &xmap,
+                                (int)((lane0 + q * F::LPL) * F::R), (int)(tile * (TT / F::R)) - F::HF, bar);
             }
         } else if constexpr (FM) {
             constexpr int R = 1 << K;            // floats per frame and lane
@@ -566,7 +583,7 @@ hbf_dec_fast_kernel(float *st, const float *x, float *y, size_t n_out, size_t nt
         for (int idx = c0 + gt; idx < c1; idx += G) {
             const int lane = idx % NL, p0 = (idx / NL) * R0;
             float out[R0];
-            if constexpr (FMT) RawItem<TI0, R0>::run_fm(smem_u32(sm), b, lane, idx / NL, out);
+            if constexpr (FMT) RawItem<TI0, R0>::template run_fm<FMT ? K : 4>(smem_u32(sm), b, lane, idx / NL, out);
             else RawItem<TI0, R0>::run(raw + lane * PR, p0, out);
             if constexpr (K == 1) {
                 if (lane < nl && FM) {
@@ -669,11 +686,12 @@ static int launch(idsp_ctx *ctx, float *st, const float *x, float *y, size_t n_o
     unsigned grid = (unsigned)((lanes + NL - 1) / NL);
     CUtensorMap xmap;
     memset(&xmap, 0, sizeof(xmap));
-    if constexpr (FM && K == 4 && NL == 8 && TT == 512 && HFS_FM_TMA) {
-        // x[frame][lane][16] as a 2-D tensor of (lanes * 16) x frames words; box = one lane pair x (1 + 32) frames
+    if constexpr (FM && fm_tma_rate(K) && HFS_FM_TMA) {
+        // x[frame][lane][R] as a 2-D tensor of (lanes * R) x frames words; box = one 128-byte line of lanes x
+        // (history + tile) frames
         const bool tune_off = getenv("IDSP_HBF_FM_LDGSTS") != nullptr;  // A/B switch: the LDGSTS gather
-        if (!tune_off && lanes * 16 < (1ull << 32) && n_out < (1ull << 31) &&
-            make_map_2d(&xmap, x, (uint64_t)lanes * 16, (uint64_t)n_out, 32, FmTma::LINES, CU_TENSOR_MAP_SWIZZLE_128B)) {
+        if (!tune_off && lanes * (1ull << K) < (1ull << 32) && n_out < (1ull << 31) &&
+            make_map_2d(&xmap, x, (uint64_t)lanes << K, (uint64_t)n_out, 32, FmTma<K>::LINES, CU_TENSOR_MAP_SWIZZLE_128B)) {
             auto kern = hbf_dec_fast_kernel<K, true, true>;
             IDSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             kern<<<grid, NT, smem, ctx->stream>>>(st, x, y, n_out, ntiles, lanes, sstride, xmap);

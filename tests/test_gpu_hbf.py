@@ -491,15 +491,16 @@ def test_chain_host_buffers(oracle):
         assert_bits_equal(st, so, "chain host state")
 
 
+@pytest.mark.parametrize("k", [4, 5])
 @pytest.mark.parametrize("taps98", [False, True])
 @pytest.mark.parametrize("lanes", [1, 2, 9, 64, 131])
-def test_dec16_frame_major_tensor_map_input(oracle, lanes, taps98):
+def test_dec16_frame_major_tensor_map_input(oracle, lanes, taps98, k):
     """frame-major /16 (`[[f32; 16]; lanes]` frames, BASELINE configs[2]): the input tiles of the tiled kernel are
     tensor-map boxes of one lane pair x 33 frames in the 128-byte swizzled layout (hbf_fast_scalar_body.cuh, FmTma).
     Odd lane counts (a box half / fully outside the tensor), one lane, several CTAs; whole tiles + a ragged tail;
     state carried over three calls; both compiled tap sets; == the oracle bit for bit."""
-    rng = np.random.default_rng(4242 + lanes)
-    k, R, TO = 4, 16, 32
+    rng = np.random.default_rng(4242 + lanes + k)
+    R, TO = 1 << k, 512 >> k
     chunks = [3 * TO, 2 * TO + 5, 4 * TO]
     n_out = sum(chunks)
     x = rng.uniform(-1, 1, (n_out, lanes, R)).astype(np.float32)
