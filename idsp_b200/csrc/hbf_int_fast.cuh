@@ -98,13 +98,14 @@ __device__ __forceinline__ void bulk_store_1d(void *dst, uint32_t src, uint32_t 
 namespace idsp {
 // Runs the tiled kernel over the first (n_in / TI) * TI input frames of every lane; *done =
 // frames covered (the generic kernel finishes the tail), or IDSP_HBF_FAST_NOT_APPLICABLE.
-// (frame-major x32 measured faster on the generic thread-per-lane kernel: 714 vs 560 GSa/s)
+// (frame-major x32 with per-thread 16-byte stores measured slower than the generic thread-per-lane kernel, 560 vs
+// 714 GSa/s; with tensor-map output tiles the tiled kernel is the default for x32 too)
 #define IDSP_DEF_INT_FAST_TRY(NAME, NS) \
     static int NAME(idsp_ctx *ctx, int k, float *state, const float *x, float *y, size_t n_in, \
                                 size_t lanes, size_t sstride, int layout, size_t *done) { \
         *done = 0; \
         const bool fm = layout == IDSP_FRAME_MAJOR; \
-        if (ctx->policy == 1 || (fm && k > 4 && ctx->policy != 2)) return IDSP_HBF_FAST_NOT_APPLICABLE; \
+        if (ctx->policy == 1 || (fm && k > 4 && ctx->policy != 2 && getenv("IDSP_HBF_FM_LDGSTS"))) return IDSP_HBF_FAST_NOT_APPLICABLE; \
         const size_t TI = (size_t)NS::TOUT >> k; \
         const size_t ntiles = n_in / TI; \
         const bool ok = ntiles >= 1 && ((((uintptr_t)x) | ((uintptr_t)y)) & 15) == 0 && (fm || (n_in % 4) == 0); \

@@ -36,18 +36,24 @@ __host__ __device__ constexpr int off_out(int K) { return off_u(K, K); }
 // staged tile of a lane pair is 32 lines of 128 bytes ([frame][pair][16 floats], 128-byte swizzle by absolute
 // shared-memory address) plus one unused line, so that the four pairs' swizzle phases stagger and the eight lanes
 // of a quarter-warp store conflict free; four `cp.async.bulk.tensor` stores move a CTA's tile.
-struct FmOut {
-    static constexpr int LINES = TOUT / 16 + 1;
-    static constexpr int BUF_LINES = 4 * LINES;
+template <int K> struct FmOut {
+    static constexpr int R = 1 << K;       // floats per output frame and lane
+    static constexpr int LPL = 32 / R;     // lanes per 128-byte line
+    static constexpr int NB = NL / LPL;    // boxes per staging buffer
+    static constexpr int FT = TOUT / R;    // frames per tile
+    static constexpr int LINES = FT + 1 - FT % 2;  // odd box pitch: the boxes' swizzle phases stagger
+    static constexpr int BUF_LINES = NB * LINES;
     // address of chunk 0 of (buffer, lane, frame); chunk c of that frame sits at the result ^ (c << 4)
     __device__ __forceinline__ static uint32_t frame_base(uint32_t stg, int buf, int lane, int frame) {
-        const uint32_t line = stg + (uint32_t)(buf * BUF_LINES + (lane >> 1) * LINES + frame) * 128u;
-        return line + (((((uint32_t)(lane & 1)) << 2) ^ (line >> 7)) & 7u) * 16u;
+        const uint32_t line = stg + (uint32_t)(buf * BUF_LINES + (lane / LPL) * LINES + frame) * 128u;
+        return line + ((((uint32_t)(lane % LPL) * (R / 4)) ^ (line >> 7)) & 7u) * 16u;
     }
 };
+__host__ __device__ constexpr bool fm_out_rate(int K) { return (K == 4 || K == 5) && NL == 8 && TOUT == 512; }
 __host__ __device__ constexpr int stage_floats(int K) {
-    const int rows = 2 * NL * OUT_PITCH, boxes = 2 * 4 * (TOUT / 16 + 1) * 32;
-    return (K == 4 && NL == 8 && TOUT == 512 && boxes > rows) ? boxes : rows;
+    const int R = 1 << K, lpl = 32 / (R > 32 ? 32 : R), ft = TOUT / R;
+    const int rows = 2 * NL * OUT_PITCH, boxes = 2 * (NL / (lpl ? lpl : 1)) * (ft + 1 - ft % 2) * 32;
+    return (fm_out_rate(K) && boxes > rows) ? boxes : rows;
 }
 __host__ __device__ constexpr int smem_floats(int K) { return off_out(K) + stage_floats(K); }
 __host__ __device__ constexpr size_t smem_bytes(int K) { return (size_t)smem_floats(K) * 4; }
@@ -85,8 +91,8 @@ template <int TI_, int R, bool FMT = false> struct IntItem {
         }
 #pragma unroll
         for (int j = 0; j < 2 * R / 4; j++) {
-            if constexpr (FMT) {  // dst_sw = FmOut::frame_base(...): 2R = 16 outputs = the four chunks of one frame
-                static_assert(!FMT || R == 8, "an item is one output frame");
+            if constexpr (FMT) {  // dst_sw = chunk 0 of the item's 16 outputs (FmOut::frame_base ^ offset in the frame)
+                static_assert(!FMT || R == 8, "an item is 16 outputs = four chunks");
                 asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst_sw ^ (uint32_t)(j << 4)), "f"(o[4 * j]),
                              "f"(o[4 * j + 1]), "f"(o[4 * j + 2]), "f"(o[4 * j + 3])
                              : "memory");
@@ -130,9 +136,10 @@ template <int K, int s, bool FMT = false> struct StageRun {
             float *dst;
             if constexpr (s == K - 1) dst = sm + off_out(K) + (obuf * NL + lane) * OUT_PITCH + 2 * n0;
             else dst = sm + off_u(K, s + 1) + lane * pitch(K, s + 1) + hist(s + 1) + 2 * n0;
-            if constexpr (FMT && s == K - 1)
+            if constexpr (FMT && s == K - 1)  // outputs 2 * n0 ..: frame (2 * n0) / 2^K, chunk ((2 * n0) % 2^K) / 4
                 IntItem<s, R, true>::run(U + lane * pitch(K, s), n0, nullptr,
-                                         FmOut::frame_base(smem_u32(sm + off_out(K)), obuf, lane, n0 / R));
+                                         FmOut<K>::frame_base(smem_u32(sm + off_out(K)), obuf, lane, (2 * n0) >> K) ^
+                                             (uint32_t)((((2 * n0) & ((1 << K) - 1)) / 4) << 4));
             else
                 IntItem<s, R>::run(U + lane * pitch(K, s), n0, dst);
         }
@@ -182,8 +189,8 @@ template <int K, bool FM, bool BQ = false, bool FMT = false>
 __global__ void __launch_bounds__(NT + (BQ ? 32 : 0), BQ ? (NT > 128 ? MINB : HFI_BQ_MINB) : MINB)
 hbf_int_fast_kernel(float *st, const float *x, float *y, size_t n_in, size_t ntiles, size_t lanes, size_t sstride,
                     Df1Op<float, false>::Params bq, const __grid_constant__ CUtensorMap ymap) {
-    static_assert(!FMT || (FM && !BQ && K == 4 && NL == 8 && TOUT == 512 && 2 * FmOut::BUF_LINES * 32 <= stage_floats(K)),
-                  "tensor-map output: frame-major x16, 8 lanes x 512 samples");
+    static_assert(!FMT || (FM && !BQ && fm_out_rate(K) && 2 * FmOut<FMT ? K : 4>::BUF_LINES * 32 <= stage_floats(K)),
+                  "tensor-map output: frame-major x16 / x32, 8 lanes x 512 samples");
     static_assert(!(BQ && FM), "the fused biquad variant is lane-major");
     constexpr int NTA = NT + (BQ ? 32 : 0);
     auto fir_sync = [&]() {
@@ -320,11 +327,12 @@ hbf_int_fast_kernel(float *st, const float *x, float *y, size_t n_in, size_t nti
         if constexpr (!FM || FMT) fence_async_smem();  // writers make the staging rows visible to the async proxy
         __syncthreads();
         if constexpr (FMT) {
+            using F = FmOut<FMT ? K : 4>;
             if (tid == 0) {
 #pragma unroll
-                for (int q = 0; q < 4; q++)  // lane pair q: columns (lane0 + 2q) * 16 .., frames 32 * i ..
-                    tma_store_2d(&ymap, smem_u32(sm + off_out(K)) + (uint32_t)(ob * FmOut::BUF_LINES + q * FmOut::LINES) * 128u,
-                                 (int)((lane0 + 2 * q) * 16), (int)(i * (TOUT / 16)));
+                for (int q = 0; q < F::NB; q++)  // box q: lanes lane0 + q * LPL .., frames i * FT ..
+                    tma_store_2d(&ymap, smem_u32(sm + off_out(K)) + (uint32_t)(ob * F::BUF_LINES + q * F::LINES) * 128u,
+                                 (int)((lane0 + q * F::LPL) * F::R), (int)(i * F::FT));
                 tma_commit();
             }
         } else if constexpr (FM) {
@@ -375,10 +383,11 @@ static int launch(idsp_ctx *ctx, float *st, const float *x, float *y, size_t n_i
     unsigned grid = (unsigned)((lanes + NL - 1) / NL);
     CUtensorMap ymap;
     memset(&ymap, 0, sizeof(ymap));
-    if constexpr (FM && !BQ && K == 4 && NL == 8 && TOUT == 512) {
-        // y[frame][lane][16] as a 2-D tensor of (lanes * 16) x frames words; box = one lane pair x 32 frames
-        if (!getenv("IDSP_HBF_FM_LDGSTS") && lanes * 16 < (1ull << 32) && n_in < (1ull << 31) &&
-            make_map_2d(&ymap, y, (uint64_t)lanes * 16, (uint64_t)n_in, 32, TOUT / 16, CU_TENSOR_MAP_SWIZZLE_128B)) {
+    if constexpr (FM && !BQ && fm_out_rate(K)) {
+        // y[frame][lane][R] as a 2-D tensor of (lanes * R) x frames words; box = one 128-byte line of lanes x the
+        // tile's frames
+        if (!getenv("IDSP_HBF_FM_LDGSTS") && lanes * (1ull << K) < (1ull << 32) && n_in < (1ull << 31) &&
+            make_map_2d(&ymap, y, (uint64_t)lanes << K, (uint64_t)n_in, 32, FmOut<K>::FT, CU_TENSOR_MAP_SWIZZLE_128B)) {
             auto kern = hbf_int_fast_kernel<K, true, false, true>;
             IDSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(K)));
             kern<<<grid, NT, smem_bytes(K), ctx->stream>>>(st, x, y, n_in, ntiles, lanes, sstride, bq, ymap);

@@ -529,14 +529,15 @@ def test_dec16_frame_major_tensor_map_input(oracle, lanes, taps98, k):
     assert_bits_equal(st.numpy(), so, "state")
 
 
+@pytest.mark.parametrize("k", [4, 5])
 @pytest.mark.parametrize("lanes", [1, 2, 9, 64, 131])
-def test_int16_frame_major_tensor_map_output(oracle, lanes):
+def test_int16_frame_major_tensor_map_output(oracle, lanes, k):
     """frame-major x16 (`[[f32; 16]; lanes]` output frames): the staged output tile leaves as four tensor-map
     stores per CTA (one lane pair x 32 frames each, 128-byte swizzled staging lines, hbf_int_fast_body.cuh FmOut).
     Odd lane counts (half / whole boxes outside the tensor are clipped), one lane, several CTAs, whole tiles +
     ragged tails, state carried over three calls == the oracle bit for bit."""
-    rng = np.random.default_rng(777 + lanes)
-    k, R, TI = 4, 16, 32
+    rng = np.random.default_rng(777 + lanes + k)
+    R, TI = 1 << k, 512 >> k
     chunks = [3 * TI, 2 * TI + 5, 4 * TI]
     n_in = sum(chunks)
     x = rng.uniform(-1, 1, (n_in, lanes)).astype(np.float32)
