@@ -54,10 +54,11 @@ __host__ __device__ constexpr int po(int K, int s) { return oddpitch(ho(K, s) + 
 // float offsets inside dynamic shared memory
 // the raw ring: S buffers of NL padded rows; the frame-major /16 tensor-map layout (FmTma: S x 4 boxes of
 // TT/16 + 1 lines of 32 floats) lives in the same space
-__host__ __device__ constexpr bool fm_tma_rate(int K) { return (K == 4 || K == 5) && NL == 8 && TT == 512; }
+__host__ __device__ constexpr bool fm_tma_rate(int K) { return K >= 2 && K <= 5 && NL == 8 && TT == 512; }
 __host__ __device__ constexpr int raw_floats(int K) {
     const int R = 1 << K, lpl = 32 / (R > 32 ? 32 : R), hf = (raw_h(K) + R - 1) / R;
-    const int rows = S * NL * raw_pitch(K), boxes = S * (NL / (lpl ? lpl : 1)) * (TT / R + hf) * 32;
+    const int nb = NL / (lpl ? lpl : 1), br = TT / R + hf;
+    const int rows = S * NL * raw_pitch(K), boxes = S * nb * (nb == 1 ? br : (br | 1)) * 32;
     return (fm_tma_rate(K) && boxes > rows) ? boxes : rows;
 }
 __host__ __device__ constexpr int off_e(int K, int s) {
@@ -135,7 +136,7 @@ template <int TI, int R> struct RawItem {
 // staggers their swizzle phase: the eight lanes of a quarter-warp that read chunk c of the same frame hit eight
 // different 16-byte slots -- conflict free without padding.  A window chunk is addressed as A ^ (c << 4) with a
 // per-item, per-frame base A.
-// General form (K = 4, 5): a frame of a lane is R = 2^K floats, LPL = 32 / R lanes share a 128-byte line, a CTA's
+// General form (K = 2 ... 5): a frame of a lane is R = 2^K floats, LPL = 32 / R lanes share a 128-byte line, a CTA's
 // NL lanes are NB = NL / LPL boxes of LINES = frames per tile + history frames; LINES is odd, so box q's swizzle
 // phase is q lines ahead of box 0's.
 template <int K> struct FmTma {
@@ -143,9 +144,10 @@ template <int K> struct FmTma {
     static constexpr int LPL = 32 / R;             // lanes per 128-byte line
     static constexpr int NB = NL / LPL;            // boxes per raw buffer
     static constexpr int HF = (raw_h(K) + R - 1) / R;  // history frames in front of a tile
-    static constexpr int LINES = TT / R + HF;      // 128-byte lines per box
+    static constexpr int BOX_ROWS = TT / R + HF;   // 128-byte lines a box delivers
+    static constexpr int LINES = NB == 1 ? BOX_ROWS : (BOX_ROWS | 1);  // box pitch in lines (odd: see above)
     static constexpr int BUF_LINES = NB * LINES;   // per raw buffer
-    static constexpr uint32_t BOX_BYTES = LINES * 128;
+    static constexpr uint32_t BOX_BYTES = BOX_ROWS * 128;
     static_assert(LPL >= 1 && NL % LPL == 0 && (NB == 1 || LINES % 2 == 1), "staggered swizzle phases need an odd box height");
     // byte address of chunk 0 of `lane`'s frame in line `line` (absolute line index from the 1024-aligned base)
     __device__ __forceinline__ static uint32_t line_base(uint32_t sm_base, int line, int lane) {
@@ -453,7 +455,7 @@ __global__ void __launch_bounds__(NT, HFS_MINB)
 hbf_dec_fast_kernel(float *st, const float *x, float *y, size_t n_out, size_t ntiles, size_t lanes,
                     size_t sstride, const __grid_constant__ CUtensorMap xmap) {
     static_assert(!FMT || (FM && fm_tma_rate(K) && S * FmTma<FMT ? K : 4>::BUF_LINES * 32 <= raw_floats(K)),
-                  "tensor-map input: frame-major /16 or /32, 8 lanes x 512 samples, inside the raw ring");
+                  "tensor-map input: frame-major /4 ... /32, 8 lanes x 512 samples, inside the raw ring");
     const size_t ylanes = FM ? lanes : 0;
     constexpr int TI0 = K - 1;
     // /2 runs the 23-tap stage on the raw stream: 16 outputs per item need a 124-float window and spill
@@ -691,7 +693,7 @@ static int launch(idsp_ctx *ctx, float *st, const float *x, float *y, size_t n_o
         // (history + tile) frames
         const bool tune_off = getenv("IDSP_HBF_FM_LDGSTS") != nullptr;  // A/B switch: the LDGSTS gather
         if (!tune_off && lanes * (1ull << K) < (1ull << 32) && n_out < (1ull << 31) &&
-            make_map_2d(&xmap, x, (uint64_t)lanes << K, (uint64_t)n_out, 32, FmTma<K>::LINES, CU_TENSOR_MAP_SWIZZLE_128B)) {
+            make_map_2d(&xmap, x, (uint64_t)lanes << K, (uint64_t)n_out, 32, FmTma<K>::BOX_ROWS, CU_TENSOR_MAP_SWIZZLE_128B)) {
             auto kern = hbf_dec_fast_kernel<K, true, true>;
             IDSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             kern<<<grid, NT, smem, ctx->stream>>>(st, x, y, n_out, ntiles, lanes, sstride, xmap);

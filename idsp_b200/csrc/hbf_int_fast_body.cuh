@@ -49,7 +49,7 @@ template <int K> struct FmOut {
         return line + ((((uint32_t)(lane % LPL) * (R / 4)) ^ (line >> 7)) & 7u) * 16u;
     }
 };
-__host__ __device__ constexpr bool fm_out_rate(int K) { return (K == 4 || K == 5) && NL == 8 && TOUT == 512; }
+__host__ __device__ constexpr bool fm_out_rate(int K) { return K >= 2 && K <= 5 && NL == 8 && TOUT == 512; }
 __host__ __device__ constexpr int stage_floats(int K) {
     const int R = 1 << K, lpl = 32 / (R > 32 ? 32 : R), ft = TOUT / R;
     const int rows = 2 * NL * OUT_PITCH, boxes = 2 * (NL / (lpl ? lpl : 1)) * (ft + 1 - ft % 2) * 32;
@@ -71,7 +71,7 @@ template <int TI_, int R, bool FMT = false> struct IntItem {
     static constexpr int H = up4(LEN);
     static constexpr int RO = H - LEN;
     static constexpr int W = up4(RO + R + LEN);
-    __device__ __forceinline__ static void run(const float *row, int n0, float *dst, uint32_t dst_sw = 0) {
+    __device__ __forceinline__ static void run(const float *row, int n0, float *dst, const uint32_t *dst_sw = nullptr) {
         float w[W];
 #pragma unroll
         for (int j = 0; j < W / 4; j++) {
@@ -91,9 +91,9 @@ template <int TI_, int R, bool FMT = false> struct IntItem {
         }
 #pragma unroll
         for (int j = 0; j < 2 * R / 4; j++) {
-            if constexpr (FMT) {  // dst_sw = chunk 0 of the item's 16 outputs (FmOut::frame_base ^ offset in the frame)
+            if constexpr (FMT) {  // dst_sw[j] = swizzled shared-memory address of the item's chunk j (FmOut)
                 static_assert(!FMT || R == 8, "an item is 16 outputs = four chunks");
-                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst_sw ^ (uint32_t)(j << 4)), "f"(o[4 * j]),
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst_sw[j]), "f"(o[4 * j]),
                              "f"(o[4 * j + 1]), "f"(o[4 * j + 2]), "f"(o[4 * j + 3])
                              : "memory");
             } else {
@@ -136,10 +136,16 @@ template <int K, int s, bool FMT = false> struct StageRun {
             float *dst;
             if constexpr (s == K - 1) dst = sm + off_out(K) + (obuf * NL + lane) * OUT_PITCH + 2 * n0;
             else dst = sm + off_u(K, s + 1) + lane * pitch(K, s + 1) + hist(s + 1) + 2 * n0;
-            if constexpr (FMT && s == K - 1)  // outputs 2 * n0 ..: frame (2 * n0) / 2^K, chunk ((2 * n0) % 2^K) / 4
-                IntItem<s, R, true>::run(U + lane * pitch(K, s), n0, nullptr,
-                                         FmOut<K>::frame_base(smem_u32(sm + off_out(K)), obuf, lane, (2 * n0) >> K) ^
-                                             (uint32_t)((((2 * n0) & ((1 << K) - 1)) / 4) << 4));
+            if constexpr (FMT && s == K - 1) {  // chunk j = outputs 2 * n0 + 4j ..: frame (..) / 2^K, chunk ((..) % 2^K) / 4
+                uint32_t d[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int o0 = 2 * n0 + 4 * j;
+                    d[j] = FmOut<K>::frame_base(smem_u32(sm + off_out(K)), obuf, lane, o0 >> K) ^
+                           (uint32_t)(((o0 & ((1 << K) - 1)) / 4) << 4);
+                }
+                IntItem<s, R, true>::run(U + lane * pitch(K, s), n0, nullptr, d);
+            }
             else
                 IntItem<s, R>::run(U + lane * pitch(K, s), n0, dst);
         }
@@ -190,7 +196,7 @@ __global__ void __launch_bounds__(NT + (BQ ? 32 : 0), BQ ? (NT > 128 ? MINB : HF
 hbf_int_fast_kernel(float *st, const float *x, float *y, size_t n_in, size_t ntiles, size_t lanes, size_t sstride,
                     Df1Op<float, false>::Params bq, const __grid_constant__ CUtensorMap ymap) {
     static_assert(!FMT || (FM && !BQ && fm_out_rate(K) && 2 * FmOut<FMT ? K : 4>::BUF_LINES * 32 <= stage_floats(K)),
-                  "tensor-map output: frame-major x16 / x32, 8 lanes x 512 samples");
+                  "tensor-map output: frame-major x4 ... x32, 8 lanes x 512 samples");
     static_assert(!(BQ && FM), "the fused biquad variant is lane-major");
     constexpr int NTA = NT + (BQ ? 32 : 0);
     auto fir_sync = [&]() {

@@ -491,7 +491,7 @@ def test_chain_host_buffers(oracle):
         assert_bits_equal(st, so, "chain host state")
 
 
-@pytest.mark.parametrize("k", [4, 5])
+@pytest.mark.parametrize("k", [2, 3, 4, 5])
 @pytest.mark.parametrize("taps98", [False, True])
 @pytest.mark.parametrize("lanes", [1, 2, 9, 64, 131])
 def test_dec16_frame_major_tensor_map_input(oracle, lanes, taps98, k):
@@ -529,7 +529,7 @@ def test_dec16_frame_major_tensor_map_input(oracle, lanes, taps98, k):
     assert_bits_equal(st.numpy(), so, "state")
 
 
-@pytest.mark.parametrize("k", [4, 5])
+@pytest.mark.parametrize("k", [2, 3, 4, 5])
 @pytest.mark.parametrize("lanes", [1, 2, 9, 64, 131])
 def test_int16_frame_major_tensor_map_output(oracle, lanes, k):
     """frame-major x16 (`[[f32; 16]; lanes]` output frames): the staged output tile leaves as four tensor-map
