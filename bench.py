@@ -1050,6 +1050,23 @@ def run_hbf(args, rank, world, local):
         if rank == 0:
             return {"profile_run": True, "value": value, "ms_per_step": ms / args.steps, "gpu_launches": int(launches)}
         return None
+    if getattr(args, "resident_only", False):  # the second layout of the default run: resident leg + roofline only
+        del xin, yout
+        torch.cuda.empty_cache()
+        if rank != 0:
+            return None
+        peak, peak_src = peak_hbm()
+        per_launch_bytes = 4.25 * n_in
+        achieved = per_launch_bytes * launches / (ms * 1e-3) / 1e9 if launches else 0.0
+        cfg_h = hbf_config(args)
+        if hl == 0:
+            cfg_h["workload"] = cfg_h["workload"].replace("lane-major", "frame-major ([[f32;16]; lanes] per frame)")
+        return {"metric": metric_name("hbf"), "value": value, "unit": "GSa/s", "n_gpus": world, "steps": args.steps,
+                "ms_per_step": ms / args.steps, "dtype": "f32", "config": cfg_h, "kernel": ctx.last_kernel,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": per_launch_bytes},
+                "gpu_launches": int(launches), "clocks": clocks,
+                "parity_check": f"first step == oracle on {sub} lanes strided over the slice (first / last 8 included) x all samples"}
     el = 8192
     xh = torch.empty(el * HBF_INPUTS, dtype=torch.float32).uniform_(-1, 1).pin_memory()
     yh = torch.empty(el * n_out, dtype=torch.float32).pin_memory()
@@ -1148,7 +1165,12 @@ def main():
 
             if line is not None:
                 line.setdefault("extra", {})
-            for name, fn, keys in (("lockin_i32", run_lockin, ("metric", "value", "unit", "n_gpus", "steps", "ms_per_step", "dtype", "config", "roofline", "gpu_launches", "parity_check")),
+            def run_hbf_fm(a, rank, world, local):  # configs[2] on the reference's own frame format [[f32; 16]; lanes]
+                a.hbf_layout, a.resident_only = 0, True  # resident leg only (the host / CPU legs are in hbf_dec16_f32)
+                return run_hbf(a, rank, world, local)
+
+            for name, fn, keys in (("hbf_dec16_f32_frame_major", run_hbf_fm, None),
+                                   ("lockin_i32", run_lockin, ("metric", "value", "unit", "n_gpus", "steps", "ms_per_step", "dtype", "config", "roofline", "gpu_launches", "parity_check")),
                                    ("lockin_sharded", run_lockin_sharded, None),
                                    ("chain_f32", run_chain, ("metric", "value", "unit", "n_gpus", "dtype", "config", "sweep", "roofline", "e2e", "parity_check"))):
                 try:
