@@ -692,7 +692,7 @@ static int launch(idsp_ctx *ctx, float *st, const float *x, float *y, size_t n_o
         // x[frame][lane][R] as a 2-D tensor of (lanes * R) x frames words; box = one 128-byte line of lanes x
         // (history + tile) frames
         const bool tune_off = getenv("IDSP_HBF_FM_LDGSTS") != nullptr;  // A/B switch: the LDGSTS gather
-        if (!tune_off && lanes * (1ull << K) < (1ull << 32) && n_out < (1ull << 31) &&
+        if (!tune_off && lanes * (1ull << K) < (1ull << 31) && n_out < (1ull << 31) &&
             make_map_2d(&xmap, x, (uint64_t)lanes << K, (uint64_t)n_out, 32, FmTma<K>::BOX_ROWS, CU_TENSOR_MAP_SWIZZLE_128B)) {
             auto kern = hbf_dec_fast_kernel<K, true, true>;
             IDSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -392,7 +392,7 @@ static int launch(idsp_ctx *ctx, float *st, const float *x, float *y, size_t n_i
     if constexpr (FM && !BQ && fm_out_rate(K)) {
         // y[frame][lane][R] as a 2-D tensor of (lanes * R) x frames words; box = one 128-byte line of lanes x the
         // tile's frames
-        if (!getenv("IDSP_HBF_FM_LDGSTS") && lanes * (1ull << K) < (1ull << 32) && n_in < (1ull << 31) &&
+        if (!getenv("IDSP_HBF_FM_LDGSTS") && lanes * (1ull << K) < (1ull << 31) && n_in < (1ull << 31) &&
             make_map_2d(&ymap, y, (uint64_t)lanes << K, (uint64_t)n_in, 32, FmOut<K>::FT, CU_TENSOR_MAP_SWIZZLE_128B)) {
             auto kern = hbf_int_fast_kernel<K, true, false, true>;
             IDSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(K)));
