@@ -747,11 +747,13 @@ static int chain_dev_strided(idsp_ctx *ctx, int log2_rate, const float ba[5], fl
     // FIR cascades are time-parallel (tiled kernels, 8 lanes per CTA), only the biquad recurrence is
     // serial per lane.  The low-rate stream goes through ctx scratch, the biquad runs in place on y.
     // Measured cross-over on B200: composed wins up to 2^14 lanes (profiles/r1_bench_chain.json).
-    // Lane-major, whole tiles, up to 2^17 lanes: tiled decimator -> low-rate scratch -> tiled interpolator
+    // Lane-major, whole tiles, up to 2^18 lanes: tiled decimator -> low-rate scratch -> tiled interpolator
     // with the biquad fused as a fifth warp (hbf_int_fast_body.cuh): two passes, 4.25 + 4.25 bytes per sample.
     // Measured on B200 against the alternatives (GSa/s at 2^10 / 2^12 / 2^14 / 2^16 / 2^18 lanes, 2^30 samples):
     // three kernels 44 / 145 / 276 / - / -, thread-per-lane fused - / - / - / 320 / 353, this path with 8-lane
-    // tiles 86 / 243 / 250 / 271 / 245 and with 16-lane tiles 71 / 221 / 313 / 337 / 304.  Short streams
+    // tiles 86 / 243 / 250 / 271 / 245 and with 16-lane tiles 71 / 221 / 313 / 337 / 304; since the biquad warp's
+    // store wait left its critical path (round 2) 16-lane tiles give 335 / 364 / 352 / 340 at 2^14 / 2^16 / 2^17 /
+    // 2^18 lanes against 322 for the single-pass kernel at 2^18 (tools/chain_crossover.py).  Short streams
     // (fewer than 8 tiles per call) and more lanes stay on the single-pass thread-per-lane kernel.
     int wide = lanes > 8192 ? 1 : 0;  // 0: 8-lane tiles, 1: 16-lane tiles
 #ifdef IDSP_TUNE
@@ -759,7 +761,7 @@ static int chain_dev_strided(idsp_ctx *ctx, int log2_rate, const float ba[5], fl
 #endif
     const size_t tile_low = hbf_int_bq_tile(log2_rate, wide);
     if (layout == IDSP_LANE_MAJOR && ctx->policy != 1 && n_low % tile_low == 0 && n_low >= 8 * tile_low &&
-        (lanes <= 131072 || ctx->policy == 2) && ((((uintptr_t)x) | ((uintptr_t)y)) & 15) == 0) {
+        (lanes <= 262144 || ctx->policy == 2) && ((((uintptr_t)x) | ((uintptr_t)y)) & 15) == 0) {
         void *low = nullptr;
         int r = idsp_scratch(ctx, n_low * lanes * sizeof(float), &low);
         if (r) return r;
