@@ -19,7 +19,8 @@ Workloads (BASELINE.json `configs`):
 `roofline`: algorithmic bytes per launch / average launch duration vs MEASURED_PEAKS.json.
 `cpu_baseline`: the CPU oracle (a C port of the reference; the Rust crate cannot be built in
            this image) timed on the host cores on a bounded sample of the same workload.
-`extra`  : the default run (any N) also measures configs[2] (hbf), configs[3] (lock-in, resident per GPU AND as the
+`extra`  : the default run (any N) also measures configs[2] (hbf, lane-major with all legs and frame-major
+           `[[f32;16]; lanes]` frames resident), configs[3] (lock-in, resident per GPU AND as the
            sharded data plane: root-resident lanes -> NCCL scatter -> lock-in -> NCCL gather / kernels storing
            into the root's buffer over NVLink) and configs[4] (chain sweep) in the same process and attaches
            their lines (a failure there is recorded, never raised).
