@@ -1065,7 +1065,8 @@ def run_hbf(args, rank, world, local):
         return {"metric": metric_name("hbf"), "value": value, "unit": "GSa/s", "n_gpus": world, "steps": args.steps,
                 "ms_per_step": ms / args.steps, "dtype": "f32", "config": cfg_h, "kernel": ctx.last_kernel,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": per_launch_bytes},
+                             "traffic": traffic_from_profiles("hbf_dec16_f32_fm_bytes_per_launch") if hl == 0 else None,
+                             "peak_source": peak_src, "algorithmic_bytes_per_launch": per_launch_bytes},
                 "gpu_launches": int(launches), "clocks": clocks,
                 "parity_check": f"first step == oracle on {sub} lanes strided over the slice (first / last 8 included) x all samples"}
     el = 8192
