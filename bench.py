@@ -488,8 +488,9 @@ def run_lockin(args, rank, world, local):
         "config": {"workload": "configs[3]: DDC lock-in i32, 1048576 lanes over 8 GPUs (131072 per GPU), 16384 frames, frame-major",
                    "lanes_per_gpu": lanes, "frames_per_step": frames, "parallelism": f"lanes sharded over {world} GPU(s), no collective"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": per_launch_bytes,
-                     "note": "~70 integer instructions per sample: issue-bound and HBM-bound ceilings nearly coincide"},
+                     "traffic": traffic_from_profiles("lockin_i32_fm_bytes_per_launch") if (lanes, frames) == (131072, 16384) else None,
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": per_launch_bytes,
+                     "note": "52 integer instructions per sample; ALU pipe 60 %, IMAD (fmaheavy) pipe 66 % busy (profiles/r2_lockin_fm_final_ncu.md): bound by the two integer pipes, not by HBM"},
         "gpu_launches": int(launches), "clocks": clocks,
         "parity_check": f"first step == oracle on {sub} lanes strided over the whole lane range (+ first / last 8) x all frames",
     }
