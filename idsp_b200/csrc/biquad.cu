@@ -32,9 +32,14 @@ template <class T> static bool f_ok(int F) {
 template <class Op>
 static int launch_packed_or_lanes(idsp_ctx *ctx, const typename Op::Params &p, const typename Op::In *x,
                                   typename Op::Out *y, size_t frames, size_t lanes, size_t sstride, int layout) {
-    if constexpr (sizeof(typename Op::In) == 2 && std::is_integral<typename Op::In>::value) {
+    if constexpr (sizeof(typename Op::In) <= 2 && std::is_integral<typename Op::In>::value) {
         constexpr size_t P = 4 / sizeof(typename Op::In);
-        if (layout == IDSP_FRAME_MAJOR && lanes % (4 * P) == 0 && frames >= 16 &&
+        // i8: four lanes per word quarter the number of threads, which only pays once there are enough lanes to
+        // keep the SMs full: 65 536 lanes 852 -> 698 GSa/s, 2^18 lanes 1 095 -> 1 448, 2^20 lanes 1 149 -> 1 939, 2^22 lanes
+        // 1 162 -> 2 013 (tools/bench_i8_packed.py); packed from 2^18 lanes on
+        static size_t i8_min_lanes = getenv("IDSP_I8_PACKED_MIN_LANES") ? (size_t)atoll(getenv("IDSP_I8_PACKED_MIN_LANES")) : (size_t)1 << 18;
+        const bool enough = sizeof(typename Op::In) == 2 || lanes >= i8_min_lanes;
+        if (enough && layout == IDSP_FRAME_MAJOR && lanes % (4 * P) == 0 && frames >= 16 &&
             (((uintptr_t)x | (uintptr_t)y) & 15) == 0) {
             int tr = tma_try_launch<PackedOp<Op>>(ctx, p, reinterpret_cast<const int32_t *>(x),
                                                   reinterpret_cast<int32_t *>(y), frames, lanes / P, sstride, layout);
