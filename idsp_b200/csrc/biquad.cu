@@ -28,7 +28,7 @@ template <class T> static bool f_ok(int F) {
 // ------------------------------------------------------------------ DF1
 // i16 frame-major: 2 adjacent lanes share a 32-bit word, so the rows go through the frame-major TMA
 // kernels as words (PackedOp, 794 -> 870 GSa/s); everything else takes the generic lane kernels
-// (i8 packed four to a word leaves too few warps per SM at 65 536 lanes: 912 -> 722, not used).
+// (i8 packed four to a word: from 2^18 lanes on, see below).
 template <class Op>
 static int launch_packed_or_lanes(idsp_ctx *ctx, const typename Op::Params &p, const typename Op::In *x,
                                   typename Op::Out *y, size_t frames, size_t lanes, size_t sstride, int layout) {
@@ -37,7 +37,8 @@ static int launch_packed_or_lanes(idsp_ctx *ctx, const typename Op::Params &p, c
         // i8: four lanes per word quarter the number of threads, which only pays once there are enough lanes to
         // keep the SMs full: 65 536 lanes 852 -> 698 GSa/s, 2^18 lanes 1 095 -> 1 448, 2^20 lanes 1 149 -> 1 939, 2^22 lanes
         // 1 162 -> 2 013 (tools/bench_i8_packed.py); packed from 2^18 lanes on
-        static size_t i8_min_lanes = getenv("IDSP_I8_PACKED_MIN_LANES") ? (size_t)atoll(getenv("IDSP_I8_PACKED_MIN_LANES")) : (size_t)1 << 18;
+        const char *e8 = getenv("IDSP_I8_PACKED_MIN_LANES");  // A/B switch, read per call (no shared mutable state)
+        const size_t i8_min_lanes = e8 ? (size_t)atoll(e8) : (size_t)1 << 18;
         const bool enough = sizeof(typename Op::In) == 2 || lanes >= i8_min_lanes;
         if (enough && layout == IDSP_FRAME_MAJOR && lanes % (4 * P) == 0 && frames >= 16 &&
             (((uintptr_t)x | (uintptr_t)y) & 15) == 0) {
