@@ -345,3 +345,32 @@ def test_last_kernel_reports_the_fallback():
     assert ctx.last_kernel.startswith("tma frame-major"), ctx.last_kernel
     Lanes(bq).block(DirectForm1.default("i32", lanes, DEV), x[1:], y[1:], 0)
     assert ctx.last_kernel == "generic frame-major", ctx.last_kernel
+
+
+@pytest.mark.parametrize("clamp", [False, True])
+def test_df1_i8_packed_four_lanes_per_word(oracle, monkeypatch, clamp):
+    """i8 frame-major from 2^18 lanes on (here forced by IDSP_I8_PACKED_MIN_LANES, read per call): four adjacent
+    lanes share a 32-bit word and ride the tensor-map kernels (PackedOp<Df1Op<i8>>); state stays one word per
+    lane.  Same bits as the oracle and as the generic kernel."""
+    import os
+
+    rng = np.random.default_rng(88 + clamp)
+    kind, lanes, frames = "i8", 4096 + 16, 37
+    bq = _coeffs(kind, rng)
+    cl = [3, -8, 8] if clamp else None
+    x = rand_samples(rng, kind, frames * lanes)
+    st0 = rand_samples(rng, kind, 4 * lanes, amp_bits=BITS[kind] - 4).reshape(4, lanes)
+    so = st0.copy()
+    want = oracle.biquad_lanes("df1", kind, bq.ba, bq.F, cl, so, x, lanes, 0, nthreads=4)
+    cfg = BiquadClamp(bq, *cl) if clamp else bq
+    ctx = ib.default_context(0)
+    for force, family in (("1", "tma"), (str(1 << 40), "generic")):
+        monkeypatch.setenv("IDSP_I8_PACKED_MIN_LANES", force)
+        so = st0.copy()
+        oracle.biquad_lanes("df1", kind, bq.ba, bq.F, cl, so, x, lanes, 0, nthreads=4)
+        st = DirectForm1(to_dev(st0), kind)
+        y = torch.empty_like(to_dev(x))
+        Lanes(cfg).block(st, to_dev(x), y, 0)
+        assert ctx.last_kernel.startswith(family), ctx.last_kernel
+        assert_bits_equal(to_np(y), want, f"packed forced={force}")
+        assert_bits_equal(st.numpy(), so)
